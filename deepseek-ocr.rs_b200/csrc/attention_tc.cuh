@@ -1,0 +1,289 @@
+// Flash-style attention for the vision towers on tcgen05 / TMEM (head_dim 64, non-causal):
+//   SAM windowed + global attention with the decomposed relative-position bias added in-kernel
+//   (replaces vision/sam.rs:804-888 + the host loop compute_relative_bias :1124-1192, which materialises a
+//   [B,12,S,S] f32 score tensor AND a same-sized bias tensor via a D2H/H2D round trip per layer), and
+//   CLIP-L attention (vision/clip.rs:349-381, 449-453).
+//
+// One CTA = 128 queries of one (batch, head); it walks the keys in blocks of KV = RB * GW keys (RB whole
+// rows of the GW-wide token grid) so that a key column's (kh, kw) is a compile-time function of its column
+// index.  Q, K and V tiles are TMA-loaded straight out of the fused qkv activation [rows, 3, H, 64] - no
+// q/k/v split or transpose pass.  S = Q K^T goes to TMEM; each softmax thread owns one query row, adds
+//   bias[q, k] = Zh[q, qh - kh + GW-1] + Zw[q, qw - kw + GW-1]
+// from registers (Z = q . rel_table^T is one small tensor-core GEMM per layer), runs the online softmax in
+// f32 and writes P (16-bit) into 128B-swizzled smem; O_blk = P V (V consumed as an MN-major operand, i.e.
+// untransposed) lands in TMEM and is folded into the f32 register accumulator.  The [S,S] matrix never
+// exists in memory.  Up to two CTAs are co-resident per SM so that one CTA's softmax (MUFU-bound)
+// overlaps the other's MMAs.
+#pragma once
+#include "ptx.cuh"
+
+namespace vattn {
+
+constexpr int kThreads = 192;  // warp0 TMA, warp1 MMA, warps 2..5 softmax (one query row per thread)
+constexpr int BQ = 128;
+constexpr int D = 64;
+
+struct Params {
+  int S;             // tokens per (batch) sequence
+  int H;             // heads
+  int nblk;          // ceil(S / KV)
+  float scale_log2;  // softmax scale * log2(e)
+  const float* Z;    // [rows, H, zw] rel-pos products (nullptr when !HAS_BIAS)
+  int zw;            // row width of Z (= 2 * zhalf)
+  int zhalf;         // column offset of the Zw half
+  void* out;         // [rows, H*64] 16-bit
+};
+
+template <int KV>
+struct Cfg {
+  static constexpr int kQBytes = BQ * D * 2;
+  static constexpr int kKVBytes = KV * D * 2;
+  static constexpr int kPAtoms = (KV + 63) / 64;
+  static constexpr int kPBytes = kPAtoms * BQ * 128;
+  static constexpr int kOffK = kQBytes;
+  static constexpr int kOffV = kOffK + 2 * kKVBytes;
+  static constexpr int kOffP = kOffV + 2 * kKVBytes;
+  static constexpr int kOffBar = kOffP + kPBytes;
+  static constexpr int kSmemBytes = kOffBar + 128;
+  static_assert(KV % 16 == 0 && KV <= 128, "KV");
+  static_assert(kKVBytes % 1024 == 0, "stage alignment");
+};
+
+template <typename T>
+__device__ __forceinline__ uint32_t pack2(float a, float b);
+template <>
+__device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+template <>
+__device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
+  __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// GW = token-grid width (0 = no bias), RB = grid rows per key block, KV = keys per block.
+template <typename T, int GW, int RB, int KV, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
+vattn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, const Params p) {
+  using C = Cfg<KV>;
+  constexpr bool HAS_BIAS = GW > 0;
+  static_assert(!HAS_BIAS || KV == RB * GW, "key block must be whole grid rows");
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBar);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;    // [2]
+  uint64_t* v_full = bars + 3;    // [2]
+  uint64_t* kv_empty = bars + 5;  // [2]
+  uint64_t* s_full = bars + 7;
+  uint64_t* p_full = bars + 8;
+  uint64_t* o_full = bars + 9;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int bh = blockIdx.y;
+  const int b = bh / p.H;
+  const int h = bh % p.H;
+  const int q0 = blockIdx.x * BQ;
+  const int row_base = b * p.S;  // first qkv row of this sequence
+  const int col_q = h * D, col_k = (p.H + h) * D, col_v = (2 * p.H + h) * D;
+
+  if (threadIdx.x == 0) {
+    if ((ptx::smem_u32(smem) & 1023u) != 0) { printf("vattn: smem base not 1024-aligned\n"); __trap(); }
+    ptx::prefetch_tmap(&tm_q);
+    ptx::prefetch_tmap(&tm_kv);
+    ptx::mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&k_full[i], 1); ptx::mbar_init(&v_full[i], 1); ptx::mbar_init(&kv_empty[i], 1); }
+    ptx::mbar_init(s_full, 1);
+    ptx::mbar_init(p_full, 128);
+    ptx::mbar_init(o_full, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, 256);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem_s = tmem;        // S: columns [0, KV)
+  const uint32_t tmem_o = tmem + 128;  // O_blk: columns [128, 192)
+
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      ptx::mbar_expect_tx(q_full, C::kQBytes);
+      ptx::tma_load_2d(smem, &tm_q, q_full, col_q, row_base + q0);
+      for (int j = 0; j < p.nblk; ++j) {
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        ptx::mbar_wait(&kv_empty[s], ph ^ 1);
+        ptx::mbar_expect_tx(&k_full[s], C::kKVBytes);
+        ptx::tma_load_2d(smem + C::kOffK + s * C::kKVBytes, &tm_kv, &k_full[s], col_k, row_base + j * KV);
+        ptx::mbar_expect_tx(&v_full[s], C::kKVBytes);
+        ptx::tma_load_2d(smem + C::kOffV + s * C::kKVBytes, &tm_kv, &v_full[s], col_v, row_base + j * KV);
+      }
+    }
+  } else if (warp == 1) {
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc_qk = ptx::idesc_f16(Elem<T>::kFmt, BQ, KV);
+      constexpr uint32_t idesc_pv = ptx::idesc_f16(Elem<T>::kFmt, BQ, D, 0, 1);  // B (= V) is MN-major
+      const uint32_t sq = ptx::smem_u32(smem);
+      const uint32_t sp = ptx::smem_u32(smem + C::kOffP);
+      auto issue_qk = [&](int j) {
+        const int s = j & 1;
+        ptx::mbar_wait(&k_full[s], (j >> 1) & 1);
+        ptx::tc_fence_after();
+        const uint32_t sk = ptx::smem_u32(smem + C::kOffK + s * C::kKVBytes);
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k)
+          ptx::mma_f16_ss(tmem_s, ptx::smem_desc_sw128(sq + k * 32, 16, 1024), ptx::smem_desc_sw128(sk + k * 32, 16, 1024),
+                          idesc_qk, k ? 1u : 0u);
+        ptx::mma_commit(s_full);
+      };
+      ptx::mbar_wait(q_full, 0);
+      issue_qk(0);
+      for (int j = 0; j < p.nblk; ++j) {
+        const int s = j & 1;
+        ptx::mbar_wait(p_full, j & 1);  // P_j in smem, S_j fully read
+        ptx::mbar_wait(&v_full[s], (j >> 1) & 1);
+        ptx::tc_fence_after();
+        const uint32_t sv = ptx::smem_u32(smem + C::kOffV + s * C::kKVBytes);
+#pragma unroll
+        for (int kk = 0; kk < KV / 16; ++kk) {
+          const uint64_t ad = ptx::smem_desc_sw128(sp + (kk >> 2) * (BQ * 128) + (kk & 3) * 32, 16, 1024);
+          const uint64_t bd = ptx::smem_desc_sw128(sv + kk * 2048, KV * 128, 1024);
+          ptx::mma_f16_ss(tmem_o, ad, bd, idesc_pv, kk ? 1u : 0u);
+        }
+        ptx::mma_commit(o_full);
+        ptx::mma_commit(&kv_empty[s]);
+        if (j + 1 < p.nblk) issue_qk(j + 1);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax / accumulate warps
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;  // query row inside the tile == TMEM lane
+    const int q = q0 + r;
+    const bool q_ok = q < p.S;
+    const int qc = q_ok ? q : p.S - 1;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    constexpr float kLog2e = 1.4426950408889634f;
+
+    float relw[HAS_BIAS ? GW : 1];
+    const float* zrow = nullptr;
+    int qh = 0;
+    if (HAS_BIAS) {
+      zrow = p.Z + ((long long)(row_base + qc) * p.H + h) * p.zw;
+      qh = qc / GW;
+      const int qw = qc - qh * GW;
+      const float* zw = zrow + p.zhalf + qw + GW - 1;
+#pragma unroll
+      for (int kw = 0; kw < GW; ++kw) relw[kw] = zw[-kw] * kLog2e;
+    }
+
+    float m = -INFINITY, l = 0.f;
+    float acc[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) acc[d] = 0.f;
+    uint8_t* prow = smem + C::kOffP + r * 128;
+    const int rsw = r & 7;
+
+    for (int j = 0; j < p.nblk; ++j) {
+      float relh[HAS_BIAS ? RB : 1];
+      if (HAS_BIAS) {
+#pragma unroll
+        for (int rr = 0; rr < RB; ++rr) {
+          const int kh = j * RB + rr;
+          relh[rr] = kh < GW ? zrow[qh - kh + GW - 1] * kLog2e : 0.f;
+        }
+      }
+      const int kvalid = p.S - j * KV;  // keys with column index >= kvalid are padding
+      ptx::mbar_wait(s_full, j & 1);
+      ptx::tc_fence_after();
+
+      // pass 1: row maximum of the biased, scaled scores (log2 domain)
+      float bmax = -INFINITY;
+#pragma unroll
+      for (int c0 = 0; c0 < KV; c0 += 16) {
+        uint32_t v[16];
+        ptx::tmem_ld_32x16(tmem_s + lane_off + c0, v);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int c = c0 + i;
+          float t = __uint_as_float(v[i]) * p.scale_log2;
+          if (HAS_BIAS) t += relw[c % GW] + relh[c / GW];
+          if (c >= kvalid) t = -INFINITY;
+          bmax = fmaxf(bmax, t);
+        }
+      }
+      const float m_new = fmaxf(m, bmax);
+      const float alpha = exp2f(m - m_new);
+      float rowsum = 0.f;
+      // pass 2: p = exp2(t - m_new), write P (16-bit) to swizzled smem
+#pragma unroll
+      for (int c0 = 0; c0 < KV; c0 += 16) {
+        uint32_t v[16];
+        ptx::tmem_ld_32x16(tmem_s + lane_off + c0, v);
+        ptx::tmem_ld_wait();
+        float e[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int c = c0 + i;
+          float t = __uint_as_float(v[i]) * p.scale_log2;
+          if (HAS_BIAS) t += relw[c % GW] + relh[c / GW];
+          float pe = exp2f(t - m_new);
+          if (c >= kvalid) pe = 0.f;
+          // the P.V product consumes the rounded value: sum what is actually multiplied
+          e[i] = Elem<T>::to(Elem<T>::from(pe));
+          rowsum += e[i];
+        }
+#pragma unroll
+        for (int g8 = 0; g8 < 2; ++g8) {
+          const int c = c0 + g8 * 8;
+          const int atom = c >> 6;
+          const int chunk = ((c & 63) >> 3) ^ rsw;
+          uint4 pk;
+          pk.x = pack2<T>(e[g8 * 8 + 0], e[g8 * 8 + 1]);
+          pk.y = pack2<T>(e[g8 * 8 + 2], e[g8 * 8 + 3]);
+          pk.z = pack2<T>(e[g8 * 8 + 4], e[g8 * 8 + 5]);
+          pk.w = pack2<T>(e[g8 * 8 + 6], e[g8 * 8 + 7]);
+          *reinterpret_cast<uint4*>(prow + atom * (BQ * 128) + chunk * 16) = pk;
+        }
+      }
+      l = l * alpha + rowsum;
+      m = m_new;
+      ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(p_full);
+
+      ptx::mbar_wait(o_full, j & 1);
+      ptx::tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < D; c0 += 16) {
+        uint32_t v[16];
+        ptx::tmem_ld_32x16(tmem_o + lane_off + c0, v);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[c0 + i] = acc[c0 + i] * alpha + __uint_as_float(v[i]);
+      }
+    }
+    if (q_ok) {
+      const float inv = 1.f / l;
+      T* orow = reinterpret_cast<T*>(p.out) + (long long)(row_base + q) * (p.H * D) + h * D;
+#pragma unroll
+      for (int c = 0; c < D; c += 8) {
+        uint4 pk;
+        pk.x = pack2<T>(acc[c + 0] * inv, acc[c + 1] * inv);
+        pk.y = pack2<T>(acc[c + 2] * inv, acc[c + 3] * inv);
+        pk.z = pack2<T>(acc[c + 4] * inv, acc[c + 5] * inv);
+        pk.w = pack2<T>(acc[c + 6] * inv, acc[c + 7] * inv);
+        *reinterpret_cast<uint4*>(orow + c) = pk;
+      }
+    }
+    ptx::tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem, 256);
+}
+
+}  // namespace vattn

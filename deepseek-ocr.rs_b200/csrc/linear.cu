@@ -1,0 +1,97 @@
+// Host launcher + instantiations of the tcgen05 linear kernel (linear_tc.cuh).
+#include "linear_tc.cuh"
+#include "kernels.h"
+#include "tmap.h"
+
+#include <stdexcept>
+#include <string>
+
+namespace dsocr {
+
+namespace {
+
+template <typename T, int BN, int NA, int NB>
+void launch_inst(const LinearCall& c, const lin::Params& p, const CUtensorMap& w0, const CUtensorMap& w1,
+                 const CUtensorMap& x, int grid, cudaStream_t stream) {
+  using C = lin::Cfg<BN, NA, NB>;
+  auto kern = lin::linear_kernel<T, BN, NA, NB>;
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes),
+               "linear: set max dynamic smem");
+    configured = true;
+  }
+  kern<<<grid, lin::kThreads, C::kSmemBytes, stream>>>(w0, w1, x, p);
+  cuda_check(cudaGetLastError(), "linear launch");
+}
+
+template <typename T, int NA, int NB>
+void launch_bn(int bn, const LinearCall& c, const lin::Params& p, const CUtensorMap& w0, const CUtensorMap& w1,
+               const CUtensorMap& x, int grid, cudaStream_t stream) {
+  switch (bn) {
+    case 32: launch_inst<T, 32, NA, NB>(c, p, w0, w1, x, grid, stream); break;
+    case 64: launch_inst<T, 64, NA, NB>(c, p, w0, w1, x, grid, stream); break;
+    case 128: launch_inst<T, 128, NA, NB>(c, p, w0, w1, x, grid, stream); break;
+    case 256:
+      if constexpr (NA == 1) { launch_inst<T, 256, NA, NB>(c, p, w0, w1, x, grid, stream); break; }
+    default: throw std::runtime_error("linear: unsupported token tile " + std::to_string(bn));
+  }
+}
+
+template <typename T>
+void launch_t(int bn, const LinearCall& c, const lin::Params& p, const CUtensorMap& w0, const CUtensorMap& w1,
+              const CUtensorMap& x, int grid, cudaStream_t stream) {
+  const int na = c.w1 ? 2 : 1;
+  const int nb = c.x_parts;
+  if (na == 1 && nb == 1) launch_bn<T, 1, 1>(bn, c, p, w0, w1, x, grid, stream);
+  else if (na == 1 && nb == 2) launch_bn<T, 1, 2>(bn, c, p, w0, w1, x, grid, stream);
+  else if (na == 2 && nb == 1) launch_bn<T, 2, 1>(bn, c, p, w0, w1, x, grid, stream);
+  else launch_bn<T, 2, 2>(bn, c, p, w0, w1, x, grid, stream);
+}
+
+}  // namespace
+
+int linear_pick_bn(long long m, bool dual) {
+  if (m <= 32) return 32;
+  if (m <= 64) return 64;
+  if (m <= 128 || dual) return 128;
+  return 256;
+}
+
+void linear(const LinearCall& c, DType dt, int num_sms, cudaStream_t stream) {
+  if (c.K % lin::BK != 0) throw std::runtime_error("linear: K must be a multiple of 64, got " + std::to_string(c.K));
+  if (c.M <= 0 && !c.tiles) return;
+  const bool dual = c.w1 != nullptr;
+  const int bn = c.bn ? c.bn : linear_pick_bn(c.tiles ? c.tile_rows_hint : c.M, dual);
+
+  lin::Params p{};
+  p.M = c.M; p.N = c.N; p.K = c.K;
+  p.x_lo_row_off = c.x_lo_row_off;
+  p.bias = c.bias; p.out = c.out; p.out_lo = c.out_lo; p.ldo = c.ldo; p.row_map = c.row_map;
+  p.act = c.act; p.out_mode = c.out_mode; p.swiglu = dual ? 1 : 0;
+  p.tiles = reinterpret_cast<const lin::Tile*>(c.tiles);
+  p.num_tiles_dev = c.num_tiles_dev;
+  p.n_w_blocks = (c.N + lin::BM - 1) / lin::BM;
+  p.nbatch = c.nbatch > 1 ? c.nbatch : 1;
+  p.out_batch_stride = c.out_batch_stride;
+  if (c.tiles) p.num_tiles = c.max_tiles;
+  else p.num_tiles = p.n_w_blocks * (int)((c.M + bn - 1) / bn) * p.nbatch;
+  if (p.num_tiles <= 0) return;
+
+  const long long w_rows = c.w_rows ? c.w_rows : c.N;
+  CUtensorMap w0 = tmap::make_2d_16bit(c.w0, w_rows, c.K, c.ldw ? c.ldw : c.K, lin::BM, lin::BK);
+  CUtensorMap w1 = dual ? tmap::make_2d_16bit(c.w1, w_rows, c.K, c.ldw ? c.ldw : c.K, lin::BM, lin::BK) : w0;
+  CUtensorMap x;
+  if (p.nbatch > 1) {
+    // X[row, batch, k]: row stride ldx elements, batch stride x_batch_stride elements.
+    x = tmap::make_3d_16bit(c.x, c.K, p.nbatch, c.x_rows, (uint64_t)c.x_batch_stride * 2, (uint64_t)c.ldx * 2, lin::BK,
+                            1, bn);
+  } else {
+    x = tmap::make_2d_16bit(c.x, c.x_rows, c.K, c.ldx ? c.ldx : c.K, bn, lin::BK);
+  }
+  const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+  if (dt == DType::BF16) launch_t<__nv_bfloat16>(bn, c, p, w0, w1, x, grid, stream);
+  else launch_t<__half>(bn, c, p, w0, w1, x, grid, stream);
+}
+
+}  // namespace dsocr

@@ -1,0 +1,104 @@
+// Kernel-level test hooks (include/dsocr_test.h).  Host f32 in/out; the kernels under test are the ones the
+// engine launches.
+#include "dsocr_test.h"
+#include "kernels.h"
+#include "util.h"
+
+#include <algorithm>
+#include <vector>
+
+using namespace dsocr;
+
+namespace {
+int sm_count() {
+  int dev = 0, n = 0;
+  cuda_check(cudaGetDevice(&dev), "cudaGetDevice");
+  cuda_check(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev), "sm count");
+  return n;
+}
+DType to_dtype(int dtype) {
+  if (dtype == DSOCR_BF16) return DType::BF16;
+  if (dtype == DSOCR_F16) return DType::F16;
+  throw std::runtime_error("dtype must be DSOCR_F16 or DSOCR_BF16");
+}
+}  // namespace
+
+extern "C" int dsocr_test_linear(int dtype, int M, int N, int K, const float* x, const float* w0, const float* w1,
+                                 const float* bias, int act, int out_mode, int x_parts, int bn, const int* row_map,
+                                 int out_rows, float* out) {
+  return guarded([&]() {
+    const DType dt = to_dtype(dtype);
+    const size_t xe = (size_t)M * K, we = (size_t)N * K, oe = (size_t)out_rows * N;
+    std::vector<uint16_t> hx = x_parts == 2 ? to16_split(x, xe, dt) : to16(x, xe, dt);
+    std::vector<uint16_t> hw0 = to16(w0, we, dt);
+    DevBuf dx(hx.size() * 2), dw0(we * 2), dw1, dbias, dmap, dout, dout_lo;
+    h2d(dx.p, hx.data(), hx.size() * 2);
+    h2d(dw0.p, hw0.data(), we * 2);
+    if (w1) { auto h = to16(w1, we, dt); dw1.alloc(we * 2); h2d(dw1.p, h.data(), we * 2); }
+    if (bias) { dbias.alloc(N * 4); h2d(dbias.p, bias, N * 4); }
+    if (row_map) { dmap.alloc(M * 4); h2d(dmap.p, row_map, M * 4); }
+    const bool f32out = out_mode >= 2;
+    dout.alloc(oe * (f32out ? 4 : 2));
+    cuda_check(cudaMemset(dout.p, 0, dout.bytes), "memset");
+    if (out_mode == 1) { dout_lo.alloc(oe * 2); cuda_check(cudaMemset(dout_lo.p, 0, oe * 2), "memset"); }
+    if (out_mode == 3) h2d(dout.p, out, oe * 4);
+
+    LinearCall c;
+    c.w0 = dw0.p; c.w1 = w1 ? dw1.p : nullptr;
+    c.x = dx.p; c.x_rows = (long long)M * x_parts; c.x_parts = x_parts; c.x_lo_row_off = M;
+    c.M = M; c.N = N; c.K = K;
+    c.bias = bias ? dbias.as<float>() : nullptr;
+    c.out = dout.p; c.out_lo = dout_lo.p; c.ldo = N; c.row_map = row_map ? dmap.as<int>() : nullptr;
+    c.act = act; c.out_mode = out_mode; c.bn = bn;
+    linear(c, dt, sm_count(), 0);
+    cuda_check(cudaDeviceSynchronize(), "linear kernel");
+    if (f32out) {
+      d2h(out, dout.p, oe * 4);
+    } else {
+      std::vector<uint16_t> ho(oe), hl;
+      d2h(ho.data(), dout.p, oe * 2);
+      if (out_mode == 1) { hl.resize(oe); d2h(hl.data(), dout_lo.p, oe * 2); }
+      for (size_t i = 0; i < oe; ++i) out[i] = f16_to_32(ho[i], dt) + (out_mode == 1 ? f16_to_32(hl[i], dt) : 0.f);
+    }
+    return 0;
+  });
+}
+
+extern "C" int dsocr_test_grouped_linear(int dtype, int E, int M, int N, int K, const int* counts, const float* x,
+                                         const float* w0, const float* w1, int x_parts, float* out) {
+  return guarded([&]() {
+    const DType dt = to_dtype(dtype);
+    const size_t xe = (size_t)M * K, we = (size_t)E * N * K, oe = (size_t)M * N;
+    std::vector<uint16_t> hx = x_parts == 2 ? to16_split(x, xe, dt) : to16(x, xe, dt);
+    std::vector<uint16_t> hw0 = to16(w0, we, dt);
+    DevBuf dx(hx.size() * 2), dw0(we * 2), dw1, dout(oe * 4), dtiles, dnt(4);
+    h2d(dx.p, hx.data(), hx.size() * 2);
+    h2d(dw0.p, hw0.data(), we * 2);
+    if (w1) { auto h = to16(w1, we, dt); dw1.alloc(we * 2); h2d(dw1.p, h.data(), we * 2); }
+    cuda_check(cudaMemset(dout.p, 0, oe * 4), "memset");
+    int maxc = 1;
+    for (int e = 0; e < E; ++e) maxc = std::max(maxc, counts[e]);
+    const int bn = linear_pick_bn(maxc, w1 != nullptr);
+    std::vector<LinearTile> tiles;
+    int row = 0;
+    for (int e = 0; e < E; ++e) {
+      for (int r0 = 0; r0 < counts[e]; r0 += bn)
+        for (int wb = 0; wb < (N + 127) / 128; ++wb)
+          tiles.push_back({e * N + wb * 128, row + r0, std::min(bn, counts[e] - r0), wb * 128});
+      row += counts[e];
+    }
+    const int nt = (int)tiles.size();
+    dtiles.alloc(std::max<size_t>(1, tiles.size()) * sizeof(LinearTile));
+    if (nt) h2d(dtiles.p, tiles.data(), tiles.size() * sizeof(LinearTile));
+    h2d(dnt.p, &nt, 4);
+    LinearCall c;
+    c.w0 = dw0.p; c.w1 = w1 ? dw1.p : nullptr; c.w_rows = (long long)E * N;
+    c.x = dx.p; c.x_rows = (long long)M * x_parts; c.x_parts = x_parts; c.x_lo_row_off = M;
+    c.M = M; c.N = N; c.K = K; c.out = dout.p; c.ldo = N; c.out_mode = 2;
+    c.tiles = dtiles.as<LinearTile>(); c.num_tiles_dev = dnt.as<int>(); c.max_tiles = nt + 7; c.bn = bn;
+    linear(c, dt, sm_count(), 0);
+    cuda_check(cudaDeviceSynchronize(), "grouped linear kernel");
+    d2h(out, dout.p, oe * 4);
+    return 0;
+  });
+}

@@ -1,0 +1,165 @@
+/* dsocr.h - C ABI of the B200-native DeepSeek-OCR per-page forward path.
+ *
+ * This is the drop-in boundary for TimmyOVO/deepseek-ocr.rs's `OcrEngine` / `load_model`
+ * (crates/core/src/inference.rs:179-209, crates/infer-deepseek/src/model/mod.rs:90-115).  A Rust shim
+ * implements `OcrEngine::decode` (model/mod.rs:2370-2454) on top of these calls; see INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain C, opaque handles, no exceptions cross the boundary;
+ *  - every call returns DSOCR_OK (0) or a negative status; the message of the last failure on the calling
+ *    thread is returned by dsocr_last_error() (same role as the reference's anyhow context chain; the
+ *    literal prefixes "vision input failed", "image embedding failed", "prompt formatting failed" and
+ *    "prompt/image embedding mismatch" are preserved because crates/server/src/generation.rs:111-115
+ *    pattern-matches them);
+ *  - host buffers are caller-owned, device memory is engine-owned;
+ *  - one engine is bound to one CUDA device ordinal and is NOT re-entrant (the reference wraps its engine in
+ *    Arc<Mutex<..>>, crates/server/src/generation.rs:84-86): serialise calls per engine;
+ *  - there is no CPU fallback: engine creation fails if no sm_100 device is present.
+ */
+#ifndef DSOCR_H_
+#define DSOCR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define DSOCR_API __attribute__((visibility("default")))
+#else
+#define DSOCR_API
+#endif
+
+typedef struct dsocr_engine dsocr_engine;
+
+enum dsocr_status {
+  DSOCR_OK = 0,
+  DSOCR_ERR_INVALID_ARGUMENT = -1,
+  DSOCR_ERR_IO = -2,
+  DSOCR_ERR_CUDA = -3,
+  DSOCR_ERR_UNSUPPORTED = -4,
+  DSOCR_ERR_INTERNAL = -5,
+  DSOCR_ERR_MISMATCH = -6 /* prompt/image embedding mismatch (maps to HTTP 400 in the reference server) */
+};
+
+/* candle DType as used by ModelLoadArgs.dtype (crates/core/src/inference.rs:179-186). */
+enum dsocr_dtype { DSOCR_F32 = 0, DSOCR_F16 = 1, DSOCR_BF16 = 2 };
+
+/* VisionSettings (crates/core/src/inference.rs:10-16). */
+typedef struct dsocr_vision_settings {
+  uint32_t base_size;  /* 1024 */
+  uint32_t image_size; /* 640  */
+  int32_t crop_mode;   /* 1    */
+} dsocr_vision_settings;
+
+/* DecodeParameters (crates/core/src/inference.rs:18-34, defaults :66-78).  Only greedy decoding is
+ * implemented on the device (do_sample must be 0; the reference's CLI/server default). */
+typedef struct dsocr_decode_params {
+  uint32_t max_new_tokens;       /* 512 */
+  int32_t do_sample;             /* 0 */
+  float repetition_penalty;      /* 1.0 (only 1.0 is supported) */
+  uint32_t no_repeat_ngram_size; /* 20; 0 or 1 disables */
+  int64_t eos_token_id;          /* < 0 disables EOS stopping */
+  int32_t use_cache;             /* 1 */
+} dsocr_decode_params;
+
+/* Progress callback == the reference's `stream: Option<&dyn Fn(usize, &[i64])>` (inference.rs:205-207):
+ * invoked synchronously on the calling thread after every accepted token with (count, all generated ids).
+ * `page` is the index inside a batched call (0 for single-page calls). */
+typedef void (*dsocr_token_cb)(void* user, int32_t page, size_t count, const int64_t* tokens);
+
+typedef struct dsocr_engine_info {
+  int32_t device_ordinal;
+  int32_t dtype; /* dsocr_dtype of the 16-bit operand type */
+  int32_t sm_count;
+  int32_t hidden_size, num_layers, vocab_size, n_routed_experts;
+  int32_t quantized; /* 1 when a DSQ snapshot is attached */
+  char device_name[64];
+} dsocr_engine_info;
+
+DSOCR_API const char* dsocr_last_error(void);
+DSOCR_API const char* dsocr_version(void);
+
+/* load_model(ModelLoadArgs{config_path, weights_path, snapshot_path, device, dtype}) -> Box<dyn OcrEngine>
+ * (model/mod.rs:90-115, :946-1105).  dsq_path may be NULL.  dtype: DSOCR_F16 or DSOCR_BF16 select the
+ * tensor-core operand type; as in the reference, accumulation / norms / softmax / residuals stay f32. */
+DSOCR_API int dsocr_engine_create(const char* config_json_path, const char* safetensors_path, const char* dsq_path,
+                                  int device_ordinal, int dtype, dsocr_engine** out);
+DSOCR_API void dsocr_engine_destroy(dsocr_engine* e);
+DSOCR_API int dsocr_engine_info_get(const dsocr_engine* e, dsocr_engine_info* info);
+
+/* image_token_count: rows `compute_image_embeddings` will produce == placeholders
+ * `build_image_placeholders` emits (model/mod.rs:2605-2689). */
+DSOCR_API int dsocr_image_token_count(uint32_t base_size, uint32_t image_size, int crop_mode, int crop_w, int crop_h);
+
+/* prepare_vision_input_from_image (model/mod.rs:1707-1758) + build_global_view (:2308-2330) +
+ * dynamic_preprocess_with_params (vision/preprocess.rs:67-138) + resize_bicubic (vision/resample.rs:101-160).
+ * Input: RGB8 HWC.  Outputs (caller-allocated): global view RGB8 [G,G,3] (G = base_size if crop_mode else
+ * image_size); tiles RGB8 [n,image_size,image_size,3] with n <= 9 (may be NULL to only query the grid);
+ * crop grid (w,h).  Bit-exact with the reference's integer resampler. */
+DSOCR_API int dsocr_preprocess(const uint8_t* rgb, int width, int height, dsocr_vision_settings vs,
+                               uint8_t* global_out, uint8_t* tiles_out, int* n_tiles, int* crop_w, int* crop_h);
+
+/* compute_image_embeddings for one page (model/mod.rs:1276-1377; VisionContext :711-924).
+ * global_chw: f32 [3,G,G] normalised as image_to_tensor does (:2332-2347); patches_nchw: f32 [n,3,P,P] or NULL.
+ * out_rows: f32 [n_rows,hidden] = [local ; global ; view_separator].  *n_rows in: capacity, out: rows written. */
+DSOCR_API int dsocr_vision_encode(dsocr_engine* e, const float* global_chw, int global_size, const float* patches_nchw,
+                                  int n_patches, int patch_size, int crop_w, int crop_h, float* out_rows, int* n_rows);
+
+/* Same, from RGB8 HWC views (normalisation fused into the patch gather on the device) and for a batch of
+ * pages that share one (global_size, patch_size) setting.  tiles of page i: tiles_u8[i] = [n_i,P,P,3] or NULL. */
+DSOCR_API int dsocr_vision_encode_u8_batch(dsocr_engine* e, int n_pages, const uint8_t* const* globals_u8,
+                                           int global_size, const uint8_t* const* tiles_u8, const int* n_tiles,
+                                           int patch_size, const int* crop_w, const int* crop_h,
+                                           float* const* out_rows, int* n_rows);
+
+/* Debug taps == SamDebugTrace / ClipDebugTrace / VisionProjectionOutputs (vision/sam.rs:130-140,
+ * vision/clip.rs:65-70, model/mod.rs:144-153) of the most recent vision call.  Copies tap `name`
+ * ("sam.patch_embed", "sam.block.3", "sam.net3", "clip.layer.7", "global_pre", ...) into out (f32). */
+DSOCR_API int dsocr_vision_tap(dsocr_engine* e, const char* name, float* out, size_t capacity, size_t* n_written);
+
+/* DeepseekOcrModel::generate (model/mod.rs:1870-2048) for a batch of independent pages decoded in lock-step:
+ * prefill (embed_tokens + inject_image_tokens :1760-1857 + 12 decoder layers + last-row lm_head), then the
+ * greedy loop with the no-repeat-ngram ban and first-index argmax of crates/core/src/sampling.rs:34-158,
+ * stopping per page at EOS (not appended) or at max_new_tokens.
+ *  input_ids[i]: i64 [T_i]; images_seq_mask[i]: u8 [T_i]; image_rows[i]: f32 [n_img_i,hidden] (host).
+ *  out_tokens[i]: i64 capacity max_new_tokens; n_out[i]: generated count. */
+DSOCR_API int dsocr_generate_batch(dsocr_engine* e, int n_pages, const int64_t* const* input_ids,
+                                   const uint8_t* const* images_seq_mask, const int* n_tokens,
+                                   const float* const* image_rows, const int* n_image_rows,
+                                   const dsocr_decode_params* params, dsocr_token_cb cb, void* user,
+                                   int64_t* const* out_tokens, int* n_out);
+
+/* Teacher-forced variant used by parity tests (== tests/baseline.rs "teacher-forced logits"): feeds
+ * forced_tokens[i][t] instead of the selected token, returns the selected tokens and, when logits_out[i] is
+ * non-NULL, the f32 logits of every step [n_steps, vocab]. */
+DSOCR_API int dsocr_generate_forced(dsocr_engine* e, int n_pages, const int64_t* const* input_ids,
+                                    const uint8_t* const* images_seq_mask, const int* n_tokens,
+                                    const float* const* image_rows, const int* n_image_rows,
+                                    const dsocr_decode_params* params, const int64_t* const* forced_tokens,
+                                    int n_steps, int64_t* const* selected_out, float* const* logits_out);
+
+/* OcrEngine::decode minus tokenizer (model/mod.rs:2370-2454): RGB8 pages -> preprocess -> vision ->
+ * build_prompt_tokens (:2536-2603; text segments are passed already tokenised: the tokenizer stays in the
+ * host language) -> generate.  prompt_segments: n_segments id arrays around the single <image> slot
+ * (n_segments == 2).  This is the end-to-end call the throughput benchmark times. */
+DSOCR_API int dsocr_decode_pages(dsocr_engine* e, int n_pages, const uint8_t* const* rgb, const int* widths,
+                                 const int* heights, dsocr_vision_settings vs, const int64_t* seg0, int n_seg0,
+                                 const int64_t* seg1, int n_seg1, int64_t image_token_id,
+                                 const dsocr_decode_params* params, dsocr_token_cb cb, void* user,
+                                 int64_t* const* out_tokens, int* n_out, int* prompt_tokens);
+
+/* Stage timings of the most recent dsocr_decode_pages / vision / generate call, in milliseconds, under the
+ * reference's Timer names (crates/core/src/benchmark.rs):
+ * 0 vision.prepare_inputs, 1 vision.compute_embeddings, 2 decode.prefill, 3 decode.iterative, 4 decode.generate */
+DSOCR_API int dsocr_last_timings(const dsocr_engine* e, double* ms_out, int n);
+
+/* Number of kernels this library launched on the engine's streams since creation. */
+DSOCR_API long long dsocr_launch_count(const dsocr_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSOCR_H_ */

@@ -1,0 +1,34 @@
+/* dsocr_test.h - kernel-level test hooks of libdsocr.so (used by tests/ only).
+ * Host f32 in, host f32 out; the hook rounds operands to the 16-bit tensor-core type, runs the CUDA kernel
+ * the engine uses for that op on device 0 and copies the result back.  Not part of the drop-in boundary. */
+#ifndef DSOCR_TEST_H_
+#define DSOCR_TEST_H_
+#include "dsocr.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* out[M,N] = epi(x[M,K] * w0[N,K]^T (+bias)); w1 != NULL -> silu(x*w0^T) * (x*w1^T).
+ * act: 0 none, 1 gelu(erf), 2 quick-gelu.  out_mode: 0 16-bit, 1 16-bit hi+lo (returned summed), 2 f32,
+ * 3 f32 accumulate into the given `out` contents.  x_parts: 1, or 2 = hi/lo split activations.
+ * bn: token tile (0 = auto).  row_map: optional int[M]. */
+DSOCR_API int dsocr_test_linear(int dtype, int M, int N, int K, const float* x, const float* w0, const float* w1,
+                                const float* bias, int act, int out_mode, int x_parts, int bn, const int* row_map,
+                                int out_rows, float* out);
+
+/* Grouped linear (MoE expert GEMM): x[M,K] rows are grouped by expert; counts[E] rows per expert (sum = M);
+ * w0/w1: [E,N,K].  out[M,N]. */
+DSOCR_API int dsocr_test_grouped_linear(int dtype, int E, int M, int N, int K, const int* counts, const float* x,
+                                        const float* w0, const float* w1, int x_parts, float* out);
+
+/* Vision attention over a qkv buffer [B*S, 3, H, 64] (16-bit after rounding) with the decomposed
+ * relative-position bias: rel_h/rel_w tables [2*g-1... already resolved to [g, g, 64]] or NULL (CLIP).
+ * grid_w * grid_h == S when tables are given.  out[B*S, H*64] f32. */
+DSOCR_API int dsocr_test_vision_attention(int dtype, int B, int S, int H, const float* qkv, int grid, const float* rel_h,
+                                          const float* rel_w, int rel_rows, float* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
