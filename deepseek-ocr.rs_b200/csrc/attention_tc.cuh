@@ -68,6 +68,7 @@ __global__ void __launch_bounds__(kThreads, MINB)
 vattn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, const Params p) {
   using C = Cfg<KV>;
   constexpr bool HAS_BIAS = GW > 0;
+  constexpr int GWD = GW > 0 ? GW : 1;  // divisor that is never zero
   static_assert(!HAS_BIAS || KV == RB * GW, "key block must be whole grid rows");
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBar);
@@ -173,8 +174,8 @@ vattn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
     int qh = 0;
     if (HAS_BIAS) {
       zrow = p.Z + ((long long)(row_base + qc) * p.H + h) * p.zw;
-      qh = qc / GW;
-      const int qw = qc - qh * GW;
+      qh = qc / GWD;
+      const int qw = qc - qh * GWD;
       const float* zw = zrow + p.zhalf + qw + GW - 1;
 #pragma unroll
       for (int kw = 0; kw < GW; ++kw) relw[kw] = zw[-kw] * kLog2e;
@@ -211,7 +212,7 @@ vattn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
         for (int i = 0; i < 16; ++i) {
           const int c = c0 + i;
           float t = __uint_as_float(v[i]) * p.scale_log2;
-          if (HAS_BIAS) t += relw[c % GW] + relh[c / GW];
+          if (HAS_BIAS) t += relw[c % GWD] + relh[c / GWD];
           if (c >= kvalid) t = -INFINITY;
           bmax = fmaxf(bmax, t);
         }
@@ -230,7 +231,7 @@ vattn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
         for (int i = 0; i < 16; ++i) {
           const int c = c0 + i;
           float t = __uint_as_float(v[i]) * p.scale_log2;
-          if (HAS_BIAS) t += relw[c % GW] + relh[c / GW];
+          if (HAS_BIAS) t += relw[c % GWD] + relh[c / GWD];
           float pe = exp2f(t - m_new);
           if (c >= kvalid) pe = 0.f;
           // the P.V product consumes the rounded value: sum what is actually multiplied

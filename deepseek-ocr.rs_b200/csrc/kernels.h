@@ -51,4 +51,23 @@ struct LinearCall {
 int linear_pick_bn(long long m, bool dual);
 void linear(const LinearCall& c, DType dt, int num_sms, cudaStream_t stream);
 
+// ------------------------------------------------------------------------- vision attention
+// qkv: [rows = B*S, 3, H, 64] 16-bit.  grid > 0: tokens form a grid x grid raster per sequence and the
+// decomposed rel-pos bias is added from Z = q . [rel_h ; rel_w]^T  ([rows, H, zw] f32, Zw half at zhalf).
+struct VAttnCall {
+  const void* qkv = nullptr;
+  long long rows = 0;
+  int B = 0, S = 0, H = 0;
+  int grid = 0;
+  const float* Z = nullptr;
+  int zw = 0, zhalf = 0;
+  void* out = nullptr;  // [rows, H*64] 16-bit
+  float scale = 0.125f;
+};
+bool vision_attention_supported(int grid);
+void vision_attention(const VAttnCall& c, DType dt, cudaStream_t stream);
+// Z = q . table^T through the tensor-core linear kernel.  table: [2*zhalf, 64] 16-bit (rel_h rows then rel_w rows).
+void vision_relpos_products(const void* qkv, long long rows, int H, const void* table, int zhalf, float* Z, DType dt,
+                            int num_sms, cudaStream_t stream);
+
 }  // namespace dsocr

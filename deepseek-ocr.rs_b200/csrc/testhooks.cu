@@ -102,3 +102,36 @@ extern "C" int dsocr_test_grouped_linear(int dtype, int E, int M, int N, int K, 
     return 0;
   });
 }
+
+extern "C" int dsocr_test_vision_attention(int dtype, int B, int S, int H, const float* qkv, int grid, const float* rel_h,
+                                           const float* rel_w, int rel_rows, float* out) {
+  return guarded([&]() {
+    const DType dt = to_dtype(dtype);
+    const long long rows = (long long)B * S;
+    const size_t qe = (size_t)rows * 3 * H * 64, oe = (size_t)rows * H * 64;
+    auto hq = to16(qkv, qe, dt);
+    DevBuf dq(qe * 2), dout(oe * 2), dz, dtab;
+    h2d(dq.p, hq.data(), qe * 2);
+    cuda_check(cudaMemset(dout.p, 0, oe * 2), "memset");
+    VAttnCall c;
+    c.qkv = dq.p; c.rows = rows; c.B = B; c.S = S; c.H = H; c.grid = grid; c.out = dout.p; c.scale = 0.125f;
+    if (grid > 0) {
+      const int zhalf = (rel_rows + 15) / 16 * 16;
+      std::vector<float> tab((size_t)2 * zhalf * 64, 0.f);
+      memcpy(tab.data(), rel_h, (size_t)rel_rows * 64 * 4);
+      memcpy(tab.data() + (size_t)zhalf * 64, rel_w, (size_t)rel_rows * 64 * 4);
+      auto ht = to16(tab.data(), tab.size(), dt);
+      dtab.alloc(ht.size() * 2);
+      h2d(dtab.p, ht.data(), ht.size() * 2);
+      dz.alloc((size_t)rows * H * 2 * zhalf * 4);
+      vision_relpos_products(dq.p, rows, H, dtab.p, zhalf, dz.as<float>(), dt, sm_count(), 0);
+      c.Z = dz.as<float>(); c.zw = 2 * zhalf; c.zhalf = zhalf;
+    }
+    vision_attention(c, dt, 0);
+    cuda_check(cudaDeviceSynchronize(), "vision attention kernel");
+    std::vector<uint16_t> ho(oe);
+    d2h(ho.data(), dout.p, oe * 2);
+    for (size_t i = 0; i < oe; ++i) out[i] = f16_to_32(ho[i], dt);
+    return 0;
+  });
+}
