@@ -27,7 +27,7 @@ void launch(const VAttnCall& c, cudaStream_t stream) {
   p.Z = c.Z; p.zw = c.zw; p.zhalf = c.zhalf; p.out = c.out;
   dim3 grid((c.S + vattn::BQ - 1) / vattn::BQ, c.B * c.H);
   kern<<<grid, vattn::kThreads, C::kSmemBytes, stream>>>(tq, tkv, p);
-  cuda_check(cudaGetLastError(), "vattn launch");
+  launch_check("vattn launch");
 }
 
 template <typename T>

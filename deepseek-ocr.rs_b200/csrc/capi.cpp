@@ -1,0 +1,303 @@
+// extern "C" boundary (include/dsocr.h).  Plain pointers and sizes in, status codes out.
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <thread>
+
+#include "dsocr.h"
+#include "engine.h"
+#include "hostmath.h"
+
+using namespace dsocr;
+
+struct dsocr_engine {
+  std::unique_ptr<Engine> impl;
+};
+
+namespace {
+int status_of(const std::exception& e) {
+  const std::string m = e.what();
+  if (m.find("prompt/image embedding mismatch") != std::string::npos) return DSOCR_ERR_MISMATCH;
+  if (m.find("CUDA") != std::string::npos || m.find("cuda") != std::string::npos) return DSOCR_ERR_CUDA;
+  if (m.find("unsupported") != std::string::npos || m.find("not supported") != std::string::npos) return DSOCR_ERR_UNSUPPORTED;
+  if (m.find("failed to read") != std::string::npos || m.find("cannot open") != std::string::npos) return DSOCR_ERR_IO;
+  return DSOCR_ERR_INTERNAL;
+}
+template <typename F>
+int api(const char* context, F&& f) {
+  try {
+    f();
+    return DSOCR_OK;
+  } catch (const std::exception& e) {
+    set_last_error(context && *context ? std::string(context) + ": " + e.what() : std::string(e.what()));
+    return status_of(e);
+  } catch (...) {
+    set_last_error("unknown error");
+    return DSOCR_ERR_INTERNAL;
+  }
+}
+void bind(dsocr_engine* e) {
+  if (!e || !e->impl) throw std::runtime_error("null engine handle");
+  cuda_check(cudaSetDevice(e->impl->device()), "cudaSetDevice");
+}
+double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+}  // namespace
+
+extern "C" int dsocr_engine_create(const char* config_json_path, const char* safetensors_path, const char* dsq_path,
+                                   int device_ordinal, int dtype, dsocr_engine** out) {
+  return api("load_model", [&] {
+    if (!config_json_path || !safetensors_path || !out) throw std::runtime_error("null argument");
+    if (dtype != DSOCR_F16 && dtype != DSOCR_BF16 && dtype != DSOCR_F32) throw std::runtime_error("invalid dtype code");
+    auto h = std::make_unique<dsocr_engine>();
+    h->impl = std::make_unique<Engine>(config_json_path, safetensors_path, dsq_path ? dsq_path : "", device_ordinal,
+                                       static_cast<DType>(dtype));
+    *out = h.release();
+  });
+}
+
+extern "C" void dsocr_engine_destroy(dsocr_engine* e) { delete e; }
+
+extern "C" int dsocr_engine_info_get(const dsocr_engine* e, dsocr_engine_info* info) {
+  return api("", [&] {
+    if (!e || !info) throw std::runtime_error("null argument");
+    const Engine& en = *e->impl;
+    memset(info, 0, sizeof(*info));
+    info->device_ordinal = en.device();
+    info->dtype = (int)en.dtype();
+    info->sm_count = en.sm_count();
+    info->hidden_size = en.cfg().hidden; info->num_layers = en.cfg().layers; info->vocab_size = en.cfg().vocab;
+    info->n_routed_experts = en.cfg().n_experts;
+    strncpy(info->device_name, en.device_name.c_str(), sizeof(info->device_name) - 1);
+  });
+}
+
+extern "C" int dsocr_engine_set_option(dsocr_engine* e, const char* name, int value) {
+  return api("", [&] {
+    bind(e);
+    const std::string n = name ? name : "";
+    if (n == "record_taps") e->impl->set_record_taps(value != 0);
+    else throw std::runtime_error("unknown option `" + n + "`");
+  });
+}
+
+extern "C" int dsocr_image_token_count(uint32_t base_size, uint32_t image_size, int crop_mode, int crop_w, int crop_h) {
+  return image_token_count((int)base_size, (int)image_size, crop_mode, crop_w, crop_h);
+}
+
+extern "C" int dsocr_preprocess(const uint8_t* rgb, int width, int height, dsocr_vision_settings vs, uint8_t* global_out,
+                                uint8_t* tiles_out, int* n_tiles, int* crop_w, int* crop_h) {
+  return api("vision input failed", [&] {
+    if (!rgb || width <= 0 || height <= 0) throw std::runtime_error("empty image");
+    const int gsz = vs.crop_mode ? (int)vs.base_size : (int)vs.image_size;
+    if (global_out) build_global_view_u8(rgb, width, height, gsz, global_out);
+    int gw = 1, gh = 1, n = 0;
+    if (vs.crop_mode) n = dynamic_preprocess_u8(rgb, width, height, (int)vs.image_size, tiles_out, &gw, &gh);
+    if (n_tiles) *n_tiles = n;
+    if (crop_w) *crop_w = gw;
+    if (crop_h) *crop_h = gh;
+  });
+}
+
+extern "C" int dsocr_vision_encode(dsocr_engine* e, const float* global_chw, int global_size, const float* patches_nchw,
+                                   int n_patches, int patch_size, int crop_w, int crop_h, float* out_rows, int* n_rows) {
+  return api("image embedding failed", [&] {
+    bind(e);
+    Engine& en = *e->impl;
+    if (!global_chw || !out_rows || !n_rows) throw std::runtime_error("null argument");
+    const size_t gbytes = (size_t)3 * global_size * global_size * 4;
+    const size_t pbytes = (size_t)n_patches * 3 * patch_size * patch_size * 4;
+    DevBuf dg(gbytes), dp(std::max<size_t>(pbytes, 16));
+    h2d(dg.p, global_chw, gbytes);
+    if (n_patches > 0) h2d(dp.p, patches_nchw, pbytes);
+    std::vector<Engine::PageViews> pages(1);
+    pages[0].n_tiles = n_patches; pages[0].crop_w = crop_w; pages[0].crop_h = crop_h;
+    std::vector<int> counts;
+    const float* rows = en.vision_encode(1, dg.p, true, global_size, dp.p, true, patch_size, pages, &counts);
+    if (counts[0] > *n_rows) throw std::runtime_error("output buffer too small for " + std::to_string(counts[0]) + " rows");
+    cuda_check(cudaStreamSynchronize(en.stream()), "vision sync");
+    d2h(out_rows, rows, (size_t)counts[0] * en.cfg().n_embed * 4);
+    *n_rows = counts[0];
+  });
+}
+
+namespace {
+// uploads u8 views and runs the vision tower; returns device rows + counts
+const float* encode_u8(Engine& en, int n_pages, const uint8_t* const* globals_u8, int G, const uint8_t* const* tiles_u8,
+                       const int* n_tiles, int P, const int* crop_w, const int* crop_h, std::vector<int>* counts,
+                       DevBuf& dg, DevBuf& dt) {
+  const size_t gbytes = (size_t)G * G * 3;
+  const size_t tbytes = (size_t)P * P * 3;
+  int total_tiles = 0;
+  std::vector<Engine::PageViews> pages(n_pages);
+  for (int p = 0; p < n_pages; ++p) {
+    pages[p].n_tiles = n_tiles ? n_tiles[p] : 0;
+    pages[p].crop_w = crop_w ? crop_w[p] : 1;
+    pages[p].crop_h = crop_h ? crop_h[p] : 1;
+    total_tiles += pages[p].n_tiles;
+  }
+  dg.ensure(gbytes * n_pages);
+  dt.ensure(std::max<size_t>(16, tbytes * total_tiles));
+  size_t toff = 0;
+  for (int p = 0; p < n_pages; ++p) {
+    cuda_check(cudaMemcpyAsync((uint8_t*)dg.p + gbytes * p, globals_u8[p], gbytes, cudaMemcpyHostToDevice, en.stream()), "global view H2D");
+    if (pages[p].n_tiles > 0) {
+      cuda_check(cudaMemcpyAsync((uint8_t*)dt.p + toff, tiles_u8[p], tbytes * pages[p].n_tiles, cudaMemcpyHostToDevice, en.stream()), "tiles H2D");
+      toff += tbytes * pages[p].n_tiles;
+    }
+  }
+  return en.vision_encode(n_pages, dg.p, false, G, dt.p, false, P, pages, counts);
+}
+}  // namespace
+
+extern "C" int dsocr_vision_encode_u8_batch(dsocr_engine* e, int n_pages, const uint8_t* const* globals_u8,
+                                            int global_size, const uint8_t* const* tiles_u8, const int* n_tiles,
+                                            int patch_size, const int* crop_w, const int* crop_h,
+                                            float* const* out_rows, int* n_rows) {
+  return api("image embedding failed", [&] {
+    bind(e);
+    Engine& en = *e->impl;
+    DevBuf dg, dt;
+    std::vector<int> counts;
+    const double t0 = now_ms();
+    const float* rows = encode_u8(en, n_pages, globals_u8, global_size, tiles_u8, n_tiles, patch_size, crop_w, crop_h, &counts, dg, dt);
+    cuda_check(cudaStreamSynchronize(en.stream()), "vision sync");
+    en.timings.vision = now_ms() - t0;
+    size_t off = 0;
+    for (int p = 0; p < n_pages; ++p) {
+      if (out_rows && out_rows[p]) d2h(out_rows[p], rows + off * en.cfg().n_embed, (size_t)counts[p] * en.cfg().n_embed * 4);
+      if (n_rows) n_rows[p] = counts[p];
+      off += counts[p];
+    }
+  });
+}
+
+extern "C" int dsocr_vision_tap(dsocr_engine* e, const char* name, float* out, size_t capacity, size_t* n_written) {
+  return api("", [&] { bind(e); e->impl->tap(name ? name : "", out, capacity, n_written); });
+}
+
+extern "C" int dsocr_generate_batch(dsocr_engine* e, int n_pages, const int64_t* const* input_ids,
+                                    const uint8_t* const* images_seq_mask, const int* n_tokens,
+                                    const float* const* image_rows, const int* n_image_rows,
+                                    const dsocr_decode_params* params, dsocr_token_cb cb, void* user,
+                                    int64_t* const* out_tokens, int* n_out) {
+  return api("", [&] {
+    bind(e);
+    if (!params) throw std::runtime_error("null decode params");
+    Engine::GenRequest rq;
+    rq.n_pages = n_pages; rq.input_ids = input_ids; rq.mask = images_seq_mask; rq.n_tokens = n_tokens;
+    rq.image_rows_host = image_rows; rq.n_image_rows = n_image_rows; rq.params = *params; rq.cb = cb; rq.user = user;
+    e->impl->generate(rq, out_tokens, n_out);
+  });
+}
+
+extern "C" int dsocr_generate_forced(dsocr_engine* e, int n_pages, const int64_t* const* input_ids,
+                                     const uint8_t* const* images_seq_mask, const int* n_tokens,
+                                     const float* const* image_rows, const int* n_image_rows,
+                                     const dsocr_decode_params* params, const int64_t* const* forced_tokens,
+                                     int n_steps, int64_t* const* selected_out, float* const* logits_out) {
+  return api("", [&] {
+    bind(e);
+    if (!params || !forced_tokens) throw std::runtime_error("null argument");
+    Engine::GenRequest rq;
+    rq.n_pages = n_pages; rq.input_ids = input_ids; rq.mask = images_seq_mask; rq.n_tokens = n_tokens;
+    rq.image_rows_host = image_rows; rq.n_image_rows = n_image_rows; rq.params = *params;
+    rq.forced = forced_tokens; rq.n_forced_steps = n_steps; rq.logits_out = logits_out;
+    std::vector<int> n_out(n_pages);
+    e->impl->generate(rq, selected_out, n_out.data());
+  });
+}
+
+extern "C" int dsocr_decode_pages(dsocr_engine* e, int n_pages, const uint8_t* const* rgb, const int* widths,
+                                  const int* heights, dsocr_vision_settings vs, const int64_t* seg0, int n_seg0,
+                                  const int64_t* seg1, int n_seg1, int64_t image_token_id,
+                                  const dsocr_decode_params* params, dsocr_token_cb cb, void* user,
+                                  int64_t* const* out_tokens, int* n_out, int* prompt_tokens) {
+  std::string stage = "vision input failed";
+  return api("", [&] {
+    try {
+      bind(e);
+      Engine& en = *e->impl;
+      if (!params) throw std::runtime_error("null decode params");
+      // ---- prepare_vision_inputs (model/mod.rs:2457-2492): integer resample / tiling on the host cores
+      const double t0 = now_ms();
+      const int G = vs.crop_mode ? (int)vs.base_size : (int)vs.image_size, P = (int)vs.image_size;
+      std::vector<std::vector<uint8_t>> globals(n_pages), tiles(n_pages);
+      std::vector<int> ntiles(n_pages, 0), cw(n_pages, 1), ch(n_pages, 1);
+      {
+        std::vector<std::thread> th;
+        std::vector<std::string> errs(n_pages);
+        const int nthreads = std::min<int>(n_pages, std::max(1u, std::thread::hardware_concurrency()));
+        for (int t = 0; t < nthreads; ++t)
+          th.emplace_back([&, t] {
+            for (int p = t; p < n_pages; p += nthreads) {
+              try {
+                if (!rgb[p] || widths[p] <= 0 || heights[p] <= 0) throw std::runtime_error("empty image");
+                globals[p].resize((size_t)G * G * 3);
+                if (widths[p] == G && heights[p] == G) memcpy(globals[p].data(), rgb[p], globals[p].size());  // identity resize
+                else build_global_view_u8(rgb[p], widths[p], heights[p], G, globals[p].data());
+                if (vs.crop_mode) {
+                  int n = dynamic_preprocess_u8(rgb[p], widths[p], heights[p], P, nullptr, &cw[p], &ch[p]);
+                  if (n > 0) {
+                    tiles[p].resize((size_t)n * P * P * 3);
+                    dynamic_preprocess_u8(rgb[p], widths[p], heights[p], P, tiles[p].data(), &cw[p], &ch[p]);
+                  }
+                  ntiles[p] = n;
+                }
+              } catch (const std::exception& ex) { errs[p] = ex.what(); }
+            }
+          });
+        for (auto& t : th) t.join();
+        for (auto& s : errs) if (!s.empty()) throw std::runtime_error(s);
+      }
+      en.timings.prepare = now_ms() - t0;
+      // ---- compute_image_embeddings
+      stage = "image embedding failed";
+      const double t1 = now_ms();
+      std::vector<const uint8_t*> gp(n_pages), tp(n_pages);
+      for (int p = 0; p < n_pages; ++p) { gp[p] = globals[p].data(); tp[p] = tiles[p].empty() ? nullptr : tiles[p].data(); }
+      DevBuf dg, dt;
+      std::vector<int> counts;
+      const float* rows = encode_u8(en, n_pages, gp.data(), G, tp.data(), ntiles.data(), P, cw.data(), ch.data(), &counts, dg, dt);
+      cuda_check(cudaStreamSynchronize(en.stream()), "vision sync");
+      en.timings.vision = now_ms() - t1;
+      // ---- build_prompt_tokens (model/mod.rs:2536-2603): BOS + seg0 + <image> x n + seg1
+      stage = "prompt formatting failed";
+      std::vector<std::vector<int64_t>> ids(n_pages);
+      std::vector<std::vector<uint8_t>> masks(n_pages);
+      std::vector<const int64_t*> idp(n_pages);
+      std::vector<const uint8_t*> mp(n_pages);
+      std::vector<int> nt(n_pages);
+      for (int p = 0; p < n_pages; ++p) {
+        const int expect = image_token_count((int)vs.base_size, (int)vs.image_size, vs.crop_mode, cw[p], ch[p]);
+        if (expect != counts[p])
+          throw std::runtime_error("placeholder count " + std::to_string(expect) + " does not match expected " + std::to_string(counts[p]));
+        ids[p].push_back(0); masks[p].push_back(0);  // bos_id = 0 (model/mod.rs:2547)
+        for (int i = 0; i < n_seg0; ++i) { ids[p].push_back(seg0[i]); masks[p].push_back(0); }
+        for (int i = 0; i < counts[p]; ++i) { ids[p].push_back(image_token_id); masks[p].push_back(1); }
+        for (int i = 0; i < n_seg1; ++i) { ids[p].push_back(seg1[i]); masks[p].push_back(0); }
+        idp[p] = ids[p].data(); mp[p] = masks[p].data(); nt[p] = (int)ids[p].size();
+        if (prompt_tokens) prompt_tokens[p] = nt[p];
+      }
+      stage = "";
+      Engine::GenRequest rq;
+      rq.n_pages = n_pages; rq.input_ids = idp.data(); rq.mask = mp.data(); rq.n_tokens = nt.data();
+      rq.image_rows_dev = rows; rq.n_image_rows = counts.data(); rq.params = *params; rq.cb = cb; rq.user = user;
+      en.generate(rq, out_tokens, n_out);
+    } catch (const std::exception& ex) {
+      throw std::runtime_error(stage.empty() ? std::string(ex.what()) : stage + ": " + ex.what());
+    }
+  });
+}
+
+extern "C" int dsocr_last_timings(const dsocr_engine* e, double* ms_out, int n) {
+  return api("", [&] {
+    if (!e || !ms_out) throw std::runtime_error("null argument");
+    const Timings& t = e->impl->timings;
+    const double v[5] = {t.prepare, t.vision, t.prefill, t.iterative, t.generate};
+    for (int i = 0; i < n && i < 5; ++i) ms_out[i] = v[i];
+  });
+}
+
+extern "C" long long dsocr_launch_count(const dsocr_engine*) { return launch_counter(); }

@@ -1,0 +1,298 @@
+// Engine implementation, part 2: the DeepSeek-V2 MoE decoder (prefill + lock-step batched greedy decode).
+// Restates DeepseekOcrModel::generate (model/mod.rs:1870-2048) for a batch of independent pages.
+#include <algorithm>
+#include <cstring>
+
+#include "engine.h"
+#include "linear_tc.cuh"
+
+namespace dsocr {
+
+// One pass of the 12 decoder layers over `rows` token rows (TransformerDecoder::forward, decoder.rs:62-196;
+// TransformerBlock::forward_internal, block.rs:123-190), then final RMSNorm + lm_head on `n_final` selected
+// rows (the reference computes logits for every prefill row, transformer/model.rs:243-270; only the last
+// row of each page is ever used, model/mod.rs:1941-1947).
+void Engine::decoder_forward(float* x, long long rows, const int* row_page, const int* row_pos, int smax,
+                             const int* final_rows, int n_final, float* logits) {
+  const ModelConfig& c = cfg_;
+  const int H = c.hidden, heads = c.heads, E = c.n_experts, K = c.topk, mi = c.moe_inter;
+  const long long S = (long long)c.moe_inter * c.n_shared;
+  const float scale = 1.0f / sqrtf((float)c.head_dim());
+  const long long n_assign = rows * K;
+  const long long inter_max = std::max<long long>(c.inter, S);
+
+  // hi/lo split 16-bit activation buffers: [2][rows][width], lo part `rows*width` elements after hi
+  void* xn16 = ws("dec_xn16", 2 * rows * H * 2).p;
+  float* xn32 = ws("dec_xn32", rows * H * 4).as<float>();
+  float* qkv = ws("dec_qkv32", rows * 3 * H * 4).as<float>();
+  float* q = ws("dec_q32", rows * H * 4).as<float>();
+  void* ctx16 = ws("dec_ctx16", 2 * rows * H * 2).p;
+  void* h16 = ws("dec_h16", 2 * rows * inter_max * 2).p;
+  int* topk_idx = ws("moe_topk_idx", n_assign * 4).as<int>();
+  float* topk_w = ws("moe_topk_w", n_assign * 4).as<float>();
+  int* counts = ws("moe_counts", 3 * E * 4 + 16).as<int>();
+  int* offsets = counts + E;
+  int* cursor = counts + 2 * E;
+  int* ntiles = counts + 3 * E;  // [2]
+  const int bn = linear_pick_bn(std::max<long long>(1, n_assign / E * 2), true);
+  const int max_chunks = (int)(n_assign / bn) + E;
+  LinearTile* tiles1 = ws("moe_tiles1", (size_t)max_chunks * (mi / 128) * sizeof(LinearTile)).as<LinearTile>();
+  LinearTile* tiles2 = ws("moe_tiles2", (size_t)max_chunks * (H / 128) * sizeof(LinearTile)).as<LinearTile>();
+  int* perm_pos = ws("moe_perm", n_assign * 4).as<int>();
+  void* xperm16 = ws("moe_xperm16", 2 * n_assign * H * 2).p;
+  void* hperm16 = ws("moe_hperm16", 2 * n_assign * mi * 2).p;
+  float* yperm = ws("moe_yperm32", n_assign * H * 4).as<float>();
+
+  for (int l = 0; l < c.layers; ++l) {
+    DecLayerW& L = dec_[l];
+    rmsnorm_split(x, L.ln1.as<float>(), xn16, rows * H, nullptr, nullptr, rows, H, c.rms_eps, dt_, stream_);
+    {
+      LinearCall lc;  // fused q/k/v projection
+      lc.w0 = L.qkv_w.p; lc.x = xn16; lc.x_rows = 2 * rows; lc.x_parts = 2; lc.x_lo_row_off = (int)rows;
+      lc.M = (int)rows; lc.N = 3 * H; lc.K = H; lc.out = qkv; lc.ldo = 3 * H; lc.out_mode = lin::OUT_F32;
+      linear(lc, dt_, num_sms_, stream_);
+    }
+    rope_kv(qkv, rope_cos_.as<float>(), rope_sin_.as<float>(), row_page, row_pos, q, kcache_[l].as<float>(),
+            vcache_[l].as<float>(), rows, heads, smax, stream_);
+    kv_attention(q, kcache_[l].as<float>(), vcache_[l].as<float>(), row_page, row_pos, ctx16, rows * H, rows, heads,
+                 smax, scale, dt_, stream_);
+    {
+      LinearCall lc;  // o_proj + residual add
+      lc.w0 = L.o_w.p; lc.x = ctx16; lc.x_rows = 2 * rows; lc.x_parts = 2; lc.x_lo_row_off = (int)rows;
+      lc.M = (int)rows; lc.N = H; lc.K = H; lc.out = x; lc.ldo = H; lc.out_mode = lin::OUT_F32_ADD;
+      linear(lc, dt_, num_sms_, stream_);
+    }
+    rmsnorm_split(x, L.ln2.as<float>(), xn16, rows * H, L.moe ? xn32 : nullptr, nullptr, rows, H, c.rms_eps, dt_, stream_);
+    if (!L.moe) {
+      {
+        LinearCall lc;  // gate/up + SwiGLU (run_dense_mlp, block.rs:1166-1177)
+        lc.w0 = L.gate_w.p; lc.w1 = L.up_w.p; lc.x = xn16; lc.x_rows = 2 * rows; lc.x_parts = 2; lc.x_lo_row_off = (int)rows;
+        lc.M = (int)rows; lc.N = c.inter; lc.K = H; lc.out = h16; lc.out_lo = (uint16_t*)h16 + rows * c.inter;
+        lc.ldo = c.inter; lc.out_mode = lin::OUT_T_SPLIT;
+        linear(lc, dt_, num_sms_, stream_);
+      }
+      {
+        LinearCall lc;
+        lc.w0 = L.down_w.p; lc.x = h16; lc.x_rows = 2 * rows; lc.x_parts = 2; lc.x_lo_row_off = (int)rows;
+        lc.M = (int)rows; lc.N = H; lc.K = c.inter; lc.out = x; lc.ldo = H; lc.out_mode = lin::OUT_F32_ADD;
+        linear(lc, dt_, num_sms_, stream_);
+      }
+    } else {
+      // run_moe (block.rs:1215-1395)
+      cuda_check(cudaMemsetAsync(counts, 0, E * 4, stream_), "moe counts memset");
+      moe_router(xn32, L.router_wt.as<float>(), topk_idx, topk_w, counts, rows, H, E, K, stream_);
+      moe_plan(counts, offsets, cursor, tiles1, ntiles, tiles2, ntiles + 1, E, bn, mi, H, stream_);
+      moe_dispatch(topk_idx, offsets, cursor, xn16, rows * H, xperm16, n_assign * H, perm_pos, n_assign, K, H, dt_, stream_);
+      {
+        LinearCall lc;  // routed experts: gate/up + SwiGLU, grouped
+        lc.w0 = L.exp_gate.p; lc.w1 = L.exp_up.p; lc.w_rows = (long long)E * mi;
+        lc.x = xperm16; lc.x_rows = 2 * n_assign; lc.x_parts = 2; lc.x_lo_row_off = (int)n_assign;
+        lc.M = (int)n_assign; lc.N = mi; lc.K = H;
+        lc.out = hperm16; lc.out_lo = (uint16_t*)hperm16 + n_assign * mi; lc.ldo = mi; lc.out_mode = lin::OUT_T_SPLIT;
+        lc.tiles = tiles1; lc.num_tiles_dev = ntiles; lc.max_tiles = max_chunks * (mi / 128); lc.bn = bn;
+        linear(lc, dt_, num_sms_, stream_);
+      }
+      {
+        LinearCall lc;  // routed experts: down, grouped
+        lc.w0 = L.exp_down.p; lc.w_rows = (long long)E * H;
+        lc.x = hperm16; lc.x_rows = 2 * n_assign; lc.x_parts = 2; lc.x_lo_row_off = (int)n_assign;
+        lc.M = (int)n_assign; lc.N = H; lc.K = mi; lc.out = yperm; lc.ldo = H; lc.out_mode = lin::OUT_F32;
+        lc.tiles = tiles2; lc.num_tiles_dev = ntiles + 1; lc.max_tiles = max_chunks * (H / 128); lc.bn = bn;
+        linear(lc, dt_, num_sms_, stream_);
+      }
+      {
+        LinearCall lc;  // shared experts (one fused SwiGLU MLP, weights.rs:390-400)
+        lc.w0 = L.sh_gate.p; lc.w1 = L.sh_up.p; lc.x = xn16; lc.x_rows = 2 * rows; lc.x_parts = 2; lc.x_lo_row_off = (int)rows;
+        lc.M = (int)rows; lc.N = (int)S; lc.K = H; lc.out = h16; lc.out_lo = (uint16_t*)h16 + rows * S; lc.ldo = S;
+        lc.out_mode = lin::OUT_T_SPLIT;
+        linear(lc, dt_, num_sms_, stream_);
+      }
+      {
+        LinearCall lc;
+        lc.w0 = L.sh_down.p; lc.x = h16; lc.x_rows = 2 * rows; lc.x_parts = 2; lc.x_lo_row_off = (int)rows;
+        lc.M = (int)rows; lc.N = H; lc.K = (int)S; lc.out = x; lc.ldo = H; lc.out_mode = lin::OUT_F32_ADD;
+        linear(lc, dt_, num_sms_, stream_);
+      }
+      moe_combine(yperm, perm_pos, topk_w, x, rows, K, H, stream_);
+    }
+    if (record_taps_) record_tap("dec.hidden." + std::to_string(l), x, rows * H);
+  }
+  // final RMSNorm + lm_head on the selected rows
+  void* xf16 = ws("dec_xf16", 2 * (size_t)n_final * H * 2).p;
+  rmsnorm_split(x, final_norm_.as<float>(), xf16, (long long)n_final * H, nullptr, final_rows, n_final, H, c.rms_eps, dt_, stream_);
+  LinearCall lc;
+  lc.w0 = lm_head_.p; lc.x = xf16; lc.x_rows = 2 * n_final; lc.x_parts = 2; lc.x_lo_row_off = n_final;
+  lc.M = n_final; lc.N = c.vocab; lc.K = H; lc.out = logits; lc.ldo = c.vocab; lc.out_mode = lin::OUT_F32;
+  linear(lc, dt_, num_sms_, stream_);
+}
+
+void Engine::generate(const GenRequest& rq, int64_t* const* out_tokens, int* n_out) {
+  const ModelConfig& c = cfg_;
+  const int P = rq.n_pages, H = c.hidden, V = c.vocab;
+  if (P <= 0) return;
+  if (rq.params.do_sample) throw std::runtime_error("sampling is not supported on the device path (greedy only)");
+  if (rq.params.repetition_penalty != 0.f && fabsf(rq.params.repetition_penalty - 1.0f) > 1e-6f)
+    throw std::runtime_error("repetition_penalty != 1.0 is not supported");
+  const bool forced = rq.forced != nullptr;
+  const int max_new = forced ? rq.n_forced_steps : (int)rq.params.max_new_tokens;
+  for (int p = 0; p < P; ++p) n_out[p] = 0;
+  if (max_new == 0) return;  // model/mod.rs:1889-1897
+
+  cudaEvent_t ev0, ev1, ev2;
+  cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventCreate(&ev2);
+  cuda_check(cudaEventRecord(ev0, stream_), "event");
+
+  // ---- host-side prompt bookkeeping
+  long long total_rows = 0, total_img = 0;
+  int max_T = 0;
+  for (int p = 0; p < P; ++p) { total_rows += rq.n_tokens[p]; total_img += rq.n_image_rows[p]; max_T = std::max(max_T, rq.n_tokens[p]); }
+  const int smax = (max_T + max_new + 15) / 16 * 16;
+  if (smax > rope_len_) throw std::runtime_error("sequence length exceeds max_position_embeddings");
+  std::vector<int> src(total_rows), row_page(total_rows), row_pos(total_rows), last_rows(P), hist((size_t)P * smax, 0), hist_len(P);
+  {
+    long long r = 0, img_base = 0;
+    for (int p = 0; p < P; ++p) {
+      int img_used = 0;
+      for (int t = 0; t < rq.n_tokens[p]; ++t, ++r) {
+        const int64_t id = rq.input_ids[p][t];
+        if (id < 0 || id >= V) throw std::runtime_error("token id out of range");
+        hist[(size_t)p * smax + t] = (int)id;
+        row_page[r] = p; row_pos[r] = t;
+        if (rq.mask && rq.mask[p] && rq.mask[p][t]) src[r] = -(int)(img_base + img_used++) - 1;
+        else src[r] = (int)id;
+      }
+      if (img_used != rq.n_image_rows[p])
+        throw std::runtime_error("image embeddings provide " + std::to_string(rq.n_image_rows[p]) +
+                                 " tokens but mask requires " + std::to_string(img_used));
+      img_base += rq.n_image_rows[p];
+      last_rows[p] = (int)r - 1;
+      hist_len[p] = rq.n_tokens[p];
+    }
+  }
+  // ---- device state
+  const float* img_rows = rq.image_rows_dev;
+  if (!img_rows && total_img > 0) {
+    float* buf = ws("gen_img_rows32", total_img * H * 4).as<float>();
+    long long off = 0;
+    for (int p = 0; p < P; ++p) {
+      if (rq.n_image_rows[p] == 0) continue;
+      cuda_check(cudaMemcpyAsync(buf + off * H, rq.image_rows_host[p], (size_t)rq.n_image_rows[p] * H * 4, cudaMemcpyHostToDevice, stream_), "image rows upload");
+      off += rq.n_image_rows[p];
+    }
+    img_rows = buf;
+  }
+  const size_t kv_bytes = (size_t)P * c.heads * smax * c.head_dim() * 4;
+  kcache_.resize(c.layers); vcache_.resize(c.layers);
+  for (int l = 0; l < c.layers; ++l) { kcache_[l].ensure(kv_bytes); vcache_[l].ensure(kv_bytes); }
+
+  const long long max_rows = std::max<long long>(total_rows, P);
+  int* d_src = ws("gen_src", max_rows * 4).as<int>();
+  int* d_row_page = ws("gen_row_page", max_rows * 4).as<int>();
+  int* d_row_pos = ws("gen_row_pos", max_rows * 4).as<int>();
+  int* d_last = ws("gen_last_rows", P * 4).as<int>();
+  int* d_hist = ws("gen_hist", (size_t)P * smax * 4).as<int>();
+  int* d_state = ws("gen_state", (size_t)P * 3 * 4).as<int>();  // hist_len | gen_count | finished
+  int* d_hist_len = d_state, *d_gen_count = d_state + P, *d_finished = d_state + 2 * P;
+  float* x = ws("gen_x32", max_rows * H * 4).as<float>();
+  float* logits = ws("gen_logits32", (size_t)P * V * 4).as<float>();
+  int* d_forced = nullptr, *d_selected = nullptr;
+  if (forced) {
+    std::vector<int> f((size_t)P * max_new);
+    for (int p = 0; p < P; ++p) for (int s = 0; s < max_new; ++s) f[(size_t)p * max_new + s] = (int)rq.forced[p][s];
+    d_forced = ws("gen_forced", f.size() * 4).as<int>();
+    d_selected = ws("gen_selected", f.size() * 4).as<int>();
+    cuda_check(cudaMemcpyAsync(d_forced, f.data(), f.size() * 4, cudaMemcpyHostToDevice, stream_), "forced upload");
+    cuda_check(cudaStreamSynchronize(stream_), "forced sync");
+  }
+  auto up = [&](int* d, const std::vector<int>& h) {
+    cuda_check(cudaMemcpyAsync(d, h.data(), h.size() * 4, cudaMemcpyHostToDevice, stream_), "prompt upload");
+  };
+  up(d_src, src); up(d_row_page, row_page); up(d_row_pos, row_pos); up(d_last, last_rows); up(d_hist, hist); up(d_hist_len, hist_len);
+  cuda_check(cudaMemsetAsync(d_gen_count, 0, (size_t)P * 2 * 4, stream_), "state memset");
+  cuda_check(cudaStreamSynchronize(stream_), "prompt upload sync");
+
+  const int ngram = (int)rq.params.no_repeat_ngram_size;
+  const int eos = forced ? -1 : (int)rq.params.eos_token_id;
+  std::vector<float> h_logits;
+  auto copy_logits = [&](int step) {
+    if (!rq.logits_out) return;
+    h_logits.resize((size_t)P * V);
+    cuda_check(cudaMemcpyAsync(h_logits.data(), logits, h_logits.size() * 4, cudaMemcpyDeviceToHost, stream_), "logits D2H");
+    cuda_check(cudaStreamSynchronize(stream_), "logits sync");
+    for (int p = 0; p < P; ++p)
+      if (rq.logits_out[p]) memcpy(rq.logits_out[p] + (size_t)step * V, h_logits.data() + (size_t)p * V, (size_t)V * 4);
+  };
+
+  // ---- prefill (model/mod.rs:1925-1947)
+  embed_gather(d_src, embed_.p, img_rows, x, total_rows, H, dt_, stream_);
+  decoder_forward(x, total_rows, d_row_page, d_row_pos, smax, d_last, P, logits);
+  copy_logits(0);
+  select_token(logits, V, d_hist, smax, d_hist_len, d_gen_count, d_finished, P, ngram, eos, max_new, d_forced, max_new, 0,
+               d_selected, max_new, stream_);
+  cuda_check(cudaEventRecord(ev1, stream_), "event");
+
+  // ---- token loop (model/mod.rs:1977-2034): every page advances one token per step
+  std::vector<int> page_ids(P), fin(P), h_hist, h_len(P), delivered(P, 0);
+  for (int p = 0; p < P; ++p) page_ids[p] = p;
+  up(d_row_page, page_ids);
+  const int sync_every = rq.cb ? 4 : 16;
+  auto deliver = [&]() {  // streaming callback: (count, all generated ids) after every accepted token
+    if (!rq.cb) return;
+    h_hist.resize((size_t)P * smax);
+    d2h(h_hist.data(), d_hist, h_hist.size() * 4);
+    d2h(h_len.data(), d_hist_len, P * 4);
+    std::vector<int64_t> toks;
+    for (int p = 0; p < P; ++p) {
+      const int gen = h_len[p] - rq.n_tokens[p];
+      for (int cnt = delivered[p] + 1; cnt <= gen; ++cnt) {
+        toks.resize(cnt);
+        for (int i = 0; i < cnt; ++i) toks[i] = h_hist[(size_t)p * smax + rq.n_tokens[p] + i];
+        rq.cb(rq.user, p, (size_t)cnt, toks.data());
+      }
+      delivered[p] = std::max(delivered[p], gen);
+    }
+  };
+  for (int step = 1; step < max_new; ++step) {
+    if ((step - 1) % sync_every == 0) {
+      cuda_check(cudaStreamSynchronize(stream_), "decode sync");
+      d2h(fin.data(), d_finished, P * 4);
+      deliver();
+      bool all = true;
+      for (int p = 0; p < P; ++p) all &= fin[p] != 0;
+      if (all) break;
+    }
+    decode_rows(d_hist, smax, d_hist_len, d_src, d_row_pos, P, stream_);
+    embed_gather(d_src, embed_.p, nullptr, x, P, H, dt_, stream_);
+    decoder_forward(x, P, d_row_page, d_row_pos, smax, d_row_page /* identity: every row */, P, logits);
+    copy_logits(step);
+    select_token(logits, V, d_hist, smax, d_hist_len, d_gen_count, d_finished, P, ngram, eos, max_new, d_forced, max_new,
+                 step, d_selected, max_new, stream_);
+  }
+  cuda_check(cudaEventRecord(ev2, stream_), "event");
+  cuda_check(cudaStreamSynchronize(stream_), "generate sync");
+  deliver();
+
+  // ---- results
+  h_hist.resize((size_t)P * smax);
+  d2h(h_hist.data(), d_hist, h_hist.size() * 4);
+  d2h(h_len.data(), d_hist_len, P * 4);
+  std::vector<int> h_sel;
+  if (forced) { h_sel.resize((size_t)P * max_new); d2h(h_sel.data(), d_selected, h_sel.size() * 4); }
+  for (int p = 0; p < P; ++p) {
+    if (forced) {
+      n_out[p] = max_new;
+      for (int s = 0; s < max_new; ++s) out_tokens[p][s] = h_sel[(size_t)p * max_new + s];
+    } else {
+      const int gen = h_len[p] - rq.n_tokens[p];
+      n_out[p] = gen;
+      for (int i = 0; i < gen; ++i) out_tokens[p][i] = h_hist[(size_t)p * smax + rq.n_tokens[p] + i];
+    }
+  }
+  float ms_prefill = 0, ms_iter = 0;
+  cudaEventElapsedTime(&ms_prefill, ev0, ev1);
+  cudaEventElapsedTime(&ms_iter, ev1, ev2);
+  timings.prefill = ms_prefill; timings.iterative = ms_iter; timings.generate = ms_prefill + ms_iter;
+  cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2);
+}
+
+}  // namespace dsocr

@@ -12,6 +12,13 @@ enum class DType : int { F32 = 0, F16 = 1, BF16 = 2 };  // values match include/
 inline void cuda_check(cudaError_t e, const char* what) {
   if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
 }
+// Every kernel launch of this library goes through launch_check: it surfaces launch errors and counts the
+// launches (dsocr_launch_count).
+long long& launch_counter();
+inline void launch_check(const char* what) {
+  ++launch_counter();
+  cuda_check(cudaGetLastError(), what);
+}
 
 // ------------------------------------------------------------------------- tensor-core linear
 struct LinearTile { int w_row0, x_row0, rows, n0; };  // == lin::Tile
@@ -69,5 +76,45 @@ void vision_attention(const VAttnCall& c, DType dt, cudaStream_t stream);
 // Z = q . table^T through the tensor-core linear kernel.  table: [2*zhalf, 64] 16-bit (rel_h rows then rel_w rows).
 void vision_relpos_products(const void* qkv, long long rows, int H, const void* table, int zhalf, float* Z, DType dt,
                             int num_sms, cudaStream_t stream);
+
+// ------------------------------------------------------------------------- vision SIMT kernels
+void patchify_u8(const uint8_t* img, void* out, int B, int G, DType dt, cudaStream_t s);
+void patchify_f32(const float* img, void* out, int B, int G, DType dt, cudaStream_t s);
+void bcast_rows(const float* src, float* dst, long long rows_per_batch, int batch, int cols, cudaStream_t s);
+void layernorm(const float* x, const float* w, const float* b, void* out16, float* out32, long long out_rows, int C,
+               float eps, int win, int g, int nw, DType dt, cudaStream_t s);
+void window_row_map(int* map, long long rows, int win, int g, int nw, cudaStream_t s);
+void cast16(const float* x, void* out, long long n, DType dt, cudaStream_t s);
+void im2col3x3(const void* in, void* out, int B, int Hin, int Win, int C, int stride, DType dt, cudaStream_t s);
+void clip_embed(const float* sam, const float* cls, const float* pos, float* out, int B, int n, int C, cudaStream_t s);
+void concat_clip_sam(const float* clip, const float* sam, void* out16, float* out32, int B, int n, int C, DType dt,
+                     cudaStream_t s);
+void scatter_tokens(const float* proj, const float* newline, const float* sep, const int* map, float* dst,
+                    long long rows, int C, cudaStream_t s);
+
+// ------------------------------------------------------------------------- decoder SIMT kernels
+void embed_gather(const int* src, const void* table, const float* img_rows, float* out, long long rows, int H, DType dt,
+                  cudaStream_t s);
+void rmsnorm_split(const float* x, const float* w, void* out16, long long lo_off_elems, float* out32,
+                   const int* row_idx, long long rows, int H, float eps, DType dt, cudaStream_t s);
+void rope_kv(const float* qkv, const float* cos_t, const float* sin_t, const int* row_page, const int* row_pos,
+             float* q_out, float* kc, float* vc, long long rows, int heads, int smax, cudaStream_t s);
+void kv_attention(const float* q, const float* kc, const float* vc, const int* row_page, const int* row_pos, void* ctx,
+                  long long lo_off_elems, long long rows, int heads, int smax, float scale, DType dt, cudaStream_t s);
+void moe_router(const float* x, const float* wgt, int* topk_idx, float* topk_w, int* counts, long long rows, int H,
+                int E, int topk, cudaStream_t s);
+void moe_plan(const int* counts, int* offsets, int* cursor, LinearTile* tiles1, int* ntiles1, LinearTile* tiles2,
+              int* ntiles2, int E, int bn, int N1, int N2, cudaStream_t s);
+void moe_dispatch(const int* topk_idx, const int* offsets, int* cursor, const void* xn, long long xn_lo_off,
+                  void* xperm, long long xperm_lo_off, int* perm_pos, long long n_assign, int topk, int H, DType dt,
+                  cudaStream_t s);
+void moe_combine(const float* y, const int* perm_pos, const float* topk_w, float* x, long long rows, int topk, int H,
+                 cudaStream_t s);
+void select_token(const float* logits, int V, int* hist, int hist_stride, int* hist_len, int* gen_count, int* finished,
+                  int n_pages, int ngram, int eos, int max_new, const int* forced, int forced_stride, int step,
+                  int* selected_out, int selected_stride, cudaStream_t s);
+void decode_rows(const int* hist, int hist_stride, const int* hist_len, int* src, int* row_pos, int n_pages,
+                 cudaStream_t s);
+void fill_i32(int* p, int v, long long n, cudaStream_t s);
 
 }  // namespace dsocr

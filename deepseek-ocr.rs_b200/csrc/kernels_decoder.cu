@@ -1,0 +1,535 @@
+// Bandwidth-bound kernels of the DeepSeek-V2 MoE decoder path: embedding gather + image-token injection,
+// RMSNorm (hi/lo split outputs), RoPE + KV-cache append, causal prefill attention, flash-decode over the KV
+// cache, MoE router/top-k, dispatch/combine, n-gram ban + first-index argmax.  f32 math throughout (the
+// reference keeps the whole decoder in f32); 128-bit accesses, warp-shuffle reductions.
+#include "kernels.h"
+#include "ptx.cuh"
+
+#include <cfloat>
+
+namespace dsocr {
+
+namespace {
+
+template <typename T>
+__device__ __forceinline__ uint32_t pack2f(float a, float b);
+template <>
+__device__ __forceinline__ uint32_t pack2f<__nv_bfloat16>(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+template <>
+__device__ __forceinline__ uint32_t pack2f<__half>(float a, float b) {
+  __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+// 4 floats -> 4 x 16-bit hi (uint2) and 4 x 16-bit lo (uint2) with lo = r16(x - hi)
+template <typename T>
+__device__ __forceinline__ void split4(const float* f, uint2& hi, uint2& lo) {
+  float r[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) r[i] = f[i] - Elem<T>::to(Elem<T>::from(f[i]));
+  hi.x = pack2f<T>(f[0], f[1]); hi.y = pack2f<T>(f[2], f[3]);
+  lo.x = pack2f<T>(r[0], r[1]); lo.y = pack2f<T>(r[2], r[3]);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+inline int blocks_for(long long n, int threads) { return (int)((n + threads - 1) / threads); }
+
+// ---------------------------------------------------------------------------------------------------
+// embed_tokens + inject_image_tokens (transformer/model.rs:116-127, model/mod.rs:1760-1857):
+// src[r] >= 0 -> embedding row src[r];  src[r] < 0 -> image row (-src[r] - 1).
+template <typename T>
+__global__ void embed_gather_kernel(const int* __restrict__ src, const T* __restrict__ table,
+                                    const float* __restrict__ img_rows, float* __restrict__ out, long long rows,
+                                    int H) {
+  const int h4 = H / 4;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * h4) return;
+  const long long r = idx / h4;
+  const int c = idx % h4;
+  const int s = src[r];
+  float4 v;
+  if (s >= 0) {
+    const uint2 raw = reinterpret_cast<const uint2*>(table + (long long)s * H)[c];
+    const T* e = reinterpret_cast<const T*>(&raw);
+    v = make_float4(Elem<T>::to(e[0]), Elem<T>::to(e[1]), Elem<T>::to(e[2]), Elem<T>::to(e[3]));
+  } else {
+    v = reinterpret_cast<const float4*>(img_rows + (long long)(-s - 1) * H)[c];
+  }
+  reinterpret_cast<float4*>(out)[idx] = v;
+}
+
+// rms_norm (block.rs:24-29): x * rsqrt(mean(x^2) + eps) * w in f32.  One warp per row.  Outputs: 16-bit hi/lo
+// split [2][lo_off rows apart] for the tensor-core GEMMs and optionally the f32 row (router input).
+// `row_idx` (optional) selects source rows (last-row-only final norm).
+template <typename T>
+__global__ void rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ w, T* __restrict__ out16,
+                               long long lo_off_elems, float* __restrict__ out32, const int* __restrict__ row_idx,
+                               long long rows, int H, float eps) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const long long src = row_idx ? row_idx[row] : row;
+  const float4* xr = reinterpret_cast<const float4*>(x + src * H);
+  const int n4 = H / 4;
+  float ss = 0.f;
+  for (int i = lane; i < n4; i += 32) {
+    const float4 v = xr[i];
+    ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  const float inv = rsqrtf(warp_sum(ss) / (float)H + eps);
+  for (int i = lane; i < n4; i += 32) {
+    const float4 v = xr[i];
+    const float4 ww = reinterpret_cast<const float4*>(w)[i];
+    float o[4] = {v.x * inv * ww.x, v.y * inv * ww.y, v.z * inv * ww.z, v.w * inv * ww.w};
+    uint2 hi, lo;
+    split4<T>(o, hi, lo);
+    reinterpret_cast<uint2*>(out16 + row * H)[i] = hi;
+    reinterpret_cast<uint2*>(out16 + lo_off_elems + row * H)[i] = lo;
+    if (out32) reinterpret_cast<float4*>(out32 + row * H)[i] = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// RoPE (block.rs:1403-1471, NeoX rotate-half over all 128 dims, tables rope.rs:172-207) applied to the q and
+// k thirds of the fused qkv projection [rows, 3, heads, 128] f32, then K/V appended to the per-page cache
+// [page][head][S_max][128] and q written as hi/lo... q stays f32 ([rows, heads, 128]).
+// One thread = 4 consecutive dims of the low half (and their partners in the high half).
+__global__ void rope_kv_kernel(const float* __restrict__ qkv, const float* __restrict__ cos_t,
+                               const float* __restrict__ sin_t, const int* __restrict__ row_page,
+                               const int* __restrict__ row_pos, float* __restrict__ q_out, float* __restrict__ kc,
+                               float* __restrict__ vc, long long rows, int heads, int smax) {
+  constexpr int D = 128;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = rows * heads * 16;  // 16 threads x 4 dims = low half (64)
+  if (idx >= total) return;
+  const int t = idx % 16;
+  const int hd = (idx / 16) % heads;
+  const long long r = idx / (16LL * heads);
+  const int pos = row_pos[r];
+  const int page = row_page[r];
+  const float4 c = reinterpret_cast<const float4*>(cos_t + (long long)pos * 64)[t];
+  const float4 s = reinterpret_cast<const float4*>(sin_t + (long long)pos * 64)[t];
+  const float* base = qkv + r * 3 * heads * D;
+  const long long cache_off = (((long long)page * heads + hd) * smax + pos) * D;
+#pragma unroll
+  for (int which = 0; which < 2; ++which) {
+    const float* src = base + (which * heads + hd) * D;
+    const float4 lo = reinterpret_cast<const float4*>(src)[t];
+    const float4 hi = reinterpret_cast<const float4*>(src + 64)[t];
+    // out = x*cos + rotate_half(x)*sin ; rotate_half = [-hi, lo]; cos/sin halves are duplicated
+    float4 olo, ohi;
+    olo.x = lo.x * c.x - hi.x * s.x; olo.y = lo.y * c.y - hi.y * s.y; olo.z = lo.z * c.z - hi.z * s.z; olo.w = lo.w * c.w - hi.w * s.w;
+    ohi.x = hi.x * c.x + lo.x * s.x; ohi.y = hi.y * c.y + lo.y * s.y; ohi.z = hi.z * c.z + lo.z * s.z; ohi.w = hi.w * c.w + lo.w * s.w;
+    float* dst = which == 0 ? q_out + (r * heads + hd) * D : kc + cache_off;
+    reinterpret_cast<float4*>(dst)[t] = olo;
+    reinterpret_cast<float4*>(dst + 64)[t] = ohi;
+  }
+  const float* vsrc = base + (2 * heads + hd) * D;
+  reinterpret_cast<float4*>(vc + cache_off)[t] = reinterpret_cast<const float4*>(vsrc)[t];
+  reinterpret_cast<float4*>(vc + cache_off + 64)[t] = reinterpret_cast<const float4*>(vsrc + 64)[t];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Attention over the KV cache, f32 (attention_forward, block.rs:446-804).  Used for both prefill (causal:
+// query at position p attends keys 0..p) and decode (one query per page).  Grid: (query, head); 4 warps split
+// the keys; each warp processes 4 keys per step with 8 lanes per key (16 dims per lane).  Output: hi/lo split
+// 16-bit context rows [rows, heads*128] feeding the o_proj GEMM.
+template <typename T>
+__global__ void __launch_bounds__(128)
+kv_attention_kernel(const float* __restrict__ q, const float* __restrict__ kc, const float* __restrict__ vc,
+                    const int* __restrict__ row_page, const int* __restrict__ row_pos, T* __restrict__ ctx,
+                    long long lo_off_elems, int heads, int smax, float scale) {
+  constexpr int D = 128;
+  const long long r = blockIdx.x;
+  const int hd = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = lane >> 3, sub = lane & 7;  // 4 key groups x 8 lanes; lane covers dims [sub*16, sub*16+16)
+  const int nkeys = row_pos[r] + 1;
+  const int page = row_page[r];
+  const float* kbase = kc + ((long long)page * heads + hd) * smax * D;
+  const float* vbase = vc + ((long long)page * heads + hd) * smax * D;
+  float qv[16];
+  {
+    const float4* qp = reinterpret_cast<const float4*>(q + (r * heads + hd) * D + sub * 16);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 t = qp[i];
+      qv[4 * i] = t.x * scale; qv[4 * i + 1] = t.y * scale; qv[4 * i + 2] = t.z * scale; qv[4 * i + 3] = t.w * scale;
+    }
+  }
+  float m = -INFINITY, l = 0.f, acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  for (int k0 = warp * 4; k0 < nkeys; k0 += 16) {
+    const int k = k0 + grp;
+    const bool ok = k < nkeys;
+    float s = 0.f;
+    float vv[16];
+    if (ok) {
+      const float4* kp = reinterpret_cast<const float4*>(kbase + (long long)k * D + sub * 16);
+      const float4* vp = reinterpret_cast<const float4*>(vbase + (long long)k * D + sub * 16);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 t = kp[i];
+        s += qv[4 * i] * t.x + qv[4 * i + 1] * t.y + qv[4 * i + 2] * t.z + qv[4 * i + 3] * t.w;
+        const float4 u = vp[i];
+        vv[4 * i] = u.x; vv[4 * i + 1] = u.y; vv[4 * i + 2] = u.z; vv[4 * i + 3] = u.w;
+      }
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (ok) {
+      const float mn = fmaxf(m, s);
+      const float a = __expf(m - mn);
+      const float p = __expf(s - mn);
+      l = l * a + p;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[i] = acc[i] * a + p * vv[i];
+      m = mn;
+    }
+  }
+  // merge the 4 key groups of the warp, then the 4 warps
+  __shared__ float sm_m[16], sm_l[16], sm_acc[16][D];
+  const int slot = warp * 4 + grp;
+  if (sub == 0) { sm_m[slot] = m; sm_l[slot] = l; }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) sm_acc[slot][sub * 16 + i] = acc[i];
+  __syncthreads();
+  const int d = threadIdx.x;  // 128 threads = 128 dims
+  float gm = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) gm = fmaxf(gm, sm_m[i]);
+  float num = 0.f, den = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float f = sm_m[i] == -INFINITY ? 0.f : __expf(sm_m[i] - gm);
+    num += f * sm_acc[i][d];
+    den += f * sm_l[i];
+  }
+  const float o = num / den;
+  const T hi = Elem<T>::from(o);
+  const long long oidx = (r * heads + hd) * D + d;
+  ctx[oidx] = hi;
+  ctx[lo_off_elems + oidx] = Elem<T>::from(o - Elem<T>::to(hi));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// MoE router (run_moe, block.rs:1263-1301): logits = x . Wg^T in f32 -> softmax over the experts -> top-k by
+// value (ties -> lowest index, the CPU reference's stable descending sort).  One warp per token; WgT is the
+// transposed gate weight [H, E] so that lanes read consecutive experts.  Also counts tokens per expert.
+template <int E>
+__global__ void router_kernel(const float* __restrict__ x, const float* __restrict__ wgt, int* __restrict__ topk_idx,
+                              float* __restrict__ topk_w, int* __restrict__ counts, long long rows, int H, int topk) {
+  constexpr int PER = (E + 31) / 32;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* xr = x + row * H;
+  float acc[PER];
+#pragma unroll
+  for (int j = 0; j < PER; ++j) acc[j] = 0.f;
+  for (int k0 = 0; k0 < H; k0 += 32) {
+    const float xv = xr[k0 + lane];
+#pragma unroll 8
+    for (int kk = 0; kk < 32; ++kk) {
+      const float xk = __shfl_sync(0xffffffffu, xv, kk);
+      const float* wrow = wgt + (long long)(k0 + kk) * E;
+#pragma unroll
+      for (int j = 0; j < PER; ++j) {
+        const int e = j * 32 + lane;
+        if (e < E) acc[j] += xk * wrow[e];
+      }
+    }
+  }
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) if (j * 32 + lane < E) mx = fmaxf(mx, acc[j]);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  float p[PER];
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    p[j] = (j * 32 + lane < E) ? expf(acc[j] - mx) : 0.f;
+    sum += p[j];
+  }
+  sum = warp_sum(sum);
+#pragma unroll
+  for (int j = 0; j < PER; ++j) p[j] = (j * 32 + lane < E) ? p[j] / sum : -1.f;
+  for (int t = 0; t < topk; ++t) {
+    float bv = -1.f; int bi = 1 << 30;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      const int e = j * 32 + lane;
+      if (e < E && (p[j] > bv || (p[j] == bv && e < bi))) { bv = p[j]; bi = e; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) {
+      topk_idx[row * topk + t] = bi;
+      topk_w[row * topk + t] = bv;
+      atomicAdd(&counts[bi], 1);
+    }
+#pragma unroll
+    for (int j = 0; j < PER; ++j) if (j * 32 + lane == bi) p[j] = -2.f;
+  }
+}
+
+// Exclusive scan of the expert counts + tile tables for the two grouped GEMMs (one block, one thread per
+// expert).  tiles1: N1 (= moe intermediate) output features per expert; tiles2: N2 (= hidden).
+__global__ void moe_plan_kernel(const int* __restrict__ counts, int* __restrict__ offsets, int* __restrict__ cursor,
+                                LinearTile* __restrict__ tiles1, int* __restrict__ ntiles1,
+                                LinearTile* __restrict__ tiles2, int* __restrict__ ntiles2, int E, int bn, int N1,
+                                int N2) {
+  __shared__ int s_off[257], s_chunk[257];
+  const int e = threadIdx.x;
+  if (e == 0) {
+    int off = 0, ch = 0;
+    for (int i = 0; i < E; ++i) {
+      s_off[i] = off; s_chunk[i] = ch;
+      const int c = counts[i];
+      off += c; ch += (c + bn - 1) / bn;
+    }
+    s_off[E] = off; s_chunk[E] = ch;
+    *ntiles1 = ch * (N1 / 128);
+    *ntiles2 = ch * (N2 / 128);
+  }
+  __syncthreads();
+  if (e >= E) return;
+  const int c = counts[e], off = s_off[e];
+  offsets[e] = off;
+  cursor[e] = 0;
+  int ch = s_chunk[e];
+  const int w1 = N1 / 128, w2 = N2 / 128;
+  for (int r0 = 0; r0 < c; r0 += bn, ++ch) {
+    const int rows = min(bn, c - r0);
+    for (int wb = 0; wb < w1; ++wb) tiles1[ch * w1 + wb] = LinearTile{e * N1 + wb * 128, off + r0, rows, wb * 128};
+    for (int wb = 0; wb < w2; ++wb) tiles2[ch * w2 + wb] = LinearTile{e * N2 + wb * 128, off + r0, rows, wb * 128};
+  }
+}
+
+// Dispatch: each (token, slot) claims a row in its expert's segment and copies the token's normed hi/lo
+// activations there.  One warp per assignment.  (The reference sorts assignments on the HOST:
+// block.rs:1303-1313; row order inside an expert does not affect any value.)
+template <typename T>
+__global__ void moe_dispatch_kernel(const int* __restrict__ topk_idx, const int* __restrict__ offsets,
+                                    int* __restrict__ cursor, const T* __restrict__ xn, long long xn_lo_off,
+                                    T* __restrict__ xperm, long long xperm_lo_off, int* __restrict__ perm_pos,
+                                    long long n_assign, int topk, int H) {
+  const long long a = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (a >= n_assign) return;
+  const int lane = threadIdx.x & 31;
+  const int e = topk_idx[a];
+  int pos = 0;
+  if (lane == 0) pos = offsets[e] + atomicAdd(&cursor[e], 1);
+  pos = __shfl_sync(0xffffffffu, pos, 0);
+  if (lane == 0) perm_pos[a] = pos;
+  const long long tok = a / topk;
+  const uint4* shi = reinterpret_cast<const uint4*>(xn + tok * H);
+  const uint4* slo = reinterpret_cast<const uint4*>(xn + xn_lo_off + tok * H);
+  uint4* dhi = reinterpret_cast<uint4*>(xperm + (long long)pos * H);
+  uint4* dlo = reinterpret_cast<uint4*>(xperm + xperm_lo_off + (long long)pos * H);
+  for (int i = lane; i < H / 8; i += 32) { dhi[i] = shi[i]; dlo[i] = slo[i]; }
+}
+
+// Combine (block.rs:1363-1381): x[token] += sum_k w_k * y[perm_pos[token,k]] in slot order (deterministic).
+__global__ void moe_combine_kernel(const float* __restrict__ y, const int* __restrict__ perm_pos,
+                                   const float* __restrict__ topk_w, float* __restrict__ x, long long rows, int topk,
+                                   int H) {
+  const int h4 = H / 4;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * h4) return;
+  const long long r = idx / h4;
+  const int c = idx % h4;
+  float4 acc = make_float4(0, 0, 0, 0);
+  for (int k = 0; k < topk; ++k) {
+    const float w = topk_w[r * topk + k];
+    const float4 v = reinterpret_cast<const float4*>(y + (long long)perm_pos[r * topk + k] * H)[c];
+    acc.x += w * v.x; acc.y += w * v.y; acc.z += w * v.z; acc.w += w * v.w;
+  }
+  float4 o = reinterpret_cast<float4*>(x)[idx];
+  o.x += acc.x; o.y += acc.y; o.z += acc.z; o.w += acc.w;
+  reinterpret_cast<float4*>(x)[idx] = o;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Token selection (crates/core/src/sampling.rs:34-158, greedy path): ban every token that would complete
+// an n-gram already present in the page's context (prompt + generated), then first-index argmax over the
+// finite logits.  One block per page.  The new token is appended to the history; pages that emitted EOS
+// (or reached their budget) are frozen.
+__global__ void __launch_bounds__(1024)
+select_token_kernel(const float* __restrict__ logits, int V, int* __restrict__ hist, int hist_stride,
+                    int* __restrict__ hist_len, int* __restrict__ gen_count, int* __restrict__ finished, int ngram,
+                    int eos, int max_new, const int* __restrict__ forced, int forced_stride, int step,
+                    int* __restrict__ selected_out, int selected_stride) {
+  const int page = blockIdx.x;
+  __shared__ int s_ban[64];
+  __shared__ int s_nban;
+  __shared__ float s_val[32];
+  __shared__ int s_idx[32];
+  if (finished[page]) return;
+  int* h = hist + (long long)page * hist_stride;
+  const int L = hist_len[page];
+  if (threadIdx.x == 0) s_nban = 0;
+  __syncthreads();
+  if (ngram > 1 && L >= ngram - 1) {
+    const int pre = ngram - 1;
+    for (int i = threadIdx.x; i + ngram <= L; i += blockDim.x) {
+      bool eq = true;
+      for (int j = 0; j < pre && eq; ++j) eq = h[i + j] == h[L - pre + j];
+      if (eq) {
+        const int slot = atomicAdd(&s_nban, 1);
+        if (slot < 64) s_ban[slot] = h[i + pre];
+      }
+    }
+  }
+  __syncthreads();
+  const int nban = min(s_nban, 64);
+  const float* lg = logits + (long long)page * V;
+  float bv = -INFINITY; int bi = INT_MAX;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) {
+    float v = lg[i];
+    if (!(fabsf(v) <= FLT_MAX)) continue;  // skip NaN / inf like the reference's is_finite filter
+    bool banned = false;
+    for (int b = 0; b < nban; ++b) banned |= (s_ban[b] == i);
+    if (banned) continue;
+    if (v > bv) { bv = v; bi = i; }  // strided ascending scan keeps the first index per thread
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { s_val[threadIdx.x >> 5] = bv; s_idx[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    bv = threadIdx.x < (blockDim.x >> 5) ? s_val[threadIdx.x] : -INFINITY;
+    bi = threadIdx.x < (blockDim.x >> 5) ? s_idx[threadIdx.x] : INT_MAX;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (threadIdx.x == 0) {
+      int tok = bi == INT_MAX ? 0 : bi;
+      if (selected_out) selected_out[(long long)page * selected_stride + step] = tok;
+      if (forced) {
+        tok = forced[(long long)page * forced_stride + step];
+      } else if (eos >= 0 && tok == eos) {
+        finished[page] = 1;  // EOS is not appended (model/mod.rs:2029-2033)
+        return;
+      }
+      h[L] = tok;
+      hist_len[page] = L + 1;
+      const int g = gen_count[page] + 1;
+      gen_count[page] = g;
+      if (g >= max_new) finished[page] = 1;
+    }
+  }
+}
+
+// Decode-step bookkeeping: for every page, the row of the next forward is its last history token at
+// position hist_len-1 (frozen pages keep recomputing their last position; their results are ignored).
+__global__ void decode_rows_kernel(const int* __restrict__ hist, int hist_stride, const int* __restrict__ hist_len,
+                                   int* __restrict__ src, int* __restrict__ row_pos, int n_pages) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pages) return;
+  const int L = hist_len[p];
+  src[p] = hist[(long long)p * hist_stride + L - 1];
+  row_pos[p] = L - 1;
+}
+
+__global__ void fill_i32_kernel(int* p, int v, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+}  // namespace
+
+#define DISPATCH_T(dt, ...)                                              \
+  do {                                                                   \
+    if ((dt) == DType::BF16) { using T = __nv_bfloat16; __VA_ARGS__; }   \
+    else { using T = __half; __VA_ARGS__; }                              \
+  } while (0)
+
+void embed_gather(const int* src, const void* table, const float* img_rows, float* out, long long rows, int H, DType dt,
+                  cudaStream_t s) {
+  DISPATCH_T(dt, (embed_gather_kernel<T><<<blocks_for(rows * (H / 4), 256), 256, 0, s>>>(src, (const T*)table, img_rows, out, rows, H)));
+  launch_check("embed_gather");
+}
+void rmsnorm_split(const float* x, const float* w, void* out16, long long lo_off_elems, float* out32,
+                   const int* row_idx, long long rows, int H, float eps, DType dt, cudaStream_t s) {
+  DISPATCH_T(dt, (rmsnorm_kernel<T><<<blocks_for(rows, 8), 256, 0, s>>>(x, w, (T*)out16, lo_off_elems, out32, row_idx, rows, H, eps)));
+  launch_check("rmsnorm");
+}
+void rope_kv(const float* qkv, const float* cos_t, const float* sin_t, const int* row_page, const int* row_pos,
+             float* q_out, float* kc, float* vc, long long rows, int heads, int smax, cudaStream_t s) {
+  rope_kv_kernel<<<blocks_for(rows * heads * 16, 256), 256, 0, s>>>(qkv, cos_t, sin_t, row_page, row_pos, q_out, kc, vc, rows, heads, smax);
+  launch_check("rope_kv");
+}
+void kv_attention(const float* q, const float* kc, const float* vc, const int* row_page, const int* row_pos, void* ctx,
+                  long long lo_off_elems, long long rows, int heads, int smax, float scale, DType dt, cudaStream_t s) {
+  dim3 grid((unsigned)rows, heads);
+  DISPATCH_T(dt, (kv_attention_kernel<T><<<grid, 128, 0, s>>>(q, kc, vc, row_page, row_pos, (T*)ctx, lo_off_elems, heads, smax, scale)));
+  launch_check("kv_attention");
+}
+void moe_router(const float* x, const float* wgt, int* topk_idx, float* topk_w, int* counts, long long rows, int H,
+                int E, int topk, cudaStream_t s) {
+  const int blocks = blocks_for(rows, 4);
+  if (E == 64) router_kernel<64><<<blocks, 128, 0, s>>>(x, wgt, topk_idx, topk_w, counts, rows, H, topk);
+  else if (E == 16) router_kernel<16><<<blocks, 128, 0, s>>>(x, wgt, topk_idx, topk_w, counts, rows, H, topk);
+  else if (E == 32) router_kernel<32><<<blocks, 128, 0, s>>>(x, wgt, topk_idx, topk_w, counts, rows, H, topk);
+  else throw std::runtime_error("router: unsupported expert count " + std::to_string(E));
+  launch_check("moe_router");
+}
+void moe_plan(const int* counts, int* offsets, int* cursor, LinearTile* tiles1, int* ntiles1, LinearTile* tiles2,
+              int* ntiles2, int E, int bn, int N1, int N2, cudaStream_t s) {
+  moe_plan_kernel<<<1, 256, 0, s>>>(counts, offsets, cursor, tiles1, ntiles1, tiles2, ntiles2, E, bn, N1, N2);
+  launch_check("moe_plan");
+}
+void moe_dispatch(const int* topk_idx, const int* offsets, int* cursor, const void* xn, long long xn_lo_off,
+                  void* xperm, long long xperm_lo_off, int* perm_pos, long long n_assign, int topk, int H, DType dt,
+                  cudaStream_t s) {
+  DISPATCH_T(dt, (moe_dispatch_kernel<T><<<blocks_for(n_assign, 8), 256, 0, s>>>(topk_idx, offsets, cursor, (const T*)xn, xn_lo_off, (T*)xperm, xperm_lo_off, perm_pos, n_assign, topk, H)));
+  launch_check("moe_dispatch");
+}
+void moe_combine(const float* y, const int* perm_pos, const float* topk_w, float* x, long long rows, int topk, int H,
+                 cudaStream_t s) {
+  moe_combine_kernel<<<blocks_for(rows * (H / 4), 256), 256, 0, s>>>(y, perm_pos, topk_w, x, rows, topk, H);
+  launch_check("moe_combine");
+}
+void select_token(const float* logits, int V, int* hist, int hist_stride, int* hist_len, int* gen_count, int* finished,
+                  int n_pages, int ngram, int eos, int max_new, const int* forced, int forced_stride, int step,
+                  int* selected_out, int selected_stride, cudaStream_t s) {
+  select_token_kernel<<<n_pages, 1024, 0, s>>>(logits, V, hist, hist_stride, hist_len, gen_count, finished, ngram, eos,
+                                               max_new, forced, forced_stride, step, selected_out, selected_stride);
+  launch_check("select_token");
+}
+void decode_rows(const int* hist, int hist_stride, const int* hist_len, int* src, int* row_pos, int n_pages,
+                 cudaStream_t s) {
+  decode_rows_kernel<<<blocks_for(n_pages, 128), 128, 0, s>>>(hist, hist_stride, hist_len, src, row_pos, n_pages);
+  launch_check("decode_rows");
+}
+void fill_i32(int* p, int v, long long n, cudaStream_t s) {
+  fill_i32_kernel<<<blocks_for(n, 256), 256, 0, s>>>(p, v, n);
+  launch_check("fill_i32");
+}
+
+}  // namespace dsocr

@@ -22,7 +22,7 @@ void launch_inst(const LinearCall& c, const lin::Params& p, const CUtensorMap& w
     configured = true;
   }
   kern<<<grid, lin::kThreads, C::kSmemBytes, stream>>>(w0, w1, x, p);
-  cuda_check(cudaGetLastError(), "linear launch");
+  launch_check("linear launch");
 }
 
 template <typename T, int NA, int NB>

@@ -80,8 +80,11 @@ inline std::vector<uint16_t> to16_split(const float* src, size_t n, DType dt) {
   return out;
 }
 
+// cudaMemcpy from pageable memory may return before the DMA has landed and only orders against the legacy
+// default stream; the engine's kernels run on their own stream, so make the copy globally visible first.
 inline void h2d(void* dst, const void* src, size_t bytes) {
   cuda_check(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice), "cudaMemcpy H2D");
+  cuda_check(cudaDeviceSynchronize(), "cudaMemcpy H2D sync");
 }
 inline void d2h(void* dst, const void* src, size_t bytes) {
   cuda_check(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost), "cudaMemcpy D2H");

@@ -89,6 +89,8 @@ DSOCR_API int dsocr_engine_create(const char* config_json_path, const char* safe
                                   int device_ordinal, int dtype, dsocr_engine** out);
 DSOCR_API void dsocr_engine_destroy(dsocr_engine* e);
 DSOCR_API int dsocr_engine_info_get(const dsocr_engine* e, dsocr_engine_info* info);
+/* Engine options: "record_taps" (0/1) keeps host copies of the debug-trace taps of the next vision call. */
+DSOCR_API int dsocr_engine_set_option(dsocr_engine* e, const char* name, int value);
 
 /* image_token_count: rows `compute_image_embeddings` will produce == placeholders
  * `build_image_placeholders` emits (model/mod.rs:2605-2689). */

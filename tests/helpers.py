@@ -1,0 +1,33 @@
+"""Shared test helpers: tiny random-init model on disk (reference checkpoint + config.json schema)."""
+from __future__ import annotations
+
+import os
+import tempfile
+from functools import lru_cache
+
+import numpy as np
+import torch
+
+from oracle import config as OC
+
+
+@lru_cache(maxsize=4)
+def tiny_model(storage: str = "bf16", seed: int = 1234):
+    cfg = OC.tiny_config()
+    ck = OC.random_checkpoint(cfg, seed=seed, storage=torch.bfloat16 if storage == "bf16" else torch.float16)
+    d = tempfile.mkdtemp(prefix="dsocr_tiny_")
+    OC.save_checkpoint(ck, os.path.join(d, "model.safetensors"))
+    cfg.save_json(os.path.join(d, "config.json"))
+    return cfg, ck, d
+
+
+def cos(a: torch.Tensor, b: torch.Tensor) -> float:
+    return torch.nn.functional.cosine_similarity(a.flatten().double(), b.flatten().double(), dim=0).item()
+
+
+def report(name: str, got: torch.Tensor, ref: torch.Tensor) -> tuple:
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    c = cos(got, ref)
+    print(f"[parity] {name}: max-abs {err:.4g} (ref max {scale:.4g}), cosine {c:.6f}")
+    return err, scale, c
