@@ -27,7 +27,7 @@ void launch(const VAttnCall& c, cudaStream_t stream) {
   p.Z = c.Z; p.zw = c.zw; p.zhalf = c.zhalf; p.out = c.out;
   dim3 grid((c.S + vattn::BQ - 1) / vattn::BQ, c.B * c.H);
   kern<<<grid, vattn::kThreads, C::kSmemBytes, stream>>>(tq, tkv, p);
-  launch_check("vattn launch");
+  launch_check(c.tag ? c.tag : "vision_attention");
 }
 
 template <typename T>
@@ -63,6 +63,7 @@ void vision_relpos_products(const void* qkv, long long rows, int H, const void* 
   c.M = (int)rows;
   c.out = Z; c.ldo = (long long)H * 2 * zhalf; c.out_batch_stride = 2 * zhalf;
   c.out_mode = lin::OUT_F32;
+  c.tag = "sam_relpos_products";
   linear(c, dt, num_sms, stream);
 }
 

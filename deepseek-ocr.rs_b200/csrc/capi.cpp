@@ -12,6 +12,13 @@ using namespace dsocr;
 
 struct dsocr_engine {
   std::unique_ptr<Engine> impl;
+  // pages staged on the device by dsocr_stage_pages (views already resized / tiled, RGB8)
+  struct Staged {
+    int n_pages = 0;
+    dsocr_vision_settings vs{};
+    std::vector<int> ntiles, cw, ch;
+    DevBuf globals, tiles;
+  } staged;
 };
 
 namespace {
@@ -78,6 +85,7 @@ extern "C" int dsocr_engine_set_option(dsocr_engine* e, const char* name, int va
     bind(e);
     const std::string n = name ? name : "";
     if (n == "record_taps") e->impl->set_record_taps(value != 0);
+    else if (n == "kv_cache_f16") e->impl->set_kv_f16(value != 0);
     else throw std::runtime_error("unknown option `" + n + "`");
   });
 }
@@ -209,6 +217,129 @@ extern "C" int dsocr_generate_forced(dsocr_engine* e, int n_pages, const int64_t
   });
 }
 
+namespace {
+void stage_pages(dsocr_engine* e, int n_pages, const uint8_t* const* rgb, const int* widths, const int* heights,
+                 dsocr_vision_settings vs) {
+  Engine& en = *e->impl;
+  auto& sg = e->staged;
+  // prepare_vision_inputs (model/mod.rs:2457-2492): integer resample / tiling on the host cores
+  const double t0 = now_ms();
+  const int G = vs.crop_mode ? (int)vs.base_size : (int)vs.image_size, P = (int)vs.image_size;
+  std::vector<std::vector<uint8_t>> globals(n_pages), tiles(n_pages);
+  sg.ntiles.assign(n_pages, 0); sg.cw.assign(n_pages, 1); sg.ch.assign(n_pages, 1);
+  sg.n_pages = n_pages; sg.vs = vs;
+  std::vector<const uint8_t*> gsrc(n_pages, nullptr);
+  {
+    std::vector<std::thread> th;
+    std::vector<std::string> errs(n_pages);
+    const int nthreads = std::min<int>(n_pages, std::max(1u, std::thread::hardware_concurrency()));
+    for (int t = 0; t < nthreads; ++t)
+      th.emplace_back([&, t] {
+        for (int p = t; p < n_pages; p += nthreads) {
+          try {
+            if (!rgb[p] || widths[p] <= 0 || heights[p] <= 0) throw std::runtime_error("empty image");
+            if (widths[p] == G && heights[p] == G) {
+              gsrc[p] = rgb[p];  // resize to the same size and paste at (0,0) is the identity
+            } else {
+              globals[p].resize((size_t)G * G * 3);
+              build_global_view_u8(rgb[p], widths[p], heights[p], G, globals[p].data());
+              gsrc[p] = globals[p].data();
+            }
+            if (vs.crop_mode) {
+              int n = dynamic_preprocess_u8(rgb[p], widths[p], heights[p], P, nullptr, &sg.cw[p], &sg.ch[p]);
+              if (n > 0) {
+                tiles[p].resize((size_t)n * P * P * 3);
+                dynamic_preprocess_u8(rgb[p], widths[p], heights[p], P, tiles[p].data(), &sg.cw[p], &sg.ch[p]);
+              }
+              sg.ntiles[p] = n;
+            }
+          } catch (const std::exception& ex) { errs[p] = ex.what(); }
+        }
+      });
+    for (auto& t : th) t.join();
+    for (auto& s : errs) if (!s.empty()) throw std::runtime_error(s);
+  }
+  const size_t gbytes = (size_t)G * G * 3, tbytes = (size_t)P * P * 3;
+  size_t total_tiles = 0;
+  for (int p = 0; p < n_pages; ++p) total_tiles += sg.ntiles[p];
+  sg.globals.ensure(gbytes * n_pages);
+  sg.tiles.ensure(std::max<size_t>(16, tbytes * total_tiles));
+  size_t toff = 0;
+  for (int p = 0; p < n_pages; ++p) {
+    cuda_check(cudaMemcpyAsync((uint8_t*)sg.globals.p + gbytes * p, gsrc[p], gbytes, cudaMemcpyHostToDevice, en.stream()), "global view H2D");
+    if (sg.ntiles[p] > 0) {
+      cuda_check(cudaMemcpyAsync((uint8_t*)sg.tiles.p + toff, tiles[p].data(), tbytes * sg.ntiles[p], cudaMemcpyHostToDevice, en.stream()), "tiles H2D");
+      toff += tbytes * sg.ntiles[p];
+    }
+  }
+  cuda_check(cudaStreamSynchronize(en.stream()), "stage sync");
+  en.timings.prepare = now_ms() - t0;
+}
+
+void decode_staged(dsocr_engine* e, const int64_t* seg0, int n_seg0, const int64_t* seg1, int n_seg1,
+                   int64_t image_token_id, const dsocr_decode_params* params, dsocr_token_cb cb, void* user,
+                   int64_t* const* out_tokens, int* n_out, int* prompt_tokens, std::string& stage) {
+  Engine& en = *e->impl;
+  auto& sg = e->staged;
+  const int n_pages = sg.n_pages;
+  if (n_pages <= 0) throw std::runtime_error("no pages staged");
+  const dsocr_vision_settings vs = sg.vs;
+  const int G = vs.crop_mode ? (int)vs.base_size : (int)vs.image_size, P = (int)vs.image_size;
+  // ---- compute_image_embeddings
+  stage = "image embedding failed";
+  const double t1 = now_ms();
+  std::vector<Engine::PageViews> pages(n_pages);
+  for (int p = 0; p < n_pages; ++p) { pages[p].n_tiles = sg.ntiles[p]; pages[p].crop_w = sg.cw[p]; pages[p].crop_h = sg.ch[p]; }
+  std::vector<int> counts;
+  const float* rows = en.vision_encode(n_pages, sg.globals.p, false, G, sg.tiles.p, false, P, pages, &counts);
+  cuda_check(cudaStreamSynchronize(en.stream()), "vision sync");
+  en.timings.vision = now_ms() - t1;
+  // ---- build_prompt_tokens (model/mod.rs:2536-2603): BOS + seg0 + <image> x n + seg1
+  stage = "prompt formatting failed";
+  std::vector<std::vector<int64_t>> ids(n_pages);
+  std::vector<std::vector<uint8_t>> masks(n_pages);
+  std::vector<const int64_t*> idp(n_pages);
+  std::vector<const uint8_t*> mp(n_pages);
+  std::vector<int> nt(n_pages);
+  for (int p = 0; p < n_pages; ++p) {
+    const int expect = image_token_count((int)vs.base_size, (int)vs.image_size, vs.crop_mode, sg.cw[p], sg.ch[p]);
+    if (expect != counts[p])
+      throw std::runtime_error("placeholder count " + std::to_string(expect) + " does not match expected " + std::to_string(counts[p]));
+    ids[p].push_back(0); masks[p].push_back(0);  // bos_id = 0 (model/mod.rs:2547)
+    for (int i = 0; i < n_seg0; ++i) { ids[p].push_back(seg0[i]); masks[p].push_back(0); }
+    for (int i = 0; i < counts[p]; ++i) { ids[p].push_back(image_token_id); masks[p].push_back(1); }
+    for (int i = 0; i < n_seg1; ++i) { ids[p].push_back(seg1[i]); masks[p].push_back(0); }
+    idp[p] = ids[p].data(); mp[p] = masks[p].data(); nt[p] = (int)ids[p].size();
+    if (prompt_tokens) prompt_tokens[p] = nt[p];
+  }
+  stage = "";
+  Engine::GenRequest rq;
+  rq.n_pages = n_pages; rq.input_ids = idp.data(); rq.mask = mp.data(); rq.n_tokens = nt.data();
+  rq.image_rows_dev = rows; rq.n_image_rows = counts.data(); rq.params = *params; rq.cb = cb; rq.user = user;
+  en.generate(rq, out_tokens, n_out);
+}
+}  // namespace
+
+extern "C" int dsocr_stage_pages(dsocr_engine* e, int n_pages, const uint8_t* const* rgb, const int* widths,
+                                 const int* heights, dsocr_vision_settings vs) {
+  return api("vision input failed", [&] { bind(e); stage_pages(e, n_pages, rgb, widths, heights, vs); });
+}
+
+extern "C" int dsocr_decode_staged(dsocr_engine* e, const int64_t* seg0, int n_seg0, const int64_t* seg1, int n_seg1,
+                                   int64_t image_token_id, const dsocr_decode_params* params, dsocr_token_cb cb,
+                                   void* user, int64_t* const* out_tokens, int* n_out, int* prompt_tokens) {
+  std::string stage;
+  return api("", [&] {
+    try {
+      bind(e);
+      if (!params) throw std::runtime_error("null decode params");
+      decode_staged(e, seg0, n_seg0, seg1, n_seg1, image_token_id, params, cb, user, out_tokens, n_out, prompt_tokens, stage);
+    } catch (const std::exception& ex) {
+      throw std::runtime_error(stage.empty() ? std::string(ex.what()) : stage + ": " + ex.what());
+    }
+  });
+}
+
 extern "C" int dsocr_decode_pages(dsocr_engine* e, int n_pages, const uint8_t* const* rgb, const int* widths,
                                   const int* heights, dsocr_vision_settings vs, const int64_t* seg0, int n_seg0,
                                   const int64_t* seg1, int n_seg1, int64_t image_token_id,
@@ -218,76 +349,29 @@ extern "C" int dsocr_decode_pages(dsocr_engine* e, int n_pages, const uint8_t* c
   return api("", [&] {
     try {
       bind(e);
-      Engine& en = *e->impl;
       if (!params) throw std::runtime_error("null decode params");
-      // ---- prepare_vision_inputs (model/mod.rs:2457-2492): integer resample / tiling on the host cores
-      const double t0 = now_ms();
-      const int G = vs.crop_mode ? (int)vs.base_size : (int)vs.image_size, P = (int)vs.image_size;
-      std::vector<std::vector<uint8_t>> globals(n_pages), tiles(n_pages);
-      std::vector<int> ntiles(n_pages, 0), cw(n_pages, 1), ch(n_pages, 1);
-      {
-        std::vector<std::thread> th;
-        std::vector<std::string> errs(n_pages);
-        const int nthreads = std::min<int>(n_pages, std::max(1u, std::thread::hardware_concurrency()));
-        for (int t = 0; t < nthreads; ++t)
-          th.emplace_back([&, t] {
-            for (int p = t; p < n_pages; p += nthreads) {
-              try {
-                if (!rgb[p] || widths[p] <= 0 || heights[p] <= 0) throw std::runtime_error("empty image");
-                globals[p].resize((size_t)G * G * 3);
-                if (widths[p] == G && heights[p] == G) memcpy(globals[p].data(), rgb[p], globals[p].size());  // identity resize
-                else build_global_view_u8(rgb[p], widths[p], heights[p], G, globals[p].data());
-                if (vs.crop_mode) {
-                  int n = dynamic_preprocess_u8(rgb[p], widths[p], heights[p], P, nullptr, &cw[p], &ch[p]);
-                  if (n > 0) {
-                    tiles[p].resize((size_t)n * P * P * 3);
-                    dynamic_preprocess_u8(rgb[p], widths[p], heights[p], P, tiles[p].data(), &cw[p], &ch[p]);
-                  }
-                  ntiles[p] = n;
-                }
-              } catch (const std::exception& ex) { errs[p] = ex.what(); }
-            }
-          });
-        for (auto& t : th) t.join();
-        for (auto& s : errs) if (!s.empty()) throw std::runtime_error(s);
-      }
-      en.timings.prepare = now_ms() - t0;
-      // ---- compute_image_embeddings
-      stage = "image embedding failed";
-      const double t1 = now_ms();
-      std::vector<const uint8_t*> gp(n_pages), tp(n_pages);
-      for (int p = 0; p < n_pages; ++p) { gp[p] = globals[p].data(); tp[p] = tiles[p].empty() ? nullptr : tiles[p].data(); }
-      DevBuf dg, dt;
-      std::vector<int> counts;
-      const float* rows = encode_u8(en, n_pages, gp.data(), G, tp.data(), ntiles.data(), P, cw.data(), ch.data(), &counts, dg, dt);
-      cuda_check(cudaStreamSynchronize(en.stream()), "vision sync");
-      en.timings.vision = now_ms() - t1;
-      // ---- build_prompt_tokens (model/mod.rs:2536-2603): BOS + seg0 + <image> x n + seg1
-      stage = "prompt formatting failed";
-      std::vector<std::vector<int64_t>> ids(n_pages);
-      std::vector<std::vector<uint8_t>> masks(n_pages);
-      std::vector<const int64_t*> idp(n_pages);
-      std::vector<const uint8_t*> mp(n_pages);
-      std::vector<int> nt(n_pages);
-      for (int p = 0; p < n_pages; ++p) {
-        const int expect = image_token_count((int)vs.base_size, (int)vs.image_size, vs.crop_mode, cw[p], ch[p]);
-        if (expect != counts[p])
-          throw std::runtime_error("placeholder count " + std::to_string(expect) + " does not match expected " + std::to_string(counts[p]));
-        ids[p].push_back(0); masks[p].push_back(0);  // bos_id = 0 (model/mod.rs:2547)
-        for (int i = 0; i < n_seg0; ++i) { ids[p].push_back(seg0[i]); masks[p].push_back(0); }
-        for (int i = 0; i < counts[p]; ++i) { ids[p].push_back(image_token_id); masks[p].push_back(1); }
-        for (int i = 0; i < n_seg1; ++i) { ids[p].push_back(seg1[i]); masks[p].push_back(0); }
-        idp[p] = ids[p].data(); mp[p] = masks[p].data(); nt[p] = (int)ids[p].size();
-        if (prompt_tokens) prompt_tokens[p] = nt[p];
-      }
-      stage = "";
-      Engine::GenRequest rq;
-      rq.n_pages = n_pages; rq.input_ids = idp.data(); rq.mask = mp.data(); rq.n_tokens = nt.data();
-      rq.image_rows_dev = rows; rq.n_image_rows = counts.data(); rq.params = *params; rq.cb = cb; rq.user = user;
-      en.generate(rq, out_tokens, n_out);
+      stage_pages(e, n_pages, rgb, widths, heights, vs);
+      decode_staged(e, seg0, n_seg0, seg1, n_seg1, image_token_id, params, cb, user, out_tokens, n_out, prompt_tokens, stage);
     } catch (const std::exception& ex) {
       throw std::runtime_error(stage.empty() ? std::string(ex.what()) : stage + ": " + ex.what());
     }
+  });
+}
+
+extern "C" int dsocr_engine_set_stream(dsocr_engine* e, void* cuda_stream) {
+  return api("", [&] { bind(e); e->impl->set_stream(reinterpret_cast<cudaStream_t>(cuda_stream)); });
+}
+
+extern "C" int dsocr_kernel_timing_begin(dsocr_engine* e) {
+  return api("", [&] { bind(e); kernel_timing_begin(e->impl->stream()); });
+}
+
+extern "C" int dsocr_kernel_timing_end(dsocr_engine* e, char* json_out, size_t capacity) {
+  return api("", [&] {
+    bind(e);
+    const std::string js = kernel_timing_end_json();
+    if (!json_out || capacity < js.size() + 1) throw std::runtime_error("timing report buffer too small");
+    memcpy(json_out, js.c_str(), js.size() + 1);
   });
 }
 

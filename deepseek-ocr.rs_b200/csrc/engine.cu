@@ -340,7 +340,14 @@ Engine::Engine(const std::string& config_path, const std::string& weights_path, 
 Engine::~Engine() {
   cudaSetDevice(device_);
   cudaDeviceSynchronize();
-  if (stream_) cudaStreamDestroy(stream_);
+  if (stream_ && owns_stream_) cudaStreamDestroy(stream_);
+}
+
+void Engine::set_stream(cudaStream_t s) {
+  cuda_check(cudaStreamSynchronize(stream_), "stream switch sync");
+  if (owns_stream_ && stream_) cudaStreamDestroy(stream_);
+  stream_ = s;
+  owns_stream_ = false;
 }
 
 DevBuf& Engine::ws(const std::string& name, size_t bytes) {
@@ -446,7 +453,7 @@ void Engine::sam_forward(int Bv, int G, const void* patches16, float* sam_out) {
   bcast_rows(sam_pos_for(g), x, T, Bv, D, stream_);
   {
     LinearCall lc;
-    lc.w0 = patch_w_.p; lc.x = patches16; lc.x_rows = rows; lc.M = (int)rows; lc.N = D; lc.K = 3 * c.sam_patch * c.sam_patch;
+    lc.tag = "sam_patch_embed"; lc.w0 = patch_w_.p; lc.x = patches16; lc.x_rows = rows; lc.M = (int)rows; lc.N = D; lc.K = 3 * c.sam_patch * c.sam_patch;
     lc.bias = patch_b_.as<float>(); lc.out = x; lc.ldo = D; lc.out_mode = lin::OUT_F32_ADD;
     linear(lc, dt_, num_sms_, stream_);
   }
@@ -461,7 +468,7 @@ void Engine::sam_forward(int Bv, int G, const void* patches16, float* sam_out) {
     layernorm(x, b.ln1_w.as<float>(), b.ln1_b.as<float>(), xn, nullptr, r, D, 1e-6f, glob ? 0 : win, g, nw, dt_, stream_);
     {
       LinearCall lc;
-      lc.w0 = b.qkv_w.p; lc.x = xn; lc.x_rows = r; lc.M = (int)r; lc.N = 3 * D; lc.K = D;
+      lc.tag = "sam_qkv"; lc.w0 = b.qkv_w.p; lc.x = xn; lc.x_rows = r; lc.M = (int)r; lc.N = 3 * D; lc.K = D;
       lc.bias = b.qkv_b.as<float>(); lc.out = qkv; lc.ldo = 3 * D; lc.out_mode = lin::OUT_T;
       linear(lc, dt_, num_sms_, stream_);
     }
@@ -472,12 +479,12 @@ void Engine::sam_forward(int Bv, int G, const void* patches16, float* sam_out) {
     {
       VAttnCall ac;
       ac.qkv = qkv; ac.rows = r; ac.B = (int)(r / S); ac.S = S; ac.H = Hh; ac.grid = size;
-      ac.Z = Z; ac.zw = 2 * zhalf; ac.zhalf = zhalf; ac.out = att; ac.scale = 0.125f;
+      ac.tag = glob ? "sam_global_attention" : "sam_window_attention"; ac.Z = Z; ac.zw = 2 * zhalf; ac.zhalf = zhalf; ac.out = att; ac.scale = 0.125f;
       vision_attention(ac, dt_, stream_);
     }
     {
       LinearCall lc;
-      lc.w0 = b.proj_w.p; lc.x = att; lc.x_rows = r; lc.M = (int)r; lc.N = D; lc.K = D;
+      lc.tag = "sam_proj"; lc.w0 = b.proj_w.p; lc.x = att; lc.x_rows = r; lc.M = (int)r; lc.N = D; lc.K = D;
       lc.bias = b.proj_b.as<float>(); lc.out = x; lc.ldo = D; lc.out_mode = lin::OUT_F32_ADD;
       lc.row_map = glob ? nullptr : wmap;
       linear(lc, dt_, num_sms_, stream_);
@@ -485,13 +492,13 @@ void Engine::sam_forward(int Bv, int G, const void* patches16, float* sam_out) {
     layernorm(x, b.ln2_w.as<float>(), b.ln2_b.as<float>(), xn, nullptr, rows, D, 1e-6f, 0, g, nw, dt_, stream_);
     {
       LinearCall lc;
-      lc.w0 = b.fc1_w.p; lc.x = xn; lc.x_rows = rows; lc.M = (int)rows; lc.N = 4 * D; lc.K = D;
+      lc.tag = "sam_fc1_gelu"; lc.w0 = b.fc1_w.p; lc.x = xn; lc.x_rows = rows; lc.M = (int)rows; lc.N = 4 * D; lc.K = D;
       lc.bias = b.fc1_b.as<float>(); lc.out = h16; lc.ldo = 4 * D; lc.out_mode = lin::OUT_T; lc.act = lin::ACT_GELU_ERF;
       linear(lc, dt_, num_sms_, stream_);
     }
     {
       LinearCall lc;
-      lc.w0 = b.fc2_w.p; lc.x = h16; lc.x_rows = rows; lc.M = (int)rows; lc.N = D; lc.K = 4 * D;
+      lc.tag = "sam_fc2"; lc.w0 = b.fc2_w.p; lc.x = h16; lc.x_rows = rows; lc.M = (int)rows; lc.N = D; lc.K = 4 * D;
       lc.bias = b.fc2_b.as<float>(); lc.out = x; lc.ldo = D; lc.out_mode = lin::OUT_F32_ADD;
       linear(lc, dt_, num_sms_, stream_);
     }
@@ -506,7 +513,7 @@ void Engine::sam_forward(int Bv, int G, const void* patches16, float* sam_out) {
   cast16(x, xn, rows * D, dt_, stream_);
   {
     LinearCall lc;
-    lc.w0 = neck0_w_.p; lc.x = xn; lc.x_rows = rows; lc.M = (int)rows; lc.N = NC; lc.K = D;
+    lc.tag = "sam_neck_conv1"; lc.w0 = neck0_w_.p; lc.x = xn; lc.x_rows = rows; lc.M = (int)rows; lc.N = NC; lc.K = D;
     lc.out = n32; lc.ldo = NC; lc.out_mode = lin::OUT_F32;
     linear(lc, dt_, num_sms_, stream_);
   }
@@ -515,7 +522,7 @@ void Engine::sam_forward(int Bv, int G, const void* patches16, float* sam_out) {
   im2col3x3(n16, col, Bv, g, g, NC, 1, dt_, stream_);
   {
     LinearCall lc;
-    lc.w0 = neck2_w_.p; lc.x = col; lc.x_rows = rows; lc.M = (int)rows; lc.N = NC; lc.K = 9 * NC;
+    lc.tag = "sam_neck_conv2"; lc.w0 = neck2_w_.p; lc.x = col; lc.x_rows = rows; lc.M = (int)rows; lc.N = NC; lc.K = 9 * NC;
     lc.out = n32; lc.ldo = NC; lc.out_mode = lin::OUT_F32;
     linear(lc, dt_, num_sms_, stream_);
   }
@@ -527,7 +534,7 @@ void Engine::sam_forward(int Bv, int G, const void* patches16, float* sam_out) {
   void* d2 = ws("sam_net2_16", rows2 * c.sam_out0 * 2).p;
   {
     LinearCall lc;
-    lc.w0 = net2_w_.p; lc.x = col; lc.x_rows = rows2; lc.M = (int)rows2; lc.N = c.sam_out0; lc.K = 9 * NC;
+    lc.tag = "sam_net2"; lc.w0 = net2_w_.p; lc.x = col; lc.x_rows = rows2; lc.M = (int)rows2; lc.N = c.sam_out0; lc.K = 9 * NC;
     lc.out = d2; lc.ldo = c.sam_out0; lc.out_mode = lin::OUT_T;
     linear(lc, dt_, num_sms_, stream_);
   }
@@ -535,7 +542,7 @@ void Engine::sam_forward(int Bv, int G, const void* patches16, float* sam_out) {
   im2col3x3(d2, col3, Bv, g2, g2, c.sam_out0, 2, dt_, stream_);
   {
     LinearCall lc;
-    lc.w0 = net3_w_.p; lc.x = col3; lc.x_rows = rows3; lc.M = (int)rows3; lc.N = c.sam_out1; lc.K = 9 * c.sam_out0;
+    lc.tag = "sam_net3"; lc.w0 = net3_w_.p; lc.x = col3; lc.x_rows = rows3; lc.M = (int)rows3; lc.N = c.sam_out1; lc.K = 9 * c.sam_out0;
     lc.out = sam_out; lc.ldo = c.sam_out1; lc.out_mode = lin::OUT_F32;
     linear(lc, dt_, num_sms_, stream_);
   }
@@ -561,31 +568,31 @@ void Engine::clip_forward(int Bv, int g3, const float* sam_out, float* clip_x) {
     layernorm(clip_x, b.ln1_w.as<float>(), b.ln1_b.as<float>(), xn, nullptr, rows, C, 1e-5f, 0, 0, 0, dt_, stream_);
     {
       LinearCall lc;
-      lc.w0 = b.qkv_w.p; lc.x = xn; lc.x_rows = rows; lc.M = (int)rows; lc.N = 3 * C; lc.K = C;
+      lc.tag = "clip_qkv"; lc.w0 = b.qkv_w.p; lc.x = xn; lc.x_rows = rows; lc.M = (int)rows; lc.N = 3 * C; lc.K = C;
       lc.bias = b.qkv_b.as<float>(); lc.out = qkv; lc.ldo = 3 * C; lc.out_mode = lin::OUT_T;
       linear(lc, dt_, num_sms_, stream_);
     }
     {
       VAttnCall ac;
-      ac.qkv = qkv; ac.rows = rows; ac.B = Bv; ac.S = S; ac.H = Hh; ac.grid = 0; ac.out = att; ac.scale = 0.125f;
+      ac.qkv = qkv; ac.rows = rows; ac.B = Bv; ac.S = S; ac.H = Hh; ac.grid = 0; ac.out = att; ac.scale = 0.125f; ac.tag = "clip_attention";
       vision_attention(ac, dt_, stream_);
     }
     {
       LinearCall lc;
-      lc.w0 = b.out_w.p; lc.x = att; lc.x_rows = rows; lc.M = (int)rows; lc.N = C; lc.K = C;
+      lc.tag = "clip_out_proj"; lc.w0 = b.out_w.p; lc.x = att; lc.x_rows = rows; lc.M = (int)rows; lc.N = C; lc.K = C;
       lc.bias = b.out_b.as<float>(); lc.out = clip_x; lc.ldo = C; lc.out_mode = lin::OUT_F32_ADD;
       linear(lc, dt_, num_sms_, stream_);
     }
     layernorm(clip_x, b.ln2_w.as<float>(), b.ln2_b.as<float>(), xn, nullptr, rows, C, 1e-5f, 0, 0, 0, dt_, stream_);
     {
       LinearCall lc;
-      lc.w0 = b.fc1_w.p; lc.x = xn; lc.x_rows = rows; lc.M = (int)rows; lc.N = 4 * C; lc.K = C;
+      lc.tag = "clip_fc1_quickgelu"; lc.w0 = b.fc1_w.p; lc.x = xn; lc.x_rows = rows; lc.M = (int)rows; lc.N = 4 * C; lc.K = C;
       lc.bias = b.fc1_b.as<float>(); lc.out = h16; lc.ldo = 4 * C; lc.out_mode = lin::OUT_T; lc.act = lin::ACT_QUICK_GELU;
       linear(lc, dt_, num_sms_, stream_);
     }
     {
       LinearCall lc;
-      lc.w0 = b.fc2_w.p; lc.x = h16; lc.x_rows = rows; lc.M = (int)rows; lc.N = C; lc.K = 4 * C;
+      lc.tag = "clip_fc2"; lc.w0 = b.fc2_w.p; lc.x = h16; lc.x_rows = rows; lc.M = (int)rows; lc.N = C; lc.K = 4 * C;
       lc.bias = b.fc2_b.as<float>(); lc.out = clip_x; lc.ldo = C; lc.out_mode = lin::OUT_F32_ADD;
       linear(lc, dt_, num_sms_, stream_);
     }
@@ -615,7 +622,7 @@ void Engine::vision_views(int Bv, int G, const void* img_dev, bool is_f32, float
     concat_clip_sam(clip_x, sam_out, pre16, pre32, nb, n, c.clip_dim, dt_, stream_);
     if (pre32) record_tap(std::string(tag) + "_pre", pre32, (size_t)nb * n * c.proj_in);
     LinearCall lc;
-    lc.w0 = proj_w_.p; lc.x = pre16; lc.x_rows = (long long)nb * n; lc.M = nb * n; lc.N = c.n_embed; lc.K = c.proj_in;
+    lc.tag = "projector"; lc.w0 = proj_w_.p; lc.x = pre16; lc.x_rows = (long long)nb * n; lc.M = nb * n; lc.N = c.n_embed; lc.K = c.proj_in;
     lc.bias = proj_b_.as<float>(); lc.out = proj_out + (size_t)b0 * n * c.n_embed; lc.ldo = c.n_embed;
     lc.out_mode = lin::OUT_F32;
     linear(lc, dt_, num_sms_, stream_);
@@ -630,6 +637,7 @@ const float* Engine::vision_encode(int n_pages, const void* globals_dev, bool gl
   int total_tiles = 0;
   for (auto& pv : pages) total_tiles += pv.n_tiles;
   const size_t grows = (size_t)n_pages * qg * qg, lrows = (size_t)total_tiles * ql * ql;
+  kernel_timing_phase("vision/");
   float* proj = ws("proj_all32", (grows + lrows) * Hd * 4).as<float>();
   vision_views(n_pages, G, globals_dev, globals_f32, proj, "global");
   if (total_tiles > 0) vision_views(total_tiles, P, tiles_dev, tiles_f32, proj + grows * Hd, "local");

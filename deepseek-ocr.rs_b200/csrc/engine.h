@@ -86,6 +86,8 @@ class Engine {
 
   int tap(const std::string& name, float* out, size_t capacity, size_t* n_written);
   void set_record_taps(bool on) { record_taps_ = on; }
+  void set_kv_f16(bool on) { kv_f16_ = on; }  // KV cache storage: f32 (reference semantics, default) or f16
+  void set_stream(cudaStream_t s);  // adopt a caller-owned stream (e.g. torch's current stream)
 
   const ModelConfig& cfg() const { return cfg_; }
   DType dtype() const { return dt_; }
@@ -114,7 +116,9 @@ class Engine {
   int device_ = 0;
   int num_sms_ = 0;
   cudaStream_t stream_ = nullptr;
+  bool owns_stream_ = true;
   bool record_taps_ = false;
+  bool kv_f16_ = false;
   std::map<std::string, std::vector<float>> taps_;
 
   // weights

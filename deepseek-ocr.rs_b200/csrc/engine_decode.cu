@@ -43,38 +43,70 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
   void* hperm16 = ws("moe_hperm16", 2 * n_assign * mi * 2).p;
   float* yperm = ws("moe_yperm32", n_assign * H * 4).as<float>();
 
+  // Small-M (decode) projections are split along K so that they fill the GPU; the f32 partials are reduced
+  // in a fixed order by the consumer kernel (RoPE, RMSNorm, SwiGLU-reduce, MoE combine) -> deterministic.
+  const int sp_qkv = linear_plan_splits(rows, 3 * H, H, num_sms_);
+  const int sp_o = linear_plan_splits(rows, H, H, num_sms_);
+  const int sp_dgu = linear_plan_splits(rows, c.inter, H, num_sms_);
+  const int sp_dd = linear_plan_splits(rows, H, c.inter, num_sms_);
+  const int sp_sgu = linear_plan_splits(rows, (int)S, H, num_sms_);
+  const int sp_sd = linear_plan_splits(rows, H, (int)S, num_sms_);
+  const long long part_elems = std::max<long long>({(long long)sp_qkv * rows * 3 * H, (long long)sp_o * rows * H,
+                                                    (long long)sp_dgu * 2 * rows * c.inter, (long long)sp_dd * rows * H,
+                                                    (long long)sp_sgu * 2 * rows * S, 1LL});
+  float* partA = ws("dec_partA32", part_elems * 4).as<float>();                       // qkv / o / gate-up partials
+  float* partB = ws("dec_partB32", std::max<long long>(sp_sd, sp_dd) * rows * H * 4).as<float>();  // down partials
+  const float* pend = nullptr;  // partials of a down/o projection still to be added to x by the next consumer
+  int pend_n = 0;
+  long long pend_stride = 0;
+
   for (int l = 0; l < c.layers; ++l) {
     DecLayerW& L = dec_[l];
-    rmsnorm_split(x, L.ln1.as<float>(), xn16, rows * H, nullptr, nullptr, rows, H, c.rms_eps, dt_, stream_);
+    rmsnorm_split(x, L.ln1.as<float>(), xn16, rows * H, nullptr, nullptr, rows, H, c.rms_eps, pend, pend_n, pend_stride, dt_, stream_);
+    pend = nullptr; pend_n = 0;
     {
       LinearCall lc;  // fused q/k/v projection
-      lc.w0 = L.qkv_w.p; lc.x = xn16; lc.x_rows = 2 * rows; lc.x_parts = 2; lc.x_lo_row_off = (int)rows;
-      lc.M = (int)rows; lc.N = 3 * H; lc.K = H; lc.out = qkv; lc.ldo = 3 * H; lc.out_mode = lin::OUT_F32;
+      lc.tag = "dec_qkv"; lc.w0 = L.qkv_w.p; lc.x = xn16; lc.x_rows = 2 * rows; lc.x_parts = 2; lc.x_lo_row_off = (int)rows;
+      lc.M = (int)rows; lc.N = 3 * H; lc.K = H; lc.ldo = 3 * H; lc.out_mode = lin::OUT_F32;
+      lc.out = sp_qkv > 1 ? partA : qkv; lc.k_splits = sp_qkv; lc.split_stride = rows * 3 * H;
       linear(lc, dt_, num_sms_, stream_);
     }
-    rope_kv(qkv, rope_cos_.as<float>(), rope_sin_.as<float>(), row_page, row_pos, q, kcache_[l].as<float>(),
-            vcache_[l].as<float>(), rows, heads, smax, stream_);
-    kv_attention(q, kcache_[l].as<float>(), vcache_[l].as<float>(), row_page, row_pos, ctx16, rows * H, rows, heads,
-                 smax, scale, dt_, stream_);
+    rope_kv(sp_qkv > 1 ? partA : qkv, rope_cos_.as<float>(), rope_sin_.as<float>(), row_page, row_pos, q,
+            kcache_[l].p, vcache_[l].p, kv_f16_, rows, heads, smax, sp_qkv, rows * 3 * H, stream_);
+    kv_attention(q, kcache_[l].p, vcache_[l].p, kv_f16_, row_page, row_pos, ctx16, rows * H, rows, heads, smax, scale,
+                 dt_, stream_);
     {
-      LinearCall lc;  // o_proj + residual add
-      lc.w0 = L.o_w.p; lc.x = ctx16; lc.x_rows = 2 * rows; lc.x_parts = 2; lc.x_lo_row_off = (int)rows;
-      lc.M = (int)rows; lc.N = H; lc.K = H; lc.out = x; lc.ldo = H; lc.out_mode = lin::OUT_F32_ADD;
+      LinearCall lc;  // o_proj (+ residual add, fused here or in the following RMSNorm when split)
+      lc.tag = "dec_o_proj"; lc.w0 = L.o_w.p; lc.x = ctx16; lc.x_rows = 2 * rows; lc.x_parts = 2; lc.x_lo_row_off = (int)rows;
+      lc.M = (int)rows; lc.N = H; lc.K = H; lc.ldo = H;
+      if (sp_o > 1) { lc.out = partA; lc.out_mode = lin::OUT_F32; lc.k_splits = sp_o; lc.split_stride = rows * H; }
+      else { lc.out = x; lc.out_mode = lin::OUT_F32_ADD; }
       linear(lc, dt_, num_sms_, stream_);
     }
-    rmsnorm_split(x, L.ln2.as<float>(), xn16, rows * H, L.moe ? xn32 : nullptr, nullptr, rows, H, c.rms_eps, dt_, stream_);
+    rmsnorm_split(x, L.ln2.as<float>(), xn16, rows * H, L.moe ? xn32 : nullptr, nullptr, rows, H, c.rms_eps,
+                  sp_o > 1 ? partA : nullptr, sp_o, rows * H, dt_, stream_);
     if (!L.moe) {
       {
         LinearCall lc;  // gate/up + SwiGLU (run_dense_mlp, block.rs:1166-1177)
-        lc.w0 = L.gate_w.p; lc.w1 = L.up_w.p; lc.x = xn16; lc.x_rows = 2 * rows; lc.x_parts = 2; lc.x_lo_row_off = (int)rows;
-        lc.M = (int)rows; lc.N = c.inter; lc.K = H; lc.out = h16; lc.out_lo = (uint16_t*)h16 + rows * c.inter;
-        lc.ldo = c.inter; lc.out_mode = lin::OUT_T_SPLIT;
+        lc.tag = "dec_dense_gate_up"; lc.w0 = L.gate_w.p; lc.w1 = L.up_w.p; lc.x = xn16; lc.x_rows = 2 * rows; lc.x_parts = 2; lc.x_lo_row_off = (int)rows;
+        lc.M = (int)rows; lc.N = c.inter; lc.K = H; lc.ldo = c.inter;
+        if (sp_dgu > 1) {
+          lc.out = partA; lc.out_mode = lin::OUT_F32_DUAL; lc.k_splits = sp_dgu; lc.dual_stride = rows * c.inter;
+          lc.split_stride = 2 * rows * c.inter;
+        } else {
+          lc.out = h16; lc.out_lo = (uint16_t*)h16 + rows * c.inter; lc.out_mode = lin::OUT_T_SPLIT;
+        }
         linear(lc, dt_, num_sms_, stream_);
+        if (sp_dgu > 1) swiglu_reduce(partA, sp_dgu, 2 * rows * c.inter, rows * c.inter, h16, rows * c.inter, rows * c.inter, dt_, stream_);
       }
       {
         LinearCall lc;
-        lc.w0 = L.down_w.p; lc.x = h16; lc.x_rows = 2 * rows; lc.x_parts = 2; lc.x_lo_row_off = (int)rows;
-        lc.M = (int)rows; lc.N = H; lc.K = c.inter; lc.out = x; lc.ldo = H; lc.out_mode = lin::OUT_F32_ADD;
+        lc.tag = "dec_dense_down"; lc.w0 = L.down_w.p; lc.x = h16; lc.x_rows = 2 * rows; lc.x_parts = 2; lc.x_lo_row_off = (int)rows;
+        lc.M = (int)rows; lc.N = H; lc.K = c.inter; lc.ldo = H;
+        if (sp_dd > 1) {
+          lc.out = partB; lc.out_mode = lin::OUT_F32; lc.k_splits = sp_dd; lc.split_stride = rows * H;
+          pend = partB; pend_n = sp_dd; pend_stride = rows * H;
+        } else { lc.out = x; lc.out_mode = lin::OUT_F32_ADD; }
         linear(lc, dt_, num_sms_, stream_);
       }
     } else {
@@ -85,7 +117,7 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
       moe_dispatch(topk_idx, offsets, cursor, xn16, rows * H, xperm16, n_assign * H, perm_pos, n_assign, K, H, dt_, stream_);
       {
         LinearCall lc;  // routed experts: gate/up + SwiGLU, grouped
-        lc.w0 = L.exp_gate.p; lc.w1 = L.exp_up.p; lc.w_rows = (long long)E * mi;
+        lc.tag = "moe_expert_gate_up"; lc.w0 = L.exp_gate.p; lc.w1 = L.exp_up.p; lc.w_rows = (long long)E * mi;
         lc.x = xperm16; lc.x_rows = 2 * n_assign; lc.x_parts = 2; lc.x_lo_row_off = (int)n_assign;
         lc.M = (int)n_assign; lc.N = mi; lc.K = H;
         lc.out = hperm16; lc.out_lo = (uint16_t*)hperm16 + n_assign * mi; lc.ldo = mi; lc.out_mode = lin::OUT_T_SPLIT;
@@ -94,7 +126,7 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
       }
       {
         LinearCall lc;  // routed experts: down, grouped
-        lc.w0 = L.exp_down.p; lc.w_rows = (long long)E * H;
+        lc.tag = "moe_expert_down"; lc.w0 = L.exp_down.p; lc.w_rows = (long long)E * H;
         lc.x = hperm16; lc.x_rows = 2 * n_assign; lc.x_parts = 2; lc.x_lo_row_off = (int)n_assign;
         lc.M = (int)n_assign; lc.N = H; lc.K = mi; lc.out = yperm; lc.ldo = H; lc.out_mode = lin::OUT_F32;
         lc.tiles = tiles2; lc.num_tiles_dev = ntiles + 1; lc.max_tiles = max_chunks * (H / 128); lc.bn = bn;
@@ -102,26 +134,34 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
       }
       {
         LinearCall lc;  // shared experts (one fused SwiGLU MLP, weights.rs:390-400)
-        lc.w0 = L.sh_gate.p; lc.w1 = L.sh_up.p; lc.x = xn16; lc.x_rows = 2 * rows; lc.x_parts = 2; lc.x_lo_row_off = (int)rows;
-        lc.M = (int)rows; lc.N = (int)S; lc.K = H; lc.out = h16; lc.out_lo = (uint16_t*)h16 + rows * S; lc.ldo = S;
-        lc.out_mode = lin::OUT_T_SPLIT;
+        lc.tag = "moe_shared_gate_up"; lc.w0 = L.sh_gate.p; lc.w1 = L.sh_up.p; lc.x = xn16; lc.x_rows = 2 * rows; lc.x_parts = 2; lc.x_lo_row_off = (int)rows;
+        lc.M = (int)rows; lc.N = (int)S; lc.K = H; lc.ldo = S;
+        if (sp_sgu > 1) {
+          lc.out = partA; lc.out_mode = lin::OUT_F32_DUAL; lc.k_splits = sp_sgu; lc.dual_stride = rows * S; lc.split_stride = 2 * rows * S;
+        } else {
+          lc.out = h16; lc.out_lo = (uint16_t*)h16 + rows * S; lc.out_mode = lin::OUT_T_SPLIT;
+        }
         linear(lc, dt_, num_sms_, stream_);
+        if (sp_sgu > 1) swiglu_reduce(partA, sp_sgu, 2 * rows * S, rows * S, h16, rows * S, rows * S, dt_, stream_);
       }
       {
         LinearCall lc;
-        lc.w0 = L.sh_down.p; lc.x = h16; lc.x_rows = 2 * rows; lc.x_parts = 2; lc.x_lo_row_off = (int)rows;
-        lc.M = (int)rows; lc.N = H; lc.K = (int)S; lc.out = x; lc.ldo = H; lc.out_mode = lin::OUT_F32_ADD;
+        lc.tag = "moe_shared_down"; lc.w0 = L.sh_down.p; lc.x = h16; lc.x_rows = 2 * rows; lc.x_parts = 2; lc.x_lo_row_off = (int)rows;
+        lc.M = (int)rows; lc.N = H; lc.K = (int)S; lc.ldo = H;
+        if (sp_sd > 1) { lc.out = partB; lc.out_mode = lin::OUT_F32; lc.k_splits = sp_sd; lc.split_stride = rows * H; }
+        else { lc.out = x; lc.out_mode = lin::OUT_F32_ADD; }
         linear(lc, dt_, num_sms_, stream_);
       }
-      moe_combine(yperm, perm_pos, topk_w, x, rows, K, H, stream_);
+      moe_combine(yperm, perm_pos, topk_w, x, rows, K, H, sp_sd > 1 ? partB : nullptr, sp_sd, rows * H, stream_);
     }
     if (record_taps_) record_tap("dec.hidden." + std::to_string(l), x, rows * H);
   }
   // final RMSNorm + lm_head on the selected rows
   void* xf16 = ws("dec_xf16", 2 * (size_t)n_final * H * 2).p;
-  rmsnorm_split(x, final_norm_.as<float>(), xf16, (long long)n_final * H, nullptr, final_rows, n_final, H, c.rms_eps, dt_, stream_);
+  rmsnorm_split(x, final_norm_.as<float>(), xf16, (long long)n_final * H, nullptr, final_rows, n_final, H, c.rms_eps,
+                pend, pend_n, pend_stride, dt_, stream_);
   LinearCall lc;
-  lc.w0 = lm_head_.p; lc.x = xf16; lc.x_rows = 2 * n_final; lc.x_parts = 2; lc.x_lo_row_off = n_final;
+  lc.tag = "lm_head"; lc.w0 = lm_head_.p; lc.x = xf16; lc.x_rows = 2 * n_final; lc.x_parts = 2; lc.x_lo_row_off = n_final;
   lc.M = n_final; lc.N = c.vocab; lc.K = H; lc.out = logits; lc.ldo = c.vocab; lc.out_mode = lin::OUT_F32;
   linear(lc, dt_, num_sms_, stream_);
 }
@@ -181,7 +221,7 @@ void Engine::generate(const GenRequest& rq, int64_t* const* out_tokens, int* n_o
     }
     img_rows = buf;
   }
-  const size_t kv_bytes = (size_t)P * c.heads * smax * c.head_dim() * 4;
+  const size_t kv_bytes = (size_t)P * c.heads * smax * c.head_dim() * (kv_f16_ ? 2 : 4);
   kcache_.resize(c.layers); vcache_.resize(c.layers);
   for (int l = 0; l < c.layers; ++l) { kcache_[l].ensure(kv_bytes); vcache_[l].ensure(kv_bytes); }
 
@@ -224,10 +264,11 @@ void Engine::generate(const GenRequest& rq, int64_t* const* out_tokens, int* n_o
   };
 
   // ---- prefill (model/mod.rs:1925-1947)
+  kernel_timing_phase("prefill/");
   embed_gather(d_src, embed_.p, img_rows, x, total_rows, H, dt_, stream_);
   decoder_forward(x, total_rows, d_row_page, d_row_pos, smax, d_last, P, logits);
   copy_logits(0);
-  select_token(logits, V, d_hist, smax, d_hist_len, d_gen_count, d_finished, P, ngram, eos, max_new, d_forced, max_new, 0,
+  select_token(logits, V, d_hist, smax, d_hist_len, d_gen_count, d_finished, P, ngram, eos, max_new, d_forced, max_new,
                d_selected, max_new, stream_);
   cuda_check(cudaEventRecord(ev1, stream_), "event");
 
@@ -252,6 +293,24 @@ void Engine::generate(const GenRequest& rq, int64_t* const* out_tokens, int* n_o
       delivered[p] = std::max(delivered[p], gen);
     }
   };
+  kernel_timing_phase("decode/");
+  // One decode step = ~170 kernels whose arguments do not change between steps (positions, token history and
+  // routing live in device memory), so after one eager step (which sizes every workspace) the step is
+  // captured once into a CUDA graph and replayed.
+  auto run_step = [&](int step) {
+    decode_rows(d_hist, smax, d_hist_len, d_src, d_row_pos, P, stream_);
+    embed_gather(d_src, embed_.p, nullptr, x, P, H, dt_, stream_);
+    decoder_forward(x, P, d_row_page, d_row_pos, smax, d_row_page /* identity: every row */, P, logits);
+    copy_logits(step);
+    select_token(logits, V, d_hist, smax, d_hist_len, d_gen_count, d_finished, P, ngram, eos, max_new, d_forced, max_new,
+                 d_selected, max_new, stream_);
+  };
+  bool use_graph = !kernel_timing_enabled() && !rq.logits_out && !record_taps_ && !getenv("DSOCR_NO_GRAPH");
+  if (use_graph && (stream_ == nullptr || stream_ == cudaStreamLegacy || stream_ == cudaStreamPerThread))
+    use_graph = false;  // the default streams cannot be captured
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+  long long graph_launches = 0;
   for (int step = 1; step < max_new; ++step) {
     if ((step - 1) % sync_every == 0) {
       cuda_check(cudaStreamSynchronize(stream_), "decode sync");
@@ -261,15 +320,31 @@ void Engine::generate(const GenRequest& rq, int64_t* const* out_tokens, int* n_o
       for (int p = 0; p < P; ++p) all &= fin[p] != 0;
       if (all) break;
     }
-    decode_rows(d_hist, smax, d_hist_len, d_src, d_row_pos, P, stream_);
-    embed_gather(d_src, embed_.p, nullptr, x, P, H, dt_, stream_);
-    decoder_forward(x, P, d_row_page, d_row_pos, smax, d_row_page /* identity: every row */, P, logits);
-    copy_logits(step);
-    select_token(logits, V, d_hist, smax, d_hist_len, d_gen_count, d_finished, P, ngram, eos, max_new, d_forced, max_new,
-                 step, d_selected, max_new, stream_);
+    if (!use_graph || step == 1) {
+      run_step(step);
+    } else if (!graph_exec) {
+      const long long before = launch_counter();
+      cuda_check(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal), "graph capture begin");
+      try {
+        run_step(step);
+      } catch (...) {
+        cudaStreamEndCapture(stream_, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        throw;
+      }
+      cuda_check(cudaStreamEndCapture(stream_, &graph), "graph capture end");
+      graph_launches = launch_counter() - before;
+      cuda_check(cudaGraphInstantiate(&graph_exec, graph, 0), "graph instantiate");
+      cuda_check(cudaGraphLaunch(graph_exec, stream_), "graph launch");
+    } else {
+      cuda_check(cudaGraphLaunch(graph_exec, stream_), "graph launch");
+      launch_counter() += graph_launches;
+    }
   }
   cuda_check(cudaEventRecord(ev2, stream_), "event");
   cuda_check(cudaStreamSynchronize(stream_), "generate sync");
+  if (graph_exec) cudaGraphExecDestroy(graph_exec);
+  if (graph) cudaGraphDestroy(graph);
   deliver();
 
   // ---- results

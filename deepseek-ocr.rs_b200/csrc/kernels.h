@@ -15,10 +15,12 @@ inline void cuda_check(cudaError_t e, const char* what) {
 // Every kernel launch of this library goes through launch_check: it surfaces launch errors and counts the
 // launches (dsocr_launch_count).
 long long& launch_counter();
-inline void launch_check(const char* what) {
-  ++launch_counter();
-  cuda_check(cudaGetLastError(), what);
-}
+void launch_check(const char* what);
+// Optional per-kernel timing: while enabled, launch_check records a CUDA event after every launch on the
+// engine stream; consecutive event deltas are aggregated by kernel name (kernels on one stream serialise).
+void kernel_timing_begin(cudaStream_t stream);
+void kernel_timing_phase(const char* phase);  // prefix for subsequently recorded kernels (string literal)
+std::string kernel_timing_end_json();
 
 // ------------------------------------------------------------------------- tensor-core linear
 struct LinearTile { int w_row0, x_row0, rows, n0; };  // == lin::Tile
@@ -53,7 +55,15 @@ struct LinearCall {
   int max_tiles = 0;
   int tile_rows_hint = 0;  // typical rows per tile, used to pick the token tile
   int bn = 0;              // force the token tile (0 = auto)
+  const char* tag = nullptr;  // kernel name for timing reports
+  // deterministic split-K: k_splits partial f32 results at out + s*split_stride (out_mode must be OUT_F32 or
+  // OUT_F32_DUAL); see linear_plan_splits
+  int k_splits = 1;
+  long long split_stride = 0;
+  long long dual_stride = 0;
 };
+// number of k-splits that fills the GPU for a small-M problem (1 = do not split)
+int linear_plan_splits(long long M, int N, int K, int num_sms);
 
 int linear_pick_bn(long long m, bool dual);
 void linear(const LinearCall& c, DType dt, int num_sms, cudaStream_t stream);
@@ -70,6 +80,7 @@ struct VAttnCall {
   int zw = 0, zhalf = 0;
   void* out = nullptr;  // [rows, H*64] 16-bit
   float scale = 0.125f;
+  const char* tag = nullptr;
 };
 bool vision_attention_supported(int grid);
 void vision_attention(const VAttnCall& c, DType dt, cudaStream_t stream);
@@ -95,12 +106,17 @@ void scatter_tokens(const float* proj, const float* newline, const float* sep, c
 // ------------------------------------------------------------------------- decoder SIMT kernels
 void embed_gather(const int* src, const void* table, const float* img_rows, float* out, long long rows, int H, DType dt,
                   cudaStream_t s);
-void rmsnorm_split(const float* x, const float* w, void* out16, long long lo_off_elems, float* out32,
-                   const int* row_idx, long long rows, int H, float eps, DType dt, cudaStream_t s);
+void rmsnorm_split(float* x, const float* w, void* out16, long long lo_off_elems, float* out32,
+                   const int* row_idx, long long rows, int H, float eps, const float* partials, int n_splits,
+                   long long split_stride, DType dt, cudaStream_t s);
+void swiglu_reduce(const float* part, int n_splits, long long split_stride, long long dual_stride, void* out16,
+                   long long lo_off_elems, long long n, DType dt, cudaStream_t s);
 void rope_kv(const float* qkv, const float* cos_t, const float* sin_t, const int* row_page, const int* row_pos,
-             float* q_out, float* kc, float* vc, long long rows, int heads, int smax, cudaStream_t s);
-void kv_attention(const float* q, const float* kc, const float* vc, const int* row_page, const int* row_pos, void* ctx,
-                  long long lo_off_elems, long long rows, int heads, int smax, float scale, DType dt, cudaStream_t s);
+             float* q_out, void* kc, void* vc, bool kv_f16, long long rows, int heads, int smax, int n_splits,
+             long long split_stride, cudaStream_t s);
+void kv_attention(const float* q, const void* kc, const void* vc, bool kv_f16, const int* row_page, const int* row_pos,
+                  void* ctx, long long lo_off_elems, long long rows, int heads, int smax, float scale, DType dt,
+                  cudaStream_t s);
 void moe_router(const float* x, const float* wgt, int* topk_idx, float* topk_w, int* counts, long long rows, int H,
                 int E, int topk, cudaStream_t s);
 void moe_plan(const int* counts, int* offsets, int* cursor, LinearTile* tiles1, int* ntiles1, LinearTile* tiles2,
@@ -109,10 +125,11 @@ void moe_dispatch(const int* topk_idx, const int* offsets, int* cursor, const vo
                   void* xperm, long long xperm_lo_off, int* perm_pos, long long n_assign, int topk, int H, DType dt,
                   cudaStream_t s);
 void moe_combine(const float* y, const int* perm_pos, const float* topk_w, float* x, long long rows, int topk, int H,
-                 cudaStream_t s);
+                 const float* partials, int n_splits, long long split_stride, cudaStream_t s);
 void select_token(const float* logits, int V, int* hist, int hist_stride, int* hist_len, int* gen_count, int* finished,
-                  int n_pages, int ngram, int eos, int max_new, const int* forced, int forced_stride, int step,
+                  int n_pages, int ngram, int eos, int max_new, const int* forced, int forced_stride,
                   int* selected_out, int selected_stride, cudaStream_t s);
+bool kernel_timing_enabled();
 void decode_rows(const int* hist, int hist_stride, const int* hist_len, int* src, int* row_pos, int n_pages,
                  cudaStream_t s);
 void fill_i32(int* p, int v, long long n, cudaStream_t s);

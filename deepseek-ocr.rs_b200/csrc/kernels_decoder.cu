@@ -73,21 +73,32 @@ __global__ void embed_gather_kernel(const int* __restrict__ src, const T* __rest
 // rms_norm (block.rs:24-29): x * rsqrt(mean(x^2) + eps) * w in f32.  One warp per row.  Outputs: 16-bit hi/lo
 // split [2][lo_off rows apart] for the tensor-core GEMMs and optionally the f32 row (router input).
 // `row_idx` (optional) selects source rows (last-row-only final norm).
+// When `partials` is given the row first absorbs the split-K partial sums of the preceding projection
+// (x[src] += sum_s partials[s][src], fixed order, written back) - the residual add fused into the norm.
 template <typename T>
-__global__ void rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ w, T* __restrict__ out16,
+__global__ void rmsnorm_kernel(float* __restrict__ x, const float* __restrict__ w, T* __restrict__ out16,
                                long long lo_off_elems, float* __restrict__ out32, const int* __restrict__ row_idx,
-                               long long rows, int H, float eps) {
+                               long long rows, int H, float eps, const float* __restrict__ partials, int n_splits,
+                               long long split_stride) {
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
   const long long src = row_idx ? row_idx[row] : row;
-  const float4* xr = reinterpret_cast<const float4*>(x + src * H);
+  float4* xr = reinterpret_cast<float4*>(x + src * H);
   const int n4 = H / 4;
   float ss = 0.f;
   for (int i = lane; i < n4; i += 32) {
-    const float4 v = xr[i];
+    float4 v = xr[i];
+    if (partials) {
+      for (int sidx = 0; sidx < n_splits; ++sidx) {
+        const float4 pv = reinterpret_cast<const float4*>(partials + sidx * split_stride + src * H)[i];
+        v.x += pv.x; v.y += pv.y; v.z += pv.z; v.w += pv.w;
+      }
+      xr[i] = v;
+    }
     ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
   }
+  if (partials) __syncwarp();
   const float inv = rsqrtf(warp_sum(ss) / (float)H + eps);
   for (int i = lane; i < n4; i += 32) {
     const float4 v = xr[i];
@@ -101,14 +112,74 @@ __global__ void rmsnorm_kernel(const float* __restrict__ x, const float* __restr
   }
 }
 
+// Decode-sized variant: one 128-thread block per row, all partial loads of a thread in flight at once.
+template <typename T, int MAXS>
+__global__ void __launch_bounds__(128)
+rmsnorm_row_kernel(float* __restrict__ x, const float* __restrict__ w, T* __restrict__ out16, long long lo_off_elems,
+                   float* __restrict__ out32, const int* __restrict__ row_idx, int H, float eps,
+                   const float* __restrict__ partials, int n_splits, long long split_stride) {
+  const long long row = blockIdx.x;
+  const long long src = row_idx ? row_idx[row] : row;
+  float4* xr = reinterpret_cast<float4*>(x + src * H);
+  const int n4 = H / 4;
+  float4 v[3];
+  float ss = 0.f;
+#pragma unroll
+  for (int it = 0; it < 3; ++it) {
+    const int i = threadIdx.x + it * 128;
+    v[it] = make_float4(0, 0, 0, 0);
+    if (i < n4) {
+      float4 a = xr[i];
+      if (partials) {
+        float4 pv[MAXS];
+#pragma unroll
+        for (int sidx = 0; sidx < MAXS; ++sidx)
+          pv[sidx] = sidx < n_splits ? reinterpret_cast<const float4*>(partials + sidx * split_stride + src * H)[i]
+                                     : make_float4(0, 0, 0, 0);
+#pragma unroll
+        for (int sidx = 0; sidx < MAXS; ++sidx) { a.x += pv[sidx].x; a.y += pv[sidx].y; a.z += pv[sidx].z; a.w += pv[sidx].w; }
+        xr[i] = a;
+      }
+      v[it] = a;
+      ss += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+    }
+  }
+  __shared__ float red[4];
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  const float inv = rsqrtf((red[0] + red[1] + red[2] + red[3]) / (float)H + eps);
+#pragma unroll
+  for (int it = 0; it < 3; ++it) {
+    const int i = threadIdx.x + it * 128;
+    if (i < n4) {
+      const float4 ww = reinterpret_cast<const float4*>(w)[i];
+      float o[4] = {v[it].x * inv * ww.x, v[it].y * inv * ww.y, v[it].z * inv * ww.z, v[it].w * inv * ww.w};
+      uint2 hi, lo;
+      split4<T>(o, hi, lo);
+      reinterpret_cast<uint2*>(out16 + row * H)[i] = hi;
+      reinterpret_cast<uint2*>(out16 + lo_off_elems + row * H)[i] = lo;
+      if (out32) reinterpret_cast<float4*>(out32 + row * H)[i] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
 // RoPE (block.rs:1403-1471, NeoX rotate-half over all 128 dims, tables rope.rs:172-207) applied to the q and
 // k thirds of the fused qkv projection [rows, 3, heads, 128] f32, then K/V appended to the per-page cache
 // [page][head][S_max][128] and q written as hi/lo... q stays f32 ([rows, heads, 128]).
 // One thread = 4 consecutive dims of the low half (and their partners in the high half).
+__device__ __forceinline__ void store4(float* p, int t, float4 v) { reinterpret_cast<float4*>(p)[t] = v; }
+__device__ __forceinline__ void store4(__half* p, int t, float4 v) {
+  __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+  uint2 u; u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+  reinterpret_cast<uint2*>(p)[t] = u;
+}
+template <typename TKV>
 __global__ void rope_kv_kernel(const float* __restrict__ qkv, const float* __restrict__ cos_t,
                                const float* __restrict__ sin_t, const int* __restrict__ row_page,
-                               const int* __restrict__ row_pos, float* __restrict__ q_out, float* __restrict__ kc,
-                               float* __restrict__ vc, long long rows, int heads, int smax) {
+                               const int* __restrict__ row_pos, float* __restrict__ q_out, TKV* __restrict__ kc,
+                               TKV* __restrict__ vc, long long rows, int heads, int smax, int n_splits,
+                               long long split_stride) {
   constexpr int D = 128;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = rows * heads * 16;  // 16 threads x 4 dims = low half (64)
@@ -122,22 +193,33 @@ __global__ void rope_kv_kernel(const float* __restrict__ qkv, const float* __res
   const float4 s = reinterpret_cast<const float4*>(sin_t + (long long)pos * 64)[t];
   const float* base = qkv + r * 3 * heads * D;
   const long long cache_off = (((long long)page * heads + hd) * smax + pos) * D;
+  auto load4 = [&](const float* p) {  // sum of the split-K partials of the qkv projection (fixed order)
+    float4 a = reinterpret_cast<const float4*>(p)[t];
+    for (int sidx = 1; sidx < n_splits; ++sidx) {
+      const float4 b = reinterpret_cast<const float4*>(p + sidx * split_stride)[t];
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    return a;
+  };
 #pragma unroll
   for (int which = 0; which < 2; ++which) {
     const float* src = base + (which * heads + hd) * D;
-    const float4 lo = reinterpret_cast<const float4*>(src)[t];
-    const float4 hi = reinterpret_cast<const float4*>(src + 64)[t];
+    const float4 lo = load4(src);
+    const float4 hi = load4(src + 64);
     // out = x*cos + rotate_half(x)*sin ; rotate_half = [-hi, lo]; cos/sin halves are duplicated
     float4 olo, ohi;
     olo.x = lo.x * c.x - hi.x * s.x; olo.y = lo.y * c.y - hi.y * s.y; olo.z = lo.z * c.z - hi.z * s.z; olo.w = lo.w * c.w - hi.w * s.w;
     ohi.x = hi.x * c.x + lo.x * s.x; ohi.y = hi.y * c.y + lo.y * s.y; ohi.z = hi.z * c.z + lo.z * s.z; ohi.w = hi.w * c.w + lo.w * s.w;
-    float* dst = which == 0 ? q_out + (r * heads + hd) * D : kc + cache_off;
-    reinterpret_cast<float4*>(dst)[t] = olo;
-    reinterpret_cast<float4*>(dst + 64)[t] = ohi;
+    if (which == 0) {
+      float* dst = q_out + (r * heads + hd) * D;
+      store4(dst, t, olo); store4(dst + 64, t, ohi);
+    } else {
+      store4(kc + cache_off, t, olo); store4(kc + cache_off + 64, t, ohi);
+    }
   }
   const float* vsrc = base + (2 * heads + hd) * D;
-  reinterpret_cast<float4*>(vc + cache_off)[t] = reinterpret_cast<const float4*>(vsrc)[t];
-  reinterpret_cast<float4*>(vc + cache_off + 64)[t] = reinterpret_cast<const float4*>(vsrc + 64)[t];
+  store4(vc + cache_off, t, load4(vsrc));
+  store4(vc + cache_off + 64, t, load4(vsrc + 64));
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -145,9 +227,25 @@ __global__ void rope_kv_kernel(const float* __restrict__ qkv, const float* __res
 // query at position p attends keys 0..p) and decode (one query per page).  Grid: (query, head); 4 warps split
 // the keys; each warp processes 4 keys per step with 8 lanes per key (16 dims per lane).  Output: hi/lo split
 // 16-bit context rows [rows, heads*128] feeding the o_proj GEMM.
-template <typename T>
+__device__ __forceinline__ void load16(const float* p, float* out) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 t = reinterpret_cast<const float4*>(p)[i];
+    out[4 * i] = t.x; out[4 * i + 1] = t.y; out[4 * i + 2] = t.z; out[4 * i + 3] = t.w;
+  }
+}
+__device__ __forceinline__ void load16(const __half* p, float* out) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const uint4 t = reinterpret_cast<const uint4*>(p)[i];
+    const __half2* h = reinterpret_cast<const __half2*>(&t);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); out[8 * i + 2 * j] = f.x; out[8 * i + 2 * j + 1] = f.y; }
+  }
+}
+template <typename T, typename TKV>
 __global__ void __launch_bounds__(128)
-kv_attention_kernel(const float* __restrict__ q, const float* __restrict__ kc, const float* __restrict__ vc,
+kv_attention_kernel(const float* __restrict__ q, const TKV* __restrict__ kc, const TKV* __restrict__ vc,
                     const int* __restrict__ row_page, const int* __restrict__ row_pos, T* __restrict__ ctx,
                     long long lo_off_elems, int heads, int smax, float scale) {
   constexpr int D = 128;
@@ -157,8 +255,8 @@ kv_attention_kernel(const float* __restrict__ q, const float* __restrict__ kc, c
   const int grp = lane >> 3, sub = lane & 7;  // 4 key groups x 8 lanes; lane covers dims [sub*16, sub*16+16)
   const int nkeys = row_pos[r] + 1;
   const int page = row_page[r];
-  const float* kbase = kc + ((long long)page * heads + hd) * smax * D;
-  const float* vbase = vc + ((long long)page * heads + hd) * smax * D;
+  const TKV* kbase = kc + ((long long)page * heads + hd) * smax * D;
+  const TKV* vbase = vc + ((long long)page * heads + hd) * smax * D;
   float qv[16];
   {
     const float4* qp = reinterpret_cast<const float4*>(q + (r * heads + hd) * D + sub * 16);
@@ -177,15 +275,11 @@ kv_attention_kernel(const float* __restrict__ q, const float* __restrict__ kc, c
     float s = 0.f;
     float vv[16];
     if (ok) {
-      const float4* kp = reinterpret_cast<const float4*>(kbase + (long long)k * D + sub * 16);
-      const float4* vp = reinterpret_cast<const float4*>(vbase + (long long)k * D + sub * 16);
+      float kk[16];
+      load16(kbase + (long long)k * D + sub * 16, kk);
+      load16(vbase + (long long)k * D + sub * 16, vv);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 t = kp[i];
-        s += qv[4 * i] * t.x + qv[4 * i + 1] * t.y + qv[4 * i + 2] * t.z + qv[4 * i + 3] * t.w;
-        const float4 u = vp[i];
-        vv[4 * i] = u.x; vv[4 * i + 1] = u.y; vv[4 * i + 2] = u.z; vv[4 * i + 3] = u.w;
-      }
+      for (int i = 0; i < 16; ++i) s += qv[i] * kk[i];
     }
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
@@ -227,66 +321,92 @@ kv_attention_kernel(const float* __restrict__ q, const float* __restrict__ kc, c
 
 // ---------------------------------------------------------------------------------------------------
 // MoE router (run_moe, block.rs:1263-1301): logits = x . Wg^T in f32 -> softmax over the experts -> top-k by
-// value (ties -> lowest index, the CPU reference's stable descending sort).  One warp per token; WgT is the
-// transposed gate weight [H, E] so that lanes read consecutive experts.  Also counts tokens per expert.
-template <int E>
-__global__ void router_kernel(const float* __restrict__ x, const float* __restrict__ wgt, int* __restrict__ topk_idx,
-                              float* __restrict__ topk_w, int* __restrict__ counts, long long rows, int H, int topk) {
-  constexpr int PER = (E + 31) / 32;
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const int lane = threadIdx.x & 31;
-  const float* xr = x + row * H;
-  float acc[PER];
+// value (ties -> lowest index, the CPU reference's stable descending sort).  One block = TOK tokens; the
+// reduction dimension is split over KS thread groups of E threads (thread = expert, coalesced reads of the
+// transposed gate weight WgT [H, E]); partial sums meet in shared memory, then one warp per token does
+// softmax + top-k with shuffles.  Also counts tokens per expert.
+template <int E, int TOK, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+router_kernel(const float* __restrict__ x, const float* __restrict__ wgt, int* __restrict__ topk_idx,
+              float* __restrict__ topk_w, int* __restrict__ counts, long long rows, int H, int topk) {
+  constexpr int KS = THREADS / E;      // k-slices
+  constexpr int PER = (E + 31) / 32;   // experts per lane in the top-k phase
+  extern __shared__ float sm[];        // x tile [TOK][H] | partials [KS][TOK][E]
+  float* xs = sm;
+  float* part = sm + TOK * H;
+  const long long row0 = (long long)blockIdx.x * TOK;
+  const int ntok = (int)min((long long)TOK, rows - row0);
+  for (int i = threadIdx.x; i < TOK * H / 4; i += THREADS) {
+    const int t = i / (H / 4);
+    float4 v = make_float4(0, 0, 0, 0);
+    if (t < ntok) v = reinterpret_cast<const float4*>(x + (row0 + t) * H)[i % (H / 4)];
+    reinterpret_cast<float4*>(xs)[i] = v;
+  }
+  __syncthreads();
+  const int e = threadIdx.x % E, ks = threadIdx.x / E;
+  const int kper = H / KS;
+  float acc[TOK];
 #pragma unroll
-  for (int j = 0; j < PER; ++j) acc[j] = 0.f;
-  for (int k0 = 0; k0 < H; k0 += 32) {
-    const float xv = xr[k0 + lane];
+  for (int t = 0; t < TOK; ++t) acc[t] = 0.f;
+  const float* wp = wgt + (long long)(ks * kper) * E + e;
+  const float* xp = xs + ks * kper;
 #pragma unroll 8
-    for (int kk = 0; kk < 32; ++kk) {
-      const float xk = __shfl_sync(0xffffffffu, xv, kk);
-      const float* wrow = wgt + (long long)(k0 + kk) * E;
+  for (int k = 0; k < kper; ++k) {
+    const float w = wp[(long long)k * E];
 #pragma unroll
-      for (int j = 0; j < PER; ++j) {
-        const int e = j * 32 + lane;
-        if (e < E) acc[j] += xk * wrow[e];
-      }
-    }
+    for (int t = 0; t < TOK; ++t) acc[t] = fmaf(xp[t * H + k], w, acc[t]);
   }
-  float mx = -INFINITY;
 #pragma unroll
-  for (int j = 0; j < PER; ++j) if (j * 32 + lane < E) mx = fmaxf(mx, acc[j]);
-  mx = warp_max(mx);
-  float sum = 0.f;
-  float p[PER];
-#pragma unroll
-  for (int j = 0; j < PER; ++j) {
-    p[j] = (j * 32 + lane < E) ? expf(acc[j] - mx) : 0.f;
-    sum += p[j];
-  }
-  sum = warp_sum(sum);
-#pragma unroll
-  for (int j = 0; j < PER; ++j) p[j] = (j * 32 + lane < E) ? p[j] / sum : -1.f;
-  for (int t = 0; t < topk; ++t) {
-    float bv = -1.f; int bi = 1 << 30;
+  for (int t = 0; t < TOK; ++t) part[(ks * TOK + t) * E + e] = acc[t];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int t = warp; t < ntok; t += THREADS / 32) {
+    float p[PER];
+    float mx = -INFINITY;
 #pragma unroll
     for (int j = 0; j < PER; ++j) {
-      const int e = j * 32 + lane;
-      if (e < E && (p[j] > bv || (p[j] == bv && e < bi))) { bv = p[j]; bi = e; }
-    }
+      const int ee = j * 32 + lane;
+      float v = -INFINITY;
+      if (ee < E) {
+        v = 0.f;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        for (int q = 0; q < KS; ++q) v += part[(q * TOK + t) * E + ee];
+      }
+      p[j] = v;
+      mx = fmaxf(mx, v);
     }
-    if (lane == 0) {
-      topk_idx[row * topk + t] = bi;
-      topk_w[row * topk + t] = bv;
-      atomicAdd(&counts[bi], 1);
-    }
+    mx = warp_max(mx);
+    float sum = 0.f;
 #pragma unroll
-    for (int j = 0; j < PER; ++j) if (j * 32 + lane == bi) p[j] = -2.f;
+    for (int j = 0; j < PER; ++j) {
+      p[j] = (j * 32 + lane < E) ? expf(p[j] - mx) : 0.f;
+      sum += p[j];
+    }
+    sum = warp_sum(sum);
+#pragma unroll
+    for (int j = 0; j < PER; ++j) p[j] = (j * 32 + lane < E) ? p[j] / sum : -1.f;
+    const long long row = row0 + t;
+    for (int k = 0; k < topk; ++k) {
+      float bv = -1.f; int bi = 1 << 30;
+#pragma unroll
+      for (int j = 0; j < PER; ++j) {
+        const int ee = j * 32 + lane;
+        if (ee < E && (p[j] > bv || (p[j] == bv && ee < bi))) { bv = p[j]; bi = ee; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+      if (lane == 0) {
+        topk_idx[row * topk + k] = bi;
+        topk_w[row * topk + k] = bv;
+        atomicAdd(&counts[bi], 1);
+      }
+#pragma unroll
+      for (int j = 0; j < PER; ++j) if (j * 32 + lane == bi) p[j] = -2.f;
+    }
   }
 }
 
@@ -350,7 +470,7 @@ __global__ void moe_dispatch_kernel(const int* __restrict__ topk_idx, const int*
 // Combine (block.rs:1363-1381): x[token] += sum_k w_k * y[perm_pos[token,k]] in slot order (deterministic).
 __global__ void moe_combine_kernel(const float* __restrict__ y, const int* __restrict__ perm_pos,
                                    const float* __restrict__ topk_w, float* __restrict__ x, long long rows, int topk,
-                                   int H) {
+                                   int H, const float* __restrict__ partials, int n_splits, long long split_stride) {
   const int h4 = H / 4;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * h4) return;
@@ -363,8 +483,35 @@ __global__ void moe_combine_kernel(const float* __restrict__ y, const int* __res
     acc.x += w * v.x; acc.y += w * v.y; acc.z += w * v.z; acc.w += w * v.w;
   }
   float4 o = reinterpret_cast<float4*>(x)[idx];
+  for (int sidx = 0; sidx < n_splits; ++sidx) {  // split-K partials of the shared-experts down projection
+    const float4 pv = reinterpret_cast<const float4*>(partials + sidx * split_stride)[idx];
+    o.x += pv.x; o.y += pv.y; o.z += pv.z; o.w += pv.w;
+  }
   o.x += acc.x; o.y += acc.y; o.z += acc.z; o.w += acc.w;
   reinterpret_cast<float4*>(x)[idx] = o;
+}
+
+// SwiGLU over split-K partials of a fused gate/up projection: g = sum_s part[s][0], u = sum_s part[s][1],
+// out = silu(g) * u as hi/lo 16-bit.  part layout: [n_splits][2][rows][N] (dual_stride = rows*N).
+template <typename T>
+__global__ void swiglu_reduce_kernel(const float* __restrict__ part, int n_splits, long long split_stride,
+                                     long long dual_stride, T* __restrict__ out16, long long lo_off_elems,
+                                     long long n4) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 g = make_float4(0, 0, 0, 0), u = make_float4(0, 0, 0, 0);
+  for (int sidx = 0; sidx < n_splits; ++sidx) {
+    const float4 a = reinterpret_cast<const float4*>(part + sidx * split_stride)[i];
+    const float4 b = reinterpret_cast<const float4*>(part + sidx * split_stride + dual_stride)[i];
+    g.x += a.x; g.y += a.y; g.z += a.z; g.w += a.w;
+    u.x += b.x; u.y += b.y; u.z += b.z; u.w += b.w;
+  }
+  float o[4] = {g.x / (1.f + __expf(-g.x)) * u.x, g.y / (1.f + __expf(-g.y)) * u.y, g.z / (1.f + __expf(-g.z)) * u.z,
+                g.w / (1.f + __expf(-g.w)) * u.w};
+  uint2 hi, lo;
+  split4<T>(o, hi, lo);
+  reinterpret_cast<uint2*>(out16)[i] = hi;
+  reinterpret_cast<uint2*>(out16 + lo_off_elems)[i] = lo;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -375,9 +522,10 @@ __global__ void moe_combine_kernel(const float* __restrict__ y, const int* __res
 __global__ void __launch_bounds__(1024)
 select_token_kernel(const float* __restrict__ logits, int V, int* __restrict__ hist, int hist_stride,
                     int* __restrict__ hist_len, int* __restrict__ gen_count, int* __restrict__ finished, int ngram,
-                    int eos, int max_new, const int* __restrict__ forced, int forced_stride, int step,
+                    int eos, int max_new, const int* __restrict__ forced, int forced_stride,
                     int* __restrict__ selected_out, int selected_stride) {
   const int page = blockIdx.x;
+  const int step = gen_count[page];  // tokens accepted so far == index of this selection (graph-replay safe)
   __shared__ int s_ban[64];
   __shared__ int s_nban;
   __shared__ float s_val[32];
@@ -474,28 +622,57 @@ void embed_gather(const int* src, const void* table, const float* img_rows, floa
   DISPATCH_T(dt, (embed_gather_kernel<T><<<blocks_for(rows * (H / 4), 256), 256, 0, s>>>(src, (const T*)table, img_rows, out, rows, H)));
   launch_check("embed_gather");
 }
-void rmsnorm_split(const float* x, const float* w, void* out16, long long lo_off_elems, float* out32,
-                   const int* row_idx, long long rows, int H, float eps, DType dt, cudaStream_t s) {
-  DISPATCH_T(dt, (rmsnorm_kernel<T><<<blocks_for(rows, 8), 256, 0, s>>>(x, w, (T*)out16, lo_off_elems, out32, row_idx, rows, H, eps)));
+void rmsnorm_split(float* x, const float* w, void* out16, long long lo_off_elems, float* out32,
+                   const int* row_idx, long long rows, int H, float eps, const float* partials, int n_splits,
+                   long long split_stride, DType dt, cudaStream_t s) {
+  if (rows <= 256 && H <= 1536 && n_splits <= 16) {
+    DISPATCH_T(dt, (rmsnorm_row_kernel<T, 16><<<(unsigned)rows, 128, 0, s>>>(x, w, (T*)out16, lo_off_elems, out32, row_idx, H, eps, partials, n_splits, split_stride)));
+  } else {
+    DISPATCH_T(dt, (rmsnorm_kernel<T><<<blocks_for(rows, 8), 256, 0, s>>>(x, w, (T*)out16, lo_off_elems, out32, row_idx, rows, H, eps, partials, n_splits, split_stride)));
+  }
   launch_check("rmsnorm");
 }
 void rope_kv(const float* qkv, const float* cos_t, const float* sin_t, const int* row_page, const int* row_pos,
-             float* q_out, float* kc, float* vc, long long rows, int heads, int smax, cudaStream_t s) {
-  rope_kv_kernel<<<blocks_for(rows * heads * 16, 256), 256, 0, s>>>(qkv, cos_t, sin_t, row_page, row_pos, q_out, kc, vc, rows, heads, smax);
+             float* q_out, void* kc, void* vc, bool kv_f16, long long rows, int heads, int smax, int n_splits,
+             long long split_stride, cudaStream_t s) {
+  const int ns = n_splits < 1 ? 1 : n_splits;
+  if (kv_f16) rope_kv_kernel<__half><<<blocks_for(rows * heads * 16, 128), 128, 0, s>>>(qkv, cos_t, sin_t, row_page, row_pos, q_out, (__half*)kc, (__half*)vc, rows, heads, smax, ns, split_stride);
+  else rope_kv_kernel<float><<<blocks_for(rows * heads * 16, 128), 128, 0, s>>>(qkv, cos_t, sin_t, row_page, row_pos, q_out, (float*)kc, (float*)vc, rows, heads, smax, ns, split_stride);
   launch_check("rope_kv");
 }
-void kv_attention(const float* q, const float* kc, const float* vc, const int* row_page, const int* row_pos, void* ctx,
-                  long long lo_off_elems, long long rows, int heads, int smax, float scale, DType dt, cudaStream_t s) {
+void kv_attention(const float* q, const void* kc, const void* vc, bool kv_f16, const int* row_page, const int* row_pos,
+                  void* ctx, long long lo_off_elems, long long rows, int heads, int smax, float scale, DType dt,
+                  cudaStream_t s) {
   dim3 grid((unsigned)rows, heads);
-  DISPATCH_T(dt, (kv_attention_kernel<T><<<grid, 128, 0, s>>>(q, kc, vc, row_page, row_pos, (T*)ctx, lo_off_elems, heads, smax, scale)));
+  if (kv_f16) {
+    DISPATCH_T(dt, (kv_attention_kernel<T, __half><<<grid, 128, 0, s>>>(q, (const __half*)kc, (const __half*)vc, row_page, row_pos, (T*)ctx, lo_off_elems, heads, smax, scale)));
+  } else {
+    DISPATCH_T(dt, (kv_attention_kernel<T, float><<<grid, 128, 0, s>>>(q, (const float*)kc, (const float*)vc, row_page, row_pos, (T*)ctx, lo_off_elems, heads, smax, scale)));
+  }
   launch_check("kv_attention");
+}
+template <int E>
+static void launch_router(const float* x, const float* wgt, int* topk_idx, float* topk_w, int* counts, long long rows,
+                          int H, int topk, cudaStream_t s) {
+  if (rows <= 512) {  // decode: one token per block, 1024 threads = 1024/E k-slices for latency hiding
+    const size_t smem = (size_t)(1 * H + 1024 * 1) * 4;
+    router_kernel<E, 1, 1024><<<(unsigned)rows, 1024, smem, s>>>(x, wgt, topk_idx, topk_w, counts, rows, H, topk);
+  } else {            // prefill: 8 tokens per block reuse every gate-weight load 8x
+    const size_t smem = (size_t)(8 * H + 256 * 8) * 4;
+    static bool configured = false;
+    if (!configured) {
+      cuda_check(cudaFuncSetAttribute(router_kernel<E, 8, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024), "router smem");
+      configured = true;
+    }
+    router_kernel<E, 8, 256><<<(unsigned)((rows + 7) / 8), 256, smem, s>>>(x, wgt, topk_idx, topk_w, counts, rows, H, topk);
+  }
 }
 void moe_router(const float* x, const float* wgt, int* topk_idx, float* topk_w, int* counts, long long rows, int H,
                 int E, int topk, cudaStream_t s) {
-  const int blocks = blocks_for(rows, 4);
-  if (E == 64) router_kernel<64><<<blocks, 128, 0, s>>>(x, wgt, topk_idx, topk_w, counts, rows, H, topk);
-  else if (E == 16) router_kernel<16><<<blocks, 128, 0, s>>>(x, wgt, topk_idx, topk_w, counts, rows, H, topk);
-  else if (E == 32) router_kernel<32><<<blocks, 128, 0, s>>>(x, wgt, topk_idx, topk_w, counts, rows, H, topk);
+  if (H % 256) throw std::runtime_error("router: hidden size must be a multiple of 256");
+  if (E == 64) launch_router<64>(x, wgt, topk_idx, topk_w, counts, rows, H, topk, s);
+  else if (E == 16) launch_router<16>(x, wgt, topk_idx, topk_w, counts, rows, H, topk, s);
+  else if (E == 32) launch_router<32>(x, wgt, topk_idx, topk_w, counts, rows, H, topk, s);
   else throw std::runtime_error("router: unsupported expert count " + std::to_string(E));
   launch_check("moe_router");
 }
@@ -511,15 +688,20 @@ void moe_dispatch(const int* topk_idx, const int* offsets, int* cursor, const vo
   launch_check("moe_dispatch");
 }
 void moe_combine(const float* y, const int* perm_pos, const float* topk_w, float* x, long long rows, int topk, int H,
-                 cudaStream_t s) {
-  moe_combine_kernel<<<blocks_for(rows * (H / 4), 256), 256, 0, s>>>(y, perm_pos, topk_w, x, rows, topk, H);
+                 const float* partials, int n_splits, long long split_stride, cudaStream_t s) {
+  moe_combine_kernel<<<blocks_for(rows * (H / 4), 128), 128, 0, s>>>(y, perm_pos, topk_w, x, rows, topk, H, partials, partials ? n_splits : 0, split_stride);
   launch_check("moe_combine");
 }
+void swiglu_reduce(const float* part, int n_splits, long long split_stride, long long dual_stride, void* out16,
+                   long long lo_off_elems, long long n, DType dt, cudaStream_t s) {
+  DISPATCH_T(dt, (swiglu_reduce_kernel<T><<<blocks_for(n / 4, 128), 128, 0, s>>>(part, n_splits, split_stride, dual_stride, (T*)out16, lo_off_elems, n / 4)));
+  launch_check("swiglu_reduce");
+}
 void select_token(const float* logits, int V, int* hist, int hist_stride, int* hist_len, int* gen_count, int* finished,
-                  int n_pages, int ngram, int eos, int max_new, const int* forced, int forced_stride, int step,
+                  int n_pages, int ngram, int eos, int max_new, const int* forced, int forced_stride,
                   int* selected_out, int selected_stride, cudaStream_t s) {
   select_token_kernel<<<n_pages, 1024, 0, s>>>(logits, V, hist, hist_stride, hist_len, gen_count, finished, ngram, eos,
-                                               max_new, forced, forced_stride, step, selected_out, selected_stride);
+                                               max_new, forced, forced_stride, selected_out, selected_stride);
   launch_check("select_token");
 }
 void decode_rows(const int* hist, int hist_stride, const int* hist_len, int* src, int* row_pos, int n_pages,

@@ -3,6 +3,7 @@
 #include "kernels.h"
 #include "tmap.h"
 
+#include <algorithm>
 #include <stdexcept>
 #include <string>
 
@@ -22,7 +23,7 @@ void launch_inst(const LinearCall& c, const lin::Params& p, const CUtensorMap& w
     configured = true;
   }
   kern<<<grid, lin::kThreads, C::kSmemBytes, stream>>>(w0, w1, x, p);
-  launch_check("linear launch");
+  launch_check(c.tag ? c.tag : "linear");
 }
 
 template <typename T, int NA, int NB>
@@ -58,6 +59,16 @@ int linear_pick_bn(long long m, bool dual) {
   return 256;
 }
 
+int linear_plan_splits(long long M, int N, int K, int num_sms) {
+  if (M > 256) return 1;
+  const int base = (N + lin::BM - 1) / lin::BM;
+  const int num_kb = K / lin::BK;
+  const int s = std::min(num_kb / 2, num_sms / base);
+  if (s < 2) return 1;
+  const int kb_per = (num_kb + s - 1) / s;
+  return (num_kb + kb_per - 1) / kb_per;  // no empty splits
+}
+
 void linear(const LinearCall& c, DType dt, int num_sms, cudaStream_t stream) {
   if (c.K % lin::BK != 0) throw std::runtime_error("linear: K must be a multiple of 64, got " + std::to_string(c.K));
   if (c.M <= 0 && !c.tiles) return;
@@ -76,6 +87,16 @@ void linear(const LinearCall& c, DType dt, int num_sms, cudaStream_t stream) {
   p.out_batch_stride = c.out_batch_stride;
   if (c.tiles) p.num_tiles = c.max_tiles;
   else p.num_tiles = p.n_w_blocks * (int)((c.M + bn - 1) / bn) * p.nbatch;
+  p.k_splits = 1; p.kb_per_split = c.K / lin::BK; p.split_stride = c.split_stride; p.dual_stride = c.dual_stride;
+  if (c.k_splits > 1) {
+    if (c.tiles) throw std::runtime_error("linear: split-K is not supported for grouped problems");
+    if (c.out_mode != lin::OUT_F32 && c.out_mode != lin::OUT_F32_DUAL) throw std::runtime_error("linear: split-K needs f32 partial outputs");
+    const int num_kb = c.K / lin::BK;
+    p.kb_per_split = (num_kb + c.k_splits - 1) / c.k_splits;
+    p.k_splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;  // no empty splits
+    if (p.k_splits != c.k_splits) throw std::runtime_error("linear: k_splits must divide the k-blocks without empty splits");
+    p.num_tiles *= p.k_splits;
+  }
   if (p.num_tiles <= 0) return;
 
   const long long w_rows = c.w_rows ? c.w_rows : c.N;

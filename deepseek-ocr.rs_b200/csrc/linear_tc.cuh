@@ -27,6 +27,7 @@ enum Out : int {
   OUT_T_SPLIT = 1,  // 16-bit hi + lo stores (out, out_lo)
   OUT_F32 = 2,      // f32 store
   OUT_F32_ADD = 3,  // f32 read-modify-write (residual add); each element has exactly one writer
+  OUT_F32_DUAL = 4, // NA == 2 without the SwiGLU: raw f32 accumulators, acc1 at out + dual_stride (split-K partials)
 };
 
 struct Tile {  // grouped problems: one entry per (group, token-chunk, weight-block)
@@ -53,6 +54,12 @@ struct Params {
   int n_w_blocks;          // ceil(N / 128) for the dense tile decode
   int nbatch;              // > 1: X is a 3-D map [rows, nbatch, K]; tiles enumerate (batch, m, w)
   long long out_batch_stride;  // elements added to the output offset per batch
+  // split-K (deterministic): tile t -> (split, m, w); split s reduces k-blocks [s*kb_per_split, ...) and stores
+  // its f32 partial at out + s*split_stride; the consumer kernel sums the partials in a fixed order.
+  int k_splits;
+  int kb_per_split;
+  long long split_stride;
+  long long dual_stride;
 };
 
 constexpr int BM = 128;  // weight rows per tile (UMMA M)
@@ -74,7 +81,19 @@ struct Cfg {
   static_assert(BN % 32 == 0 && BN <= 256, "BN");
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// gelu(x) = 0.5 x (1 + erf(x / sqrt 2)).  erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the
+// 16-bit output rounding): 1 rcp + 1 ex2 + 7 FMA, branch-free.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float e = exp2f(-z * z * 1.4426950408889634f);
+  const float erf_abs = 1.0f - poly * t * e;
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
 __device__ __forceinline__ float quick_gelu(float x) { return x / (1.0f + __expf(-1.702f * x)); }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 
@@ -118,8 +137,10 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
 
   const int tiles_per_batch = p.n_w_blocks * ((p.M + BN - 1) / BN);
-  auto decode_tile = [&](int t, int& w_row0, int& x_row0, int& rows, int& n0, int& batch) {
-    batch = 0;
+  const int base_tiles = tiles_per_batch * p.nbatch;
+  auto decode_tile = [&](int t, int& w_row0, int& x_row0, int& rows, int& n0, int& batch, int& split) {
+    batch = 0; split = 0;
+    if (p.k_splits > 1) { split = t / base_tiles; t -= split * base_tiles; }
     if (p.tiles) {
       const Tile tl = p.tiles[t];
       w_row0 = tl.w_row0; x_row0 = tl.x_row0; rows = tl.rows; n0 = tl.n0;
@@ -137,9 +158,10 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_constant__
     if (ptx::elect_one()) {
       int stage = 0; uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        int w_row0, x_row0, rows, n0, batch;
-        decode_tile(t, w_row0, x_row0, rows, n0, batch);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        int w_row0, x_row0, rows, n0, batch, split;
+        decode_tile(t, w_row0, x_row0, rows, n0, batch, split);
+        const int kb0 = split * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* st = smem + stage * C::kStageBytes;
           ptx::mbar_expect_tx(&full[stage], C::kStageBytes);
@@ -168,7 +190,12 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_constant__
         ptx::mbar_wait(&tempty[buf], bphase ^ 1);
         ptx::tc_fence_after();
         const uint32_t d0 = tmem_base + buf * C::kAccCols;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        int kb0 = 0, kb1 = num_kb;
+        if (p.k_splits > 1) {
+          const int split = t / base_tiles;
+          kb0 = split * p.kb_per_split; kb1 = min(num_kb, kb0 + p.kb_per_split);
+        }
+        for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&full[stage], phase);
           ptx::tc_fence_after();
           const uint32_t sa = ptx::smem_u32(smem + stage * C::kStageBytes);
@@ -181,7 +208,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_constant__
 #pragma unroll
               for (int b = 0; b < NB; ++b) {
                 const uint64_t bd = ptx::smem_desc_sw128(sb + b * C::kBBytes + k * 32, 16, 1024);
-                ptx::mma_f16_ss(d0 + a * BN, ad, bd, idesc, (kb | k | b) ? 1u : 0u);
+                ptx::mma_f16_ss(d0 + a * BN, ad, bd, idesc, ((kb - kb0) | k | b) ? 1u : 0u);
               }
             }
           }
@@ -200,15 +227,15 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_constant__
     constexpr int kChunksPerHalf = (kChunks + 1) / 2;
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-      int w_row0, x_row0, rows, n0, batch;
-      decode_tile(t, w_row0, x_row0, rows, n0, batch);
+      int w_row0, x_row0, rows, n0, batch, split;
+      decode_tile(t, w_row0, x_row0, rows, n0, batch, split);
       const int buf = it & 1;
       const uint32_t bphase = (it >> 1) & 1;
       ptx::mbar_wait(&tfull[buf], bphase);
       ptx::tc_fence_after();
       const int n = n0 + quarter * 32 + lane;  // output feature owned by this thread
       const bool n_ok = n < p.N;
-      const float bias = (p.bias && n_ok) ? p.bias[n] : 0.f;
+      const float bias = (p.bias && n_ok && split == 0) ? p.bias[n] : 0.f;
       const uint32_t trow = tmem_base + buf * C::kAccCols + ((uint32_t)(quarter * 32) << 16);
       for (int c = half * kChunksPerHalf; c < min(kChunks, (half + 1) * kChunksPerHalf); ++c) {
         if (c * 32 >= rows) break;  // warp-uniform
@@ -216,36 +243,74 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_constant__
         ptx::tmem_ld_32x32(trow + c * 32, v);
         uint32_t u[32];
         if (NA == 2) ptx::tmem_ld_32x32(trow + BN + c * 32, u);
+        // output row of token j of this chunk: lane j fetches it once, broadcast below
+        long long my_orow = x_row0 + c * 32 + lane;
+        if (p.row_map) my_orow = (c * 32 + lane < rows) ? p.row_map[my_orow] : -1;
         ptx::tmem_ld_wait();
+        float r[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const int m = c * 32 + j;
-          if (m >= rows || !n_ok) continue;
-          float r = __uint_as_float(v[j]) + bias;
-          if (NA == 2) {
-            r = silu(r) * __uint_as_float(u[j]);
+          float t = __uint_as_float(v[j]) + bias;
+          if (NA == 2 && p.out_mode == OUT_F32_DUAL) {
+            // raw partial accumulators; acc1 is stored below
+          } else if (NA == 2) {
+            t = silu(t) * __uint_as_float(u[j]);
           } else if (p.act == ACT_GELU_ERF) {
-            r = gelu_erf(r);
+            t = gelu_erf(t);
           } else if (p.act == ACT_QUICK_GELU) {
-            r = quick_gelu(r);
+            t = quick_gelu(t);
           }
-          long long orow = x_row0 + m;
-          if (p.row_map) {
-            const int mapped = p.row_map[orow];
-            if (mapped < 0) continue;
-            orow = mapped;
+          r[j] = t;
+        }
+        const int nvalid = min(32, rows - c * 32);
+        const long long col = n + (long long)batch * p.out_batch_stride + (long long)split * p.split_stride;
+        if (p.row_map) {
+          // remapped rows (SAM window un-partition): only the residual-add mode uses this path
+          float old[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const long long orow = __shfl_sync(0xffffffffu, my_orow, j);
+            old[j] = (j < nvalid && n_ok && orow >= 0) ? reinterpret_cast<const float*>(p.out)[orow * p.ldo + col] : 0.f;
           }
-          const long long o = orow * p.ldo + n + batch * p.out_batch_stride;
-          if (p.out_mode == OUT_T) {
-            reinterpret_cast<T*>(p.out)[o] = Elem<T>::from(r);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const long long orow = __shfl_sync(0xffffffffu, my_orow, j);
+            if (j < nvalid && n_ok && orow >= 0) reinterpret_cast<float*>(p.out)[orow * p.ldo + col] = old[j] + r[j];
+          }
+        } else if (n_ok) {
+          const long long base = (long long)(x_row0 + c * 32) * p.ldo + col;
+          if (p.out_mode == OUT_F32_ADD) {
+            // read-modify-write: issue all loads first so their latencies overlap
+            float* ptr = reinterpret_cast<float*>(p.out) + base;
+            float old[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) old[j] = j < nvalid ? ptr[j * p.ldo] : 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < nvalid) ptr[j * p.ldo] = old[j] + r[j];
+          } else if (p.out_mode == OUT_T) {
+            T* ptr = reinterpret_cast<T*>(p.out) + base;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < nvalid) ptr[j * p.ldo] = Elem<T>::from(r[j]);
           } else if (p.out_mode == OUT_T_SPLIT) {
-            const T hi = Elem<T>::from(r);
-            reinterpret_cast<T*>(p.out)[o] = hi;
-            reinterpret_cast<T*>(p.out_lo)[o] = Elem<T>::from(r - Elem<T>::to(hi));
-          } else if (p.out_mode == OUT_F32) {
-            reinterpret_cast<float*>(p.out)[o] = r;
+            T* ptr = reinterpret_cast<T*>(p.out) + base;
+            T* ptr_lo = reinterpret_cast<T*>(p.out_lo) + base;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (j < nvalid) {
+                const T hi = Elem<T>::from(r[j]);
+                ptr[j * p.ldo] = hi;
+                ptr_lo[j * p.ldo] = Elem<T>::from(r[j] - Elem<T>::to(hi));
+              }
+            }
           } else {
-            reinterpret_cast<float*>(p.out)[o] += r;
+            float* ptr = reinterpret_cast<float*>(p.out) + base;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (j < nvalid) {
+                ptr[j * p.ldo] = r[j];
+                if (NA == 2 && p.out_mode == OUT_F32_DUAL) ptr[j * p.ldo + p.dual_stride] = __uint_as_float(u[j]);
+              }
+            }
           }
         }
       }

@@ -233,6 +233,44 @@ class OcrEngine:
         return [DecodeOutcome(n_prompt[i], n_out[i], outs[i][: n_out[i]].tolist()) for i in range(n)]
 
 
+    # -- staged variant (device-resident pages) ---------------------------------------------------
+    def stage_pages(self, pages_rgb: Sequence[np.ndarray], vs: VisionSettings):
+        n = len(pages_rgb)
+        imgs = [np.ascontiguousarray(p, dtype=np.uint8) for p in pages_rgb]
+        ws = (C.c_int * n)(*[p.shape[1] for p in imgs])
+        hs = (C.c_int * n)(*[p.shape[0] for p in imgs])
+        check(self._lib.dsocr_stage_pages(self._h, n, _ptr_array(imgs, C.c_uint8), ws, hs, vs.c()), "stage_pages")
+        self._staged_n = n
+
+    def decode_staged(self, seg0: Sequence[int], seg1: Sequence[int], image_token_id: int, params: DecodeParameters
+                      ) -> List[DecodeOutcome]:
+        n = self._staged_n
+        s0 = np.asarray(seg0, dtype=np.int64)
+        s1 = np.asarray(seg1, dtype=np.int64)
+        outs = [np.zeros(max(1, params.max_new_tokens), dtype=np.int64) for _ in range(n)]
+        n_out = (C.c_int * n)()
+        n_prompt = (C.c_int * n)()
+        p = params.c()
+        i64 = C.POINTER(C.c_int64)
+        check(self._lib.dsocr_decode_staged(self._h, s0.ctypes.data_as(i64), len(s0), s1.ctypes.data_as(i64), len(s1),
+                                            C.c_int64(image_token_id), C.byref(p), C.cast(None, TOKEN_CB), None,
+                                            _ptr_array(outs, C.c_int64), n_out, n_prompt), "decode_staged")
+        return [DecodeOutcome(n_prompt[i], n_out[i], outs[i][: n_out[i]].tolist()) for i in range(n)]
+
+    def set_stream(self, cuda_stream: int):
+        check(self._lib.dsocr_engine_set_stream(self._h, C.c_void_p(cuda_stream)), "set_stream")
+
+    def kernel_timing_begin(self):
+        check(self._lib.dsocr_kernel_timing_begin(self._h), "kernel_timing_begin")
+
+    def kernel_timing_end(self) -> list:
+        import json
+
+        buf = C.create_string_buffer(1 << 16)
+        check(self._lib.dsocr_kernel_timing_end(self._h, buf, len(buf)), "kernel_timing_end")
+        return json.loads(buf.value.decode())
+
+
 def load_model(config_path: str, weights_path: str, snapshot_path: Optional[str] = None, device: int = 0,
                dtype: str = "bf16") -> OcrEngine:
     """`load_model(ModelLoadArgs)` (model/mod.rs:90-115)."""

@@ -89,7 +89,9 @@ DSOCR_API int dsocr_engine_create(const char* config_json_path, const char* safe
                                   int device_ordinal, int dtype, dsocr_engine** out);
 DSOCR_API void dsocr_engine_destroy(dsocr_engine* e);
 DSOCR_API int dsocr_engine_info_get(const dsocr_engine* e, dsocr_engine_info* info);
-/* Engine options: "record_taps" (0/1) keeps host copies of the debug-trace taps of the next vision call. */
+/* Engine options: "record_taps" (0/1) keeps host copies of the debug-trace taps of the next vision call;
+ * "kv_cache_f16" (0/1) stores the KV cache in f16 instead of the reference's f32 (model/mod.rs:82-88): half the
+ * decode-attention bytes, K/V rounded to 11 bits (off by default; parity numbers are quoted for both). */
 DSOCR_API int dsocr_engine_set_option(dsocr_engine* e, const char* name, int value);
 
 /* image_token_count: rows `compute_image_embeddings` will produce == placeholders
@@ -152,6 +154,24 @@ DSOCR_API int dsocr_decode_pages(dsocr_engine* e, int n_pages, const uint8_t* co
                                  const int64_t* seg1, int n_seg1, int64_t image_token_id,
                                  const dsocr_decode_params* params, dsocr_token_cb cb, void* user,
                                  int64_t* const* out_tokens, int* n_out, int* prompt_tokens);
+
+/* The two halves of dsocr_decode_pages, for callers that keep pages resident on the device:
+ * dsocr_stage_pages = host integer preprocessing + host->device copy of the RGB8 views (engine-owned);
+ * dsocr_decode_staged = vision + prompt build + generate on the staged views (no image H2D traffic). */
+DSOCR_API int dsocr_stage_pages(dsocr_engine* e, int n_pages, const uint8_t* const* rgb, const int* widths,
+                                const int* heights, dsocr_vision_settings vs);
+DSOCR_API int dsocr_decode_staged(dsocr_engine* e, const int64_t* seg0, int n_seg0, const int64_t* seg1, int n_seg1,
+                                  int64_t image_token_id, const dsocr_decode_params* params, dsocr_token_cb cb,
+                                  void* user, int64_t* const* out_tokens, int* n_out, int* prompt_tokens);
+
+/* Run all engine work on a caller-owned CUDA stream (cudaStream_t passed as void*), e.g. torch's current
+ * stream, so that the caller's CUDA events bracket the engine's kernels. */
+DSOCR_API int dsocr_engine_set_stream(dsocr_engine* e, void* cuda_stream);
+
+/* Per-kernel device timing (CUDA events after every launch while enabled).  dsocr_kernel_timing_end writes a
+ * JSON array [{"name": "decode/lm_head", "launches": n, "ms": t}, ...] into json_out. */
+DSOCR_API int dsocr_kernel_timing_begin(dsocr_engine* e);
+DSOCR_API int dsocr_kernel_timing_end(dsocr_engine* e, char* json_out, size_t capacity);
 
 /* Stage timings of the most recent dsocr_decode_pages / vision / generate call, in milliseconds, under the
  * reference's Timer names (crates/core/src/benchmark.rs):

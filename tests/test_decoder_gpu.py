@@ -118,3 +118,32 @@ def test_max_new_tokens_zero_and_mismatch_error(setup):
     assert eng.generate_batch(ids, masks, rows, DecodeParameters(0))[0] == []
     with pytest.raises(DsocrError, match="image embeddings provide"):
         eng.generate_batch(ids, masks, [rows[0][:3]], DecodeParameters(4))
+
+
+def test_kv_cache_f16_option(setup):
+    """Optional f16 KV cache (the reference stores f32): logits stay within 5e-3 of max|logit| and the
+    teacher-forced argmax agrees on >= 95 % of steps (BASELINE.json target)."""
+    from dsocr.engine import DecodeParameters
+
+    cfg, ck, eng, oracle = setup
+    ids, masks, rows = _prompts(cfg, [48, 17], seed=13)
+    steps = 24
+    g = torch.Generator().manual_seed(2)
+    forced = [torch.randint(2, cfg.vocab_size - 2, (steps,), generator=g).tolist() for _ in ids]
+    params = DecodeParameters(max_new_tokens=steps, no_repeat_ngram_size=20, eos_token_id=None)
+    eng.set_option("kv_cache_f16", 1)
+    try:
+        sel, logits = eng.generate_forced(ids, masks, rows, params, forced, want_logits=True)
+    finally:
+        eng.set_option("kv_cache_f16", 0)
+    for p in range(len(ids)):
+        ref_logits = []
+        ref_sel = oracle.generate(ids[p], masks[p], torch.from_numpy(rows[p]), steps, 20, None, forced=forced[p],
+                                  logits_out=ref_logits)
+        ref = torch.stack(ref_logits)
+        got = torch.from_numpy(logits[p])
+        err, scale, c = report(f"f16-KV teacher-forced logits page {p}", got, ref)
+        agree = sum(int(a == b) for a, b in zip(sel[p], ref_sel)) / steps
+        print(f"[parity] f16-KV argmax agreement page {p}: {agree:.3f}")
+        assert err <= 5e-3 * scale
+        assert agree >= 0.95
