@@ -1,0 +1,84 @@
+"""CPU-side checks of the C-ABI library: it loads, exports every symbol the headers declare, its host-only entry
+points (integer preprocessing) are bit-exact with the oracle, and it refuses to run without a GPU (no CPU fallback)."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import preprocess as P
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as ge
+    from dsocr.binding import LIB_PATH, lib as load
+
+    if not LIB_PATH.exists():
+        ge.build()
+    return load()
+
+
+def _declared_symbols():
+    names = []
+    for hdr in sorted((ROOT / "include").glob("*.h")):
+        text = hdr.read_text()
+        names += re.findall(r"DSOCR_API\s+[\w\s\*]+?\b(dsocr_\w+)\s*\(", text)
+    return sorted(set(names))
+
+
+def test_every_declared_symbol_is_exported(lib):
+    names = _declared_symbols()
+    assert len(names) >= 20
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_version_and_error_plumbing(lib):
+    assert b"sm_100a" in lib.dsocr_version()
+    lib.dsocr_last_error.restype = C.c_char_p
+    assert isinstance(lib.dsocr_last_error(), bytes)
+
+
+def test_image_token_count(lib):
+    assert lib.dsocr_image_token_count(1024, 640, 1, 2, 3) == 903
+    assert lib.dsocr_image_token_count(1024, 1024, 0, 1, 1) == 273
+    assert lib.dsocr_image_token_count(1024, 640, 1, 1, 1) == 273
+
+
+@pytest.mark.parametrize("w,h", [(1654, 2339), (700, 500), (333, 517), (2852, 1756), (640, 640), (100, 80), (1000, 3000)])
+def test_preprocess_bit_exact_with_oracle(lib, w, h):
+    """dsocr_preprocess == vision/resample.rs + vision/preprocess.rs + build_global_view restated by the oracle."""
+    from dsocr.engine import VisionSettingsC
+
+    rng = np.random.RandomState(w + h)
+    img = rng.randint(0, 256, (h, w, 3), dtype=np.uint8)
+    g = np.empty((1024, 1024, 3), np.uint8)
+    tiles = np.empty((9, 640, 640, 3), np.uint8)
+    n, cw, ch = C.c_int(), C.c_int(), C.c_int()
+    u8 = C.POINTER(C.c_uint8)
+    st = lib.dsocr_preprocess(img.ctypes.data_as(u8), w, h, VisionSettingsC(1024, 640, 1), g.ctypes.data_as(u8),
+                              tiles.ctypes.data_as(u8), C.byref(n), C.byref(cw), C.byref(ch))
+    assert st == 0
+    ref = P.prepare_vision_input(img, 1024, 640, True)
+    assert (cw.value, ch.value) == tuple(ref["crop_shape"]) and n.value == len(ref["tiles"])
+    assert np.array_equal(g, ref["global"])
+    for i, t in enumerate(ref["tiles"]):
+        assert np.array_equal(tiles[i], t)
+
+
+def test_engine_creation_fails_loudly_without_gpu(lib, tmp_path):
+    """No CPU fallback: on a box without an sm_100 device load_model must fail with a clear message."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    h = C.c_void_p()
+    st = lib.dsocr_engine_create(b"/nonexistent/config.json", b"/nonexistent/model.safetensors", None, 0, 2, C.byref(h))
+    assert st != 0 and not h.value
+    lib.dsocr_last_error.restype = C.c_char_p
+    msg = lib.dsocr_last_error().decode()
+    assert "load_model" in msg and ("CUDA" in msg or "cuda" in msg or "device" in msg), msg

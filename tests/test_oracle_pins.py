@@ -1,0 +1,177 @@
+"""Pin the CPU oracle against everything reproducible offline: the reference's own self-contained
+tests, Pillow, torch's antialiased interpolate, and vLLM's independent PyTorch statement of the SAM helpers."""
+import ast
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+from PIL import Image
+
+from oracle import decoder as D
+from oracle import preprocess as P
+from oracle import vision as V
+from oracle.config import tiny_config, random_checkpoint
+
+
+# --- integer preprocessing ---------------------------------------------------------------------
+@pytest.mark.parametrize("src,dst", [((517, 333), (200, 128)), ((1654, 2339), (724, 1024)), ((2852, 1756), (1024, 630)),
+                                     ((800, 600), (640, 480)), ((641, 1281), (640, 1280))])
+def test_resize_bicubic_bit_exact_with_pillow_on_downscale(src, dst):
+    """vision/resample.rs restates Pillow's fixed-point bicubic; bit-identical for downscales."""
+    rng = np.random.RandomState(src[0])
+    img = rng.randint(0, 256, (src[1], src[0], 3), dtype=np.uint8)
+    got = P.resize_bicubic(img, dst[0], dst[1])
+    ref = np.asarray(Image.fromarray(img).resize(dst, Image.BICUBIC))
+    assert np.array_equal(got, ref)
+
+
+def test_resize_bicubic_upscale_follows_resample_rs_not_pillow():
+    """round_half_towards_zero uses ceil(v+0.5) for negative v (resample.rs:18-24) -> differs from Pillow on upscales."""
+    rng = np.random.RandomState(0)
+    img = rng.randint(0, 256, (333, 517, 3), dtype=np.uint8)
+    got = P.resize_bicubic(img, 700, 500)
+    ref = np.asarray(Image.fromarray(img).resize((700, 500), Image.BICUBIC))
+    assert got.shape == ref.shape and not np.array_equal(got, ref)
+    assert np.abs(got.astype(int) - ref).max() <= 32
+
+
+def test_tile_grid_selection_and_token_counts():
+    assert P.select_tile_grid(1654, 2339, 640) == (2, 3)          # A4 portrait (903 image tokens)
+    assert P.select_tile_grid(2852, 1756, 640) == (3, 2)          # assets/sample_1.png
+    assert P.image_token_count(1024, 640, True, (2, 3)) == 903
+    assert P.image_token_count(1024, 1024, False, None) == 273     # Base-1024
+    assert P.image_token_count(1024, 640, True, (1, 1)) == 273     # small image: no local tokens
+    tiles, crop = P.dynamic_preprocess(np.zeros((600, 640, 3), np.uint8), 640)
+    assert tiles == [] and crop == (1, 1)                          # preprocess.rs:72-80
+
+
+def test_global_view_letterbox_matches_survey_probe():
+    """sample_1.png is 2852x1756 -> Base mode letterboxes to 1024x630 on the 127-grey canvas."""
+    img = np.full((1756, 2852, 3), 255, np.uint8)
+    g = P.build_global_view(img, 1024)
+    rows = np.where((g == 255).all(axis=(1, 2)))[0]
+    assert len(rows) == 630 and rows[0] == 197 and (g[0] == 127).all()
+
+
+def test_round_ties_to_even():
+    assert [P.round_ties_to_even(v) for v in (0.5, 1.5, 2.5, -0.5, -1.5, 2.4, 2.6)] == [0.0, 2.0, 2.0, -0.0, -2.0, 2.0, 3.0]
+
+
+# --- reference's own self-contained tests --------------------------------------------------------
+def test_window_partition_math_matches_reference_test():
+    """crates/infer-deepseek/tests/vision_sam.rs:70-81: 64x48 tokens, window 14 -> 70x56, 5x4 tiles."""
+    x = torch.zeros(1, 64, 48, 8)
+    win, (hp, wp) = V.window_partition(x, 14)
+    assert (hp, wp) == (70, 56) and win.shape[0] == 5 * 4 and win.shape[1:3] == (14, 14)
+    back = V.window_unpartition(win, 14, (hp, wp), (64, 48))
+    assert back.shape == x.shape
+
+
+def test_clip_position_embedding_257_to_101_tokens():
+    """crates/infer-deepseek/tests/vision_clip.rs:24-34."""
+    cfg = tiny_config()
+    ck = {k: v for k, v in random_checkpoint(tiny_config(clip_layers=0, sam_depth=0, num_layers=0), seed=1).items()}
+    clip = V.ClipOracle(cfg, ck)
+    pos = clip.adapt_pos(101)
+    assert pos.shape == (101, 1024)
+    assert torch.equal(pos[0], clip.p["embeddings.position_embedding.weight"][0])  # cls row kept
+    assert torch.equal(clip.adapt_pos(257), clip.p["embeddings.position_embedding.weight"])
+
+
+# --- independent implementations available offline -----------------------------------------------
+@pytest.mark.parametrize("src,dst", [(64, 40), (16, 10), (16, 24), (64, 32)])
+def test_aa_bicubic_matches_torch_interpolate(src, dst):
+    """vision/sam.rs:1000-1123 == F.interpolate(bicubic, antialias=True, align_corners=False) (2e-6)."""
+    g = torch.Generator().manual_seed(src * 100 + dst)
+    x = torch.randn(1, 8, src, src, generator=g)
+    got = V.bicubic_resize_antialiased(x, dst, dst)
+    ref = F.interpolate(x, size=(dst, dst), mode="bicubic", antialias=True, align_corners=False)
+    assert (got - ref).abs().max().item() < 5e-6
+
+
+_VLLM_DEEPENCODER = "/opt/prime-rl/.venv/lib/python3.12/site-packages/vllm/model_executor/models/deepencoder.py"
+
+
+def _vllm_functions(names):
+    src = open(_VLLM_DEEPENCODER).read()
+    tree = ast.parse(src)
+    ns = {"torch": torch, "F": F, "math": math, "nn": torch.nn}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in names:
+            exec(compile(ast.Module([node], []), _VLLM_DEEPENCODER, "exec"), ns)
+    return ns
+
+
+@pytest.mark.skipif(not os.path.exists(_VLLM_DEEPENCODER), reason="vLLM deepencoder.py not installed")
+@pytest.mark.parametrize("size,table_len", [(14, 27), (64, 127), (40, 127), (32, 127)])
+def test_rel_pos_matches_vllm_deepencoder(size, table_len):
+    """get_rel_pos / add_decomposed_rel_pos (vision/sam.rs:1124-1247) vs vLLM's PyTorch statement of SAM."""
+    ns = _vllm_functions({"get_rel_pos", "add_decomposed_rel_pos"})
+    g = torch.Generator().manual_seed(size)
+    rel_h = torch.randn(table_len, 64, generator=g)
+    rel_w = torch.randn(table_len, 64, generator=g)
+    q = torch.randn(3, size * size, 64, generator=g)
+    mine_h = V.get_rel_pos(size, size, rel_h)
+    ref_h = ns["get_rel_pos"](size, size, rel_h)
+    assert torch.allclose(mine_h, ref_h, atol=1e-6)
+    ref_bh, ref_bw = ns["add_decomposed_rel_pos"](q, rel_h, rel_w, (size, size), (size, size))
+    q5 = q.reshape(3, size, size, 64)
+    mine_bh = torch.einsum("bhwd,hkd->bhwk", q5, mine_h)
+    mine_bw = torch.einsum("bhwd,wkd->bhwk", q5, V.get_rel_pos(size, size, rel_w))
+    assert torch.allclose(mine_bh.reshape(ref_bh.shape[0], -1), ref_bh.reshape(ref_bh.shape[0], -1), atol=1e-4)
+    assert torch.allclose(mine_bw.reshape(ref_bw.shape[0], -1), ref_bw.reshape(ref_bw.shape[0], -1), atol=1e-4)
+
+
+@pytest.mark.skipif(not os.path.exists(_VLLM_DEEPENCODER), reason="vLLM deepencoder.py not installed")
+def test_window_partition_matches_vllm_deepencoder():
+    ns = _vllm_functions({"window_partition", "window_unpartition"})
+    x = torch.randn(2, 40, 40, 16)
+    mine, pad = V.window_partition(x, 14)
+    ref, pad_ref = ns["window_partition"](x, 14)
+    assert pad == tuple(pad_ref) and torch.equal(mine, ref)
+    assert torch.equal(V.window_unpartition(mine, 14, pad, (40, 40)), ns["window_unpartition"](ref, 14, pad_ref, (40, 40)))
+
+
+# --- decoder-side semantics ------------------------------------------------------------------------
+def test_rope_matches_neox_rotate_half_and_is_norm_preserving():
+    cos, sin = D.rope_tables(10000.0, 128, torch.arange(5, 9))
+    assert cos.shape == (4, 128) and torch.equal(cos[:, :64], cos[:, 64:])
+    x = torch.randn(10, 4, 128)
+    y = D.apply_rope(x, cos, sin)
+    assert torch.allclose(x.norm(dim=-1), y.norm(dim=-1), atol=1e-4)
+    assert torch.allclose(D.apply_rope(x, *D.rope_tables(10000.0, 128, torch.zeros(4))), x)
+
+
+def test_banned_ngram_tokens_semantics():
+    """crates/core/src/sampling.rs:141-158."""
+    seq = [1, 2, 3, 9, 1, 2, 3, 7, 1, 2]
+    assert D.banned_ngram_tokens(seq, 3) == {3}
+    assert D.banned_ngram_tokens(seq + [3], 4) == {9, 7}
+    assert D.banned_ngram_tokens([1, 2], 20) == set()
+    assert D.banned_ngram_tokens(seq, 1) == set()
+
+
+def test_first_index_argmax_and_ban():
+    logits = torch.tensor([0.1, 3.0, 3.0, -1.0])
+    assert D.select_token_greedy(logits, [5], 20) == 1                     # torch.argmax tie-break: first index
+    assert D.select_token_greedy(logits, [0, 1, 0], 2) == 2                # token 1 banned (bigram 0,1 seen)
+
+
+def test_moe_router_tie_break_lowest_index():
+    cfg = tiny_config(num_layers=2, n_routed_experts=16)
+    ck = random_checkpoint(cfg, seed=3)
+    ck["model.layers.1.mlp.gate.weight"] = torch.zeros_like(ck["model.layers.1.mlp.gate.weight"])  # all scores tie
+    taps = {}
+    D.DecoderOracle(cfg, ck).moe(torch.randn(3, cfg.hidden_size), 1, taps)
+    assert taps["topk_idx"][0].tolist() == [list(range(cfg.num_experts_per_tok))] * 3
+
+
+def test_build_prompt_tokens_mismatch_message():
+    cfg = tiny_config()
+    with pytest.raises(AssertionError, match="prompt/image embedding mismatch"):
+        D.build_prompt_tokens([[1, 2]], [5], cfg)
+    ids, mask = D.build_prompt_tokens([[], [7, 8]], [3], cfg)
+    assert ids == [0, cfg.image_token_id, cfg.image_token_id, cfg.image_token_id, 7, 8] and mask == [0, 1, 1, 1, 0, 0]
