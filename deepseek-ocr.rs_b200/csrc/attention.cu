@@ -34,7 +34,7 @@ template <typename T>
 void dispatch(const VAttnCall& c, cudaStream_t stream) {
   switch (c.grid) {
     case 0: launch<T, 0, 0, 128, 2>(c, stream); break;
-    case 64: launch<T, 64, 2, 128, 1>(c, stream); break;
+    case 64: launch<T, 64, 2, 128, 2>(c, stream); break;
     case 40: launch<T, 40, 2, 80, 2>(c, stream); break;
     case 32: launch<T, 32, 4, 128, 2>(c, stream); break;
     case 16: launch<T, 16, 8, 128, 2>(c, stream); break;

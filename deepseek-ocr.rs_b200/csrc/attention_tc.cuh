@@ -11,9 +11,11 @@
 //   bias[q, k] = Zh[q, qh - kh + GW-1] + Zw[q, qw - kw + GW-1]
 // from registers (Z = q . rel_table^T is one small tensor-core GEMM per layer), runs the online softmax in
 // f32 and writes P (16-bit) into 128B-swizzled smem; O_blk = P V (V consumed as an MN-major operand, i.e.
-// untransposed) lands in TMEM and is folded into the f32 register accumulator.  The [S,S] matrix never
-// exists in memory.  Up to two CTAs are co-resident per SM so that one CTA's softmax (MUFU-bound)
-// overlaps the other's MMAs.
+// untransposed) accumulates in TMEM across key blocks.  The running maximum is updated lazily: O (TMEM) and
+// the row sum are rescaled only when a block's maximum exceeds the reference maximum by more than 2^8, so in
+// the steady state the softmax threads never touch O and never wait for the P.V product.  The [S,S] matrix
+// never exists in memory.  Two CTAs are co-resident per SM (<= 168 registers, 256 TMEM columns, ~112 KB smem
+// each) so that one CTA's softmax (MUFU-bound) overlaps the other's MMAs and TMA waits.
 #pragma once
 #include "ptx.cuh"
 
@@ -152,7 +154,7 @@ vattn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
         for (int kk = 0; kk < KV / 16; ++kk) {
           const uint64_t ad = ptx::smem_desc_sw128(sp + (kk >> 2) * (BQ * 128) + (kk & 3) * 32, 16, 1024);
           const uint64_t bd = ptx::smem_desc_sw128(sv + kk * 2048, KV * 128, 1024);
-          ptx::mma_f16_ss(tmem_o, ad, bd, idesc_pv, kk ? 1u : 0u);
+          ptx::mma_f16_ss(tmem_o, ad, bd, idesc_pv, (j | kk) ? 1u : 0u);
         }
         ptx::mma_commit(o_full);
         ptx::mma_commit(&kv_empty[s]);
@@ -181,12 +183,10 @@ vattn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
       for (int kw = 0; kw < GW; ++kw) relw[kw] = zw[-kw] * kLog2e;
     }
 
-    float m = -INFINITY, l = 0.f;
-    float acc[D];
-#pragma unroll
-    for (int d = 0; d < D; ++d) acc[d] = 0.f;
+    float m = -INFINITY, l = 0.f;  // m: reference maximum (log2 domain) all stored probabilities are relative to
     uint8_t* prow = smem + C::kOffP + r * 128;
     const int rsw = r & 7;
+    constexpr float kRescaleThreshold = 8.0f;  // p <= 2^8 stays well inside the f16 / bf16 / f32-accumulate range
 
     for (int j = 0; j < p.nblk; ++j) {
       float relh[HAS_BIAS ? RB : 1];
@@ -197,12 +197,15 @@ vattn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
           relh[rr] = kh < GW ? zrow[qh - kh + GW - 1] * kLog2e : 0.f;
         }
       }
-      const int kvalid = p.S - j * KV;  // keys with column index >= kvalid are padding
+      const int kvalid = p.S - j * KV;  // keys with column index >= kvalid are padding (last block only)
+      const bool tail = kvalid < KV;
       ptx::mbar_wait(s_full, j & 1);
       ptx::tc_fence_after();
 
-      // pass 1: row maximum of the biased, scaled scores (log2 domain)
-      float bmax = -INFINITY;
+      // pass 1: block maximum of t = S*scale*log2e + relw[kw] (+ relh[kh] added per grid row afterwards)
+      float gmax[HAS_BIAS ? RB : 1];
+#pragma unroll
+      for (int rr = 0; rr < (HAS_BIAS ? RB : 1); ++rr) gmax[rr] = -INFINITY;
 #pragma unroll
       for (int c0 = 0; c0 < KV; c0 += 16) {
         uint32_t v[16];
@@ -211,16 +214,43 @@ vattn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int c = c0 + i;
-          float t = __uint_as_float(v[i]) * p.scale_log2;
-          if (HAS_BIAS) t += relw[c % GWD] + relh[c / GWD];
-          if (c >= kvalid) t = -INFINITY;
-          bmax = fmaxf(bmax, t);
+          float t = HAS_BIAS ? fmaf(__uint_as_float(v[i]), p.scale_log2, relw[c % GWD]) : __uint_as_float(v[i]) * p.scale_log2;
+          if (tail && c >= kvalid) t = -INFINITY;
+          gmax[HAS_BIAS ? c / GWD : 0] = fmaxf(gmax[HAS_BIAS ? c / GWD : 0], t);
         }
       }
-      const float m_new = fmaxf(m, bmax);
-      const float alpha = exp2f(m - m_new);
+      float bmax = -INFINITY;
+#pragma unroll
+      for (int rr = 0; rr < (HAS_BIAS ? RB : 1); ++rr) bmax = fmaxf(bmax, gmax[rr] + (HAS_BIAS ? relh[rr] : 0.f));
+      // lazy rescale: move the reference maximum only when the block maximum exceeds it by > 2^8; O (TMEM)
+      // and l follow.  tcgen05.ld/st are warp-collective, so the TMEM part is taken warp-uniformly
+      // (lanes that keep their maximum rescale by 1).
+      const bool need = bmax > m + kRescaleThreshold;
+      float alpha = 1.f;
+      if (need) {
+        alpha = ptx::ex2_approx(m - bmax);  // first block: ex2(-inf) = 0
+        l *= alpha;
+        m = bmax;
+      }
+      if (j > 0 && __any_sync(0xffffffffu, need)) {
+        ptx::mbar_wait(o_full, (j - 1) & 1);  // P.V of the previous block has landed in O
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int c0 = 0; c0 < D; c0 += 16) {
+          uint32_t v[16];
+          ptx::tmem_ld_32x16(tmem_o + lane_off + c0, v);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+          ptx::tmem_st_32x16(tmem_o + lane_off + c0, v);
+        }
+        ptx::tmem_st_wait();
+      }
+      // pass 2: p = 2^(t + relh - m), written (16-bit) to swizzled smem
+      float mrow[HAS_BIAS ? RB : 1];
+#pragma unroll
+      for (int rr = 0; rr < (HAS_BIAS ? RB : 1); ++rr) mrow[rr] = m - (HAS_BIAS ? relh[rr] : 0.f);
       float rowsum = 0.f;
-      // pass 2: p = exp2(t - m_new), write P (16-bit) to swizzled smem
 #pragma unroll
       for (int c0 = 0; c0 < KV; c0 += 16) {
         uint32_t v[16];
@@ -230,13 +260,11 @@ vattn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int c = c0 + i;
-          float t = __uint_as_float(v[i]) * p.scale_log2;
-          if (HAS_BIAS) t += relw[c % GWD] + relh[c / GWD];
-          float pe = exp2f(t - m_new);
-          if (c >= kvalid) pe = 0.f;
-          // the P.V product consumes the rounded value: sum what is actually multiplied
-          e[i] = Elem<T>::to(Elem<T>::from(pe));
-          rowsum += e[i];
+          const float t = HAS_BIAS ? fmaf(__uint_as_float(v[i]), p.scale_log2, relw[c % GWD]) : __uint_as_float(v[i]) * p.scale_log2;
+          float pe = ptx::ex2_approx(t - mrow[HAS_BIAS ? c / GWD : 0]);
+          if (tail && c >= kvalid) pe = 0.f;
+          e[i] = pe;
+          rowsum += pe;
         }
 #pragma unroll
         for (int g8 = 0; g8 < 2; ++g8) {
@@ -251,34 +279,31 @@ vattn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
           *reinterpret_cast<uint4*>(prow + atom * (BQ * 128) + chunk * 16) = pk;
         }
       }
-      l = l * alpha + rowsum;
-      m = m_new;
+      l += rowsum;
       ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       ptx::tc_fence_before();
       ptx::mbar_arrive(p_full);
-
-      ptx::mbar_wait(o_full, j & 1);
-      ptx::tc_fence_after();
-#pragma unroll
-      for (int c0 = 0; c0 < D; c0 += 16) {
-        uint32_t v[16];
-        ptx::tmem_ld_32x16(tmem_o + lane_off + c0, v);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) acc[c0 + i] = acc[c0 + i] * alpha + __uint_as_float(v[i]);
-      }
     }
-    if (q_ok) {
-      const float inv = 1.f / l;
-      T* orow = reinterpret_cast<T*>(p.out) + (long long)(row_base + q) * (p.H * D) + h * D;
+    // epilogue: O / l
+    ptx::mbar_wait(o_full, (p.nblk - 1) & 1);
+    ptx::tc_fence_after();
+    const float inv = 1.f / l;
+    T* orow = reinterpret_cast<T*>(p.out) + (long long)(row_base + qc) * (p.H * D) + h * D;
 #pragma unroll
-      for (int c = 0; c < D; c += 8) {
-        uint4 pk;
-        pk.x = pack2<T>(acc[c + 0] * inv, acc[c + 1] * inv);
-        pk.y = pack2<T>(acc[c + 2] * inv, acc[c + 3] * inv);
-        pk.z = pack2<T>(acc[c + 4] * inv, acc[c + 5] * inv);
-        pk.w = pack2<T>(acc[c + 6] * inv, acc[c + 7] * inv);
-        *reinterpret_cast<uint4*>(orow + c) = pk;
+    for (int c0 = 0; c0 < D; c0 += 16) {
+      uint32_t v[16];
+      ptx::tmem_ld_32x16(tmem_o + lane_off + c0, v);
+      ptx::tmem_ld_wait();
+      if (q_ok) {
+#pragma unroll
+        for (int g8 = 0; g8 < 2; ++g8) {
+          uint4 pk;
+          pk.x = pack2<T>(__uint_as_float(v[g8 * 8 + 0]) * inv, __uint_as_float(v[g8 * 8 + 1]) * inv);
+          pk.y = pack2<T>(__uint_as_float(v[g8 * 8 + 2]) * inv, __uint_as_float(v[g8 * 8 + 3]) * inv);
+          pk.z = pack2<T>(__uint_as_float(v[g8 * 8 + 4]) * inv, __uint_as_float(v[g8 * 8 + 5]) * inv);
+          pk.w = pack2<T>(__uint_as_float(v[g8 * 8 + 6]) * inv, __uint_as_float(v[g8 * 8 + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + c0 + g8 * 8) = pk;
+        }
       }
     }
     ptx::tc_fence_before();

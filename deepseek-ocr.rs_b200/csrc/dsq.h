@@ -1,0 +1,86 @@
+// DSQ snapshot container reader (crates/dsq/src/lib.rs:14-15, 60-110, 208-306, 314-391) and the device-side
+// representation of a quantised linear layer.
+#pragma once
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "util.h"
+
+namespace dsocr {
+
+enum class DsqDType : uint32_t { F32 = 0, F16 = 1, Q8_0 = 8, Q4K = 12, Q6K = 14, BF16 = 16 };
+
+struct DsqRecord {
+  std::string name;
+  uint32_t out_dim = 0, in_dim = 0;
+  DsqDType q_dtype = DsqDType::Q8_0;
+  uint64_t q_offset = 0, q_len = 0;
+  uint64_t bias_offset = 0, bias_len = 0;
+  uint32_t bias_dtype = 0;
+  bool has_bias = false;
+};
+
+class DsqReader {
+ public:
+  explicit DsqReader(const std::string& path);
+  ~DsqReader();
+  DsqReader(const DsqReader&) = delete;
+  const DsqRecord* find(const std::string& name) const;
+  const uint8_t* bytes(const DsqRecord& r) const { return base_ + r.q_offset; }
+  const std::vector<DsqRecord>& records() const { return records_; }
+  DsqDType default_dtype() const { return default_dtype_; }
+  std::string model_id, backend, candle_version;
+
+ private:
+  int fd_ = -1;
+  size_t size_ = 0;
+  const uint8_t* base_ = nullptr;
+  DsqDType default_dtype_ = DsqDType::Q8_0;
+  std::vector<DsqRecord> records_;
+  std::map<std::string, size_t> index_;
+};
+
+inline int dsq_block_elems(DsqDType t) { return t == DsqDType::Q8_0 ? 32 : (t == DsqDType::Q4K || t == DsqDType::Q6K) ? 256 : 0; }
+inline int dsq_block_bytes(DsqDType t) { return t == DsqDType::Q8_0 ? 34 : t == DsqDType::Q4K ? 144 : t == DsqDType::Q6K ? 210 : 0; }
+
+// Device storage of one quantised weight matrix [N, K] (or E stacked matrices).  The on-disk ggml blocks are
+// re-laid out at load time into 16-byte-friendly planes (same byte count):
+//   Q8_0 : qs  int8 [N][K]          | d f16 [N][K/32]
+//   Q4_K : blk [N][K/256][144]      (as on disk: f16 d, f16 dmin, u8 scales[12], u8 qs[128])
+//   Q6_K : ql u8 [N][K/2] | qh u8 [N][K/4] | sc i8 [N][K/16] | d f16 [N][K/256]
+//   F16/BF16/F32 records: converted to f32 [N][K] (float fallback of the exporter's chain)
+struct QuantWeight {
+  DsqDType fmt = DsqDType::Q8_0;
+  long long N = 0;  // rows of one matrix (experts are stacked: total rows = N * count)
+  int K = 0;
+  int count = 1;
+  DevBuf a, b, c, d;  // planes as listed above (a is the main plane)
+  size_t bytes() const { return a.bytes + b.bytes + c.bytes + d.bytes; }
+};
+
+// Host-side repacking of `rows` rows of on-disk blocks into the planes of `dst` starting at row `row0`.
+void dsq_upload_rows(QuantWeight& dst, long long row0, const uint8_t* src, DsqDType src_fmt, long long rows);
+void dsq_alloc(QuantWeight& w, DsqDType fmt, long long N, int K, int count);
+
+// out[r, n] (+)= sum_k x[xr(r), k] * dequant(W[e(r)])[n, k]   with xr(r) = r / x_row_div and
+// e(r) = row_expert ? row_expert[r] : 0.  f32 activations, f32 accumulation.
+struct DsqGemvCall {
+  const QuantWeight* w = nullptr;
+  const float* x = nullptr;
+  long long ldx = 0;
+  int x_row_div = 1;
+  const int* row_expert = nullptr;
+  float* out = nullptr;
+  long long ldo = 0;
+  long long rows = 0;
+  bool accumulate = false;
+  const char* tag = "dsq_gemv";
+};
+void dsq_gemv(const DsqGemvCall& c, cudaStream_t stream);
+// h[i] = silu(g[i]) * u[i]
+void swiglu_f32(const float* g, const float* u, float* h, long long n, cudaStream_t stream);
+
+}  // namespace dsocr

@@ -332,6 +332,9 @@ Engine::Engine(const std::string& config_path, const std::string& weights_path, 
   device_name = prop.name;
   num_sms_ = prop.multiProcessorCount;
   cuda_check(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking), "cudaStreamCreate");
+  cuda_check(cudaStreamCreateWithFlags(&stream2_, cudaStreamNonBlocking), "cudaStreamCreate");
+  cuda_check(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming), "cudaEventCreate");
+  cuda_check(cudaEventCreateWithFlags(&ev_join_, cudaEventDisableTiming), "cudaEventCreate");
   cfg_ = parse_config(config_path);
   load_weights(weights_path);
   cuda_check(cudaDeviceSynchronize(), "weight upload");
@@ -341,6 +344,9 @@ Engine::~Engine() {
   cudaSetDevice(device_);
   cudaDeviceSynchronize();
   if (stream_ && owns_stream_) cudaStreamDestroy(stream_);
+  if (stream2_) cudaStreamDestroy(stream2_);
+  if (ev_fork_) cudaEventDestroy(ev_fork_);
+  if (ev_join_) cudaEventDestroy(ev_join_);
 }
 
 void Engine::set_stream(cudaStream_t s) {

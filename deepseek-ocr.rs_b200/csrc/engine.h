@@ -117,6 +117,8 @@ class Engine {
   int num_sms_ = 0;
   cudaStream_t stream_ = nullptr;
   bool owns_stream_ = true;
+  cudaStream_t stream2_ = nullptr;  // side branch (shared experts) forked from stream_
+  cudaEvent_t ev_fork_ = nullptr, ev_join_ = nullptr;
   bool record_taps_ = false;
   bool kv_f16_ = false;
   std::map<std::string, std::vector<float>> taps_;

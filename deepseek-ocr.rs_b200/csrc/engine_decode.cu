@@ -34,6 +34,7 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
   int* offsets = counts + E;
   int* cursor = counts + 2 * E;
   int* ntiles = counts + 3 * E;  // [2]
+  cuda_check(cudaMemsetAsync(counts, 0, E * 4, stream_), "moe counts memset");  // moe_plan re-zeroes after use
   const int bn = linear_pick_bn(std::max<long long>(1, n_assign / E * 2), true);
   const int max_chunks = (int)(n_assign / bn) + E;
   LinearTile* tiles1 = ws("moe_tiles1", (size_t)max_chunks * (mi / 128) * sizeof(LinearTile)).as<LinearTile>();
@@ -110,8 +111,14 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
         linear(lc, dt_, num_sms_, stream_);
       }
     } else {
-      // run_moe (block.rs:1215-1395)
-      cuda_check(cudaMemsetAsync(counts, 0, E * 4, stream_), "moe counts memset");
+      // run_moe (block.rs:1215-1395).  In decode the shared-experts branch (3 small kernels) runs on a forked
+      // stream next to the routed branch (router/plan/dispatch/2 grouped GEMMs): both are latency-bound.
+      const bool fork = rows <= 256 && !kernel_timing_enabled();
+      cudaStream_t sb = fork ? stream2_ : stream_;
+      if (fork) {
+        cuda_check(cudaEventRecord(ev_fork_, stream_), "fork record");
+        cuda_check(cudaStreamWaitEvent(sb, ev_fork_, 0), "fork wait");
+      }
       moe_router(xn32, L.router_wt.as<float>(), topk_idx, topk_w, counts, rows, H, E, K, stream_);
       moe_plan(counts, offsets, cursor, tiles1, ntiles, tiles2, ntiles + 1, E, bn, mi, H, stream_);
       moe_dispatch(topk_idx, offsets, cursor, xn16, rows * H, xperm16, n_assign * H, perm_pos, n_assign, K, H, dt_, stream_);
@@ -141,8 +148,8 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
         } else {
           lc.out = h16; lc.out_lo = (uint16_t*)h16 + rows * S; lc.out_mode = lin::OUT_T_SPLIT;
         }
-        linear(lc, dt_, num_sms_, stream_);
-        if (sp_sgu > 1) swiglu_reduce(partA, sp_sgu, 2 * rows * S, rows * S, h16, rows * S, rows * S, dt_, stream_);
+        linear(lc, dt_, num_sms_, sb);
+        if (sp_sgu > 1) swiglu_reduce(partA, sp_sgu, 2 * rows * S, rows * S, h16, rows * S, rows * S, dt_, sb);
       }
       {
         LinearCall lc;
@@ -150,7 +157,11 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
         lc.M = (int)rows; lc.N = H; lc.K = (int)S; lc.ldo = H;
         if (sp_sd > 1) { lc.out = partB; lc.out_mode = lin::OUT_F32; lc.k_splits = sp_sd; lc.split_stride = rows * H; }
         else { lc.out = x; lc.out_mode = lin::OUT_F32_ADD; }
-        linear(lc, dt_, num_sms_, stream_);
+        linear(lc, dt_, num_sms_, sb);
+      }
+      if (fork) {
+        cuda_check(cudaEventRecord(ev_join_, sb), "join record");
+        cuda_check(cudaStreamWaitEvent(stream_, ev_join_, 0), "join wait");
       }
       moe_combine(yperm, perm_pos, topk_w, x, rows, K, H, sp_sd > 1 ? partB : nullptr, sp_sd, rows * H, stream_);
     }
@@ -235,6 +246,8 @@ void Engine::generate(const GenRequest& rq, int64_t* const* out_tokens, int* n_o
   int* d_hist_len = d_state, *d_gen_count = d_state + P, *d_finished = d_state + 2 * P;
   float* x = ws("gen_x32", max_rows * H * 4).as<float>();
   float* logits = ws("gen_logits32", (size_t)P * V * 4).as<float>();
+  float* sel_scratch = ws("gen_select_scratch", (size_t)P * kSelectScratchPerPage * 4).as<float>();
+  cuda_check(cudaMemsetAsync(sel_scratch, 0, (size_t)P * kSelectScratchPerPage * 4, stream_), "select scratch memset");
   int* d_forced = nullptr, *d_selected = nullptr;
   if (forced) {
     std::vector<int> f((size_t)P * max_new);
@@ -269,7 +282,7 @@ void Engine::generate(const GenRequest& rq, int64_t* const* out_tokens, int* n_o
   decoder_forward(x, total_rows, d_row_page, d_row_pos, smax, d_last, P, logits);
   copy_logits(0);
   select_token(logits, V, d_hist, smax, d_hist_len, d_gen_count, d_finished, P, ngram, eos, max_new, d_forced, max_new,
-               d_selected, max_new, stream_);
+               d_selected, max_new, sel_scratch, stream_);
   cuda_check(cudaEventRecord(ev1, stream_), "event");
 
   // ---- token loop (model/mod.rs:1977-2034): every page advances one token per step
@@ -303,7 +316,7 @@ void Engine::generate(const GenRequest& rq, int64_t* const* out_tokens, int* n_o
     decoder_forward(x, P, d_row_page, d_row_pos, smax, d_row_page /* identity: every row */, P, logits);
     copy_logits(step);
     select_token(logits, V, d_hist, smax, d_hist_len, d_gen_count, d_finished, P, ngram, eos, max_new, d_forced, max_new,
-                 d_selected, max_new, stream_);
+                 d_selected, max_new, sel_scratch, stream_);
   };
   bool use_graph = !kernel_timing_enabled() && !rq.logits_out && !record_taps_ && !getenv("DSOCR_NO_GRAPH");
   if (use_graph && (stream_ == nullptr || stream_ == cudaStreamLegacy || stream_ == cudaStreamPerThread))

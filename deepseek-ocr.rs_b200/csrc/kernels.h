@@ -119,7 +119,7 @@ void kv_attention(const float* q, const void* kc, const void* vc, bool kv_f16, c
                   cudaStream_t s);
 void moe_router(const float* x, const float* wgt, int* topk_idx, float* topk_w, int* counts, long long rows, int H,
                 int E, int topk, cudaStream_t s);
-void moe_plan(const int* counts, int* offsets, int* cursor, LinearTile* tiles1, int* ntiles1, LinearTile* tiles2,
+void moe_plan(int* counts, int* offsets, int* cursor, LinearTile* tiles1, int* ntiles1, LinearTile* tiles2,
               int* ntiles2, int E, int bn, int N1, int N2, cudaStream_t s);
 void moe_dispatch(const int* topk_idx, const int* offsets, int* cursor, const void* xn, long long xn_lo_off,
                   void* xperm, long long xperm_lo_off, int* perm_pos, long long n_assign, int topk, int H, DType dt,
@@ -128,7 +128,8 @@ void moe_combine(const float* y, const int* perm_pos, const float* topk_w, float
                  const float* partials, int n_splits, long long split_stride, cudaStream_t s);
 void select_token(const float* logits, int V, int* hist, int hist_stride, int* hist_len, int* gen_count, int* finished,
                   int n_pages, int ngram, int eos, int max_new, const int* forced, int forced_stride,
-                  int* selected_out, int selected_stride, cudaStream_t s);
+                  int* selected_out, int selected_stride, float* scratch, cudaStream_t s);
+constexpr int kSelectScratchPerPage = 16 * 2 + 1;  // 32-bit words of select_token scratch per page
 bool kernel_timing_enabled();
 void decode_rows(const int* hist, int hist_stride, const int* hist_len, int* src, int* row_pos, int n_pages,
                  cudaStream_t s);

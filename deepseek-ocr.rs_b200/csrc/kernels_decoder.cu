@@ -412,7 +412,7 @@ router_kernel(const float* __restrict__ x, const float* __restrict__ wgt, int* _
 
 // Exclusive scan of the expert counts + tile tables for the two grouped GEMMs (one block, one thread per
 // expert).  tiles1: N1 (= moe intermediate) output features per expert; tiles2: N2 (= hidden).
-__global__ void moe_plan_kernel(const int* __restrict__ counts, int* __restrict__ offsets, int* __restrict__ cursor,
+__global__ void moe_plan_kernel(int* __restrict__ counts, int* __restrict__ offsets, int* __restrict__ cursor,
                                 LinearTile* __restrict__ tiles1, int* __restrict__ ntiles1,
                                 LinearTile* __restrict__ tiles2, int* __restrict__ ntiles2, int E, int bn, int N1,
                                 int N2) {
@@ -432,6 +432,7 @@ __global__ void moe_plan_kernel(const int* __restrict__ counts, int* __restrict_
   __syncthreads();
   if (e >= E) return;
   const int c = counts[e], off = s_off[e];
+  counts[e] = 0;  // ready for the next layer's router (the buffer is zero-initialised once per call)
   offsets[e] = off;
   cursor[e] = 0;
   int ch = s_chunk[e];
@@ -519,18 +520,23 @@ __global__ void swiglu_reduce_kernel(const float* __restrict__ part, int n_split
 // an n-gram already present in the page's context (prompt + generated), then first-index argmax over the
 // finite logits.  One block per page.  The new token is appended to the history; pages that emitted EOS
 // (or reached their budget) are frozen.
-__global__ void __launch_bounds__(1024)
+constexpr int kSelChunks = 16;   // vocabulary chunks (blocks) per page
+constexpr int kSelThreads = 256;
+__global__ void __launch_bounds__(kSelThreads)
 select_token_kernel(const float* __restrict__ logits, int V, int* __restrict__ hist, int hist_stride,
                     int* __restrict__ hist_len, int* __restrict__ gen_count, int* __restrict__ finished, int ngram,
                     int eos, int max_new, const int* __restrict__ forced, int forced_stride,
-                    int* __restrict__ selected_out, int selected_stride) {
-  const int page = blockIdx.x;
-  const int step = gen_count[page];  // tokens accepted so far == index of this selection (graph-replay safe)
+                    int* __restrict__ selected_out, int selected_stride, float* __restrict__ part_val,
+                    int* __restrict__ part_idx, int* __restrict__ tickets) {
+  const int page = blockIdx.y;
+  const int chunk = blockIdx.x;
   __shared__ int s_ban[64];
   __shared__ int s_nban;
-  __shared__ float s_val[32];
-  __shared__ int s_idx[32];
+  __shared__ float s_val[kSelThreads / 32];
+  __shared__ int s_idx[kSelThreads / 32];
+  __shared__ int s_last;
   if (finished[page]) return;
+  const int step = gen_count[page];  // tokens accepted so far == index of this selection (graph-replay safe)
   int* h = hist + (long long)page * hist_stride;
   const int L = hist_len[page];
   if (threadIdx.x == 0) s_nban = 0;
@@ -549,14 +555,26 @@ select_token_kernel(const float* __restrict__ logits, int V, int* __restrict__ h
   __syncthreads();
   const int nban = min(s_nban, 64);
   const float* lg = logits + (long long)page * V;
+  const int per = ((V + kSelChunks - 1) / kSelChunks + 3) & ~3;  // chunk length, multiple of 4
+  const int c0 = chunk * per, c1 = min(V, c0 + per);
   float bv = -INFINITY; int bi = INT_MAX;
-  for (int i = threadIdx.x; i < V; i += blockDim.x) {
-    float v = lg[i];
-    if (!(fabsf(v) <= FLT_MAX)) continue;  // skip NaN / inf like the reference's is_finite filter
-    bool banned = false;
-    for (int b = 0; b < nban; ++b) banned |= (s_ban[b] == i);
-    if (banned) continue;
-    if (v > bv) { bv = v; bi = i; }  // strided ascending scan keeps the first index per thread
+  for (int i = c0 + threadIdx.x * 4; i < c1; i += kSelThreads * 4) {
+    float v4[4];
+    if (i + 3 < c1 && ((reinterpret_cast<uintptr_t>(lg + i) & 15) == 0)) {
+      const float4 t = *reinterpret_cast<const float4*>(lg + i);
+      v4[0] = t.x; v4[1] = t.y; v4[2] = t.z; v4[3] = t.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v4[k] = (i + k < c1) ? lg[i + k] : -INFINITY;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float v = v4[k];
+      if (!(fabsf(v) <= FLT_MAX)) continue;  // skip NaN / inf like the reference's is_finite filter
+      bool banned = false;
+      for (int b = 0; b < nban; ++b) banned |= (s_ban[b] == i + k);
+      if (!banned && v > bv) { bv = v; bi = i + k; }  // ascending scan keeps the first index per thread
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -566,31 +584,38 @@ select_token_kernel(const float* __restrict__ logits, int V, int* __restrict__ h
   }
   if ((threadIdx.x & 31) == 0) { s_val[threadIdx.x >> 5] = bv; s_idx[threadIdx.x >> 5] = bi; }
   __syncthreads();
-  if (threadIdx.x < 32) {
-    bv = threadIdx.x < (blockDim.x >> 5) ? s_val[threadIdx.x] : -INFINITY;
-    bi = threadIdx.x < (blockDim.x >> 5) ? s_idx[threadIdx.x] : INT_MAX;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-    }
-    if (threadIdx.x == 0) {
-      int tok = bi == INT_MAX ? 0 : bi;
-      if (selected_out) selected_out[(long long)page * selected_stride + step] = tok;
-      if (forced) {
-        tok = forced[(long long)page * forced_stride + step];
-      } else if (eos >= 0 && tok == eos) {
-        finished[page] = 1;  // EOS is not appended (model/mod.rs:2029-2033)
-        return;
-      }
-      h[L] = tok;
-      hist_len[page] = L + 1;
-      const int g = gen_count[page] + 1;
-      gen_count[page] = g;
-      if (g >= max_new) finished[page] = 1;
-    }
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kSelThreads / 32; ++w)
+      if (s_val[w] > bv || (s_val[w] == bv && s_idx[w] < bi)) { bv = s_val[w]; bi = s_idx[w]; }
+    part_val[page * kSelChunks + chunk] = bv;
+    part_idx[page * kSelChunks + chunk] = bi;
+    __threadfence();
+    s_last = atomicAdd(&tickets[page], 1) == kSelChunks - 1;
   }
+  __syncthreads();
+  if (!s_last || threadIdx.x != 0) return;
+  // last block of this page: reduce the chunk winners and do the bookkeeping
+  __threadfence();
+  tickets[page] = 0;
+  bv = -INFINITY; bi = INT_MAX;
+  for (int c = 0; c < kSelChunks; ++c) {
+    const float v = reinterpret_cast<volatile float*>(part_val)[page * kSelChunks + c];
+    const int ix = reinterpret_cast<volatile int*>(part_idx)[page * kSelChunks + c];
+    if (v > bv || (v == bv && ix < bi)) { bv = v; bi = ix; }
+  }
+  int tok = bi == INT_MAX ? 0 : bi;
+  if (selected_out) selected_out[(long long)page * selected_stride + step] = tok;
+  if (forced) {
+    tok = forced[(long long)page * forced_stride + step];
+  } else if (eos >= 0 && tok == eos) {
+    finished[page] = 1;  // EOS is not appended (model/mod.rs:2029-2033)
+    return;
+  }
+  h[L] = tok;
+  hist_len[page] = L + 1;
+  const int g = gen_count[page] + 1;
+  gen_count[page] = g;
+  if (g >= max_new) finished[page] = 1;
 }
 
 // Decode-step bookkeeping: for every page, the row of the next forward is its last history token at
@@ -676,7 +701,7 @@ void moe_router(const float* x, const float* wgt, int* topk_idx, float* topk_w, 
   else throw std::runtime_error("router: unsupported expert count " + std::to_string(E));
   launch_check("moe_router");
 }
-void moe_plan(const int* counts, int* offsets, int* cursor, LinearTile* tiles1, int* ntiles1, LinearTile* tiles2,
+void moe_plan(int* counts, int* offsets, int* cursor, LinearTile* tiles1, int* ntiles1, LinearTile* tiles2,
               int* ntiles2, int E, int bn, int N1, int N2, cudaStream_t s) {
   moe_plan_kernel<<<1, 256, 0, s>>>(counts, offsets, cursor, tiles1, ntiles1, tiles2, ntiles2, E, bn, N1, N2);
   launch_check("moe_plan");
@@ -699,9 +724,14 @@ void swiglu_reduce(const float* part, int n_splits, long long split_stride, long
 }
 void select_token(const float* logits, int V, int* hist, int hist_stride, int* hist_len, int* gen_count, int* finished,
                   int n_pages, int ngram, int eos, int max_new, const int* forced, int forced_stride,
-                  int* selected_out, int selected_stride, cudaStream_t s) {
-  select_token_kernel<<<n_pages, 1024, 0, s>>>(logits, V, hist, hist_stride, hist_len, gen_count, finished, ngram, eos,
-                                               max_new, forced, forced_stride, selected_out, selected_stride);
+                  int* selected_out, int selected_stride, float* scratch, cudaStream_t s) {
+  // scratch: [n_pages*16] f32 values | [n_pages*16] i32 indices | [n_pages] i32 tickets (zero-initialised)
+  float* part_val = scratch;
+  int* part_idx = reinterpret_cast<int*>(scratch + (size_t)n_pages * kSelChunks);
+  int* tickets = part_idx + (size_t)n_pages * kSelChunks;
+  select_token_kernel<<<dim3(kSelChunks, n_pages), kSelThreads, 0, s>>>(logits, V, hist, hist_stride, hist_len, gen_count,
+                                                                      finished, ngram, eos, max_new, forced, forced_stride,
+                                                                      selected_out, selected_stride, part_val, part_idx, tickets);
   launch_check("select_token");
 }
 void decode_rows(const int* hist, int hist_stride, const int* hist_len, int* src, int* row_pos, int n_pages,

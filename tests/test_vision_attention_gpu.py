@@ -93,3 +93,22 @@ def test_sam_attention_peaked_scores():
     y = run_attn(BF16, qkv, B, S, H, grid, rel_h, rel_w)
     r = ref_attn(BF16, qkv, B, S, H, grid, rel_h, rel_w)
     _check(y, r, BF16)
+
+
+@pytest.mark.parametrize("grid", [0, 40, 64])
+def test_attention_lazy_rescale_non_uniform(grid):
+    """Key norms ramp up along the sequence and only some query rows are large, so the reference maximum of
+    individual rows (not whole warps) moves by more than the lazy-rescale threshold at many key blocks."""
+    g = torch.Generator().manual_seed(7 + grid)
+    S = grid * grid if grid else 777
+    B, H = 1, 2
+    qkv = torch.randn(B * S, 3, H, 64, generator=g)
+    ramp = torch.linspace(0.2, 5.0, S).reshape(S, 1, 1)
+    qkv[:, 1] *= ramp                       # keys grow along the sequence
+    qkv[::3, 0] *= 6.0                      # every third query row is "hot"
+    qkv = qkv.reshape(B * S, 3 * H * 64)
+    rel_h = torch.randn(2 * grid - 1, 64, generator=g) * 0.3 if grid else None
+    rel_w = torch.randn(2 * grid - 1, 64, generator=g) * 0.3 if grid else None
+    y = run_attn(BF16, qkv, B, S, H, grid, rel_h, rel_w)
+    r = ref_attn(BF16, qkv, B, S, H, grid, rel_h, rel_w)
+    _check(y, r, BF16)
