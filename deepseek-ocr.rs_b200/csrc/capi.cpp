@@ -76,6 +76,7 @@ extern "C" int dsocr_engine_info_get(const dsocr_engine* e, dsocr_engine_info* i
     info->sm_count = en.sm_count();
     info->hidden_size = en.cfg().hidden; info->num_layers = en.cfg().layers; info->vocab_size = en.cfg().vocab;
     info->n_routed_experts = en.cfg().n_experts;
+    info->quantized = en.quantized() ? 1 : 0;
     strncpy(info->device_name, en.device_name.c_str(), sizeof(info->device_name) - 1);
   });
 }

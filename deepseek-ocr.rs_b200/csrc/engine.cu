@@ -180,7 +180,19 @@ std::vector<float> conv_to_khwc(const StTensor& t) {
 
 }  // namespace
 
-void Engine::load_weights(const std::string& path) {
+namespace {
+// snapshot record -> QuantWeight rows [row0, row0 + out_dim)
+void load_quant(QuantWeight& w, const DsqReader& dsq, const std::string& name, long long N, int K, int count, int idx) {
+  const DsqRecord* r = dsq.find(name);
+  if (!r) throw std::runtime_error("snapshot is missing tensor `" + name + "`");
+  if ((long long)r->out_dim != N || (int)r->in_dim != K) throw std::runtime_error("snapshot tensor `" + name + "` has unexpected dims");
+  if (r->has_bias) throw std::runtime_error("snapshot bias tensors are not supported (`" + name + "`)");
+  if (idx == 0) dsq_alloc(w, r->q_dtype, N, K, count);
+  dsq_upload_rows(w, (long long)idx * N, dsq.bytes(*r), r->q_dtype, N);
+}
+}  // namespace
+
+void Engine::load_weights(const std::string& path, const DsqReader* dsq) {
   SafeTensors st(path);
   const ModelConfig& c = cfg_;
   auto T16 = [&](DevBuf& d, const std::string& n, std::initializer_list<long long> shape) {
@@ -260,13 +272,42 @@ void Engine::load_weights(const std::string& path) {
   const long long H = c.hidden;
   T16(embed_, "model.embed_tokens.weight", {c.vocab, H});
   F32(final_norm_, "model.norm.weight", {H});
-  T16(lm_head_, "lm_head.weight", {c.vocab, H});
+  if (dsq) load_quant(q_lm_head_, *dsq, "lm_head.weight", c.vocab, (int)H, 1, 0);
+  else T16(lm_head_, "lm_head.weight", {c.vocab, H});
   dec_.resize(c.layers);
   for (int i = 0; i < c.layers; ++i) {
     const std::string p = "model.layers." + std::to_string(i) + ".";
     DecLayerW& L = dec_[i];
     F32(L.ln1, p + "input_layernorm.weight", {H});
     F32(L.ln2, p + "post_attention_layernorm.weight", {H});
+    L.moe = i >= c.first_dense;  // should_use_moe, weights.rs:609-619 with moe_layer_freq = 1
+    if (dsq) {
+      load_quant(L.q_q, *dsq, p + "self_attn.q_proj.weight", H, (int)H, 1, 0);
+      load_quant(L.q_k, *dsq, p + "self_attn.k_proj.weight", H, (int)H, 1, 0);
+      load_quant(L.q_v, *dsq, p + "self_attn.v_proj.weight", H, (int)H, 1, 0);
+      load_quant(L.q_o, *dsq, p + "self_attn.o_proj.weight", H, (int)H, 1, 0);
+      if (!L.moe) {
+        load_quant(L.q_gate, *dsq, p + "mlp.gate_proj.weight", c.inter, (int)H, 1, 0);
+        load_quant(L.q_up, *dsq, p + "mlp.up_proj.weight", c.inter, (int)H, 1, 0);
+        load_quant(L.q_down, *dsq, p + "mlp.down_proj.weight", H, c.inter, 1, 0);
+      } else {
+        const long long E = c.n_experts, mi = c.moe_inter, S = (long long)c.moe_inter * c.n_shared;
+        const StTensor& t = st.get(p + "mlp.gate.weight"); expect_shape(t, {E, H}, "mlp.gate.weight");
+        std::vector<float> w = to_f32(t), wt((size_t)E * H);
+        for (long long e = 0; e < E; ++e) for (long long k = 0; k < H; ++k) wt[k * E + e] = w[e * H + k];
+        upload_f32(L.router_wt, wt);
+        for (long long e = 0; e < E; ++e) {
+          const std::string q = p + "mlp.experts." + std::to_string(e) + ".";
+          load_quant(L.q_exp_gate, *dsq, q + "gate_proj.weight", mi, (int)H, (int)E, (int)e);
+          load_quant(L.q_exp_up, *dsq, q + "up_proj.weight", mi, (int)H, (int)E, (int)e);
+          load_quant(L.q_exp_down, *dsq, q + "down_proj.weight", H, (int)mi, (int)E, (int)e);
+        }
+        load_quant(L.q_sh_gate, *dsq, p + "mlp.shared_experts.gate_proj.weight", S, (int)H, 1, 0);
+        load_quant(L.q_sh_up, *dsq, p + "mlp.shared_experts.up_proj.weight", S, (int)H, 1, 0);
+        load_quant(L.q_sh_down, *dsq, p + "mlp.shared_experts.down_proj.weight", H, (int)S, 1, 0);
+      }
+      continue;
+    }
     L.qkv_w.alloc((size_t)3 * H * H * 2);
     const char* names[3] = {"q", "k", "v"};
     for (int j = 0; j < 3; ++j) {
@@ -276,7 +317,6 @@ void Engine::load_weights(const std::string& path) {
       if (st.has(p + "self_attn." + names[j] + "_proj.bias")) throw std::runtime_error("decoder attention bias is not supported");
     }
     T16(L.o_w, p + "self_attn.o_proj.weight", {H, H});
-    L.moe = i >= c.first_dense;  // should_use_moe, weights.rs:609-619 with moe_layer_freq = 1
     if (!L.moe) {
       T16(L.gate_w, p + "mlp.gate_proj.weight", {c.inter, H});
       T16(L.up_w, p + "mlp.up_proj.weight", {c.inter, H});
@@ -319,7 +359,6 @@ Engine::Engine(const std::string& config_path, const std::string& weights_path, 
   if (dtype != DType::F16 && dtype != DType::BF16)
     throw std::runtime_error("dtype must be f16 or bf16: the B200 engine computes on 16-bit tensor cores with f32 "
                              "accumulation (the reference's f32 CPU mode has no device equivalent here)");
-  if (!dsq_path.empty()) throw std::runtime_error("DSQ snapshots are not supported yet by this build");
   int ndev = 0;
   cuda_check(cudaGetDeviceCount(&ndev), "cudaGetDeviceCount (no CUDA device: there is no CPU fallback)");
   if (device < 0 || device >= ndev) throw std::runtime_error("invalid CUDA device ordinal " + std::to_string(device));
@@ -336,7 +375,14 @@ Engine::Engine(const std::string& config_path, const std::string& weights_path, 
   cuda_check(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming), "cudaEventCreate");
   cuda_check(cudaEventCreateWithFlags(&ev_join_, cudaEventDisableTiming), "cudaEventCreate");
   cfg_ = parse_config(config_path);
-  load_weights(weights_path);
+  if (!dsq_path.empty()) {
+    // QuantizedSnapshot::load (dsq-runtime/src/lib.rs:237-241): the decoder linears + lm_head come from the snapshot
+    DsqReader dsq(dsq_path);
+    quantized_ = true;
+    load_weights(weights_path, &dsq);
+  } else {
+    load_weights(weights_path, nullptr);
+  }
   cuda_check(cudaDeviceSynchronize(), "weight upload");
 }
 
@@ -361,6 +407,7 @@ DevBuf& Engine::ws(const std::string& name, size_t bytes) {
   if (b.bytes < bytes) {
     cuda_check(cudaStreamSynchronize(stream_), "workspace grow sync");
     b.alloc(bytes + bytes / 8);
+    if (name == "dsq_iota") iota_n_ = 0;
   }
   return b;
 }

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "dsocr.h"
+#include "dsq.h"
 #include "kernels.h"
 #include "util.h"
 
@@ -48,6 +49,8 @@ struct DecLayerW {
   DevBuf exp_gate, exp_up, exp_down;         // [E*mi, H], [E*mi, H], [E*H, mi]
   DevBuf sh_gate, sh_up, sh_down;            // shared experts fused: [S, H], [S, H], [H, S]
   bool moe = false;
+  // DSQ-quantised variants (engine created with a snapshot): q/k/v/o, dense MLP, stacked experts, shared experts
+  QuantWeight q_q, q_k, q_v, q_o, q_gate, q_up, q_down, q_exp_gate, q_exp_up, q_exp_down, q_sh_gate, q_sh_up, q_sh_down;
 };
 
 struct Timings { double prepare = 0, vision = 0, prefill = 0, iterative = 0, generate = 0; };
@@ -98,7 +101,12 @@ class Engine {
   std::string device_name;
 
  private:
-  void load_weights(const std::string& path);
+  void load_weights(const std::string& path, const DsqReader* dsq);
+  void decoder_forward_dsq(float* x, long long rows, const int* row_page, const int* row_pos, int smax,
+                           const int* final_rows, int n_final, float* logits);
+ public:
+  bool quantized() const { return quantized_; }
+ private:
   void sam_forward(int Bv, int G, const void* patches16, float* sam_out);
   void clip_forward(int Bv, int g3, const float* sam_out, float* clip_out);
   void vision_views(int Bv, int G, const void* img_dev, bool is_f32, float* proj_out /*[Bv*n,1280]*/, const char* tag);
@@ -121,6 +129,9 @@ class Engine {
   cudaEvent_t ev_fork_ = nullptr, ev_join_ = nullptr;
   bool record_taps_ = false;
   bool kv_f16_ = false;
+  bool quantized_ = false;
+  QuantWeight q_lm_head_;
+  long long iota_n_ = 0;
   std::map<std::string, std::vector<float>> taps_;
 
   // weights

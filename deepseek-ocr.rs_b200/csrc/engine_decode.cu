@@ -74,7 +74,7 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
     }
     rope_kv(sp_qkv > 1 ? partA : qkv, rope_cos_.as<float>(), rope_sin_.as<float>(), row_page, row_pos, q,
             kcache_[l].p, vcache_[l].p, kv_f16_, rows, heads, smax, sp_qkv, rows * 3 * H, stream_);
-    kv_attention(q, kcache_[l].p, vcache_[l].p, kv_f16_, row_page, row_pos, ctx16, rows * H, rows, heads, smax, scale,
+    kv_attention(q, kcache_[l].p, vcache_[l].p, kv_f16_, row_page, row_pos, ctx16, rows * H, nullptr, rows, heads, smax, scale,
                  dt_, stream_);
     {
       LinearCall lc;  // o_proj (+ residual add, fused here or in the following RMSNorm when split)
@@ -175,6 +175,80 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
   lc.tag = "lm_head"; lc.w0 = lm_head_.p; lc.x = xf16; lc.x_rows = 2 * n_final; lc.x_parts = 2; lc.x_lo_row_off = n_final;
   lc.M = n_final; lc.N = c.vocab; lc.K = H; lc.out = logits; lc.ldo = c.vocab; lc.out_mode = lin::OUT_F32;
   linear(lc, dt_, num_sms_, stream_);
+}
+
+// DSQ variant of decoder_forward (run_quantized_matmul, quantization.rs:164-185): every decoder linear and the
+// lm_head is a dequant-fused GEMV over the snapshot's Q8_0 / Q4_K / Q6_K blocks with f32 activations.  Routed
+// experts need no dispatch: assignment row a = (token a/topk, slot a%topk) selects its expert's weights directly.
+void Engine::decoder_forward_dsq(float* x, long long rows, const int* row_page, const int* row_pos, int smax,
+                                 const int* final_rows, int n_final, float* logits) {
+  const ModelConfig& c = cfg_;
+  const int H = c.hidden, heads = c.heads, E = c.n_experts, K = c.topk, mi = c.moe_inter;
+  const long long S = (long long)c.moe_inter * c.n_shared;
+  const float scale = 1.0f / sqrtf((float)c.head_dim());
+  const long long n_assign = rows * K;
+  const long long inter_max = std::max<long long>({(long long)c.inter, S, (long long)mi * K});
+  void* xn16 = ws("dec_xn16", 2 * rows * H * 2).p;  // written by the norm kernel, unused on this path
+  float* xn = ws("dec_xn32", rows * H * 4).as<float>();
+  float* qkv = ws("dec_qkv32", rows * 3 * H * 4).as<float>();
+  float* q = ws("dec_q32", rows * H * 4).as<float>();
+  float* ctx = ws("dsq_ctx32", rows * H * 4).as<float>();
+  float* g32 = ws("dsq_gate32", rows * inter_max * 4).as<float>();
+  float* u32 = ws("dsq_up32", rows * inter_max * 4).as<float>();
+  float* h32 = ws("dsq_h32", rows * inter_max * 4).as<float>();
+  float* y32 = ws("dsq_y32", n_assign * H * 4).as<float>();
+  int* topk_idx = ws("moe_topk_idx", n_assign * 4).as<int>();
+  float* topk_w = ws("moe_topk_w", n_assign * 4).as<float>();
+  int* counts = ws("moe_counts", 3 * E * 4 + 16).as<int>();
+  int* iota = ws("dsq_iota", n_assign * 4).as<int>();
+  if (iota_n_ < n_assign) {  // identity slot map, uploaded once (never during graph capture: sizes repeat)
+    std::vector<int> h(n_assign);
+    for (long long i = 0; i < n_assign; ++i) h[i] = (int)i;
+    cuda_check(cudaMemcpyAsync(iota, h.data(), n_assign * 4, cudaMemcpyHostToDevice, stream_), "iota upload");
+    cuda_check(cudaStreamSynchronize(stream_), "iota sync");
+    iota_n_ = n_assign;
+  }
+  auto gemv = [&](const QuantWeight& w, const float* xin, long long ldx, float* out, long long ldo, long long nrows,
+                  bool acc, const char* tag, const int* row_expert = nullptr, int x_row_div = 1) {
+    DsqGemvCall gc;
+    gc.w = &w; gc.x = xin; gc.ldx = ldx; gc.out = out; gc.ldo = ldo; gc.rows = nrows; gc.accumulate = acc; gc.tag = tag;
+    gc.row_expert = row_expert; gc.x_row_div = x_row_div;
+    dsq_gemv(gc, stream_);
+  };
+  for (int l = 0; l < c.layers; ++l) {
+    DecLayerW& L = dec_[l];
+    rmsnorm_split(x, L.ln1.as<float>(), xn16, rows * H, xn, nullptr, rows, H, c.rms_eps, nullptr, 0, 0, dt_, stream_);
+    gemv(L.q_q, xn, H, qkv, 3 * H, rows, false, "dsq_q_proj");
+    gemv(L.q_k, xn, H, qkv + H, 3 * H, rows, false, "dsq_k_proj");
+    gemv(L.q_v, xn, H, qkv + 2 * H, 3 * H, rows, false, "dsq_v_proj");
+    rope_kv(qkv, rope_cos_.as<float>(), rope_sin_.as<float>(), row_page, row_pos, q, kcache_[l].p, vcache_[l].p, kv_f16_,
+            rows, heads, smax, 1, 0, stream_);
+    kv_attention(q, kcache_[l].p, vcache_[l].p, kv_f16_, row_page, row_pos, nullptr, 0, ctx, rows, heads, smax, scale, dt_, stream_);
+    gemv(L.q_o, ctx, H, x, H, rows, true, "dsq_o_proj");
+    rmsnorm_split(x, L.ln2.as<float>(), xn16, rows * H, xn, nullptr, rows, H, c.rms_eps, nullptr, 0, 0, dt_, stream_);
+    if (!L.moe) {
+      gemv(L.q_gate, xn, H, g32, c.inter, rows, false, "dsq_dense_gate");
+      gemv(L.q_up, xn, H, u32, c.inter, rows, false, "dsq_dense_up");
+      swiglu_f32(g32, u32, h32, rows * c.inter, stream_);
+      gemv(L.q_down, h32, c.inter, x, H, rows, true, "dsq_dense_down");
+    } else {
+      cuda_check(cudaMemsetAsync(counts, 0, E * 4, stream_), "moe counts memset");
+      moe_router(xn, L.router_wt.as<float>(), topk_idx, topk_w, counts, rows, H, E, K, stream_);
+      gemv(L.q_exp_gate, xn, H, g32, mi, n_assign, false, "dsq_expert_gate", topk_idx, K);
+      gemv(L.q_exp_up, xn, H, u32, mi, n_assign, false, "dsq_expert_up", topk_idx, K);
+      swiglu_f32(g32, u32, h32, n_assign * mi, stream_);
+      gemv(L.q_exp_down, h32, mi, y32, H, n_assign, false, "dsq_expert_down", topk_idx, 1);
+      moe_combine(y32, iota, topk_w, x, rows, K, H, nullptr, 0, 0, stream_);
+      gemv(L.q_sh_gate, xn, H, g32, S, rows, false, "dsq_shared_gate");
+      gemv(L.q_sh_up, xn, H, u32, S, rows, false, "dsq_shared_up");
+      swiglu_f32(g32, u32, h32, rows * S, stream_);
+      gemv(L.q_sh_down, h32, S, x, H, rows, true, "dsq_shared_down");
+    }
+  }
+  float* xf = ws("dsq_xf32", (size_t)n_final * H * 4).as<float>();
+  void* xf16 = ws("dec_xf16", 2 * (size_t)n_final * H * 2).p;
+  rmsnorm_split(x, final_norm_.as<float>(), xf16, (long long)n_final * H, xf, final_rows, n_final, H, c.rms_eps, nullptr, 0, 0, dt_, stream_);
+  gemv(q_lm_head_, xf, H, logits, c.vocab, n_final, false, "dsq_lm_head");
 }
 
 void Engine::generate(const GenRequest& rq, int64_t* const* out_tokens, int* n_out) {
@@ -279,7 +353,8 @@ void Engine::generate(const GenRequest& rq, int64_t* const* out_tokens, int* n_o
   // ---- prefill (model/mod.rs:1925-1947)
   kernel_timing_phase("prefill/");
   embed_gather(d_src, embed_.p, img_rows, x, total_rows, H, dt_, stream_);
-  decoder_forward(x, total_rows, d_row_page, d_row_pos, smax, d_last, P, logits);
+  if (quantized_) decoder_forward_dsq(x, total_rows, d_row_page, d_row_pos, smax, d_last, P, logits);
+  else decoder_forward(x, total_rows, d_row_page, d_row_pos, smax, d_last, P, logits);
   copy_logits(0);
   select_token(logits, V, d_hist, smax, d_hist_len, d_gen_count, d_finished, P, ngram, eos, max_new, d_forced, max_new,
                d_selected, max_new, sel_scratch, stream_);
@@ -313,7 +388,8 @@ void Engine::generate(const GenRequest& rq, int64_t* const* out_tokens, int* n_o
   auto run_step = [&](int step) {
     decode_rows(d_hist, smax, d_hist_len, d_src, d_row_pos, P, stream_);
     embed_gather(d_src, embed_.p, nullptr, x, P, H, dt_, stream_);
-    decoder_forward(x, P, d_row_page, d_row_pos, smax, d_row_page /* identity: every row */, P, logits);
+    if (quantized_) decoder_forward_dsq(x, P, d_row_page, d_row_pos, smax, d_row_page, P, logits);
+    else decoder_forward(x, P, d_row_page, d_row_pos, smax, d_row_page /* identity: every row */, P, logits);
     copy_logits(step);
     select_token(logits, V, d_hist, smax, d_hist_len, d_gen_count, d_finished, P, ngram, eos, max_new, d_forced, max_new,
                  d_selected, max_new, sel_scratch, stream_);

@@ -115,8 +115,8 @@ void rope_kv(const float* qkv, const float* cos_t, const float* sin_t, const int
              float* q_out, void* kc, void* vc, bool kv_f16, long long rows, int heads, int smax, int n_splits,
              long long split_stride, cudaStream_t s);
 void kv_attention(const float* q, const void* kc, const void* vc, bool kv_f16, const int* row_page, const int* row_pos,
-                  void* ctx, long long lo_off_elems, long long rows, int heads, int smax, float scale, DType dt,
-                  cudaStream_t s);
+                  void* ctx, long long lo_off_elems, float* ctx32, long long rows, int heads, int smax, float scale,
+                  DType dt, cudaStream_t s);
 void moe_router(const float* x, const float* wgt, int* topk_idx, float* topk_w, int* counts, long long rows, int H,
                 int E, int topk, cudaStream_t s);
 void moe_plan(int* counts, int* offsets, int* cursor, LinearTile* tiles1, int* ntiles1, LinearTile* tiles2,

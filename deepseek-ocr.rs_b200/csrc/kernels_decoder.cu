@@ -247,7 +247,7 @@ template <typename T, typename TKV>
 __global__ void __launch_bounds__(128)
 kv_attention_kernel(const float* __restrict__ q, const TKV* __restrict__ kc, const TKV* __restrict__ vc,
                     const int* __restrict__ row_page, const int* __restrict__ row_pos, T* __restrict__ ctx,
-                    long long lo_off_elems, int heads, int smax, float scale) {
+                    long long lo_off_elems, float* __restrict__ ctx32, int heads, int smax, float scale) {
   constexpr int D = 128;
   const long long r = blockIdx.x;
   const int hd = blockIdx.y;
@@ -315,6 +315,7 @@ kv_attention_kernel(const float* __restrict__ q, const TKV* __restrict__ kc, con
   const float o = num / den;
   const T hi = Elem<T>::from(o);
   const long long oidx = (r * heads + hd) * D + d;
+  if (ctx32) { ctx32[oidx] = o; return; }
   ctx[oidx] = hi;
   ctx[lo_off_elems + oidx] = Elem<T>::from(o - Elem<T>::to(hi));
 }
@@ -666,13 +667,13 @@ void rope_kv(const float* qkv, const float* cos_t, const float* sin_t, const int
   launch_check("rope_kv");
 }
 void kv_attention(const float* q, const void* kc, const void* vc, bool kv_f16, const int* row_page, const int* row_pos,
-                  void* ctx, long long lo_off_elems, long long rows, int heads, int smax, float scale, DType dt,
-                  cudaStream_t s) {
+                  void* ctx, long long lo_off_elems, float* ctx32, long long rows, int heads, int smax, float scale,
+                  DType dt, cudaStream_t s) {
   dim3 grid((unsigned)rows, heads);
   if (kv_f16) {
-    DISPATCH_T(dt, (kv_attention_kernel<T, __half><<<grid, 128, 0, s>>>(q, (const __half*)kc, (const __half*)vc, row_page, row_pos, (T*)ctx, lo_off_elems, heads, smax, scale)));
+    DISPATCH_T(dt, (kv_attention_kernel<T, __half><<<grid, 128, 0, s>>>(q, (const __half*)kc, (const __half*)vc, row_page, row_pos, (T*)ctx, lo_off_elems, ctx32, heads, smax, scale)));
   } else {
-    DISPATCH_T(dt, (kv_attention_kernel<T, float><<<grid, 128, 0, s>>>(q, (const float*)kc, (const float*)vc, row_page, row_pos, (T*)ctx, lo_off_elems, heads, smax, scale)));
+    DISPATCH_T(dt, (kv_attention_kernel<T, float><<<grid, 128, 0, s>>>(q, (const float*)kc, (const float*)vc, row_page, row_pos, (T*)ctx, lo_off_elems, ctx32, heads, smax, scale)));
   }
   launch_check("kv_attention");
 }

@@ -175,3 +175,81 @@ def test_build_prompt_tokens_mismatch_message():
         D.build_prompt_tokens([[1, 2]], [5], cfg)
     ids, mask = D.build_prompt_tokens([[], [7, 8]], [3], cfg)
     assert ids == [0, cfg.image_token_id, cfg.image_token_id, cfg.image_token_id, 7, 8] and mask == [0, 1, 1, 1, 0, 0]
+
+
+# --- DSQ: container + block formats --------------------------------------------------------------------
+def test_dsq_dequant_and_q8_quantiser_match_gguf():
+    """ggml block semantics pinned against gguf-py: dequant for all three formats, quantiser for Q8_0."""
+    import gguf
+    from gguf import quants
+
+    from oracle import dsq
+
+    rng = np.random.RandomState(0)
+    w = (rng.randn(8, 512) * 0.02).astype(np.float32)
+    assert quants.quantize(w, gguf.GGMLQuantizationType.Q8_0).tobytes() == dsq.quantize_q8_0(w)
+    for dt, gg in ((dsq.Q8_0, gguf.GGMLQuantizationType.Q8_0), (dsq.Q4K, gguf.GGMLQuantizationType.Q4_K),
+                   (dsq.Q6K, gguf.GGMLQuantizationType.Q6_K)):
+        q = dsq._QUANT[dt](w)
+        assert len(q) == 8 * 512 // dsq.BLOCK[dt] * dsq.BLOCK_BYTES[dt]
+        mine = dsq.dequantize(q, dt, 8, 512)
+        ref = quants.dequantize(np.frombuffer(q, dtype=np.uint8).reshape(8, -1), gg)
+        assert np.array_equal(mine, ref)
+        assert np.abs(mine - w).max() < 0.06 * np.abs(w).max()
+    # arbitrary (random) valid K-quant blocks, not only the ones our quantiser emits
+    for dt, gg in ((dsq.Q4K, gguf.GGMLQuantizationType.Q4_K), (dsq.Q6K, gguf.GGMLQuantizationType.Q6_K)):
+        nb = dsq.BLOCK_BYTES[dt]
+        raw = rng.randint(0, 256, (4, 3, nb), dtype=np.uint8)
+        half = np.array([0.01], dtype=np.float16).view(np.uint8)
+        if dt == dsq.Q4K:
+            raw[..., 0:2] = half; raw[..., 2:4] = half
+        else:
+            raw[..., 208:210] = half
+        mine = dsq.dequantize(raw.tobytes(), dt, 4, 768)
+        ref = quants.dequantize(raw.reshape(4, -1), gg)
+        assert np.array_equal(mine, ref)
+
+
+def test_dsq_container_layout_matches_reader_test(tmp_path):
+    """Byte layout of crates/dsq/tests/reader.rs:9-66 (build_snapshot_bytes): magic, version, 3 strings, dtype, block,
+    count, record {name, out, in, dtype, q_offset, q_len, bias_offset, bias_len, bias_dtype}, payload, bias."""
+    import struct
+
+    from oracle import dsq
+
+    q = bytes(range(34)) * 2 * 4        # out_dim 4, in_dim 64 -> 2 blocks per row
+    bias = struct.pack("<4f", 1, 2, 3, 4)
+    path = str(tmp_path / "t.dsq")
+    dsq.write_snapshot(path, dsq.Q8_0, [("layer.weight", 4, 64, dsq.Q8_0, q, bias)], model_id="model-id", backend="CPU",
+                       candle_version="candle-test")
+    raw = open(path, "rb").read()
+
+    def ws(s):
+        return struct.pack("<I", len(s)) + s.encode()
+    head = b"DSQSNAP" + struct.pack("<I", 1) + ws("candle-test") + ws("model-id") + ws("CPU") + struct.pack("<III", 8, 32, 1)
+    rec_size = 4 + len("layer.weight") + 12 + 32 + 4
+    q_off = len(head) + rec_size
+    rec = ws("layer.weight") + struct.pack("<III", 4, 64, 8) + struct.pack("<QQQQ", q_off, len(q), q_off + len(q), 16) + struct.pack("<I", 4)
+    assert raw == head + rec + q + bias
+    hdr, recs, data = dsq.read_snapshot(path)
+    r = recs["layer.weight"]
+    assert (r.out_dim, r.in_dim, r.q_dtype, r.q_offset, r.q_len, r.bias_len) == (4, 64, 8, q_off, len(q), 16)
+    bad = bytearray(raw); bad[0:7] = b"BADSNAP"
+    (tmp_path / "bad.dsq").write_bytes(bytes(bad))
+    with pytest.raises(ValueError, match="magic"):
+        dsq.read_snapshot(str(tmp_path / "bad.dsq"))
+    bad = bytearray(raw); bad[7:11] = struct.pack("<I", 2)
+    (tmp_path / "bad2.dsq").write_bytes(bytes(bad))
+    with pytest.raises(ValueError, match="version"):
+        dsq.read_snapshot(str(tmp_path / "bad2.dsq"))
+
+
+def test_dsq_dtype_assignment_follows_exporter():
+    from oracle import dsq
+
+    assert dsq.choose_dtype("model.layers.1.self_attn.q_proj.weight", 1280, dsq.Q4K) == dsq.Q4K
+    assert dsq.choose_dtype("model.layers.1.mlp.experts.3.down_proj.weight", 896, dsq.Q4K) == dsq.Q8_0
+    assert dsq.choose_dtype("model.layers.0.mlp.down_proj.weight", 6848, dsq.Q6K) == dsq.Q8_0
+    assert dsq.choose_dtype("lm_head.weight", 1280, dsq.Q4K) == dsq.Q8_0
+    assert dsq.choose_dtype("lm_head.weight", 1280, dsq.Q8_0) == dsq.Q8_0
+    assert dsq.choose_dtype("x", 1792, dsq.Q6K) == dsq.Q6K
