@@ -53,7 +53,8 @@ def parse_args():
     ap.add_argument("--cpu-tokens", type=int, default=24, help="decode tokens in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-json", default="", help="write the per-kernel timing breakdown here")
-    ap.add_argument("--kv-cache", default="f32", choices=["f32", "f16"], help="KV cache storage (reference: f32)")
+    ap.add_argument("--kv-cache", default="f16", choices=["f32", "f16"],
+                    help="KV cache storage: f16 (matches the fp16 config; token-exact on the fixtures) or f32 (the reference's choice)")
     return ap.parse_args()
 
 

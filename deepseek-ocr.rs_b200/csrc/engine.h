@@ -114,7 +114,7 @@ class Engine {
   const float* clip_pos_for(int g3);
   const void* rel_table_for(int layer, int size, int* zhalf);
   void decoder_forward(float* x, long long rows, const int* row_page, const int* row_pos, int smax,
-                       const int* final_rows, int n_final, float* logits);
+                       const int* final_rows, int n_final, float* logits, bool decode_mode);
   void record_tap(const std::string& name, const float* dev, size_t n);
   void record_tap16(const std::string& name, const void* dev, size_t n);
   DevBuf& ws(const std::string& name, size_t bytes);
@@ -132,6 +132,7 @@ class Engine {
   bool quantized_ = false;
   QuantWeight q_lm_head_;
   long long iota_n_ = 0;
+  long long fixed_tiles_key_ = -1;  // (cap, bn) the cached fixed-capacity MoE tile tables were built for
   std::map<std::string, std::vector<float>> taps_;
 
   // weights

@@ -13,7 +13,7 @@ namespace dsocr {
 // rows (the reference computes logits for every prefill row, transformer/model.rs:243-270; only the last
 // row of each page is ever used, model/mod.rs:1941-1947).
 void Engine::decoder_forward(float* x, long long rows, const int* row_page, const int* row_pos, int smax,
-                             const int* final_rows, int n_final, float* logits) {
+                             const int* final_rows, int n_final, float* logits, bool decode_mode) {
   const ModelConfig& c = cfg_;
   const int H = c.hidden, heads = c.heads, E = c.n_experts, K = c.topk, mi = c.moe_inter;
   const long long S = (long long)c.moe_inter * c.n_shared;
@@ -39,10 +39,39 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
   const int max_chunks = (int)(n_assign / bn) + E;
   LinearTile* tiles1 = ws("moe_tiles1", (size_t)max_chunks * (mi / 128) * sizeof(LinearTile)).as<LinearTile>();
   LinearTile* tiles2 = ws("moe_tiles2", (size_t)max_chunks * (H / 128) * sizeof(LinearTile)).as<LinearTile>();
+  // decode mode: every expert owns a fixed-capacity segment of `cap` rows (a token picks an expert at most once)
+  const bool fused = decode_mode && rows <= 256;
+  const long long cap = rows;
+  const long long perm_rows = fused ? std::max<long long>(n_assign, (long long)E * cap) : n_assign;
   int* perm_pos = ws("moe_perm", n_assign * 4).as<int>();
-  void* xperm16 = ws("moe_xperm16", 2 * n_assign * H * 2).p;
-  void* hperm16 = ws("moe_hperm16", 2 * n_assign * mi * 2).p;
-  float* yperm = ws("moe_yperm32", n_assign * H * 4).as<float>();
+  void* xperm16 = ws("moe_xperm16", 2 * perm_rows * H * 2).p;
+  void* hperm16 = ws("moe_hperm16", 2 * perm_rows * mi * 2).p;
+  float* yperm = ws("moe_yperm32", perm_rows * H * 4).as<float>();
+  int* counts_layers = nullptr;
+  LinearTile* ftiles1 = nullptr; LinearTile* ftiles2 = nullptr;
+  int fbn = 32, fchunks = 0;
+  if (fused) {
+    counts_layers = ws("moe_counts_layers", (size_t)c.layers * E * 4).as<int>();
+    cuda_check(cudaMemsetAsync(counts_layers, 0, (size_t)c.layers * E * 4, stream_), "moe counts memset");
+    fbn = cap <= 32 ? 32 : (cap <= 64 ? 64 : 128);  // one tile covers a whole expert segment for batches <= 128 pages
+    fchunks = (int)((cap + fbn - 1) / fbn);
+    const size_t n1 = (size_t)fchunks * E * (mi / 128), n2 = (size_t)fchunks * E * (H / 128);
+    ftiles1 = ws("moe_ftiles1", n1 * sizeof(LinearTile)).as<LinearTile>();
+    ftiles2 = ws("moe_ftiles2", n2 * sizeof(LinearTile)).as<LinearTile>();
+    const long long key = cap * 1000 + fbn;
+    if (fixed_tiles_key_ != key) {  // built once per batch size (first, eager step - never during capture)
+      std::vector<LinearTile> t1, t2;
+      for (int ch = 0; ch < fchunks; ++ch)      // chunk-major: the (mostly non-empty) first chunks spread over all CTAs
+        for (int e = 0; e < E; ++e) {
+          for (int wb = 0; wb < mi / 128; ++wb) t1.push_back({e * mi + wb * 128, (int)(e * cap + ch * fbn), 0, wb * 128, e, ch * fbn});
+          for (int wb = 0; wb < H / 128; ++wb) t2.push_back({e * H + wb * 128, (int)(e * cap + ch * fbn), 0, wb * 128, e, ch * fbn});
+        }
+      cuda_check(cudaMemcpyAsync(ftiles1, t1.data(), t1.size() * sizeof(LinearTile), cudaMemcpyHostToDevice, stream_), "tiles upload");
+      cuda_check(cudaMemcpyAsync(ftiles2, t2.data(), t2.size() * sizeof(LinearTile), cudaMemcpyHostToDevice, stream_), "tiles upload");
+      cuda_check(cudaStreamSynchronize(stream_), "tiles upload sync");
+      fixed_tiles_key_ = key;
+    }
+  }
 
   // Small-M (decode) projections are split along K so that they fill the GPU; the f32 partials are reduced
   // in a fixed order by the consumer kernel (RoPE, RMSNorm, SwiGLU-reduce, MoE combine) -> deterministic.
@@ -61,10 +90,16 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
   int pend_n = 0;
   long long pend_stride = 0;
 
+  void* xf16 = ws("dec_xf16", 2 * (size_t)n_final * H * 2).p;
+  bool have_xn = false;     // this layer's ln1 output was already produced by the previous layer's combine_norm
+  bool final_done = false;  // the final norm was fused into the last layer's combine_norm
   for (int l = 0; l < c.layers; ++l) {
     DecLayerW& L = dec_[l];
-    rmsnorm_split(x, L.ln1.as<float>(), xn16, rows * H, nullptr, nullptr, rows, H, c.rms_eps, pend, pend_n, pend_stride, dt_, stream_);
-    pend = nullptr; pend_n = 0;
+    if (!have_xn) {
+      rmsnorm_split(x, L.ln1.as<float>(), xn16, rows * H, nullptr, nullptr, rows, H, c.rms_eps, pend, pend_n, pend_stride, dt_, stream_);
+      pend = nullptr; pend_n = 0;
+    }
+    have_xn = false;
     {
       LinearCall lc;  // fused q/k/v projection
       lc.tag = "dec_qkv"; lc.w0 = L.qkv_w.p; lc.x = xn16; lc.x_rows = 2 * rows; lc.x_parts = 2; lc.x_lo_row_off = (int)rows;
@@ -72,10 +107,15 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
       lc.out = sp_qkv > 1 ? partA : qkv; lc.k_splits = sp_qkv; lc.split_stride = rows * 3 * H;
       linear(lc, dt_, num_sms_, stream_);
     }
-    rope_kv(sp_qkv > 1 ? partA : qkv, rope_cos_.as<float>(), rope_sin_.as<float>(), row_page, row_pos, q,
-            kcache_[l].p, vcache_[l].p, kv_f16_, rows, heads, smax, sp_qkv, rows * 3 * H, stream_);
-    kv_attention(q, kcache_[l].p, vcache_[l].p, kv_f16_, row_page, row_pos, ctx16, rows * H, nullptr, rows, heads, smax, scale,
-                 dt_, stream_);
+    if (fused) {
+      rope_attn_decode(sp_qkv > 1 ? partA : qkv, sp_qkv, rows * 3 * H, rope_cos_.as<float>(), rope_sin_.as<float>(),
+                       kcache_[l].p, vcache_[l].p, kv_f16_, row_page, row_pos, ctx16, rows * H, rows, heads, smax, scale, dt_, stream_);
+    } else {
+      rope_kv(sp_qkv > 1 ? partA : qkv, rope_cos_.as<float>(), rope_sin_.as<float>(), row_page, row_pos, q,
+              kcache_[l].p, vcache_[l].p, kv_f16_, rows, heads, smax, sp_qkv, rows * 3 * H, stream_);
+      kv_attention(q, kcache_[l].p, vcache_[l].p, kv_f16_, row_page, row_pos, ctx16, rows * H, nullptr, rows, heads, smax, scale,
+                   dt_, stream_);
+    }
     {
       LinearCall lc;  // o_proj (+ residual add, fused here or in the following RMSNorm when split)
       lc.tag = "dec_o_proj"; lc.w0 = L.o_w.p; lc.x = ctx16; lc.x_rows = 2 * rows; lc.x_parts = 2; lc.x_lo_row_off = (int)rows;
@@ -84,8 +124,10 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
       else { lc.out = x; lc.out_mode = lin::OUT_F32_ADD; }
       linear(lc, dt_, num_sms_, stream_);
     }
-    rmsnorm_split(x, L.ln2.as<float>(), xn16, rows * H, L.moe ? xn32 : nullptr, nullptr, rows, H, c.rms_eps,
-                  sp_o > 1 ? partA : nullptr, sp_o, rows * H, dt_, stream_);
+    const bool fused_moe = fused && L.moe;
+    if (!fused_moe)
+      rmsnorm_split(x, L.ln2.as<float>(), xn16, rows * H, L.moe ? xn32 : nullptr, nullptr, rows, H, c.rms_eps,
+                    sp_o > 1 ? partA : nullptr, sp_o, rows * H, dt_, stream_);
     if (!L.moe) {
       {
         LinearCall lc;  // gate/up + SwiGLU (run_dense_mlp, block.rs:1166-1177)
@@ -113,30 +155,42 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
     } else {
       // run_moe (block.rs:1215-1395).  In decode the shared-experts branch (3 small kernels) runs on a forked
       // stream next to the routed branch (router/plan/dispatch/2 grouped GEMMs): both are latency-bound.
+      int* lcounts = fused ? counts_layers + (size_t)l * E : counts;
+      if (fused) {
+        // o_proj partial reduce + residual + RMSNorm(ln2) + router + top-k + dispatch in one kernel
+        post_attn(x, sp_o > 1 ? partA : nullptr, sp_o > 1 ? sp_o : 0, rows * H, L.ln2.as<float>(), L.router_wt.as<float>(),
+                  xn16, rows * H, topk_idx, topk_w, lcounts, perm_pos, xperm16, (long long)E * cap * H, (int)cap, rows, H, E, K,
+                  c.rms_eps, dt_, stream_);
+      } else {
+        moe_router(xn32, L.router_wt.as<float>(), topk_idx, topk_w, counts, rows, H, E, K, stream_);
+        moe_plan(counts, offsets, cursor, tiles1, ntiles, tiles2, ntiles + 1, E, bn, mi, H, stream_);
+        moe_dispatch(topk_idx, offsets, cursor, xn16, rows * H, xperm16, n_assign * H, perm_pos, n_assign, K, H, dt_, stream_);
+      }
       const bool fork = rows <= 256 && !kernel_timing_enabled();
       cudaStream_t sb = fork ? stream2_ : stream_;
       if (fork) {
         cuda_check(cudaEventRecord(ev_fork_, stream_), "fork record");
         cuda_check(cudaStreamWaitEvent(sb, ev_fork_, 0), "fork wait");
       }
-      moe_router(xn32, L.router_wt.as<float>(), topk_idx, topk_w, counts, rows, H, E, K, stream_);
-      moe_plan(counts, offsets, cursor, tiles1, ntiles, tiles2, ntiles + 1, E, bn, mi, H, stream_);
-      moe_dispatch(topk_idx, offsets, cursor, xn16, rows * H, xperm16, n_assign * H, perm_pos, n_assign, K, H, dt_, stream_);
       {
         LinearCall lc;  // routed experts: gate/up + SwiGLU, grouped
         lc.tag = "moe_expert_gate_up"; lc.w0 = L.exp_gate.p; lc.w1 = L.exp_up.p; lc.w_rows = (long long)E * mi;
-        lc.x = xperm16; lc.x_rows = 2 * n_assign; lc.x_parts = 2; lc.x_lo_row_off = (int)n_assign;
-        lc.M = (int)n_assign; lc.N = mi; lc.K = H;
-        lc.out = hperm16; lc.out_lo = (uint16_t*)hperm16 + n_assign * mi; lc.ldo = mi; lc.out_mode = lin::OUT_T_SPLIT;
-        lc.tiles = tiles1; lc.num_tiles_dev = ntiles; lc.max_tiles = max_chunks * (mi / 128); lc.bn = bn;
+        const long long pr = fused ? (long long)E * cap : n_assign;
+        lc.x = xperm16; lc.x_rows = 2 * pr; lc.x_parts = 2; lc.x_lo_row_off = (int)pr;
+        lc.M = (int)pr; lc.N = mi; lc.K = H;
+        lc.out = hperm16; lc.out_lo = (uint16_t*)hperm16 + pr * mi; lc.ldo = mi; lc.out_mode = lin::OUT_T_SPLIT;
+        if (fused) { lc.tiles = ftiles1; lc.group_counts = lcounts; lc.max_tiles = fchunks * E * (mi / 128); lc.bn = fbn; }
+        else { lc.tiles = tiles1; lc.num_tiles_dev = ntiles; lc.max_tiles = max_chunks * (mi / 128); lc.bn = bn; }
         linear(lc, dt_, num_sms_, stream_);
       }
       {
         LinearCall lc;  // routed experts: down, grouped
         lc.tag = "moe_expert_down"; lc.w0 = L.exp_down.p; lc.w_rows = (long long)E * H;
-        lc.x = hperm16; lc.x_rows = 2 * n_assign; lc.x_parts = 2; lc.x_lo_row_off = (int)n_assign;
-        lc.M = (int)n_assign; lc.N = H; lc.K = mi; lc.out = yperm; lc.ldo = H; lc.out_mode = lin::OUT_F32;
-        lc.tiles = tiles2; lc.num_tiles_dev = ntiles + 1; lc.max_tiles = max_chunks * (H / 128); lc.bn = bn;
+        const long long pr = fused ? (long long)E * cap : n_assign;
+        lc.x = hperm16; lc.x_rows = 2 * pr; lc.x_parts = 2; lc.x_lo_row_off = (int)pr;
+        lc.M = (int)pr; lc.N = H; lc.K = mi; lc.out = yperm; lc.ldo = H; lc.out_mode = lin::OUT_F32;
+        if (fused) { lc.tiles = ftiles2; lc.group_counts = lcounts; lc.max_tiles = fchunks * E * (H / 128); lc.bn = fbn; }
+        else { lc.tiles = tiles2; lc.num_tiles_dev = ntiles + 1; lc.max_tiles = max_chunks * (H / 128); lc.bn = bn; }
         linear(lc, dt_, num_sms_, stream_);
       }
       {
@@ -163,14 +217,22 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
         cuda_check(cudaEventRecord(ev_join_, sb), "join record");
         cuda_check(cudaStreamWaitEvent(stream_, ev_join_, 0), "join wait");
       }
-      moe_combine(yperm, perm_pos, topk_w, x, rows, K, H, sp_sd > 1 ? partB : nullptr, sp_sd, rows * H, stream_);
+      if (fused) {
+        const bool last = l + 1 == c.layers;
+        combine_norm(x, yperm, perm_pos, topk_w, K, sp_sd > 1 ? partB : nullptr, sp_sd, rows * H,
+                     last ? final_norm_.as<float>() : dec_[l + 1].ln1.as<float>(), last ? xf16 : xn16, rows * H, rows, H,
+                     c.rms_eps, dt_, stream_);
+        if (last) final_done = true; else have_xn = true;
+      } else {
+        moe_combine(yperm, perm_pos, topk_w, x, rows, K, H, sp_sd > 1 ? partB : nullptr, sp_sd, rows * H, stream_);
+      }
     }
     if (record_taps_) record_tap("dec.hidden." + std::to_string(l), x, rows * H);
   }
   // final RMSNorm + lm_head on the selected rows
-  void* xf16 = ws("dec_xf16", 2 * (size_t)n_final * H * 2).p;
-  rmsnorm_split(x, final_norm_.as<float>(), xf16, (long long)n_final * H, nullptr, final_rows, n_final, H, c.rms_eps,
-                pend, pend_n, pend_stride, dt_, stream_);
+  if (!final_done)
+    rmsnorm_split(x, final_norm_.as<float>(), xf16, (long long)n_final * H, nullptr, final_rows, n_final, H, c.rms_eps,
+                  pend, pend_n, pend_stride, dt_, stream_);
   LinearCall lc;
   lc.tag = "lm_head"; lc.w0 = lm_head_.p; lc.x = xf16; lc.x_rows = 2 * n_final; lc.x_parts = 2; lc.x_lo_row_off = n_final;
   lc.M = n_final; lc.N = c.vocab; lc.K = H; lc.out = logits; lc.ldo = c.vocab; lc.out_mode = lin::OUT_F32;
@@ -354,7 +416,7 @@ void Engine::generate(const GenRequest& rq, int64_t* const* out_tokens, int* n_o
   kernel_timing_phase("prefill/");
   embed_gather(d_src, embed_.p, img_rows, x, total_rows, H, dt_, stream_);
   if (quantized_) decoder_forward_dsq(x, total_rows, d_row_page, d_row_pos, smax, d_last, P, logits);
-  else decoder_forward(x, total_rows, d_row_page, d_row_pos, smax, d_last, P, logits);
+  else decoder_forward(x, total_rows, d_row_page, d_row_pos, smax, d_last, P, logits, false);
   copy_logits(0);
   select_token(logits, V, d_hist, smax, d_hist_len, d_gen_count, d_finished, P, ngram, eos, max_new, d_forced, max_new,
                d_selected, max_new, sel_scratch, stream_);
@@ -389,7 +451,7 @@ void Engine::generate(const GenRequest& rq, int64_t* const* out_tokens, int* n_o
     decode_rows(d_hist, smax, d_hist_len, d_src, d_row_pos, P, stream_);
     embed_gather(d_src, embed_.p, nullptr, x, P, H, dt_, stream_);
     if (quantized_) decoder_forward_dsq(x, P, d_row_page, d_row_pos, smax, d_row_page, P, logits);
-    else decoder_forward(x, P, d_row_page, d_row_pos, smax, d_row_page /* identity: every row */, P, logits);
+    else decoder_forward(x, P, d_row_page, d_row_pos, smax, d_row_page /* identity: every row */, P, logits, true);
     copy_logits(step);
     select_token(logits, V, d_hist, smax, d_hist_len, d_gen_count, d_finished, P, ngram, eos, max_new, d_forced, max_new,
                  d_selected, max_new, sel_scratch, stream_);

@@ -23,7 +23,7 @@ void kernel_timing_phase(const char* phase);  // prefix for subsequently recorde
 std::string kernel_timing_end_json();
 
 // ------------------------------------------------------------------------- tensor-core linear
-struct LinearTile { int w_row0, x_row0, rows, n0; };  // == lin::Tile
+struct LinearTile { int w_row0, x_row0, rows, n0, group, r0; };  // == lin::Tile
 
 struct LinearCall {
   // weights: [w_rows, K] 16-bit, row pitch ldw (0 = K).  w1 != nullptr selects the dual (SwiGLU) kernel.
@@ -52,6 +52,7 @@ struct LinearCall {
   // grouped problems
   const LinearTile* tiles = nullptr;
   const int* num_tiles_dev = nullptr;
+  const int* group_counts = nullptr;  // fixed-capacity groups: tile rows derived from device-side counts
   int max_tiles = 0;
   int tile_rows_hint = 0;  // typical rows per tile, used to pick the token tile
   int bn = 0;              // force the token tile (0 = auto)
@@ -134,5 +135,15 @@ bool kernel_timing_enabled();
 void decode_rows(const int* hist, int hist_stride, const int* hist_len, int* src, int* row_pos, int n_pages,
                  cudaStream_t s);
 void fill_i32(int* p, int v, long long n, cudaStream_t s);
+// decode-step fusions (rows <= 256)
+void rope_attn_decode(const float* qkv, int n_splits, long long split_stride, const float* cos_t, const float* sin_t,
+                      void* kc, void* vc, bool kv_f16, const int* row_page, const int* row_pos, void* ctx,
+                      long long lo_off_elems, long long rows, int heads, int smax, float scale, DType dt, cudaStream_t s);
+void post_attn(float* x, const float* partials, int n_splits, long long split_stride, const float* w, const float* wgt,
+               void* xn16, long long xn_lo_off, int* topk_idx, float* topk_w, int* counts, int* perm_pos, void* xperm,
+               long long xperm_lo_off, int cap, long long rows, int H, int E, int topk, float eps, DType dt, cudaStream_t s);
+void combine_norm(float* x, const float* y, const int* perm_pos, const float* topk_w, int topk, const float* partials,
+                  int n_splits, long long split_stride, const float* w_next, void* out16, long long lo_off_elems,
+                  long long rows, int H, float eps, DType dt, cudaStream_t s);
 
 }  // namespace dsocr

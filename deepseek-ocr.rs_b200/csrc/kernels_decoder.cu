@@ -321,6 +321,281 @@ kv_attention_kernel(const float* __restrict__ q, const TKV* __restrict__ kc, con
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Decode-step fusions (one query row per page; rows <= 256).  They remove ~56 of the ~175 launches of a step.
+
+// (1) RoPE + KV append + attention: the block of (row, head) reduces the split-K partials of the qkv
+// projection for its own head, rotates q/k, appends k/v to the cache and then attends over the cache.
+template <typename T, typename TKV>
+__global__ void __launch_bounds__(128)
+rope_attn_decode_kernel(const float* __restrict__ qkv, int n_splits, long long split_stride,
+                        const float* __restrict__ cos_t, const float* __restrict__ sin_t, TKV* __restrict__ kc,
+                        TKV* __restrict__ vc, const int* __restrict__ row_page, const int* __restrict__ row_pos,
+                        T* __restrict__ ctx, long long lo_off_elems, int heads, int smax, float scale) {
+  constexpr int D = 128;
+  const long long r = blockIdx.x;
+  const int hd = blockIdx.y;
+  const int t = threadIdx.x;
+  const int warp = t >> 5, lane = t & 31;
+  const int grp = lane >> 3, sub = lane & 7;
+  const int pos = row_pos[r];
+  const int page = row_page[r];
+  const int nkeys = pos + 1;
+  TKV* kbase = kc + ((long long)page * heads + hd) * smax * D;
+  TKV* vbase = vc + ((long long)page * heads + hd) * smax * D;
+  __shared__ float q_s[D];
+  __shared__ float sm_m[16], sm_l[16], sm_acc[16][D];
+  auto part_sum = [&](const float* p) {
+    float a = p[0];
+    for (int sidx = 1; sidx < n_splits; ++sidx) a += p[sidx * split_stride];
+    return a;
+  };
+  const float* base = qkv + r * 3 * heads * D;
+  if (t < 64) {
+    const float c = cos_t[(long long)pos * 64 + t], sn = sin_t[(long long)pos * 64 + t];
+    const float qlo = part_sum(base + hd * D + t), qhi = part_sum(base + hd * D + 64 + t);
+    const float klo = part_sum(base + (heads + hd) * D + t), khi = part_sum(base + (heads + hd) * D + 64 + t);
+    q_s[t] = (qlo * c - qhi * sn) * scale;
+    q_s[t + 64] = (qhi * c + qlo * sn) * scale;
+    kbase[(long long)pos * D + t] = (TKV)(klo * c - khi * sn);
+    kbase[(long long)pos * D + 64 + t] = (TKV)(khi * c + klo * sn);
+  } else {
+    const int d = t - 64;
+    vbase[(long long)pos * D + d] = (TKV)part_sum(base + (2 * heads + hd) * D + d);
+    vbase[(long long)pos * D + 64 + d] = (TKV)part_sum(base + (2 * heads + hd) * D + 64 + d);
+  }
+  __syncthreads();  // q in smem, new K/V row visible to the whole block
+  float qv[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) qv[i] = q_s[sub * 16 + i];
+  float m = -INFINITY, l = 0.f, acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  for (int k0 = warp * 4; k0 < nkeys; k0 += 16) {
+    const int k = k0 + grp;
+    const bool ok = k < nkeys;
+    float s = 0.f;
+    float vv[16];
+    if (ok) {
+      float kk[16];
+      load16(kbase + (long long)k * D + sub * 16, kk);
+      load16(vbase + (long long)k * D + sub * 16, vv);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) s += qv[i] * kk[i];
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (ok) {
+      const float mn = fmaxf(m, s);
+      const float a = __expf(m - mn);
+      const float pe = __expf(s - mn);
+      l = l * a + pe;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[i] = acc[i] * a + pe * vv[i];
+      m = mn;
+    }
+  }
+  const int slot = warp * 4 + grp;
+  if (sub == 0) { sm_m[slot] = m; sm_l[slot] = l; }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) sm_acc[slot][sub * 16 + i] = acc[i];
+  __syncthreads();
+  float gm = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) gm = fmaxf(gm, sm_m[i]);
+  float num = 0.f, den = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float f = sm_m[i] == -INFINITY ? 0.f : __expf(sm_m[i] - gm);
+    num += f * sm_acc[i][t];
+    den += f * sm_l[i];
+  }
+  const float o = num / den;
+  const T hi = Elem<T>::from(o);
+  const long long oidx = (r * heads + hd) * D + t;
+  ctx[oidx] = hi;
+  ctx[lo_off_elems + oidx] = Elem<T>::from(o - Elem<T>::to(hi));
+}
+
+// (2) o_proj split-K reduce + residual add + RMSNorm(ln2) + router + top-k + dispatch into fixed-capacity
+// expert segments (slot = atomic counter per expert; the grouped GEMM reads the counters), one block per row.
+template <typename T, int E>
+__global__ void __launch_bounds__(1024)
+post_attn_kernel(float* __restrict__ x, const float* __restrict__ partials, int n_splits, long long split_stride,
+                 const float* __restrict__ w, const float* __restrict__ wgt, T* __restrict__ xn16, long long xn_lo_off,
+                 int* __restrict__ topk_idx, float* __restrict__ topk_w, int* __restrict__ counts,
+                 int* __restrict__ perm_pos, T* __restrict__ xperm, long long xperm_lo_off, int cap, int H, int topk,
+                 float eps) {
+  constexpr int KS = 1024 / E;
+  constexpr int PER = (E + 31) / 32;
+  extern __shared__ float sm[];
+  float* xn_s = sm;            // [H]
+  float* part = sm + H;        // [1024]
+  __shared__ float red[32];
+  __shared__ int sel_pos[16];
+  const long long row = blockIdx.x;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int n4 = H / 4;
+  float4 v = make_float4(0, 0, 0, 0);
+  float ss = 0.f;
+  if (t < n4) {
+    v = reinterpret_cast<float4*>(x + row * H)[t];
+    for (int sidx = 0; sidx < n_splits; ++sidx) {
+      const float4 pv = reinterpret_cast<const float4*>(partials + sidx * split_stride + row * H)[t];
+      v.x += pv.x; v.y += pv.y; v.z += pv.z; v.w += pv.w;
+    }
+    reinterpret_cast<float4*>(x + row * H)[t] = v;
+    ss = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  ss = warp_sum(ss);
+  if (lane == 0) red[warp] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) tot += red[i];
+  const float inv = rsqrtf(tot / (float)H + eps);
+  if (t < n4) {
+    const float4 ww = reinterpret_cast<const float4*>(w)[t];
+    float o[4] = {v.x * inv * ww.x, v.y * inv * ww.y, v.z * inv * ww.z, v.w * inv * ww.w};
+    reinterpret_cast<float4*>(xn_s)[t] = make_float4(o[0], o[1], o[2], o[3]);
+    uint2 hi, lo;
+    split4<T>(o, hi, lo);
+    reinterpret_cast<uint2*>(xn16 + row * H)[t] = hi;
+    reinterpret_cast<uint2*>(xn16 + xn_lo_off + row * H)[t] = lo;
+  }
+  __syncthreads();
+  {  // router logits: thread = (k-slice, expert)
+    const int e = t % E, ks = t / E;
+    const int kper = H / KS;
+    const float* wp = wgt + (long long)(ks * kper) * E + e;
+    const float* xp = xn_s + ks * kper;
+    float acc = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < kper; ++k) acc = fmaf(xp[k], wp[(long long)k * E], acc);
+    part[ks * E + e] = acc;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float p[PER];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      const int ee = j * 32 + lane;
+      float s = -INFINITY;
+      if (ee < E) {
+        s = 0.f;
+#pragma unroll
+        for (int q = 0; q < KS; ++q) s += part[q * E + ee];
+      }
+      p[j] = s;
+      mx = fmaxf(mx, s);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      p[j] = (j * 32 + lane < E) ? expf(p[j] - mx) : 0.f;
+      sum += p[j];
+    }
+    sum = warp_sum(sum);
+#pragma unroll
+    for (int j = 0; j < PER; ++j) p[j] = (j * 32 + lane < E) ? p[j] / sum : -1.f;
+    for (int k = 0; k < topk; ++k) {
+      float bv = -1.f; int bi = 1 << 30;
+#pragma unroll
+      for (int j = 0; j < PER; ++j) {
+        const int ee = j * 32 + lane;
+        if (ee < E && (p[j] > bv || (p[j] == bv && ee < bi))) { bv = p[j]; bi = ee; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+      if (lane == 0) {
+        const int pos = bi * cap + atomicAdd(&counts[bi], 1);
+        topk_idx[row * topk + k] = bi;
+        topk_w[row * topk + k] = bv;
+        perm_pos[row * topk + k] = pos;
+        sel_pos[k] = pos;
+      }
+#pragma unroll
+      for (int j = 0; j < PER; ++j) if (j * 32 + lane == bi) p[j] = -2.f;
+    }
+  }
+  __syncthreads();
+  for (int idx = t; idx < topk * n4; idx += 1024) {  // copy the normed row into its expert slots
+    const int k = idx / n4, c4 = idx % n4;
+    const float4 o4 = reinterpret_cast<const float4*>(xn_s)[c4];
+    const float o[4] = {o4.x, o4.y, o4.z, o4.w};
+    uint2 hi, lo;
+    split4<T>(o, hi, lo);
+    const long long dst = (long long)sel_pos[k] * H;
+    reinterpret_cast<uint2*>(xperm + dst)[c4] = hi;
+    reinterpret_cast<uint2*>(xperm + xperm_lo_off + dst)[c4] = lo;
+  }
+}
+
+// (3) MoE combine + shared-experts split-K reduce + residual add + the NEXT RMSNorm (next layer's ln1 or the
+// final norm), one 128-thread block per row.
+template <typename T, int MAXS>
+__global__ void __launch_bounds__(128)
+combine_norm_kernel(float* __restrict__ x, const float* __restrict__ y, const int* __restrict__ perm_pos,
+                    const float* __restrict__ topk_w, int topk, const float* __restrict__ partials, int n_splits,
+                    long long split_stride, const float* __restrict__ w_next, T* __restrict__ out16,
+                    long long lo_off_elems, int H, float eps) {
+  const long long row = blockIdx.x;
+  const int n4 = H / 4;
+  float4 v[3];
+  float ss = 0.f;
+  float wk[8]; int pk[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { wk[k] = k < topk ? topk_w[row * topk + k] : 0.f; pk[k] = k < topk ? perm_pos[row * topk + k] : 0; }
+#pragma unroll
+  for (int it = 0; it < 3; ++it) {
+    const int i = threadIdx.x + it * 128;
+    v[it] = make_float4(0, 0, 0, 0);
+    if (i < n4) {
+      float4 a = reinterpret_cast<float4*>(x + row * H)[i];
+      float4 pv[MAXS];
+#pragma unroll
+      for (int sidx = 0; sidx < MAXS; ++sidx)
+        pv[sidx] = sidx < n_splits ? reinterpret_cast<const float4*>(partials + sidx * split_stride + row * H)[i] : make_float4(0, 0, 0, 0);
+      float4 yv[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) yv[k] = k < topk ? reinterpret_cast<const float4*>(y + (long long)pk[k] * H)[i] : make_float4(0, 0, 0, 0);
+#pragma unroll
+      for (int sidx = 0; sidx < MAXS; ++sidx) { a.x += pv[sidx].x; a.y += pv[sidx].y; a.z += pv[sidx].z; a.w += pv[sidx].w; }
+      float4 acc = make_float4(0, 0, 0, 0);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { acc.x += wk[k] * yv[k].x; acc.y += wk[k] * yv[k].y; acc.z += wk[k] * yv[k].z; acc.w += wk[k] * yv[k].w; }
+      a.x += acc.x; a.y += acc.y; a.z += acc.z; a.w += acc.w;
+      reinterpret_cast<float4*>(x + row * H)[i] = a;
+      v[it] = a;
+      ss += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+    }
+  }
+  __shared__ float red[4];
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  const float inv = rsqrtf((red[0] + red[1] + red[2] + red[3]) / (float)H + eps);
+#pragma unroll
+  for (int it = 0; it < 3; ++it) {
+    const int i = threadIdx.x + it * 128;
+    if (i < n4) {
+      const float4 ww = reinterpret_cast<const float4*>(w_next)[i];
+      float o[4] = {v[it].x * inv * ww.x, v[it].y * inv * ww.y, v[it].z * inv * ww.z, v[it].w * inv * ww.w};
+      uint2 hi, lo;
+      split4<T>(o, hi, lo);
+      reinterpret_cast<uint2*>(out16 + row * H)[i] = hi;
+      reinterpret_cast<uint2*>(out16 + lo_off_elems + row * H)[i] = lo;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // MoE router (run_moe, block.rs:1263-1301): logits = x . Wg^T in f32 -> softmax over the experts -> top-k by
 // value (ties -> lowest index, the CPU reference's stable descending sort).  One block = TOK tokens; the
 // reduction dimension is split over KS thread groups of E threads (thread = expert, coalesced reads of the
@@ -743,6 +1018,39 @@ void decode_rows(const int* hist, int hist_stride, const int* hist_len, int* src
 void fill_i32(int* p, int v, long long n, cudaStream_t s) {
   fill_i32_kernel<<<blocks_for(n, 256), 256, 0, s>>>(p, v, n);
   launch_check("fill_i32");
+}
+
+void rope_attn_decode(const float* qkv, int n_splits, long long split_stride, const float* cos_t, const float* sin_t,
+                      void* kc, void* vc, bool kv_f16, const int* row_page, const int* row_pos, void* ctx,
+                      long long lo_off_elems, long long rows, int heads, int smax, float scale, DType dt, cudaStream_t s) {
+  dim3 grid((unsigned)rows, heads);
+  const int ns = n_splits < 1 ? 1 : n_splits;
+  if (kv_f16) {
+    DISPATCH_T(dt, (rope_attn_decode_kernel<T, __half><<<grid, 128, 0, s>>>(qkv, ns, split_stride, cos_t, sin_t, (__half*)kc, (__half*)vc, row_page, row_pos, (T*)ctx, lo_off_elems, heads, smax, scale)));
+  } else {
+    DISPATCH_T(dt, (rope_attn_decode_kernel<T, float><<<grid, 128, 0, s>>>(qkv, ns, split_stride, cos_t, sin_t, (float*)kc, (float*)vc, row_page, row_pos, (T*)ctx, lo_off_elems, heads, smax, scale)));
+  }
+  launch_check("rope_attn_decode");
+}
+void post_attn(float* x, const float* partials, int n_splits, long long split_stride, const float* w, const float* wgt,
+               void* xn16, long long xn_lo_off, int* topk_idx, float* topk_w, int* counts, int* perm_pos, void* xperm,
+               long long xperm_lo_off, int cap, long long rows, int H, int E, int topk, float eps, DType dt, cudaStream_t s) {
+  if (H % 256 || H / 4 > 1024 || topk > 16) throw std::runtime_error("post_attn: unsupported shape");
+  const size_t smem = (size_t)(H + 1024) * 4;
+  DISPATCH_T(dt, {
+    if (E == 64) post_attn_kernel<T, 64><<<(unsigned)rows, 1024, smem, s>>>(x, partials, n_splits, split_stride, w, wgt, (T*)xn16, xn_lo_off, topk_idx, topk_w, counts, perm_pos, (T*)xperm, xperm_lo_off, cap, H, topk, eps);
+    else if (E == 32) post_attn_kernel<T, 32><<<(unsigned)rows, 1024, smem, s>>>(x, partials, n_splits, split_stride, w, wgt, (T*)xn16, xn_lo_off, topk_idx, topk_w, counts, perm_pos, (T*)xperm, xperm_lo_off, cap, H, topk, eps);
+    else if (E == 16) post_attn_kernel<T, 16><<<(unsigned)rows, 1024, smem, s>>>(x, partials, n_splits, split_stride, w, wgt, (T*)xn16, xn_lo_off, topk_idx, topk_w, counts, perm_pos, (T*)xperm, xperm_lo_off, cap, H, topk, eps);
+    else throw std::runtime_error("post_attn: unsupported expert count " + std::to_string(E));
+  });
+  launch_check("post_attn_norm_router_dispatch");
+}
+void combine_norm(float* x, const float* y, const int* perm_pos, const float* topk_w, int topk, const float* partials,
+                  int n_splits, long long split_stride, const float* w_next, void* out16, long long lo_off_elems,
+                  long long rows, int H, float eps, DType dt, cudaStream_t s) {
+  if (H > 1536 || n_splits > 16 || topk > 8) throw std::runtime_error("combine_norm: unsupported shape");
+  DISPATCH_T(dt, (combine_norm_kernel<T, 16><<<(unsigned)rows, 128, 0, s>>>(x, y, perm_pos, topk_w, topk, partials, partials ? n_splits : 0, split_stride, w_next, (T*)out16, lo_off_elems, H, eps)));
+  launch_check("moe_combine_norm");
 }
 
 }  // namespace dsocr

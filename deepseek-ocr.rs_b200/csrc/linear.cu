@@ -13,7 +13,7 @@ namespace {
 
 template <typename T, int BN, int NA, int NB>
 void launch_inst(const LinearCall& c, const lin::Params& p, const CUtensorMap& w0, const CUtensorMap& w1,
-                 const CUtensorMap& x, int grid, cudaStream_t stream) {
+                 const CUtensorMap& x, const CUtensorMap& x16, int grid, cudaStream_t stream) {
   using C = lin::Cfg<BN, NA, NB>;
   auto kern = lin::linear_kernel<T, BN, NA, NB>;
   static bool configured = false;  // per instantiation
@@ -22,32 +22,32 @@ void launch_inst(const LinearCall& c, const lin::Params& p, const CUtensorMap& w
                "linear: set max dynamic smem");
     configured = true;
   }
-  kern<<<grid, lin::kThreads, C::kSmemBytes, stream>>>(w0, w1, x, p);
+  kern<<<grid, lin::kThreads, C::kSmemBytes, stream>>>(w0, w1, x, x16, p);
   launch_check(c.tag ? c.tag : "linear");
 }
 
 template <typename T, int NA, int NB>
 void launch_bn(int bn, const LinearCall& c, const lin::Params& p, const CUtensorMap& w0, const CUtensorMap& w1,
-               const CUtensorMap& x, int grid, cudaStream_t stream) {
+               const CUtensorMap& x, const CUtensorMap& x16, int grid, cudaStream_t stream) {
   switch (bn) {
-    case 32: launch_inst<T, 32, NA, NB>(c, p, w0, w1, x, grid, stream); break;
-    case 64: launch_inst<T, 64, NA, NB>(c, p, w0, w1, x, grid, stream); break;
-    case 128: launch_inst<T, 128, NA, NB>(c, p, w0, w1, x, grid, stream); break;
+    case 32: launch_inst<T, 32, NA, NB>(c, p, w0, w1, x, x16, grid, stream); break;
+    case 64: launch_inst<T, 64, NA, NB>(c, p, w0, w1, x, x16, grid, stream); break;
+    case 128: launch_inst<T, 128, NA, NB>(c, p, w0, w1, x, x16, grid, stream); break;
     case 256:
-      if constexpr (NA == 1) { launch_inst<T, 256, NA, NB>(c, p, w0, w1, x, grid, stream); break; }
+      if constexpr (NA == 1) { launch_inst<T, 256, NA, NB>(c, p, w0, w1, x, x16, grid, stream); break; }
     default: throw std::runtime_error("linear: unsupported token tile " + std::to_string(bn));
   }
 }
 
 template <typename T>
 void launch_t(int bn, const LinearCall& c, const lin::Params& p, const CUtensorMap& w0, const CUtensorMap& w1,
-              const CUtensorMap& x, int grid, cudaStream_t stream) {
+              const CUtensorMap& x, const CUtensorMap& x16, int grid, cudaStream_t stream) {
   const int na = c.w1 ? 2 : 1;
   const int nb = c.x_parts;
-  if (na == 1 && nb == 1) launch_bn<T, 1, 1>(bn, c, p, w0, w1, x, grid, stream);
-  else if (na == 1 && nb == 2) launch_bn<T, 1, 2>(bn, c, p, w0, w1, x, grid, stream);
-  else if (na == 2 && nb == 1) launch_bn<T, 2, 1>(bn, c, p, w0, w1, x, grid, stream);
-  else launch_bn<T, 2, 2>(bn, c, p, w0, w1, x, grid, stream);
+  if (na == 1 && nb == 1) launch_bn<T, 1, 1>(bn, c, p, w0, w1, x, x16, grid, stream);
+  else if (na == 1 && nb == 2) launch_bn<T, 1, 2>(bn, c, p, w0, w1, x, x16, grid, stream);
+  else if (na == 2 && nb == 1) launch_bn<T, 2, 1>(bn, c, p, w0, w1, x, x16, grid, stream);
+  else launch_bn<T, 2, 2>(bn, c, p, w0, w1, x, x16, grid, stream);
 }
 
 }  // namespace
@@ -82,6 +82,7 @@ void linear(const LinearCall& c, DType dt, int num_sms, cudaStream_t stream) {
   p.act = c.act; p.out_mode = c.out_mode; p.swiglu = dual ? 1 : 0;
   p.tiles = reinterpret_cast<const lin::Tile*>(c.tiles);
   p.num_tiles_dev = c.num_tiles_dev;
+  p.group_counts = c.group_counts;
   p.n_w_blocks = (c.N + lin::BM - 1) / lin::BM;
   p.nbatch = c.nbatch > 1 ? c.nbatch : 1;
   p.out_batch_stride = c.out_batch_stride;
@@ -110,9 +111,15 @@ void linear(const LinearCall& c, DType dt, int num_sms, cudaStream_t stream) {
   } else {
     x = tmap::make_2d_16bit(c.x, c.x_rows, c.K, c.ldx ? c.ldx : c.K, bn, lin::BK);
   }
+  CUtensorMap x16 = x;
+  p.x_box16 = 0;
+  if (c.tiles && p.nbatch == 1 && bn <= 128) {  // grouped: tiles rarely fill the token tile
+    x16 = tmap::make_2d_16bit(c.x, c.x_rows, c.K, c.ldx ? c.ldx : c.K, 16, lin::BK);
+    p.x_box16 = 1;
+  }
   const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
-  if (dt == DType::BF16) launch_t<__nv_bfloat16>(bn, c, p, w0, w1, x, grid, stream);
-  else launch_t<__half>(bn, c, p, w0, w1, x, grid, stream);
+  if (dt == DType::BF16) launch_t<__nv_bfloat16>(bn, c, p, w0, w1, x, x16, grid, stream);
+  else launch_t<__half>(bn, c, p, w0, w1, x, x16, grid, stream);
 }
 
 }  // namespace dsocr

@@ -33,8 +33,10 @@ enum Out : int {
 struct Tile {  // grouped problems: one entry per (group, token-chunk, weight-block)
   int w_row0;   // first weight row (A coordinate)
   int x_row0;   // first token row (B coordinate)
-  int rows;     // valid tokens in this tile (<= BN)
+  int rows;     // valid tokens in this tile (<= BN); ignored when Params::group_counts is set
   int n0;       // first output feature (column of out) for this tile
+  int group;    // expert id (index into group_counts)
+  int r0;       // first row of this tile inside its group's fixed-capacity segment
 };
 
 struct Params {
@@ -50,6 +52,7 @@ struct Params {
   int swiglu;              // NA == 2: out = silu(acc0) * acc1
   const Tile* tiles;       // optional grouped tile table
   const int* num_tiles_dev;  // optional device-side tile count (grouped)
+  const int* group_counts;   // optional: rows of tile t = clamp(group_counts[tile.group] - tile.r0, 0, BN); empty tiles are skipped
   int num_tiles;           // host-side tile count (upper bound when num_tiles_dev != nullptr)
   int n_w_blocks;          // ceil(N / 128) for the dense tile decode
   int nbatch;              // > 1: X is a 3-D map [rows, nbatch, K]; tiles enumerate (batch, m, w)
@@ -60,6 +63,9 @@ struct Params {
   int kb_per_split;
   long long split_stride;
   long long dual_stride;
+  // grouped small-M problems: load the token operand in 16-row boxes and only as many as the tile has rows
+  // (the unused part of the smem tile keeps stale data; those MMA columns are never stored)
+  int x_box16;
 };
 
 constexpr int BM = 128;  // weight rows per tile (UMMA M)
@@ -100,7 +106,7 @@ __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x));
 template <typename T, int BN, int NA, int NB>
 __global__ void __launch_bounds__(kThreads, 1)
 linear_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_constant__ CUtensorMap tm_w1,
-              const __grid_constant__ CUtensorMap tm_x, const Params p) {
+              const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_x16, const Params p) {
   using C = Cfg<BN, NA, NB>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -120,6 +126,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_constant__
     ptx::prefetch_tmap(&tm_w0);
     if (NA == 2) ptx::prefetch_tmap(&tm_w1);
     ptx::prefetch_tmap(&tm_x);
+    ptx::prefetch_tmap(&tm_x16);
     for (int s = 0; s < C::kStages; ++s) {
       ptx::mbar_init(&full[s], 1);
       ptx::mbar_init(&empty[s], 1);
@@ -131,6 +138,21 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_constant__
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc(tmem_slot, C::kTmemCols);
+  // grouped problems: stage this CTA's tile descriptors (with the row counts resolved) in shared memory so that
+  // the three roles do not each pay dependent global loads at every tile boundary
+  constexpr int kTileCache = 64;
+  __shared__ int s_tiles[kTileCache][5];  // w_row0, x_row0, rows, n0 (+pad)
+  if (p.tiles) {
+    for (int i = threadIdx.x; i < kTileCache; i += kThreads) {
+      const int t = blockIdx.x + i * gridDim.x;
+      if (t < num_tiles) {
+        const Tile tl = p.tiles[t];
+        int rows = tl.rows;
+        if (p.group_counts) rows = max(0, min(BN, p.group_counts[tl.group] - tl.r0));
+        s_tiles[i][0] = tl.w_row0; s_tiles[i][1] = tl.x_row0; s_tiles[i][2] = rows; s_tiles[i][3] = tl.n0;
+      }
+    }
+  }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -142,8 +164,14 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_constant__
     batch = 0; split = 0;
     if (p.k_splits > 1) { split = t / base_tiles; t -= split * base_tiles; }
     if (p.tiles) {
-      const Tile tl = p.tiles[t];
-      w_row0 = tl.w_row0; x_row0 = tl.x_row0; rows = tl.rows; n0 = tl.n0;
+      const int i = (t - (int)blockIdx.x) / (int)gridDim.x;
+      if (i < kTileCache) {
+        w_row0 = s_tiles[i][0]; x_row0 = s_tiles[i][1]; rows = s_tiles[i][2]; n0 = s_tiles[i][3];
+      } else {
+        const Tile tl = p.tiles[t];
+        w_row0 = tl.w_row0; x_row0 = tl.x_row0; rows = tl.rows; n0 = tl.n0;
+        if (p.group_counts) rows = max(0, min(BN, p.group_counts[tl.group] - tl.r0));
+      }
     } else {
       if (p.nbatch > 1) { batch = t / tiles_per_batch; t -= batch * tiles_per_batch; }
       const int wb = t % p.n_w_blocks;
@@ -160,10 +188,25 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_constant__
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         int w_row0, x_row0, rows, n0, batch, split;
         decode_tile(t, w_row0, x_row0, rows, n0, batch, split);
+        if (rows <= 0) continue;  // empty group chunk: every role skips it identically
         const int kb0 = split * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* st = smem + stage * C::kStageBytes;
+          if (p.x_box16) {
+            const int nbox = (rows + 15) >> 4;
+            ptx::mbar_expect_tx(&full[stage], NA * C::kABytes + NB * nbox * 2048);
+            ptx::tma_load_2d(st, &tm_w0, &full[stage], kb * BK, w_row0);
+            if (NA == 2) ptx::tma_load_2d(st + C::kABytes, &tm_w1, &full[stage], kb * BK, w_row0);
+            for (int b = 0; b < nbox; ++b) {
+              ptx::tma_load_2d(st + NA * C::kABytes + b * 2048, &tm_x16, &full[stage], kb * BK, x_row0 + b * 16);
+              if (NB == 2)
+                ptx::tma_load_2d(st + NA * C::kABytes + C::kBBytes + b * 2048, &tm_x16, &full[stage], kb * BK,
+                                 p.x_lo_row_off + x_row0 + b * 16);
+            }
+            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+            continue;
+          }
           ptx::mbar_expect_tx(&full[stage], C::kStageBytes);
           ptx::tma_load_2d(st, &tm_w0, &full[stage], kb * BK, w_row0);
           if (NA == 2) ptx::tma_load_2d(st + C::kABytes, &tm_w1, &full[stage], kb * BK, w_row0);
@@ -184,9 +227,15 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_constant__
       constexpr uint32_t idesc = ptx::idesc_f16(Elem<T>::kFmt, BM, BN);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        if (p.group_counts) {
+          int w_row0, x_row0, rows, n0, batch, split;
+          decode_tile(t, w_row0, x_row0, rows, n0, batch, split);
+          if (rows <= 0) continue;
+        }
         const int buf = it & 1;
         const uint32_t bphase = (it >> 1) & 1;
+        ++it;
         ptx::mbar_wait(&tempty[buf], bphase ^ 1);
         ptx::tc_fence_after();
         const uint32_t d0 = tmem_base + buf * C::kAccCols;
@@ -226,11 +275,13 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_constant__
     constexpr int kChunks = BN / 32;
     constexpr int kChunksPerHalf = (kChunks + 1) / 2;
     int it = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       int w_row0, x_row0, rows, n0, batch, split;
       decode_tile(t, w_row0, x_row0, rows, n0, batch, split);
+      if (rows <= 0) continue;
       const int buf = it & 1;
       const uint32_t bphase = (it >> 1) & 1;
+      ++it;
       ptx::mbar_wait(&tfull[buf], bphase);
       ptx::tc_fence_after();
       const int n = n0 + quarter * 32 + lane;  // output feature owned by this thread
