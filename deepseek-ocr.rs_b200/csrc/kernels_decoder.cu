@@ -320,6 +320,85 @@ kv_attention_kernel(const float* __restrict__ q, const TKV* __restrict__ kc, con
   ctx[lo_off_elems + oidx] = Elem<T>::from(o - Elem<T>::to(hi));
 }
 
+// Prefill variant: one warp per query row (4 rows per block share the K/V rows they read through L1), the
+// 4 key groups of the warp are merged with shuffles.  Causal: row at position p attends keys 0..p.
+template <typename T, typename TKV>
+__global__ void __launch_bounds__(128)
+kv_attention_prefill_kernel(const float* __restrict__ q, const TKV* __restrict__ kc, const TKV* __restrict__ vc,
+                            const int* __restrict__ row_page, const int* __restrict__ row_pos, T* __restrict__ ctx,
+                            long long lo_off_elems, float* __restrict__ ctx32, long long rows, int heads, int smax,
+                            float scale) {
+  constexpr int D = 128;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * 4 + warp;
+  if (r >= rows) return;
+  const int hd = blockIdx.y;
+  const int grp = lane >> 3, sub = lane & 7;
+  const int nkeys = row_pos[r] + 1;
+  const int page = row_page[r];
+  const TKV* kbase = kc + ((long long)page * heads + hd) * smax * D;
+  const TKV* vbase = vc + ((long long)page * heads + hd) * smax * D;
+  float qv[16];
+  load16(q + (r * heads + hd) * D + sub * 16, qv);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) qv[i] *= scale;
+  float m = -INFINITY, l = 0.f, acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  for (int k0 = 0; k0 < nkeys; k0 += 4) {
+    const int k = k0 + grp;
+    const bool ok = k < nkeys;
+    float s = 0.f;
+    float vv[16];
+    if (ok) {
+      float kk[16];
+      load16(kbase + (long long)k * D + sub * 16, kk);
+      load16(vbase + (long long)k * D + sub * 16, vv);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) s += qv[i] * kk[i];
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (ok) {
+      const float mn = fmaxf(m, s);
+      const float a = __expf(m - mn);
+      const float pe = __expf(s - mn);
+      l = l * a + pe;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[i] = acc[i] * a + pe * vv[i];
+      m = mn;
+    }
+  }
+#pragma unroll
+  for (int off = 8; off <= 16; off <<= 1) {  // merge the 4 key groups (lanes with equal `sub`)
+    const float mo = __shfl_xor_sync(0xffffffffu, m, off);
+    const float lo = __shfl_xor_sync(0xffffffffu, l, off);
+    const float mn = fmaxf(m, mo);
+    const float a = m == -INFINITY ? 0.f : __expf(m - mn);
+    const float b = mo == -INFINITY ? 0.f : __expf(mo - mn);
+    l = l * a + lo * b;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float ao = __shfl_xor_sync(0xffffffffu, acc[i], off);
+      acc[i] = acc[i] * a + ao * b;
+    }
+    m = mn;
+  }
+  if (grp == 0) {
+    const float inv = 1.f / l;
+    const long long oidx = (r * heads + hd) * D + sub * 16;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float o = acc[i] * inv;
+      if (ctx32) { ctx32[oidx + i] = o; continue; }
+      const T hi = Elem<T>::from(o);
+      ctx[oidx + i] = hi;
+      ctx[lo_off_elems + oidx + i] = Elem<T>::from(o - Elem<T>::to(hi));
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Decode-step fusions (one query row per page; rows <= 256).  They remove ~56 of the ~175 launches of a step.
 
@@ -343,7 +422,8 @@ rope_attn_decode_kernel(const float* __restrict__ qkv, int n_splits, long long s
   TKV* kbase = kc + ((long long)page * heads + hd) * smax * D;
   TKV* vbase = vc + ((long long)page * heads + hd) * smax * D;
   __shared__ float q_s[D];
-  __shared__ float sm_m[16], sm_l[16], sm_acc[16][D];
+  constexpr int NS = 16;  // 4 warps x 4 key groups (8 warps measured slower: the smem merge outweighs the extra loads in flight)
+  __shared__ float sm_m[NS], sm_l[NS], sm_acc[NS][D];
   auto part_sum = [&](const float* p) {
     float a = p[0];
     for (int sidx = 1; sidx < n_splits; ++sidx) a += p[sidx * split_stride];
@@ -358,7 +438,7 @@ rope_attn_decode_kernel(const float* __restrict__ qkv, int n_splits, long long s
     q_s[t + 64] = (qhi * c + qlo * sn) * scale;
     kbase[(long long)pos * D + t] = (TKV)(klo * c - khi * sn);
     kbase[(long long)pos * D + 64 + t] = (TKV)(khi * c + klo * sn);
-  } else {
+  } else if (t < 128) {
     const int d = t - 64;
     vbase[(long long)pos * D + d] = (TKV)part_sum(base + (2 * heads + hd) * D + d);
     vbase[(long long)pos * D + 64 + d] = (TKV)part_sum(base + (2 * heads + hd) * D + 64 + d);
@@ -370,7 +450,7 @@ rope_attn_decode_kernel(const float* __restrict__ qkv, int n_splits, long long s
   float m = -INFINITY, l = 0.f, acc[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-  for (int k0 = warp * 4; k0 < nkeys; k0 += 16) {
+  for (int k0 = warp * 4; k0 < nkeys; k0 += NS) {
     const int k = k0 + grp;
     const bool ok = k < nkeys;
     float s = 0.f;
@@ -402,10 +482,10 @@ rope_attn_decode_kernel(const float* __restrict__ qkv, int n_splits, long long s
   __syncthreads();
   float gm = -INFINITY;
 #pragma unroll
-  for (int i = 0; i < 16; ++i) gm = fmaxf(gm, sm_m[i]);
+  for (int i = 0; i < NS; ++i) gm = fmaxf(gm, sm_m[i]);
   float num = 0.f, den = 0.f;
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
+  for (int i = 0; i < NS; ++i) {
     const float f = sm_m[i] == -INFINITY ? 0.f : __expf(sm_m[i] - gm);
     num += f * sm_acc[i][t];
     den += f * sm_l[i];
@@ -944,6 +1024,16 @@ void rope_kv(const float* qkv, const float* cos_t, const float* sin_t, const int
 void kv_attention(const float* q, const void* kc, const void* vc, bool kv_f16, const int* row_page, const int* row_pos,
                   void* ctx, long long lo_off_elems, float* ctx32, long long rows, int heads, int smax, float scale,
                   DType dt, cudaStream_t s) {
+  if (rows > 256) {  // prefill: warp-per-row variant
+    dim3 pgrid((unsigned)((rows + 3) / 4), heads);
+    if (kv_f16) {
+      DISPATCH_T(dt, (kv_attention_prefill_kernel<T, __half><<<pgrid, 128, 0, s>>>(q, (const __half*)kc, (const __half*)vc, row_page, row_pos, (T*)ctx, lo_off_elems, ctx32, rows, heads, smax, scale)));
+    } else {
+      DISPATCH_T(dt, (kv_attention_prefill_kernel<T, float><<<pgrid, 128, 0, s>>>(q, (const float*)kc, (const float*)vc, row_page, row_pos, (T*)ctx, lo_off_elems, ctx32, rows, heads, smax, scale)));
+    }
+    launch_check("kv_attention");
+    return;
+  }
   dim3 grid((unsigned)rows, heads);
   if (kv_f16) {
     DISPATCH_T(dt, (kv_attention_kernel<T, __half><<<grid, 128, 0, s>>>(q, (const __half*)kc, (const __half*)vc, row_page, row_pos, (T*)ctx, lo_off_elems, ctx32, heads, smax, scale)));

@@ -147,3 +147,17 @@ def test_kv_cache_f16_option(setup):
         print(f"[parity] f16-KV argmax agreement page {p}: {agree:.3f}")
         assert err <= 5e-3 * scale
         assert agree >= 0.95
+
+
+def test_large_prefill_batch_paths(setup):
+    """> 256 prompt rows in one call: exercises the prefill-sized kernels (warp-per-row cache attention, 128-token
+    grouped expert tiles, unsplit projections) that the small fixtures above never reach."""
+    from dsocr.engine import DecodeParameters
+
+    cfg, ck, eng, oracle = setup
+    ids, masks, rows = _prompts(cfg, [273, 150, 97, 201], seed=21)
+    assert sum(len(x) for x in ids) > 700
+    got = eng.generate_batch(ids, masks, rows, DecodeParameters(max_new_tokens=6, eos_token_id=None))
+    for p in range(len(ids)):
+        ref = oracle.generate(ids[p], masks[p], torch.from_numpy(rows[p]), 6, 20, None)
+        assert got[p] == ref
