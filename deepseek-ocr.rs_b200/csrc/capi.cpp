@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstring>
+#include <map>
 #include <thread>
 
 #include "dsocr.h"
@@ -19,9 +20,16 @@ struct dsocr_engine {
     std::vector<int> ntiles, cw, ch;
     DevBuf globals, tiles;
   } staged;
+  // device-side integer preprocessing: cached coefficient tables per (in, out) size + scratch
+  struct DevCoef { DevBuf start, len, coef; int ksize = 0; };
+  std::map<std::pair<int, int>, DevCoef> coefs;
+  DevBuf pages_raw, horiz;
+  bool host_preprocess = false;
 };
 
 namespace {
+void gpu_prepare_page(dsocr_engine* e, const uint8_t* src, int w, int h, dsocr_vision_settings vs, uint8_t* global_dst,
+                      uint8_t* tiles_dst, int gw, int gh, int n_tiles);
 int status_of(const std::exception& e) {
   const std::string m = e.what();
   if (m.find("prompt/image embedding mismatch") != std::string::npos) return DSOCR_ERR_MISMATCH;
@@ -87,6 +95,7 @@ extern "C" int dsocr_engine_set_option(dsocr_engine* e, const char* name, int va
     const std::string n = name ? name : "";
     if (n == "record_taps") e->impl->set_record_taps(value != 0);
     else if (n == "kv_cache_f16") e->impl->set_kv_f16(value != 0);
+    else if (n == "host_preprocess") e->host_preprocess = value != 0;
     else throw std::runtime_error("unknown option `" + n + "`");
   });
 }
@@ -103,6 +112,27 @@ extern "C" int dsocr_preprocess(const uint8_t* rgb, int width, int height, dsocr
     if (global_out) build_global_view_u8(rgb, width, height, gsz, global_out);
     int gw = 1, gh = 1, n = 0;
     if (vs.crop_mode) n = dynamic_preprocess_u8(rgb, width, height, (int)vs.image_size, tiles_out, &gw, &gh);
+    if (n_tiles) *n_tiles = n;
+    if (crop_w) *crop_w = gw;
+    if (crop_h) *crop_h = gh;
+  });
+}
+
+extern "C" int dsocr_preprocess_gpu(dsocr_engine* e, const uint8_t* rgb, int width, int height, dsocr_vision_settings vs,
+                                    uint8_t* global_out, uint8_t* tiles_out, int* n_tiles, int* crop_w, int* crop_h) {
+  return api("vision input failed", [&] {
+    bind(e);
+    Engine& en = *e->impl;
+    if (!rgb || width <= 0 || height <= 0) throw std::runtime_error("empty image");
+    const int G = vs.crop_mode ? (int)vs.base_size : (int)vs.image_size, P = (int)vs.image_size;
+    int gw = 1, gh = 1, n = 0;
+    if (vs.crop_mode) n = dynamic_preprocess_u8(rgb, width, height, P, nullptr, &gw, &gh);
+    DevBuf src((size_t)width * height * 3), dg((size_t)G * G * 3), dt(std::max<size_t>(16, (size_t)n * P * P * 3));
+    h2d(src.p, rgb, (size_t)width * height * 3);
+    gpu_prepare_page(e, src.as<uint8_t>(), width, height, vs, dg.as<uint8_t>(), dt.as<uint8_t>(), gw, gh, n);
+    cuda_check(cudaStreamSynchronize(en.stream()), "preprocess sync");
+    if (global_out) d2h(global_out, dg.p, (size_t)G * G * 3);
+    if (tiles_out && n > 0) d2h(tiles_out, dt.p, (size_t)n * P * P * 3);
     if (n_tiles) *n_tiles = n;
     if (crop_w) *crop_w = gw;
     if (crop_h) *crop_h = gh;
@@ -219,8 +249,90 @@ extern "C" int dsocr_generate_forced(dsocr_engine* e, int n_pages, const int64_t
 }
 
 namespace {
+const dsocr_engine::DevCoef& coef_for(dsocr_engine* e, int in_size, int out_size) {
+  auto key = std::make_pair(in_size, out_size);
+  auto it = e->coefs.find(key);
+  if (it == e->coefs.end()) {
+    ResampleCoeffs rc = resample_coeffs_public(in_size, out_size);
+    dsocr_engine::DevCoef d;
+    d.ksize = rc.ksize;
+    d.start.alloc(rc.start.size() * 4); h2d(d.start.p, rc.start.data(), rc.start.size() * 4);
+    d.len.alloc(rc.len.size() * 4); h2d(d.len.p, rc.len.data(), rc.len.size() * 4);
+    d.coef.alloc(rc.coef.size() * 4); h2d(d.coef.p, rc.coef.data(), rc.coef.size() * 4);
+    it = e->coefs.emplace(key, std::move(d)).first;
+  }
+  return it->second;
+}
+
+// resize_bicubic on the device: src [h,w,3] u8 -> either the global canvas or the tile stack (see resample_v)
+void gpu_resize(dsocr_engine* e, const uint8_t* src, int w, int h, int dw, int dh, uint8_t* dst, int canvas, int x_off,
+                int y_off, int tile, int tiles_w) {
+  Engine& en = *e->impl;
+  const auto& cx = coef_for(e, w, dw);
+  const auto& cy = coef_for(e, h, dh);
+  if (e->horiz.bytes < (size_t)h * dw * 3) {
+    cuda_check(cudaStreamSynchronize(en.stream()), "horiz grow sync");
+    e->horiz.alloc((size_t)h * dw * 3);
+  }
+  resample_h(src, w, h, e->horiz.as<uint8_t>(), dw, cx.start.as<int>(), cx.len.as<int>(), cx.coef.as<int>(), cx.ksize, en.stream());
+  resample_v(e->horiz.as<uint8_t>(), dw, dh, dst, cy.start.as<int>(), cy.len.as<int>(), cy.coef.as<int>(), cy.ksize, canvas,
+             x_off, y_off, tile, tiles_w, en.stream());
+}
+
+// prepare_vision_input_from_image for one page already resident on the device (raw RGB8)
+void gpu_prepare_page(dsocr_engine* e, const uint8_t* src, int w, int h, dsocr_vision_settings vs, uint8_t* global_dst,
+                      uint8_t* tiles_dst, int gw, int gh, int n_tiles) {
+  Engine& en = *e->impl;
+  const int G = vs.crop_mode ? (int)vs.base_size : (int)vs.image_size, P = (int)vs.image_size;
+  if (w == G && h == G) {
+    cuda_check(cudaMemcpyAsync(global_dst, src, (size_t)G * G * 3, cudaMemcpyDeviceToDevice, en.stream()), "global copy");
+  } else {
+    int nw, nh, xo, yo;
+    global_view_geometry(w, h, G, &nw, &nh, &xo, &yo);
+    cuda_check(cudaMemsetAsync(global_dst, 127, (size_t)G * G * 3, en.stream()), "canvas fill");
+    gpu_resize(e, src, w, h, nw, nh, global_dst, G, xo, yo, 0, 0);
+  }
+  if (n_tiles > 0) gpu_resize(e, src, w, h, P * gw, P * gh, tiles_dst, 0, 0, 0, P, gw);
+}
+
+void stage_pages_gpu(dsocr_engine* e, int n_pages, const uint8_t* const* rgb, const int* widths, const int* heights,
+                     dsocr_vision_settings vs) {
+  Engine& en = *e->impl;
+  auto& sg = e->staged;
+  const double t0 = now_ms();
+  const int G = vs.crop_mode ? (int)vs.base_size : (int)vs.image_size, P = (int)vs.image_size;
+  sg.ntiles.assign(n_pages, 0); sg.cw.assign(n_pages, 1); sg.ch.assign(n_pages, 1);
+  sg.n_pages = n_pages; sg.vs = vs;
+  size_t raw_bytes = 0, total_tiles = 0;
+  std::vector<size_t> raw_off(n_pages);
+  for (int p = 0; p < n_pages; ++p) {
+    if (!rgb[p] || widths[p] <= 0 || heights[p] <= 0) throw std::runtime_error("empty image");
+    raw_off[p] = raw_bytes;
+    raw_bytes += ((size_t)widths[p] * heights[p] * 3 + 255) & ~(size_t)255;
+    if (vs.crop_mode) sg.ntiles[p] = dynamic_preprocess_u8(rgb[p], widths[p], heights[p], P, nullptr, &sg.cw[p], &sg.ch[p]);
+    total_tiles += sg.ntiles[p];
+  }
+  const size_t gbytes = (size_t)G * G * 3, tbytes = (size_t)P * P * 3;
+  if (e->pages_raw.bytes < raw_bytes || sg.globals.bytes < gbytes * n_pages || sg.tiles.bytes < std::max<size_t>(16, tbytes * total_tiles))
+    cuda_check(cudaStreamSynchronize(en.stream()), "stage grow sync");
+  e->pages_raw.ensure(raw_bytes);
+  sg.globals.ensure(gbytes * n_pages);
+  sg.tiles.ensure(std::max<size_t>(16, tbytes * total_tiles));
+  size_t toff = 0;
+  for (int p = 0; p < n_pages; ++p) {
+    uint8_t* src = e->pages_raw.as<uint8_t>() + raw_off[p];
+    cuda_check(cudaMemcpyAsync(src, rgb[p], (size_t)widths[p] * heights[p] * 3, cudaMemcpyHostToDevice, en.stream()), "page H2D");
+    gpu_prepare_page(e, src, widths[p], heights[p], vs, sg.globals.as<uint8_t>() + gbytes * p, sg.tiles.as<uint8_t>() + toff,
+                     sg.cw[p], sg.ch[p], sg.ntiles[p]);
+    toff += tbytes * sg.ntiles[p];
+  }
+  cuda_check(cudaStreamSynchronize(en.stream()), "stage sync");
+  en.timings.prepare = now_ms() - t0;
+}
+
 void stage_pages(dsocr_engine* e, int n_pages, const uint8_t* const* rgb, const int* widths, const int* heights,
                  dsocr_vision_settings vs) {
+  if (!e->host_preprocess) { stage_pages_gpu(e, n_pages, rgb, widths, heights, vs); return; }
   Engine& en = *e->impl;
   auto& sg = e->staged;
   // prepare_vision_inputs (model/mod.rs:2457-2492): integer resample / tiling on the host cores

@@ -189,6 +189,21 @@ double round_ties_to_even(double value) {
 }
 }  // namespace
 
+ResampleCoeffs resample_coeffs_public(int in_size, int out_size) {
+  Coeffs c = resample_coeffs(in_size, out_size);
+  ResampleCoeffs r;
+  r.start = std::move(c.start); r.len = std::move(c.len); r.coef = std::move(c.c); r.ksize = c.ksize;
+  return r;
+}
+
+void global_view_geometry(int w, int h, int base, int* nw, int* nh, int* x_off, int* y_off) {
+  const double scale = std::min((double)base / (double)w, (double)base / (double)h);
+  *nw = (int)std::min(std::max(round_ties_to_even((double)w * scale), 1.0), (double)base);
+  *nh = (int)std::min(std::max(round_ties_to_even((double)h * scale), 1.0), (double)base);
+  *x_off = (int)round_ties_to_even(((double)base - (double)*nw) * 0.5);
+  *y_off = (int)round_ties_to_even(((double)base - (double)*nh) * 0.5);
+}
+
 void resize_bicubic_u8(const uint8_t* src, int sw, int sh, uint8_t* dst, int dw, int dh) {
   if (dw == 0 || dh == 0) return;
   const Coeffs cx = resample_coeffs(sw, dw), cy = resample_coeffs(sh, dh);

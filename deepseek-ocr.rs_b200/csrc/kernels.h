@@ -104,6 +104,11 @@ void concat_clip_sam(const float* clip, const float* sam, void* out16, float* ou
 void scatter_tokens(const float* proj, const float* newline, const float* sep, const int* map, float* dst,
                     long long rows, int C, cudaStream_t s);
 
+void resample_h(const uint8_t* src, int sw, int sh, uint8_t* dst, int dw, const int* start, const int* len,
+                const int* coef, int ksize, cudaStream_t s);
+void resample_v(const uint8_t* horiz, int dw, int dh, uint8_t* dst, const int* start, const int* len, const int* coef,
+                int ksize, int canvas, int x_off, int y_off, int tile, int tiles_w, cudaStream_t s);
+
 // ------------------------------------------------------------------------- decoder SIMT kernels
 void embed_gather(const int* src, const void* table, const float* img_rows, float* out, long long rows, int H, DType dt,
                   cudaStream_t s);

@@ -338,3 +338,82 @@ void scatter_tokens(const float* proj, const float* newline, const float* sep, c
 }
 
 }  // namespace dsocr
+
+// ---------------------------------------------------------------------------------------------------
+// Integer bicubic resample on the device, bit-exact with vision/resample.rs:101-160 (22-bit fixed-point
+// coefficients computed on the host exactly as compute_resample_coeffs does, i64 accumulation, u8 intermediate
+// after the horizontal pass).  The vertical pass writes straight into the destination layout: either the
+// 127-grey global canvas at (x_off, y_off) (build_global_view, model/mod.rs:2308-2330) or the row-major
+// tile stack of dynamic_preprocess (vision/preprocess.rs:113-127).
+namespace dsocr {
+namespace {
+constexpr int kPrecisionBits = 22;
+
+__global__ void resample_h_kernel(const uint8_t* __restrict__ src, int sw, int sh, uint8_t* __restrict__ dst, int dw,
+                                  const int* __restrict__ start, const int* __restrict__ len,
+                                  const int* __restrict__ coef, int ksize) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)sh * dw) return;
+  const int x = idx % dw;
+  const int y = idx / dw;
+  const int s0 = start[x], n = len[x];
+  const int* w = coef + (long long)x * ksize;
+  const uint8_t* p = src + ((long long)y * sw + s0) * 3;
+  long long a0 = 1ll << (kPrecisionBits - 1), a1 = a0, a2 = a0;
+  for (int i = 0; i < n; ++i, p += 3) {
+    const long long wi = w[i];
+    a0 += (long long)p[0] * wi; a1 += (long long)p[1] * wi; a2 += (long long)p[2] * wi;
+  }
+  uint8_t* o = dst + idx * 3;
+  o[0] = (uint8_t)min(255ll, max(0ll, a0 >> kPrecisionBits));
+  o[1] = (uint8_t)min(255ll, max(0ll, a1 >> kPrecisionBits));
+  o[2] = (uint8_t)min(255ll, max(0ll, a2 >> kPrecisionBits));
+}
+
+// tile == 0: write into a canvas of side `canvas` at (x_off, y_off), clipped; tile > 0: write into the tile
+// stack [n][tile][tile][3] of a (tiles_w * tile)-wide image.
+__global__ void resample_v_kernel(const uint8_t* __restrict__ horiz, int dw, int dh, uint8_t* __restrict__ dst,
+                                  const int* __restrict__ start, const int* __restrict__ len,
+                                  const int* __restrict__ coef, int ksize, int canvas, int x_off, int y_off, int tile,
+                                  int tiles_w) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)dh * dw) return;
+  const int x = idx % dw;
+  const int y = idx / dw;
+  const int s0 = start[y], n = len[y];
+  const int* w = coef + (long long)y * ksize;
+  const uint8_t* p = horiz + ((long long)s0 * dw + x) * 3;
+  long long a0 = 1ll << (kPrecisionBits - 1), a1 = a0, a2 = a0;
+  for (int i = 0; i < n; ++i, p += (long long)dw * 3) {
+    const long long wi = w[i];
+    a0 += (long long)p[0] * wi; a1 += (long long)p[1] * wi; a2 += (long long)p[2] * wi;
+  }
+  uint8_t* o;
+  if (tile > 0) {
+    const int t = (y / tile) * tiles_w + (x / tile);
+    o = dst + (((long long)t * tile + (y % tile)) * tile + (x % tile)) * 3;
+  } else {
+    const int cy = y + y_off, cx = x + x_off;
+    if (cy < 0 || cy >= canvas || cx < 0 || cx >= canvas) return;
+    o = dst + ((long long)cy * canvas + cx) * 3;
+  }
+  o[0] = (uint8_t)min(255ll, max(0ll, a0 >> kPrecisionBits));
+  o[1] = (uint8_t)min(255ll, max(0ll, a1 >> kPrecisionBits));
+  o[2] = (uint8_t)min(255ll, max(0ll, a2 >> kPrecisionBits));
+}
+}  // namespace
+
+void resample_h(const uint8_t* src, int sw, int sh, uint8_t* dst, int dw, const int* start, const int* len,
+                const int* coef, int ksize, cudaStream_t s) {
+  const long long n = (long long)sh * dw;
+  resample_h_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, sw, sh, dst, dw, start, len, coef, ksize);
+  launch_check("resample_h");
+}
+void resample_v(const uint8_t* horiz, int dw, int dh, uint8_t* dst, const int* start, const int* len, const int* coef,
+                int ksize, int canvas, int x_off, int y_off, int tile, int tiles_w, cudaStream_t s) {
+  const long long n = (long long)dh * dw;
+  resample_v_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(horiz, dw, dh, dst, start, len, coef, ksize, canvas, x_off,
+                                                               y_off, tile, tiles_w);
+  launch_check("resample_v");
+}
+}  // namespace dsocr

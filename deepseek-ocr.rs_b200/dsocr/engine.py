@@ -140,6 +140,18 @@ class OcrEngine:
                                          tiles.ctypes.data_as(u8), C.byref(n), C.byref(cw), C.byref(ch)), "preprocess")
         return gout, tiles[: n.value].copy(), (cw.value, ch.value)
 
+    def preprocess_gpu(self, rgb: np.ndarray, vs: VisionSettings):
+        h, w = rgb.shape[:2]
+        rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+        g = vs.base_size if vs.crop_mode else vs.image_size
+        gout = np.empty((g, g, 3), dtype=np.uint8)
+        tiles = np.empty((9, vs.image_size, vs.image_size, 3), dtype=np.uint8)
+        n, cw, ch = C.c_int(), C.c_int(), C.c_int()
+        u8 = C.POINTER(C.c_uint8)
+        check(self._lib.dsocr_preprocess_gpu(self._h, rgb.ctypes.data_as(u8), w, h, vs.c(), gout.ctypes.data_as(u8),
+                                             tiles.ctypes.data_as(u8), C.byref(n), C.byref(cw), C.byref(ch)), "preprocess_gpu")
+        return gout, tiles[: n.value].copy(), (cw.value, ch.value)
+
     # -- compute_image_embeddings -----------------------------------------------------------------
     def vision_encode(self, global_chw: np.ndarray, patches: Optional[np.ndarray], crop_shape) -> np.ndarray:
         g = np.ascontiguousarray(global_chw, dtype=np.float32)

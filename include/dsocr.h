@@ -91,7 +91,8 @@ DSOCR_API void dsocr_engine_destroy(dsocr_engine* e);
 DSOCR_API int dsocr_engine_info_get(const dsocr_engine* e, dsocr_engine_info* info);
 /* Engine options: "record_taps" (0/1) keeps host copies of the debug-trace taps of the next vision call;
  * "kv_cache_f16" (0/1) stores the KV cache in f16 instead of the reference's f32 (model/mod.rs:82-88): half the
- * decode-attention bytes, K/V rounded to 11 bits (off by default; parity numbers are quoted for both). */
+ * decode-attention bytes, K/V rounded to 11 bits (off by default; parity numbers are quoted for both);
+ * "host_preprocess" (0/1) runs the integer resample / tiling on the host cores instead of the device. */
 DSOCR_API int dsocr_engine_set_option(dsocr_engine* e, const char* name, int value);
 
 /* image_token_count: rows `compute_image_embeddings` will produce == placeholders
@@ -105,6 +106,12 @@ DSOCR_API int dsocr_image_token_count(uint32_t base_size, uint32_t image_size, i
  * crop grid (w,h).  Bit-exact with the reference's integer resampler. */
 DSOCR_API int dsocr_preprocess(const uint8_t* rgb, int width, int height, dsocr_vision_settings vs,
                                uint8_t* global_out, uint8_t* tiles_out, int* n_tiles, int* crop_w, int* crop_h);
+
+/* Same as dsocr_preprocess but with the resample / tiling kernels of the engine's device (the path
+ * dsocr_stage_pages / dsocr_decode_pages use; option "host_preprocess" = 1 selects the host cores instead).
+ * Bit-exact with dsocr_preprocess. */
+DSOCR_API int dsocr_preprocess_gpu(dsocr_engine* e, const uint8_t* rgb, int width, int height, dsocr_vision_settings vs,
+                                   uint8_t* global_out, uint8_t* tiles_out, int* n_tiles, int* crop_w, int* crop_h);
 
 /* compute_image_embeddings for one page (model/mod.rs:1276-1377; VisionContext :711-924).
  * global_chw: f32 [3,G,G] normalised as image_to_tensor does (:2332-2347); patches_nchw: f32 [n,3,P,P] or NULL.

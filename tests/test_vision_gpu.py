@@ -113,3 +113,21 @@ def test_preprocess_bit_exact_with_oracle(setup):
         assert tiles.shape[0] == len(ref["tiles"])
         for a, b in zip(tiles, ref["tiles"]):
             assert np.array_equal(a, b)
+
+
+def test_gpu_preprocess_bit_exact_with_oracle(setup):
+    """Device integer resampler / tiler (resample_h / resample_v kernels) == oracle restatement of vision/resample.rs,
+    including an upscale (where resample.rs deliberately differs from Pillow) and the no-crop small-image case."""
+    from dsocr.engine import VisionSettings
+
+    cfg, ck, eng, oracle = setup
+    rng = np.random.RandomState(1)
+    for (w, h) in [(1654, 2339), (700, 500), (333, 517), (2852, 1756), (640, 640), (100, 80), (1024, 1024)]:
+        img = rng.randint(0, 256, (h, w, 3), dtype=np.uint8)
+        g, tiles, crop = eng.preprocess_gpu(img, VisionSettings(1024, 640, True))
+        ref = P.prepare_vision_input(img, 1024, 640, True)
+        assert crop == tuple(ref["crop_shape"]), (w, h)
+        assert np.array_equal(g, ref["global"]), (w, h)
+        assert tiles.shape[0] == len(ref["tiles"])
+        for a, b in zip(tiles, ref["tiles"]):
+            assert np.array_equal(a, b), (w, h)
