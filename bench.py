@@ -175,11 +175,13 @@ def cpu_reference_sample(args, cfg, ckdir: Path, page: np.ndarray, max_new: int)
 
 
 # ------------------------------------------------------------------------------------------- roofline
-def kernel_model(cfg, name: str, args, pages: int, hbm_gbs: float, tf_peak: float) -> dict | None:
+def kernel_model(cfg, name: str, args, pages: int, hbm_gbs: float, tf_peak: float, active_experts: float | None = None) -> dict | None:
     """Algorithmic bytes / flops of one launch of a named kernel (DESIGN.md 'Kernels')."""
     H, V, E, mi, K = cfg.hidden_size, cfg.vocab_size, cfg.n_routed_experts, cfg.moe_intermediate_size, cfg.num_experts_per_tok
     S = mi * cfg.n_shared_experts
     B = pages
+    # routed-expert weight segments one launch really streams: measured (dsocr_moe_stats) when available
+    Ea = active_experts if active_experts else min(E, B * K)
     phase, _, k = name.partition("/")
     if phase == "decode":
         act = lambda kk, nn, parts=2: B * kk * 2 * parts + B * nn * 4  # noqa: E731
@@ -189,8 +191,8 @@ def kernel_model(cfg, name: str, args, pages: int, hbm_gbs: float, tf_peak: floa
             "dec_o_proj": H * H * 2 + act(H, H),
             "dec_dense_gate_up": 2 * cfg.intermediate_size * H * 2 + act(H, cfg.intermediate_size),
             "dec_dense_down": H * cfg.intermediate_size * 2 + act(cfg.intermediate_size, H),
-            "moe_expert_gate_up": min(E, B * K) * 2 * mi * H * 2 + B * K * (H * 4 + mi * 4),
-            "moe_expert_down": min(E, B * K) * H * mi * 2 + B * K * (mi * 4 + H * 4),
+            "moe_expert_gate_up": Ea * 2 * mi * H * 2 + B * K * (H * 4 + mi * 4),
+            "moe_expert_down": Ea * H * mi * 2 + B * K * (mi * 4 + H * 4),
             "moe_shared_gate_up": 2 * S * H * 2 + act(H, S),
             "moe_shared_down": H * S * 2 + act(S, H),
         }
@@ -319,9 +321,15 @@ def main():
     d2h_bytes = gen_tokens * 8
 
     # one extra step with per-kernel CUDA-event timing for the roofline / breakdown (not part of the timed value)
+    eng.set_option("moe_stats", 1)
+    eng.moe_stats()
     eng.kernel_timing_begin()
     step_resident()
     kt = eng.kernel_timing_end()
+    seg, nsteps = eng.moe_stats()
+    eng.set_option("moe_stats", 0)
+    moe_layers = sum(1 for l in range(cfg.num_layers) if l >= cfg.first_k_dense_replace)
+    active_experts = seg / max(1.0, nsteps * moe_layers) if nsteps else None
     kt.sort(key=lambda r: -r["ms"])
     total_kernel_ms = sum(r["ms"] for r in kt)
     if args.profile_json and rank == 0:
@@ -329,7 +337,7 @@ def main():
 
     roof = None
     for r in kt:
-        m = kernel_model(cfg, r["name"], args, args.pages, hbm_peak, tf_sustained)
+        m = kernel_model(cfg, r["name"], args, args.pages, hbm_peak, tf_sustained, active_experts)
         if m is None:
             continue
         avg_s = r["ms"] / r["launches"] * 1e-3
@@ -339,7 +347,8 @@ def main():
             ach = m["flops"] / avg_s / 1e12
         roof = {"kernel": r["name"], "bound": m["bound"], "achieved": ach, "peak": m["peak"], "unit": m["unit"],
                 "frac": ach / m["peak"], "traffic": None, "launches_per_step": r["launches"],
-                "avg_launch_us": avg_s * 1e6, "share_of_step": r["ms"] / total_kernel_ms, "peak_source": peak_src,
+                "avg_launch_us": avg_s * 1e6,
+                "active_experts_per_layer": active_experts, "share_of_step": r["ms"] / total_kernel_ms, "peak_source": peak_src,
                 "timed": "CUDA events after every launch on the engine stream, one extra profiled step"}
         break
 

@@ -95,6 +95,7 @@ extern "C" int dsocr_engine_set_option(dsocr_engine* e, const char* name, int va
     const std::string n = name ? name : "";
     if (n == "record_taps") e->impl->set_record_taps(value != 0);
     else if (n == "kv_cache_f16") e->impl->set_kv_f16(value != 0);
+    else if (n == "moe_stats") e->impl->set_moe_stats(value != 0);
     else if (n == "host_preprocess") e->host_preprocess = value != 0;
     else throw std::runtime_error("unknown option `" + n + "`");
   });
@@ -494,6 +495,16 @@ extern "C" int dsocr_last_timings(const dsocr_engine* e, double* ms_out, int n) 
     const Timings& t = e->impl->timings;
     const double v[5] = {t.prepare, t.vision, t.prefill, t.iterative, t.generate};
     for (int i = 0; i < n && i < 5; ++i) ms_out[i] = v[i];
+  });
+}
+
+extern "C" int dsocr_moe_stats(dsocr_engine* e, double* out2) {
+  return api("", [&] {
+    if (!e || !out2) throw std::runtime_error("null argument");
+    bind(e);
+    unsigned long long v[2];
+    e->impl->moe_stats(v);
+    out2[0] = (double)v[0]; out2[1] = (double)v[1];
   });
 }
 

@@ -90,6 +90,9 @@ class Engine {
   int tap(const std::string& name, float* out, size_t capacity, size_t* n_written);
   void set_record_taps(bool on) { record_taps_ = on; }
   void set_kv_f16(bool on) { kv_f16_ = on; }  // KV cache storage: f32 (reference semantics, default) or f16
+  void set_moe_stats(bool on);
+  // diagnostics: {sum over decode steps of non-empty (layer, expert) segments, decode steps counted}; resets them
+  void moe_stats(unsigned long long out[2]);
   void set_stream(cudaStream_t s);  // adopt a caller-owned stream (e.g. torch's current stream)
 
   const ModelConfig& cfg() const { return cfg_; }
@@ -129,6 +132,8 @@ class Engine {
   cudaEvent_t ev_fork_ = nullptr, ev_join_ = nullptr;
   bool record_taps_ = false;
   bool kv_f16_ = false;
+  bool moe_stats_ = false;
+  DevBuf moe_stats_dev_;
   bool quantized_ = false;
   QuantWeight q_lm_head_;
   long long iota_n_ = 0;

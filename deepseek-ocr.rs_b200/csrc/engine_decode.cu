@@ -229,6 +229,9 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
     }
     if (record_taps_) record_tap("dec.hidden." + std::to_string(l), x, rows * H);
   }
+  if (moe_stats_ && counts_layers) {
+    moe_active_stat(counts_layers, c.layers * E, moe_stats_dev_.as<unsigned long long>(), stream_);
+  }
   // final RMSNorm + lm_head on the selected rows
   if (!final_done)
     rmsnorm_split(x, final_norm_.as<float>(), xf16, (long long)n_final * H, nullptr, final_rows, n_final, H, c.rms_eps,
@@ -237,6 +240,22 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
   lc.tag = "lm_head"; lc.w0 = lm_head_.p; lc.x = xf16; lc.x_rows = 2 * n_final; lc.x_parts = 2; lc.x_lo_row_off = n_final;
   lc.M = n_final; lc.N = c.vocab; lc.K = H; lc.out = logits; lc.ldo = c.vocab; lc.out_mode = lin::OUT_F32;
   linear(lc, dt_, num_sms_, stream_);
+}
+
+void Engine::set_moe_stats(bool on) {
+  moe_stats_ = on;
+  if (on && !moe_stats_dev_.p) {
+    moe_stats_dev_.alloc(16);
+    cuda_check(cudaMemset(moe_stats_dev_.p, 0, 16), "stats reset");
+  }
+}
+
+void Engine::moe_stats(unsigned long long out[2]) {
+  out[0] = out[1] = 0;
+  if (!moe_stats_dev_.p) return;
+  cuda_check(cudaStreamSynchronize(stream_), "stats sync");
+  cuda_check(cudaMemcpy(out, moe_stats_dev_.p, 16, cudaMemcpyDeviceToHost), "stats copy");
+  cuda_check(cudaMemset(moe_stats_dev_.p, 0, 16), "stats reset");
 }
 
 // DSQ variant of decoder_forward (run_quantized_matmul, quantization.rs:164-185): every decoder linear and the

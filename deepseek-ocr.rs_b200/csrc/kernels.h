@@ -140,6 +140,7 @@ bool kernel_timing_enabled();
 void decode_rows(const int* hist, int hist_stride, const int* hist_len, int* src, int* row_pos, int n_pages,
                  cudaStream_t s);
 void fill_i32(int* p, int v, long long n, cudaStream_t s);
+void moe_active_stat(const int* counts, int n, unsigned long long* stats, cudaStream_t s);
 // decode-step fusions (rows <= 256)
 void rope_attn_decode(const float* qkv, int n_splits, long long split_stride, const float* cos_t, const float* sin_t,
                       void* kc, void* vc, bool kv_f16, const int* row_page, const int* row_pos, void* ctx,

@@ -6,6 +6,7 @@
 #include "ptx.cuh"
 
 #include <cfloat>
+#include <cstdlib>
 
 namespace dsocr {
 
@@ -486,6 +487,145 @@ rope_attn_decode_kernel(const float* __restrict__ qkv, int n_splits, long long s
   float num = 0.f, den = 0.f;
 #pragma unroll
   for (int i = 0; i < NS; ++i) {
+    const float f = sm_m[i] == -INFINITY ? 0.f : __expf(sm_m[i] - gm);
+    num += f * sm_acc[i][t];
+    den += f * sm_l[i];
+  }
+  const float o = num / den;
+  const T hi = Elem<T>::from(o);
+  const long long oidx = (r * heads + hd) * D + t;
+  ctx[oidx] = hi;
+  ctx[lo_off_elems + oidx] = Elem<T>::from(o - Elem<T>::to(hi));
+}
+
+// (1b) Same fusion, but the cached K/V rows of the (page, head) stream through shared memory with 1-D bulk
+// copies (cp.async.bulk, 16 KB per stage, double-buffered per block) instead of per-lane register loads:
+// the bytes in flight no longer depend on occupancy / registers.  The new token's k/v stay in shared memory
+// and are folded in as the last key (the cache rows written by this block are not re-read).
+template <typename T, typename TKV>
+__global__ void __launch_bounds__(128)
+rope_attn_decode_bulk_kernel(const float* __restrict__ qkv, int n_splits, long long split_stride,
+                             const float* __restrict__ cos_t, const float* __restrict__ sin_t, TKV* __restrict__ kc,
+                             TKV* __restrict__ vc, const int* __restrict__ row_page, const int* __restrict__ row_pos,
+                             T* __restrict__ ctx, long long lo_off_elems, int heads, int smax, float scale) {
+  constexpr int D = 128;
+  constexpr int KT = 8192 / (D * (int)sizeof(TKV));  // keys per stage tile: 32 (f16) / 16 (f32) -> 8 KB per K or V tile
+  constexpr int NST = 2;  // 2 stages x 16 KB: 5 blocks per SM -> ~70 KB of K/V in flight per SM, one wave for 64 pages x 10 heads
+  extern __shared__ __align__(128) uint8_t dyn[];
+  TKV* tiles = reinterpret_cast<TKV*>(dyn);  // [NST][2][KT][D]
+  __shared__ uint64_t full[NST];
+  __shared__ float q_s[D], knew[D], vnew[D];
+  __shared__ float sm_m[16], sm_l[16], sm_acc[16][D];
+  const long long r = blockIdx.x;
+  const int hd = blockIdx.y;
+  const int t = threadIdx.x;
+  const int warp = t >> 5, lane = t & 31;
+  const int grp = lane >> 3, sub = lane & 7;
+  const int pos = row_pos[r];
+  const int page = row_page[r];
+  TKV* kbase = kc + ((long long)page * heads + hd) * smax * D;
+  TKV* vbase = vc + ((long long)page * heads + hd) * smax * D;
+  const int ntiles = (pos + KT - 1) / KT;  // cached keys 0..pos-1
+  if (t == 0) {
+    for (int s = 0; s < NST; ++s) ptx::mbar_init(&full[s], 1);
+    ptx::fence_barrier_init();
+  }
+  __syncthreads();
+  auto issue = [&](int tile) {
+    const int s = tile % NST;
+    const int nk = min(KT, pos - tile * KT);
+    const uint32_t bytes = (uint32_t)nk * D * sizeof(TKV);
+    ptx::mbar_expect_tx(&full[s], 2 * bytes);
+    ptx::bulk_load(tiles + ((size_t)s * 2 + 0) * KT * D, kbase + (long long)tile * KT * D, bytes, &full[s]);
+    ptx::bulk_load(tiles + ((size_t)s * 2 + 1) * KT * D, vbase + (long long)tile * KT * D, bytes, &full[s]);
+  };
+  if (t == 0) for (int i = 0; i < NST - 1 && i < ntiles; ++i) issue(i);
+
+  auto part_sum = [&](const float* p) {
+    float a = p[0];
+    for (int sidx = 1; sidx < n_splits; ++sidx) a += p[sidx * split_stride];
+    return a;
+  };
+  const float* base = qkv + r * 3 * heads * D;
+  if (t < 64) {
+    const float c = cos_t[(long long)pos * 64 + t], sn = sin_t[(long long)pos * 64 + t];
+    const float qlo = part_sum(base + hd * D + t), qhi = part_sum(base + hd * D + 64 + t);
+    const float klo = part_sum(base + (heads + hd) * D + t), khi = part_sum(base + (heads + hd) * D + 64 + t);
+    q_s[t] = (qlo * c - qhi * sn) * scale;
+    q_s[t + 64] = (qhi * c + qlo * sn) * scale;
+    const TKV k0 = (TKV)(klo * c - khi * sn), k1 = (TKV)(khi * c + klo * sn);
+    kbase[(long long)pos * D + t] = k0;
+    kbase[(long long)pos * D + 64 + t] = k1;
+    knew[t] = (float)k0; knew[t + 64] = (float)k1;  // what later steps will read back from the cache
+  } else {
+    const int d = t - 64;
+    const TKV v0 = (TKV)part_sum(base + (2 * heads + hd) * D + d), v1 = (TKV)part_sum(base + (2 * heads + hd) * D + 64 + d);
+    vbase[(long long)pos * D + d] = v0;
+    vbase[(long long)pos * D + 64 + d] = v1;
+    vnew[d] = (float)v0; vnew[d + 64] = (float)v1;
+  }
+  __syncthreads();
+  float qv[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) qv[i] = q_s[sub * 16 + i];
+  float m = -INFINITY, l = 0.f, acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  auto fold = [&](float s, const float* vv) {
+    const float mn = fmaxf(m, s);
+    const float a = __expf(m - mn);
+    const float pe = __expf(s - mn);
+    l = l * a + pe;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = acc[i] * a + pe * vv[i];
+    m = mn;
+  };
+  for (int tile = 0; tile < ntiles; ++tile) {
+    const int s = tile % NST;
+    if (t == 0 && tile + NST - 1 < ntiles) issue(tile + NST - 1);  // its stage was released by the sync below
+    ptx::mbar_wait(&full[s], (tile / NST) & 1);
+    const TKV* kt = tiles + ((size_t)s * 2 + 0) * KT * D;
+    const TKV* vt = tiles + ((size_t)s * 2 + 1) * KT * D;
+    const int nk = min(KT, pos - tile * KT);
+#pragma unroll
+    for (int pass = 0; pass < KT / 16; ++pass) {
+      const int k = pass * 16 + warp * 4 + grp;
+      const bool ok = k < nk;
+      float sc = 0.f, vv[16];
+      if (ok) {
+        float kk[16];
+        load16(kt + k * D + sub * 16, kk);
+        load16(vt + k * D + sub * 16, vv);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) sc += qv[i] * kk[i];
+      }
+      sc += __shfl_xor_sync(0xffffffffu, sc, 1);
+      sc += __shfl_xor_sync(0xffffffffu, sc, 2);
+      sc += __shfl_xor_sync(0xffffffffu, sc, 4);
+      if (ok) fold(sc, vv);
+    }
+    __syncthreads();  // everyone is done with stage s before it is refilled
+  }
+  if (warp == 0 && grp == 0) {  // the new token itself (key index pos)
+    float sc = 0.f, vv[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { sc += qv[i] * knew[sub * 16 + i]; vv[i] = vnew[sub * 16 + i]; }
+    sc += __shfl_xor_sync(0x000000ffu, sc, 1);
+    sc += __shfl_xor_sync(0x000000ffu, sc, 2);
+    sc += __shfl_xor_sync(0x000000ffu, sc, 4);
+    fold(sc, vv);
+  }
+  const int slot = warp * 4 + grp;
+  if (sub == 0) { sm_m[slot] = m; sm_l[slot] = l; }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) sm_acc[slot][sub * 16 + i] = acc[i];
+  __syncthreads();
+  float gm = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) gm = fmaxf(gm, sm_m[i]);
+  float num = 0.f, den = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
     const float f = sm_m[i] == -INFINITY ? 0.f : __expf(sm_m[i] - gm);
     num += f * sm_acc[i][t];
     den += f * sm_l[i];
@@ -985,6 +1125,22 @@ __global__ void decode_rows_kernel(const int* __restrict__ hist, int hist_stride
   row_pos[p] = L - 1;
 }
 
+// diagnostics: stats[0] += number of non-empty (layer, expert) segments of this step, stats[1] += 1
+__global__ void moe_active_stat_kernel(const int* __restrict__ counts, int n, unsigned long long* stats) {
+  int c = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) c += counts[i] > 0;
+  c = __reduce_add_sync(0xffffffffu, c);
+  __shared__ int part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += part[w];
+    stats[0] += (unsigned long long)t;
+    stats[1] += 1ull;
+  }
+}
+
 __global__ void fill_i32_kernel(int* p, int v, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -1105,6 +1261,11 @@ void decode_rows(const int* hist, int hist_stride, const int* hist_len, int* src
   decode_rows_kernel<<<blocks_for(n_pages, 128), 128, 0, s>>>(hist, hist_stride, hist_len, src, row_pos, n_pages);
   launch_check("decode_rows");
 }
+void moe_active_stat(const int* counts, int n, unsigned long long* stats, cudaStream_t s) {
+  moe_active_stat_kernel<<<1, 256, 0, s>>>(counts, n, stats);
+  launch_check("moe_active_stat");
+}
+
 void fill_i32(int* p, int v, long long n, cudaStream_t s) {
   fill_i32_kernel<<<blocks_for(n, 256), 256, 0, s>>>(p, v, n);
   launch_check("fill_i32");
@@ -1115,7 +1276,15 @@ void rope_attn_decode(const float* qkv, int n_splits, long long split_stride, co
                       long long lo_off_elems, long long rows, int heads, int smax, float scale, DType dt, cudaStream_t s) {
   dim3 grid((unsigned)rows, heads);
   const int ns = n_splits < 1 ? 1 : n_splits;
-  if (kv_f16) {
+  static const bool use_bulk = getenv("DSOCR_ATTN_NO_BULK") == nullptr;
+  constexpr int kDyn = 2 * 2 * 8192;  // NST stages x (K, V) x 8 KB
+  if (use_bulk) {
+    if (kv_f16) {
+      DISPATCH_T(dt, (rope_attn_decode_bulk_kernel<T, __half><<<grid, 128, kDyn, s>>>(qkv, ns, split_stride, cos_t, sin_t, (__half*)kc, (__half*)vc, row_page, row_pos, (T*)ctx, lo_off_elems, heads, smax, scale)));
+    } else {
+      DISPATCH_T(dt, (rope_attn_decode_bulk_kernel<T, float><<<grid, 128, kDyn, s>>>(qkv, ns, split_stride, cos_t, sin_t, (float*)kc, (float*)vc, row_page, row_pos, (T*)ctx, lo_off_elems, heads, smax, scale)));
+    }
+  } else if (kv_f16) {
     DISPATCH_T(dt, (rope_attn_decode_kernel<T, __half><<<grid, 128, 0, s>>>(qkv, ns, split_stride, cos_t, sin_t, (__half*)kc, (__half*)vc, row_page, row_pos, (T*)ctx, lo_off_elems, heads, smax, scale)));
   } else {
     DISPATCH_T(dt, (rope_attn_decode_kernel<T, float><<<grid, 128, 0, s>>>(qkv, ns, split_stride, cos_t, sin_t, (float*)kc, (float*)vc, row_page, row_pos, (T*)ctx, lo_off_elems, heads, smax, scale)));

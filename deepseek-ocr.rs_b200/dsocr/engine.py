@@ -117,6 +117,12 @@ class OcrEngine:
                                          C.byref(n)), "tap")
         return out
 
+    def moe_stats(self) -> tuple:
+        """(non-empty (layer, expert) segments summed over decode steps, decode steps) since the last read."""
+        v = (C.c_double * 2)()
+        check(self._lib.dsocr_moe_stats(self._h, v), "moe_stats")
+        return float(v[0]), float(v[1])
+
     def launch_count(self) -> int:
         return int(self._lib.dsocr_launch_count(self._h))
 

@@ -185,6 +185,11 @@ DSOCR_API int dsocr_kernel_timing_end(dsocr_engine* e, char* json_out, size_t ca
  * 0 vision.prepare_inputs, 1 vision.compute_embeddings, 2 decode.prefill, 3 decode.iterative, 4 decode.generate */
 DSOCR_API int dsocr_last_timings(const dsocr_engine* e, double* ms_out, int n);
 
+/* Diagnostics for the roofline model (no reference counterpart): with option "moe_stats" = 1 every batched decode
+ * step adds the number of routed-expert weight segments it actually touched (non-empty (layer, expert) pairs) to
+ * out2[0] and 1 to out2[1].  Reading resets both. */
+DSOCR_API int dsocr_moe_stats(dsocr_engine* e, double* out2);
+
 /* Number of kernels this library launched on the engine's streams since creation. */
 DSOCR_API long long dsocr_launch_count(const dsocr_engine* e);
 
