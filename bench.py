@@ -191,8 +191,9 @@ def kernel_model(cfg, name: str, args, pages: int, hbm_gbs: float, tf_peak: floa
             "dec_o_proj": H * H * 2 + act(H, H),
             "dec_dense_gate_up": 2 * cfg.intermediate_size * H * 2 + act(H, cfg.intermediate_size),
             "dec_dense_down": H * cfg.intermediate_size * 2 + act(cfg.intermediate_size, H),
-            "moe_expert_gate_up": Ea * 2 * mi * H * 2 + B * K * (H * 4 + mi * 4),
-            "moe_expert_down": Ea * H * mi * 2 + B * K * (mi * 4 + H * 4),
+            # routed experts actually hit + the shared experts, which run as extra groups of the same grouped GEMM
+            "moe_expert_gate_up": (Ea + cfg.n_shared_experts) * 2 * mi * H * 2 + B * (K + cfg.n_shared_experts) * (H * 4 + mi * 4),
+            "moe_expert_down": (Ea + cfg.n_shared_experts) * H * mi * 2 + B * (K + cfg.n_shared_experts) * (mi * 4 + H * 4),
             "moe_shared_gate_up": 2 * S * H * 2 + act(H, S),
             "moe_shared_down": H * S * 2 + act(S, H),
         }

@@ -330,7 +330,10 @@ void Engine::load_weights(const std::string& path, const DsqReader* dsq) {
         upload_f32(L.router_wt, wt);
         if (st.has(p + "mlp.gate.e_score_correction_bias")) throw std::runtime_error("router score-correction bias is not supported");
       }
-      L.exp_gate.alloc((size_t)E * mi * H * 2); L.exp_up.alloc((size_t)E * mi * H * 2); L.exp_down.alloc((size_t)E * H * mi * 2);
+      // routed experts stacked as groups 0..E-1; the shared experts are appended as groups E.. (each mi wide) so the
+      // decode path runs them inside the same grouped GEMMs
+      const long long Eg = E + c.n_shared;
+      L.exp_gate.alloc((size_t)Eg * mi * H * 2); L.exp_up.alloc((size_t)Eg * mi * H * 2); L.exp_down.alloc((size_t)Eg * H * mi * 2);
       for (long long e = 0; e < E; ++e) {
         const std::string q = p + "mlp.experts." + std::to_string(e) + ".";
         const StTensor& tg = st.get(q + "gate_proj.weight"); expect_shape(tg, {mi, H}, q + "gate_proj.weight");
@@ -343,6 +346,18 @@ void Engine::load_weights(const std::string& path, const DsqReader* dsq) {
       T16(L.sh_gate, p + "mlp.shared_experts.gate_proj.weight", {S, H});
       T16(L.sh_up, p + "mlp.shared_experts.up_proj.weight", {S, H});
       T16(L.sh_down, p + "mlp.shared_experts.down_proj.weight", {H, S});
+      upload16_into(L.exp_gate.p, (size_t)E * mi * H, st.get(p + "mlp.shared_experts.gate_proj.weight"), dt_);
+      upload16_into(L.exp_up.p, (size_t)E * mi * H, st.get(p + "mlp.shared_experts.up_proj.weight"), dt_);
+      {
+        // down_proj [H, S] -> per shared expert s the column block [H, mi] (y = sum_s W[:, s*mi:(s+1)*mi] h_s)
+        const std::vector<float> w = to_f32(st.get(p + "mlp.shared_experts.down_proj.weight"));
+        std::vector<float> blk((size_t)H * mi);
+        for (long long sidx = 0; sidx < c.n_shared; ++sidx) {
+          for (long long n = 0; n < H; ++n) memcpy(&blk[(size_t)n * mi], &w[(size_t)n * S + sidx * mi], (size_t)mi * 4);
+          const auto h = to16(blk.data(), blk.size(), dt_);
+          h2d((uint8_t*)L.exp_down.p + (size_t)(E + sidx) * H * mi * 2, h.data(), h.size() * 2);
+        }
+      }
     }
   }
   rope_len_ = 8192;

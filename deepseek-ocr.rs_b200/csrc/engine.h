@@ -137,7 +137,6 @@ class Engine {
   bool quantized_ = false;
   QuantWeight q_lm_head_;
   long long iota_n_ = 0;
-  long long fixed_tiles_key_ = -1;  // (cap, bn) the cached fixed-capacity MoE tile tables were built for
   std::map<std::string, std::vector<float>> taps_;
 
   // weights

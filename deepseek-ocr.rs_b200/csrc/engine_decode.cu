@@ -42,35 +42,19 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
   // decode mode: every expert owns a fixed-capacity segment of `cap` rows (a token picks an expert at most once)
   const bool fused = decode_mode && rows <= 256;
   const long long cap = rows;
-  const long long perm_rows = fused ? std::max<long long>(n_assign, (long long)E * cap) : n_assign;
+  const int Eg = E + c.n_shared;  // decode: routed experts + the shared experts as extra groups of the grouped GEMMs
+  const long long perm_rows = fused ? std::max<long long>(n_assign, (long long)Eg * cap) : n_assign;
   int* perm_pos = ws("moe_perm", n_assign * 4).as<int>();
   void* xperm16 = ws("moe_xperm16", 2 * perm_rows * H * 2).p;
   void* hperm16 = ws("moe_hperm16", 2 * perm_rows * mi * 2).p;
   float* yperm = ws("moe_yperm32", perm_rows * H * 4).as<float>();
   int* counts_layers = nullptr;
-  LinearTile* ftiles1 = nullptr; LinearTile* ftiles2 = nullptr;
-  int fbn = 32, fchunks = 0;
+  int fbn = 32;
   if (fused) {
-    counts_layers = ws("moe_counts_layers", (size_t)c.layers * E * 4).as<int>();
-    cuda_check(cudaMemsetAsync(counts_layers, 0, (size_t)c.layers * E * 4, stream_), "moe counts memset");
-    fbn = cap <= 32 ? 32 : (cap <= 64 ? 64 : 128);  // one tile covers a whole expert segment for batches <= 128 pages
-    fchunks = (int)((cap + fbn - 1) / fbn);
-    const size_t n1 = (size_t)fchunks * E * (mi / 128), n2 = (size_t)fchunks * E * (H / 128);
-    ftiles1 = ws("moe_ftiles1", n1 * sizeof(LinearTile)).as<LinearTile>();
-    ftiles2 = ws("moe_ftiles2", n2 * sizeof(LinearTile)).as<LinearTile>();
-    const long long key = cap * 1000 + fbn;
-    if (fixed_tiles_key_ != key) {  // built once per batch size (first, eager step - never during capture)
-      std::vector<LinearTile> t1, t2;
-      for (int ch = 0; ch < fchunks; ++ch)      // chunk-major: the (mostly non-empty) first chunks spread over all CTAs
-        for (int e = 0; e < E; ++e) {
-          for (int wb = 0; wb < mi / 128; ++wb) t1.push_back({e * mi + wb * 128, (int)(e * cap + ch * fbn), 0, wb * 128, e, ch * fbn});
-          for (int wb = 0; wb < H / 128; ++wb) t2.push_back({e * H + wb * 128, (int)(e * cap + ch * fbn), 0, wb * 128, e, ch * fbn});
-        }
-      cuda_check(cudaMemcpyAsync(ftiles1, t1.data(), t1.size() * sizeof(LinearTile), cudaMemcpyHostToDevice, stream_), "tiles upload");
-      cuda_check(cudaMemcpyAsync(ftiles2, t2.data(), t2.size() * sizeof(LinearTile), cudaMemcpyHostToDevice, stream_), "tiles upload");
-      cuda_check(cudaStreamSynchronize(stream_), "tiles upload sync");
-      fixed_tiles_key_ = key;
-    }
+    counts_layers = ws("moe_counts_layers", (size_t)c.layers * Eg * 4).as<int>();
+    cuda_check(cudaMemsetAsync(counts_layers, 0, (size_t)c.layers * Eg * 4, stream_), "moe counts memset");
+    // token tile of the expert GEMMs; the kernel enumerates the non-empty (expert, chunk, block) units itself
+    fbn = cap <= 32 ? 32 : (cap <= 64 ? 64 : 128);
   }
 
   // Small-M (decode) projections are split along K so that they fill the GPU; the f32 partials are reduced
@@ -155,18 +139,18 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
     } else {
       // run_moe (block.rs:1215-1395).  In decode the shared-experts branch (3 small kernels) runs on a forked
       // stream next to the routed branch (router/plan/dispatch/2 grouped GEMMs): both are latency-bound.
-      int* lcounts = fused ? counts_layers + (size_t)l * E : counts;
+      int* lcounts = fused ? counts_layers + (size_t)l * Eg : counts;
       if (fused) {
         // o_proj partial reduce + residual + RMSNorm(ln2) + router + top-k + dispatch in one kernel
         post_attn(x, sp_o > 1 ? partA : nullptr, sp_o > 1 ? sp_o : 0, rows * H, L.ln2.as<float>(), L.router_wt.as<float>(),
-                  xn16, rows * H, topk_idx, topk_w, lcounts, perm_pos, xperm16, (long long)E * cap * H, (int)cap, rows, H, E, K,
-                  c.rms_eps, dt_, stream_);
+                  xn16, rows * H, topk_idx, topk_w, lcounts, perm_pos, xperm16, (long long)Eg * cap * H, (int)cap, rows, H, E, K,
+                  c.n_shared, c.rms_eps, dt_, stream_);
       } else {
         moe_router(xn32, L.router_wt.as<float>(), topk_idx, topk_w, counts, rows, H, E, K, stream_);
         moe_plan(counts, offsets, cursor, tiles1, ntiles, tiles2, ntiles + 1, E, bn, mi, H, stream_);
         moe_dispatch(topk_idx, offsets, cursor, xn16, rows * H, xperm16, n_assign * H, perm_pos, n_assign, K, H, dt_, stream_);
       }
-      const bool fork = rows <= 256 && !kernel_timing_enabled();
+      const bool fork = !fused && rows <= 256 && !kernel_timing_enabled();
       cudaStream_t sb = fork ? stream2_ : stream_;
       if (fork) {
         cuda_check(cudaEventRecord(ev_fork_, stream_), "fork record");
@@ -174,26 +158,26 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
       }
       {
         LinearCall lc;  // routed experts: gate/up + SwiGLU, grouped
-        lc.tag = "moe_expert_gate_up"; lc.w0 = L.exp_gate.p; lc.w1 = L.exp_up.p; lc.w_rows = (long long)E * mi;
-        const long long pr = fused ? (long long)E * cap : n_assign;
+        lc.tag = "moe_expert_gate_up"; lc.w0 = L.exp_gate.p; lc.w1 = L.exp_up.p; lc.w_rows = (long long)(fused ? Eg : E) * mi;
+        const long long pr = fused ? (long long)Eg * cap : n_assign;
         lc.x = xperm16; lc.x_rows = 2 * pr; lc.x_parts = 2; lc.x_lo_row_off = (int)pr;
         lc.M = (int)pr; lc.N = mi; lc.K = H;
         lc.out = hperm16; lc.out_lo = (uint16_t*)hperm16 + pr * mi; lc.ldo = mi; lc.out_mode = lin::OUT_T_SPLIT;
-        if (fused) { lc.tiles = ftiles1; lc.group_counts = lcounts; lc.max_tiles = fchunks * E * (mi / 128); lc.bn = fbn; }
+        if (fused) { lc.dyn_groups = Eg; lc.dyn_cap = (int)cap; lc.group_counts = lcounts; lc.bn = fbn; }
         else { lc.tiles = tiles1; lc.num_tiles_dev = ntiles; lc.max_tiles = max_chunks * (mi / 128); lc.bn = bn; }
         linear(lc, dt_, num_sms_, stream_);
       }
       {
         LinearCall lc;  // routed experts: down, grouped
-        lc.tag = "moe_expert_down"; lc.w0 = L.exp_down.p; lc.w_rows = (long long)E * H;
-        const long long pr = fused ? (long long)E * cap : n_assign;
+        lc.tag = "moe_expert_down"; lc.w0 = L.exp_down.p; lc.w_rows = (long long)(fused ? Eg : E) * H;
+        const long long pr = fused ? (long long)Eg * cap : n_assign;
         lc.x = hperm16; lc.x_rows = 2 * pr; lc.x_parts = 2; lc.x_lo_row_off = (int)pr;
         lc.M = (int)pr; lc.N = H; lc.K = mi; lc.out = yperm; lc.ldo = H; lc.out_mode = lin::OUT_F32;
-        if (fused) { lc.tiles = ftiles2; lc.group_counts = lcounts; lc.max_tiles = fchunks * E * (H / 128); lc.bn = fbn; }
+        if (fused) { lc.dyn_groups = Eg; lc.dyn_cap = (int)cap; lc.group_counts = lcounts; lc.bn = fbn; }
         else { lc.tiles = tiles2; lc.num_tiles_dev = ntiles + 1; lc.max_tiles = max_chunks * (H / 128); lc.bn = bn; }
         linear(lc, dt_, num_sms_, stream_);
       }
-      {
+      if (!fused) {
         LinearCall lc;  // shared experts (one fused SwiGLU MLP, weights.rs:390-400)
         lc.tag = "moe_shared_gate_up"; lc.w0 = L.sh_gate.p; lc.w1 = L.sh_up.p; lc.x = xn16; lc.x_rows = 2 * rows; lc.x_parts = 2; lc.x_lo_row_off = (int)rows;
         lc.M = (int)rows; lc.N = (int)S; lc.K = H; lc.ldo = S;
@@ -205,7 +189,7 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
         linear(lc, dt_, num_sms_, sb);
         if (sp_sgu > 1) swiglu_reduce(partA, sp_sgu, 2 * rows * S, rows * S, h16, rows * S, rows * S, dt_, sb);
       }
-      {
+      if (!fused) {
         LinearCall lc;
         lc.tag = "moe_shared_down"; lc.w0 = L.sh_down.p; lc.x = h16; lc.x_rows = 2 * rows; lc.x_parts = 2; lc.x_lo_row_off = (int)rows;
         lc.M = (int)rows; lc.N = H; lc.K = (int)S; lc.ldo = H;
@@ -219,9 +203,9 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
       }
       if (fused) {
         const bool last = l + 1 == c.layers;
-        combine_norm(x, yperm, perm_pos, topk_w, K, sp_sd > 1 ? partB : nullptr, sp_sd, rows * H,
+        combine_norm(x, yperm, perm_pos, topk_w, K, nullptr, 0, rows * H,
                      last ? final_norm_.as<float>() : dec_[l + 1].ln1.as<float>(), last ? xf16 : xn16, rows * H, rows, H,
-                     c.rms_eps, dt_, stream_);
+                     c.rms_eps, c.n_shared, (int)(E * cap), (int)cap, dt_, stream_);
         if (last) final_done = true; else have_xn = true;
       } else {
         moe_combine(yperm, perm_pos, topk_w, x, rows, K, H, sp_sd > 1 ? partB : nullptr, sp_sd, rows * H, stream_);
@@ -230,7 +214,7 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
     if (record_taps_) record_tap("dec.hidden." + std::to_string(l), x, rows * H);
   }
   if (moe_stats_ && counts_layers) {
-    moe_active_stat(counts_layers, c.layers * E, moe_stats_dev_.as<unsigned long long>(), stream_);
+    moe_active_stat(counts_layers, c.layers * Eg, moe_stats_dev_.as<unsigned long long>(), stream_);
   }
   // final RMSNorm + lm_head on the selected rows
   if (!final_done)
@@ -256,6 +240,9 @@ void Engine::moe_stats(unsigned long long out[2]) {
   cuda_check(cudaStreamSynchronize(stream_), "stats sync");
   cuda_check(cudaMemcpy(out, moe_stats_dev_.p, 16, cudaMemcpyDeviceToHost), "stats copy");
   cuda_check(cudaMemset(moe_stats_dev_.p, 0, 16), "stats reset");
+  // the shared experts ride along as always-populated groups; report routed experts only
+  const unsigned long long shared = out[1] * (unsigned long long)(cfg_.n_shared * std::max(0, cfg_.layers - cfg_.first_dense));
+  out[0] = out[0] > shared ? out[0] - shared : 0;
 }
 
 // DSQ variant of decoder_forward (run_quantized_matmul, quantization.rs:164-185): every decoder linear and the

@@ -53,6 +53,9 @@ struct LinearCall {
   const LinearTile* tiles = nullptr;
   const int* num_tiles_dev = nullptr;
   const int* group_counts = nullptr;  // fixed-capacity groups: tile rows derived from device-side counts
+  // fixed-capacity groups scheduled on the device: group g = weight rows [g*N, +N), token rows [g*dyn_cap, +count)
+  int dyn_groups = 0;
+  int dyn_cap = 0;
   int max_tiles = 0;
   int tile_rows_hint = 0;  // typical rows per tile, used to pick the token tile
   int bn = 0;              // force the token tile (0 = auto)
@@ -147,9 +150,10 @@ void rope_attn_decode(const float* qkv, int n_splits, long long split_stride, co
                       long long lo_off_elems, long long rows, int heads, int smax, float scale, DType dt, cudaStream_t s);
 void post_attn(float* x, const float* partials, int n_splits, long long split_stride, const float* w, const float* wgt,
                void* xn16, long long xn_lo_off, int* topk_idx, float* topk_w, int* counts, int* perm_pos, void* xperm,
-               long long xperm_lo_off, int cap, long long rows, int H, int E, int topk, float eps, DType dt, cudaStream_t s);
+               long long xperm_lo_off, int cap, long long rows, int H, int E, int topk, int n_shared, float eps, DType dt,
+               cudaStream_t s);
 void combine_norm(float* x, const float* y, const int* perm_pos, const float* topk_w, int topk, const float* partials,
                   int n_splits, long long split_stride, const float* w_next, void* out16, long long lo_off_elems,
-                  long long rows, int H, float eps, DType dt, cudaStream_t s);
+                  long long rows, int H, float eps, int n_shared, int shared_row0, int cap, DType dt, cudaStream_t s);
 
 }  // namespace dsocr

@@ -645,7 +645,7 @@ post_attn_kernel(float* __restrict__ x, const float* __restrict__ partials, int 
                  const float* __restrict__ w, const float* __restrict__ wgt, T* __restrict__ xn16, long long xn_lo_off,
                  int* __restrict__ topk_idx, float* __restrict__ topk_w, int* __restrict__ counts,
                  int* __restrict__ perm_pos, T* __restrict__ xperm, long long xperm_lo_off, int cap, int H, int topk,
-                 float eps) {
+                 int n_shared, float eps) {
   constexpr int KS = 1024 / E;
   constexpr int PER = (E + 31) / 32;
   extern __shared__ float sm[];
@@ -745,13 +745,15 @@ post_attn_kernel(float* __restrict__ x, const float* __restrict__ partials, int 
     }
   }
   __syncthreads();
-  for (int idx = t; idx < topk * n4; idx += 1024) {  // copy the normed row into its expert slots
+  // the shared experts ride in the same grouped GEMMs as groups E, E+1, ...: every token, slot = its row
+  if (row == 0 && t < n_shared) counts[E + t] = (int)gridDim.x;
+  for (int idx = t; idx < (topk + n_shared) * n4; idx += 1024) {  // copy the normed row into its expert slots
     const int k = idx / n4, c4 = idx % n4;
     const float4 o4 = reinterpret_cast<const float4*>(xn_s)[c4];
     const float o[4] = {o4.x, o4.y, o4.z, o4.w};
     uint2 hi, lo;
     split4<T>(o, hi, lo);
-    const long long dst = (long long)sel_pos[k] * H;
+    const long long dst = (k < topk ? (long long)sel_pos[k] : (long long)(E + k - topk) * cap + row) * H;
     reinterpret_cast<uint2*>(xperm + dst)[c4] = hi;
     reinterpret_cast<uint2*>(xperm + xperm_lo_off + dst)[c4] = lo;
   }
@@ -764,7 +766,7 @@ __global__ void __launch_bounds__(128)
 combine_norm_kernel(float* __restrict__ x, const float* __restrict__ y, const int* __restrict__ perm_pos,
                     const float* __restrict__ topk_w, int topk, const float* __restrict__ partials, int n_splits,
                     long long split_stride, const float* __restrict__ w_next, T* __restrict__ out16,
-                    long long lo_off_elems, int H, float eps) {
+                    long long lo_off_elems, int H, float eps, int n_shared, int shared_row0, int cap) {
   const long long row = blockIdx.x;
   const int n4 = H / 4;
   float4 v[3];
@@ -772,6 +774,11 @@ combine_norm_kernel(float* __restrict__ x, const float* __restrict__ y, const in
   float wk[8]; int pk[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) { wk[k] = k < topk ? topk_w[row * topk + k] : 0.f; pk[k] = k < topk ? perm_pos[row * topk + k] : 0; }
+  // shared experts computed as extra groups of the grouped GEMM: rows shared_row0 + s*cap + row, weight 1
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if (k >= topk && k < topk + n_shared) { wk[k] = 1.f; pk[k] = shared_row0 + (k - topk) * cap + (int)row; }
+  topk += n_shared;
 #pragma unroll
   for (int it = 0; it < 3; ++it) {
     const int i = threadIdx.x + it * 128;
@@ -1293,22 +1300,23 @@ void rope_attn_decode(const float* qkv, int n_splits, long long split_stride, co
 }
 void post_attn(float* x, const float* partials, int n_splits, long long split_stride, const float* w, const float* wgt,
                void* xn16, long long xn_lo_off, int* topk_idx, float* topk_w, int* counts, int* perm_pos, void* xperm,
-               long long xperm_lo_off, int cap, long long rows, int H, int E, int topk, float eps, DType dt, cudaStream_t s) {
-  if (H % 256 || H / 4 > 1024 || topk > 16) throw std::runtime_error("post_attn: unsupported shape");
+               long long xperm_lo_off, int cap, long long rows, int H, int E, int topk, int n_shared, float eps, DType dt,
+               cudaStream_t s) {
+  if (H % 256 || H / 4 > 1024 || topk > 16 || rows > cap) throw std::runtime_error("post_attn: unsupported shape");
   const size_t smem = (size_t)(H + 1024) * 4;
   DISPATCH_T(dt, {
-    if (E == 64) post_attn_kernel<T, 64><<<(unsigned)rows, 1024, smem, s>>>(x, partials, n_splits, split_stride, w, wgt, (T*)xn16, xn_lo_off, topk_idx, topk_w, counts, perm_pos, (T*)xperm, xperm_lo_off, cap, H, topk, eps);
-    else if (E == 32) post_attn_kernel<T, 32><<<(unsigned)rows, 1024, smem, s>>>(x, partials, n_splits, split_stride, w, wgt, (T*)xn16, xn_lo_off, topk_idx, topk_w, counts, perm_pos, (T*)xperm, xperm_lo_off, cap, H, topk, eps);
-    else if (E == 16) post_attn_kernel<T, 16><<<(unsigned)rows, 1024, smem, s>>>(x, partials, n_splits, split_stride, w, wgt, (T*)xn16, xn_lo_off, topk_idx, topk_w, counts, perm_pos, (T*)xperm, xperm_lo_off, cap, H, topk, eps);
+    if (E == 64) post_attn_kernel<T, 64><<<(unsigned)rows, 1024, smem, s>>>(x, partials, n_splits, split_stride, w, wgt, (T*)xn16, xn_lo_off, topk_idx, topk_w, counts, perm_pos, (T*)xperm, xperm_lo_off, cap, H, topk, n_shared, eps);
+    else if (E == 32) post_attn_kernel<T, 32><<<(unsigned)rows, 1024, smem, s>>>(x, partials, n_splits, split_stride, w, wgt, (T*)xn16, xn_lo_off, topk_idx, topk_w, counts, perm_pos, (T*)xperm, xperm_lo_off, cap, H, topk, n_shared, eps);
+    else if (E == 16) post_attn_kernel<T, 16><<<(unsigned)rows, 1024, smem, s>>>(x, partials, n_splits, split_stride, w, wgt, (T*)xn16, xn_lo_off, topk_idx, topk_w, counts, perm_pos, (T*)xperm, xperm_lo_off, cap, H, topk, n_shared, eps);
     else throw std::runtime_error("post_attn: unsupported expert count " + std::to_string(E));
   });
   launch_check("post_attn_norm_router_dispatch");
 }
 void combine_norm(float* x, const float* y, const int* perm_pos, const float* topk_w, int topk, const float* partials,
                   int n_splits, long long split_stride, const float* w_next, void* out16, long long lo_off_elems,
-                  long long rows, int H, float eps, DType dt, cudaStream_t s) {
-  if (H > 1536 || n_splits > 16 || topk > 8) throw std::runtime_error("combine_norm: unsupported shape");
-  DISPATCH_T(dt, (combine_norm_kernel<T, 16><<<(unsigned)rows, 128, 0, s>>>(x, y, perm_pos, topk_w, topk, partials, partials ? n_splits : 0, split_stride, w_next, (T*)out16, lo_off_elems, H, eps)));
+                  long long rows, int H, float eps, int n_shared, int shared_row0, int cap, DType dt, cudaStream_t s) {
+  if (H > 1536 || n_splits > 16 || topk + n_shared > 8) throw std::runtime_error("combine_norm: unsupported shape");
+  DISPATCH_T(dt, (combine_norm_kernel<T, 16><<<(unsigned)rows, 128, 0, s>>>(x, y, perm_pos, topk_w, topk, partials, partials ? n_splits : 0, split_stride, w_next, (T*)out16, lo_off_elems, H, eps, n_shared, shared_row0, cap)));
   launch_check("moe_combine_norm");
 }
 

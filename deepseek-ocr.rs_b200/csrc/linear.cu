@@ -71,7 +71,7 @@ int linear_plan_splits(long long M, int N, int K, int num_sms) {
 
 void linear(const LinearCall& c, DType dt, int num_sms, cudaStream_t stream) {
   if (c.K % lin::BK != 0) throw std::runtime_error("linear: K must be a multiple of 64, got " + std::to_string(c.K));
-  if (c.M <= 0 && !c.tiles) return;
+  if (c.M <= 0 && !c.tiles && !c.dyn_groups) return;
   const bool dual = c.w1 != nullptr;
   const int bn = c.bn ? c.bn : linear_pick_bn(c.tiles ? c.tile_rows_hint : c.M, dual);
 
@@ -86,7 +86,13 @@ void linear(const LinearCall& c, DType dt, int num_sms, cudaStream_t stream) {
   p.n_w_blocks = (c.N + lin::BM - 1) / lin::BM;
   p.nbatch = c.nbatch > 1 ? c.nbatch : 1;
   p.out_batch_stride = c.out_batch_stride;
-  if (c.tiles) p.num_tiles = c.max_tiles;
+  if (c.dyn_groups) {
+    if (!c.group_counts || !c.bn || c.N % lin::BM || c.dyn_groups > 256 || c.k_splits > 1 || p.nbatch > 1)
+      throw std::runtime_error("linear: device-scheduled groups need counts, a fixed token tile and N % 128 == 0");
+    p.dyn_groups = c.dyn_groups; p.dyn_wpg = c.N / lin::BM; p.dyn_cap = c.dyn_cap; p.dyn_w_rows = c.N;
+    p.num_tiles = c.dyn_groups * p.dyn_wpg * ((c.dyn_cap + bn - 1) / bn);  // upper bound; the kernel compacts
+    if (p.num_tiles > 64 * num_sms) throw std::runtime_error("linear: too many grouped units for the tile cache");
+  } else if (c.tiles) p.num_tiles = c.max_tiles;
   else p.num_tiles = p.n_w_blocks * (int)((c.M + bn - 1) / bn) * p.nbatch;
   p.k_splits = 1; p.kb_per_split = c.K / lin::BK; p.split_stride = c.split_stride; p.dual_stride = c.dual_stride;
   if (c.k_splits > 1) {
@@ -113,7 +119,7 @@ void linear(const LinearCall& c, DType dt, int num_sms, cudaStream_t stream) {
   }
   CUtensorMap x16 = x;
   p.x_box16 = 0;
-  if (c.tiles && p.nbatch == 1 && bn <= 128) {  // grouped: tiles rarely fill the token tile
+  if ((c.tiles || c.dyn_groups) && p.nbatch == 1 && bn <= 128) {  // grouped: tiles rarely fill the token tile
     x16 = tmap::make_2d_16bit(c.x, c.x_rows, c.K, c.ldx ? c.ldx : c.K, 16, lin::BK);
     p.x_box16 = 1;
   }

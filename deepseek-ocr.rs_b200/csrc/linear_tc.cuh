@@ -66,6 +66,14 @@ struct Params {
   // grouped small-M problems: load the token operand in 16-row boxes and only as many as the tile has rows
   // (the unused part of the smem tile keeps stale data; those MMA columns are never stored)
   int x_box16;
+  // fixed-capacity groups scheduled on the device (decode-time MoE): group g owns weight rows
+  // [g*dyn_w_rows, +dyn_w_rows) and token rows [g*dyn_cap, +group_counts[g]).  Every CTA derives the same compact
+  // list of non-empty (group, token-chunk, weight-block) units from group_counts and takes every gridDim-th unit,
+  // so the work stays balanced however few groups are populated.
+  int dyn_groups;
+  int dyn_wpg;     // weight blocks (of 128 rows) per group
+  int dyn_cap;
+  int dyn_w_rows;
 };
 
 constexpr int BM = 128;  // weight rows per tile (UMMA M)
@@ -120,7 +128,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_constant__
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_kb = p.K / BK;
-  const int num_tiles = p.num_tiles_dev ? min(*p.num_tiles_dev, p.num_tiles) : p.num_tiles;
+  int num_tiles = p.num_tiles_dev ? min(*p.num_tiles_dev, p.num_tiles) : p.num_tiles;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_w0);
@@ -141,8 +149,50 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_constant__
   // grouped problems: stage this CTA's tile descriptors (with the row counts resolved) in shared memory so that
   // the three roles do not each pay dependent global loads at every tile boundary
   constexpr int kTileCache = 64;
+  constexpr int kMaxGroups = 256;
   __shared__ int s_tiles[kTileCache][5];  // w_row0, x_row0, rows, n0 (+pad)
-  if (p.tiles) {
+  __shared__ int s_prefix[kMaxGroups + 1];
+  if (p.dyn_groups) {
+    if (warp == 2) {  // exclusive prefix of units per group
+      int carry = 0;
+      for (int base = 0; base < p.dyn_groups; base += 32) {
+        const int g = base + lane;
+        int u = 0;
+        if (g < p.dyn_groups) u = ((p.group_counts[g] + BN - 1) / BN) * p.dyn_wpg;
+        int inc = u;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += v;
+        }
+        if (g < p.dyn_groups) s_prefix[g] = carry + inc - u;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+      }
+      if (lane == 0) s_prefix[p.dyn_groups] = carry;
+    }
+    __syncthreads();
+    num_tiles = s_prefix[p.dyn_groups];
+    if (num_tiles > kTileCache * (int)gridDim.x) {
+      if (threadIdx.x == 0) printf("linear_kernel: %d grouped units exceed the per-CTA tile cache\n", num_tiles);
+      __trap();
+    }
+    for (int i = threadIdx.x; i < kTileCache; i += kThreads) {
+      const int u = blockIdx.x + i * gridDim.x;
+      if (u < num_tiles) {
+        int lo = 0, hi = p.dyn_groups;  // s_prefix[lo] <= u < s_prefix[hi]
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          if (s_prefix[mid] <= u) lo = mid; else hi = mid;
+        }
+        const int local = u - s_prefix[lo];
+        const int ch = local / p.dyn_wpg, wb = local - ch * p.dyn_wpg;
+        s_tiles[i][0] = lo * p.dyn_w_rows + wb * BM;
+        s_tiles[i][1] = lo * p.dyn_cap + ch * BN;
+        s_tiles[i][2] = min(BN, p.group_counts[lo] - ch * BN);
+        s_tiles[i][3] = wb * BM;
+      }
+    }
+  } else if (p.tiles) {
     for (int i = threadIdx.x; i < kTileCache; i += kThreads) {
       const int t = blockIdx.x + i * gridDim.x;
       if (t < num_tiles) {
@@ -163,9 +213,9 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_constant__
   auto decode_tile = [&](int t, int& w_row0, int& x_row0, int& rows, int& n0, int& batch, int& split) {
     batch = 0; split = 0;
     if (p.k_splits > 1) { split = t / base_tiles; t -= split * base_tiles; }
-    if (p.tiles) {
+    if (p.tiles || p.dyn_groups) {
       const int i = (t - (int)blockIdx.x) / (int)gridDim.x;
-      if (i < kTileCache) {
+      if (i < kTileCache) {  // always true for dyn_groups (checked above)
         w_row0 = s_tiles[i][0]; x_row0 = s_tiles[i][1]; rows = s_tiles[i][2]; n0 = s_tiles[i][3];
       } else {
         const Tile tl = p.tiles[t];

@@ -103,6 +103,33 @@ extern "C" int dsocr_test_grouped_linear(int dtype, int E, int M, int N, int K, 
   });
 }
 
+extern "C" int dsocr_test_fixedcap_linear(int dtype, int E, int cap, int N, int K, const int* counts, const float* x,
+                                          const float* w0, const float* w1, int x_parts, float* out) {
+  return guarded([&]() {
+    const DType dt = to_dtype(dtype);
+    const int M = E * cap;
+    const size_t xe = (size_t)M * K, we = (size_t)E * N * K, oe = (size_t)M * N;
+    std::vector<uint16_t> hx = x_parts == 2 ? to16_split(x, xe, dt) : to16(x, xe, dt);
+    std::vector<uint16_t> hw0 = to16(w0, we, dt);
+    DevBuf dx(hx.size() * 2), dw0(we * 2), dw1, dout(oe * 4), dcounts((size_t)E * 4);
+    h2d(dx.p, hx.data(), hx.size() * 2);
+    h2d(dw0.p, hw0.data(), we * 2);
+    h2d(dcounts.p, counts, (size_t)E * 4);
+    if (w1) { auto h = to16(w1, we, dt); dw1.alloc(we * 2); h2d(dw1.p, h.data(), we * 2); }
+    cuda_check(cudaMemset(dout.p, 0, oe * 4), "memset");
+    LinearCall c;
+    c.w0 = dw0.p; c.w1 = w1 ? dw1.p : nullptr; c.w_rows = (long long)E * N;
+    c.x = dx.p; c.x_rows = (long long)M * x_parts; c.x_parts = x_parts; c.x_lo_row_off = M;
+    c.M = M; c.N = N; c.K = K; c.out = dout.p; c.ldo = N; c.out_mode = 2;
+    c.dyn_groups = E; c.dyn_cap = cap; c.group_counts = dcounts.as<int>();
+    c.bn = cap <= 32 ? 32 : (cap <= 64 ? 64 : 128);
+    linear(c, dt, sm_count(), 0);
+    cuda_check(cudaDeviceSynchronize(), "fixed-capacity grouped linear kernel");
+    d2h(out, dout.p, oe * 4);
+    return 0;
+  });
+}
+
 extern "C" int dsocr_test_vision_attention(int dtype, int B, int S, int H, const float* qkv, int grid, const float* rel_h,
                                            const float* rel_w, int rel_rows, float* out) {
   return guarded([&]() {

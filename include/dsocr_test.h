@@ -22,6 +22,12 @@ DSOCR_API int dsocr_test_linear(int dtype, int M, int N, int K, const float* x, 
 DSOCR_API int dsocr_test_grouped_linear(int dtype, int E, int M, int N, int K, const int* counts, const float* x,
                                         const float* w0, const float* w1, int x_parts, float* out);
 
+/* Decode-time MoE expert GEMM with fixed-capacity segments: expert e owns rows [e*cap, e*cap + counts[e]) of
+ * x[E*cap, K] / out[E*cap, N]; the kernel enumerates the non-empty (expert, chunk, block) units on the device.
+ * Rows past counts[e] are left untouched (zero). */
+DSOCR_API int dsocr_test_fixedcap_linear(int dtype, int E, int cap, int N, int K, const int* counts, const float* x,
+                                         const float* w0, const float* w1, int x_parts, float* out);
+
 /* Vision attention over a qkv buffer [B*S, 3, H, 64] (16-bit after rounding) with the decomposed
  * relative-position bias: rel_h/rel_w tables [2*g-1... already resolved to [g, g, 64]] or NULL (CLIP).
  * grid_w * grid_h == S when tables are given.  out[B*S, H*64] f32. */

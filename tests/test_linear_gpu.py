@@ -161,3 +161,32 @@ def test_grouped_linear_matches_per_expert(dual):
             r[row:row + c] = ref_linear(BF16, x[row:row + c], w0[e], w1=w1[e] if dual else None, x_parts=2)
         row += c
     assert torch.allclose(y, r, rtol=1e-3, atol=2e-3 * r.abs().max().item())
+
+
+@pytest.mark.parametrize("dual,cap", [(False, 64), (True, 64), (True, 24), (False, 200), (True, 130)])
+def test_fixed_capacity_grouped_linear_device_scheduled(dual, cap):
+    """Decode-time expert GEMM: units are enumerated on the device from the per-expert counts (empty experts and
+    partially filled segments in any mix); result must equal the per-expert reference, untouched rows stay zero."""
+    g = torch.Generator().manual_seed(11 + cap)
+    E, N, K = 64, 896 if dual else 1280, 1280 if dual else 896
+    counts = torch.randint(0, min(cap, 12) + 1, (E,), generator=g).numpy().astype(np.int32)
+    counts[[0, 5, 6, 7, 63]] = 0
+    counts[9] = cap
+    counts[40] = max(1, cap - 1)
+    x = torch.randn(E * cap, K, generator=g)
+    w0 = torch.randn(E, N, K, generator=g) * 0.03
+    w1 = torch.randn(E, N, K, generator=g) * 0.03 if dual else None
+    out = np.zeros((E * cap, N), dtype=np.float32)
+    st = lib().dsocr_test_fixedcap_linear(
+        BF16, E, cap, N, K, counts.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), _fp(np.ascontiguousarray(x.numpy())),
+        _fp(np.ascontiguousarray(w0.numpy())), _fp(np.ascontiguousarray(w1.numpy())) if dual else None, 2, _fp(out))
+    check(st, "dsocr_test_fixedcap_linear")
+    y = torch.from_numpy(out)
+    r = torch.zeros(E * cap, N)
+    for e in range(E):
+        c = int(counts[e])
+        if c:
+            r[e * cap:e * cap + c] = ref_linear(BF16, x[e * cap:e * cap + c], w0[e], w1=w1[e] if dual else None, x_parts=2)
+    assert torch.allclose(y, r, rtol=1e-3, atol=2e-3 * r.abs().max().item())
+    for e in range(E):
+        assert not y[e * cap + int(counts[e]):(e + 1) * cap].any()
