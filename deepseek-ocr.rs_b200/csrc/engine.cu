@@ -192,6 +192,14 @@ void load_quant(QuantWeight& w, const DsqReader& dsq, const std::string& name, l
 }
 }  // namespace
 
+void Engine::retile_inplace(DevBuf& w, long long n, int k) {
+  if (k % 64 || (n % 128 && w.bytes < (size_t)n * k * 2)) throw std::runtime_error("retile: unsupported weight shape");
+  DevBuf t(retiled_bytes(n, k));
+  retile_weights(w.p, t.p, n, k, 0);
+  cuda_check(cudaDeviceSynchronize(), "weight retile");
+  w = std::move(t);
+}
+
 void Engine::load_weights(const std::string& path, const DsqReader* dsq) {
   SafeTensors st(path);
   const ModelConfig& c = cfg_;
@@ -359,6 +367,28 @@ void Engine::load_weights(const std::string& path, const DsqReader* dsq) {
         }
       }
     }
+  }
+  if (w_tiled_ && !dsq) {
+    // decode streams every decoder weight once per step: store them as contiguous, pre-swizzled 16 KB tiles
+    const long long E = c.n_experts + c.n_shared, mi = c.moe_inter, S = (long long)c.moe_inter * c.n_shared;
+    retile_inplace(lm_head_, c.vocab, (int)H);
+    for (DecLayerW& L : dec_) {
+      retile_inplace(L.qkv_w, 3 * H, (int)H);
+      retile_inplace(L.o_w, H, (int)H);
+      if (!L.moe) {
+        retile_inplace(L.gate_w, c.inter, (int)H);
+        retile_inplace(L.up_w, c.inter, (int)H);
+        retile_inplace(L.down_w, H, c.inter);
+      } else {
+        retile_inplace(L.exp_gate, E * mi, (int)H);
+        retile_inplace(L.exp_up, E * mi, (int)H);
+        retile_inplace(L.exp_down, E * H, (int)mi);
+        retile_inplace(L.sh_gate, S, (int)H);
+        retile_inplace(L.sh_up, S, (int)H);
+        retile_inplace(L.sh_down, H, (int)S);
+      }
+    }
+    cuda_check(cudaDeviceSynchronize(), "weight retile");
   }
   rope_len_ = 8192;
   std::vector<float> cs, sn;

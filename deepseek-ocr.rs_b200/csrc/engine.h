@@ -1,6 +1,7 @@
 // Engine: device-resident weights + the per-page forward path (vision encode, prefill, batched decode).
 // Mirrors DeepseekOcrModel (crates/infer-deepseek/src/model/mod.rs) behind the C ABI of include/dsocr.h.
 #pragma once
+#include <cstdlib>
 #include <map>
 #include <memory>
 #include <string>
@@ -134,6 +135,10 @@ class Engine {
   bool kv_f16_ = false;
   bool moe_stats_ = false;
   DevBuf moe_stats_dev_;
+  bool w_tiled_ = getenv("DSOCR_NO_TILED") == nullptr;  // decoder weights in the pre-tiled streaming layout
+  void retile_inplace(DevBuf& w, long long n, int k);
+  bool streamk_ = getenv("DSOCR_NO_STREAMK") == nullptr;  // A/B switch: balanced static units instead
+  DevBuf sk_ws_, sk_flags_;  // stream-K partial slots + hand-off flags of the decode-time expert GEMMs
   bool quantized_ = false;
   QuantWeight q_lm_head_;
   long long iota_n_ = 0;

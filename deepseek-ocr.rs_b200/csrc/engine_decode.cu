@@ -55,6 +55,12 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
     cuda_check(cudaMemsetAsync(counts_layers, 0, (size_t)c.layers * Eg * 4, stream_), "moe counts memset");
     // token tile of the expert GEMMs; the kernel enumerates the non-empty (expert, chunk, block) units itself
     fbn = cap <= 32 ? 32 : (cap <= 64 ? 64 : 128);
+    if (const char* e = getenv("DSOCR_MOE_BN")) fbn = atoi(e);  // experiment switch
+    if (!sk_flags_.p) {  // stream-K hand-off flags: zero once, the kernel returns them zeroed
+      sk_flags_.alloc((size_t)num_sms_ * 8);
+      cuda_check(cudaMemsetAsync(sk_flags_.p, 0, (size_t)num_sms_ * 8, stream_), "stream-K flags");
+      sk_ws_.alloc(linear_streamk_ws_bytes(num_sms_));
+    }
   }
 
   // Small-M (decode) projections are split along K so that they fill the GPU; the f32 partials are reduced
@@ -89,7 +95,7 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
       lc.tag = "dec_qkv"; lc.w0 = L.qkv_w.p; lc.x = xn16; lc.x_rows = 2 * rows; lc.x_parts = 2; lc.x_lo_row_off = (int)rows;
       lc.M = (int)rows; lc.N = 3 * H; lc.K = H; lc.ldo = 3 * H; lc.out_mode = lin::OUT_F32;
       lc.out = sp_qkv > 1 ? partA : qkv; lc.k_splits = sp_qkv; lc.split_stride = rows * 3 * H;
-      linear(lc, dt_, num_sms_, stream_);
+      lc.w_tiled = w_tiled_; linear(lc, dt_, num_sms_, stream_);
     }
     if (fused) {
       rope_attn_decode(sp_qkv > 1 ? partA : qkv, sp_qkv, rows * 3 * H, rope_cos_.as<float>(), rope_sin_.as<float>(),
@@ -106,7 +112,7 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
       lc.M = (int)rows; lc.N = H; lc.K = H; lc.ldo = H;
       if (sp_o > 1) { lc.out = partA; lc.out_mode = lin::OUT_F32; lc.k_splits = sp_o; lc.split_stride = rows * H; }
       else { lc.out = x; lc.out_mode = lin::OUT_F32_ADD; }
-      linear(lc, dt_, num_sms_, stream_);
+      lc.w_tiled = w_tiled_; linear(lc, dt_, num_sms_, stream_);
     }
     const bool fused_moe = fused && L.moe;
     if (!fused_moe)
@@ -123,7 +129,7 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
         } else {
           lc.out = h16; lc.out_lo = (uint16_t*)h16 + rows * c.inter; lc.out_mode = lin::OUT_T_SPLIT;
         }
-        linear(lc, dt_, num_sms_, stream_);
+        lc.w_tiled = w_tiled_; linear(lc, dt_, num_sms_, stream_);
         if (sp_dgu > 1) swiglu_reduce(partA, sp_dgu, 2 * rows * c.inter, rows * c.inter, h16, rows * c.inter, rows * c.inter, dt_, stream_);
       }
       {
@@ -134,7 +140,7 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
           lc.out = partB; lc.out_mode = lin::OUT_F32; lc.k_splits = sp_dd; lc.split_stride = rows * H;
           pend = partB; pend_n = sp_dd; pend_stride = rows * H;
         } else { lc.out = x; lc.out_mode = lin::OUT_F32_ADD; }
-        linear(lc, dt_, num_sms_, stream_);
+        lc.w_tiled = w_tiled_; linear(lc, dt_, num_sms_, stream_);
       }
     } else {
       // run_moe (block.rs:1215-1395).  In decode the shared-experts branch (3 small kernels) runs on a forked
@@ -163,9 +169,9 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
         lc.x = xperm16; lc.x_rows = 2 * pr; lc.x_parts = 2; lc.x_lo_row_off = (int)pr;
         lc.M = (int)pr; lc.N = mi; lc.K = H;
         lc.out = hperm16; lc.out_lo = (uint16_t*)hperm16 + pr * mi; lc.ldo = mi; lc.out_mode = lin::OUT_T_SPLIT;
-        if (fused) { lc.dyn_groups = Eg; lc.dyn_cap = (int)cap; lc.group_counts = lcounts; lc.bn = fbn; }
+        if (fused) { lc.dyn_groups = Eg; lc.dyn_cap = (int)cap; lc.group_counts = lcounts; lc.bn = fbn; if (streamk_) { lc.sk_ws = sk_ws_.as<float>(); lc.sk_flags = sk_flags_.as<int>(); } }
         else { lc.tiles = tiles1; lc.num_tiles_dev = ntiles; lc.max_tiles = max_chunks * (mi / 128); lc.bn = bn; }
-        linear(lc, dt_, num_sms_, stream_);
+        lc.w_tiled = w_tiled_; linear(lc, dt_, num_sms_, stream_);
       }
       {
         LinearCall lc;  // routed experts: down, grouped
@@ -173,9 +179,9 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
         const long long pr = fused ? (long long)Eg * cap : n_assign;
         lc.x = hperm16; lc.x_rows = 2 * pr; lc.x_parts = 2; lc.x_lo_row_off = (int)pr;
         lc.M = (int)pr; lc.N = H; lc.K = mi; lc.out = yperm; lc.ldo = H; lc.out_mode = lin::OUT_F32;
-        if (fused) { lc.dyn_groups = Eg; lc.dyn_cap = (int)cap; lc.group_counts = lcounts; lc.bn = fbn; }
+        if (fused) { lc.dyn_groups = Eg; lc.dyn_cap = (int)cap; lc.group_counts = lcounts; lc.bn = fbn; if (streamk_) { lc.sk_ws = sk_ws_.as<float>(); lc.sk_flags = sk_flags_.as<int>(); } }
         else { lc.tiles = tiles2; lc.num_tiles_dev = ntiles + 1; lc.max_tiles = max_chunks * (H / 128); lc.bn = bn; }
-        linear(lc, dt_, num_sms_, stream_);
+        lc.w_tiled = w_tiled_; linear(lc, dt_, num_sms_, stream_);
       }
       if (!fused) {
         LinearCall lc;  // shared experts (one fused SwiGLU MLP, weights.rs:390-400)
@@ -186,7 +192,7 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
         } else {
           lc.out = h16; lc.out_lo = (uint16_t*)h16 + rows * S; lc.out_mode = lin::OUT_T_SPLIT;
         }
-        linear(lc, dt_, num_sms_, sb);
+        lc.w_tiled = w_tiled_; linear(lc, dt_, num_sms_, sb);
         if (sp_sgu > 1) swiglu_reduce(partA, sp_sgu, 2 * rows * S, rows * S, h16, rows * S, rows * S, dt_, sb);
       }
       if (!fused) {
@@ -195,7 +201,7 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
         lc.M = (int)rows; lc.N = H; lc.K = (int)S; lc.ldo = H;
         if (sp_sd > 1) { lc.out = partB; lc.out_mode = lin::OUT_F32; lc.k_splits = sp_sd; lc.split_stride = rows * H; }
         else { lc.out = x; lc.out_mode = lin::OUT_F32_ADD; }
-        linear(lc, dt_, num_sms_, sb);
+        lc.w_tiled = w_tiled_; linear(lc, dt_, num_sms_, sb);
       }
       if (fork) {
         cuda_check(cudaEventRecord(ev_join_, sb), "join record");
@@ -223,7 +229,7 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
   LinearCall lc;
   lc.tag = "lm_head"; lc.w0 = lm_head_.p; lc.x = xf16; lc.x_rows = 2 * n_final; lc.x_parts = 2; lc.x_lo_row_off = n_final;
   lc.M = n_final; lc.N = c.vocab; lc.K = H; lc.out = logits; lc.ldo = c.vocab; lc.out_mode = lin::OUT_F32;
-  linear(lc, dt_, num_sms_, stream_);
+  lc.w_tiled = w_tiled_; linear(lc, dt_, num_sms_, stream_);
 }
 
 void Engine::set_moe_stats(bool on) {

@@ -31,6 +31,7 @@ struct LinearCall {
   const void* w1 = nullptr;
   long long w_rows = 0;  // 0 = N
   long long ldw = 0;
+  bool w_tiled = false;  // w0/w1 are in the pre-tiled streaming layout (retile_weights); rows padded to 128
   // activations: [x_rows, K] 16-bit, row pitch ldx (0 = K); x_parts = 2 adds the lo part at row x_lo_row_off
   const void* x = nullptr;
   long long x_rows = 0;
@@ -56,6 +57,10 @@ struct LinearCall {
   // fixed-capacity groups scheduled on the device: group g = weight rows [g*N, +N), token rows [g*dyn_cap, +count)
   int dyn_groups = 0;
   int dyn_cap = 0;
+  // stream-K workspace for the device-scheduled groups: num_sms slots of 2*128*128 floats and 2*num_sms ints that are
+  // zero before the first launch (the kernel hands them back zeroed); see linear_streamk_ws_bytes
+  float* sk_ws = nullptr;
+  int* sk_flags = nullptr;
   int max_tiles = 0;
   int tile_rows_hint = 0;  // typical rows per tile, used to pick the token tile
   int bn = 0;              // force the token tile (0 = auto)
@@ -70,6 +75,12 @@ struct LinearCall {
 int linear_plan_splits(long long M, int N, int K, int num_sms);
 
 int linear_pick_bn(long long m, bool dual);
+// Re-lays a row-major 16-bit weight [n, k] (k % 64 == 0) out as 128x64 tiles, each 16 KB contiguous and already in
+// the 128B-swizzled shared-memory order (tile index = row_block * k/64 + k_block); rows are padded to a multiple of
+// 128 with zeros.  dst needs retiled_bytes(n, k).
+inline size_t retiled_bytes(long long n, long long k) { return (size_t)((n + 127) / 128) * 128 * (size_t)k * 2; }
+void retile_weights(const void* src, void* dst, long long n, int k, cudaStream_t s);
+inline size_t linear_streamk_ws_bytes(int num_sms) { return (size_t)num_sms * 2 * 128 * 128 * 4; }
 void linear(const LinearCall& c, DType dt, int num_sms, cudaStream_t stream);
 
 // ------------------------------------------------------------------------- vision attention

@@ -1148,6 +1148,24 @@ __global__ void moe_active_stat_kernel(const int* __restrict__ counts, int n, un
   }
 }
 
+// row-major [n, k] 16-bit -> 128x64 tiles in 128B-swizzled order (one thread per 16-byte chunk of the output)
+__global__ void retile_weights_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, long long n, int k,
+                                      long long n_chunks) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_chunks) return;
+  const int num_kb = k / 64;
+  const long long tile = idx >> 10;          // 1024 chunks of 16 B per tile
+  const int within = (int)(idx & 1023);
+  const int r = within >> 3, qs = within & 7;  // row inside the tile, swizzled chunk position
+  const int q = qs ^ (r & 7);                  // logical 16-byte chunk of that row stored at position qs
+  const long long nb = tile / num_kb;
+  const int kb = (int)(tile - nb * num_kb);
+  const long long row = nb * 128 + r;
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (row < n) v = src[(row * k + kb * 64 + q * 8) >> 3];
+  dst[idx] = v;
+}
+
 __global__ void fill_i32_kernel(int* p, int v, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -1271,6 +1289,13 @@ void decode_rows(const int* hist, int hist_stride, const int* hist_len, int* src
 void moe_active_stat(const int* counts, int n, unsigned long long* stats, cudaStream_t s) {
   moe_active_stat_kernel<<<1, 256, 0, s>>>(counts, n, stats);
   launch_check("moe_active_stat");
+}
+
+void retile_weights(const void* src, void* dst, long long n, int k, cudaStream_t s) {
+  if (k % 64) throw std::runtime_error("retile_weights: k must be a multiple of 64");
+  const long long n_chunks = (long long)(retiled_bytes(n, k) / 16);
+  retile_weights_kernel<<<blocks_for(n_chunks, 256), 256, 0, s>>>((const uint4*)src, (uint4*)dst, n, k, n_chunks);
+  launch_check("retile_weights");
 }
 
 void fill_i32(int* p, int v, long long n, cudaStream_t s) {

@@ -1,5 +1,6 @@
 // Host launcher + instantiations of the tcgen05 linear kernel (linear_tc.cuh).
 #include "linear_tc.cuh"
+#include "linear_sk.cuh"
 #include "kernels.h"
 #include "tmap.h"
 
@@ -50,6 +51,56 @@ void launch_t(int bn, const LinearCall& c, const lin::Params& p, const CUtensorM
   else launch_bn<T, 2, 2>(bn, c, p, w0, w1, x, x16, grid, stream);
 }
 
+template <typename T, int BN, int NA>
+void launch_sk_inst(const LinearCall& c, const lin::SkParams& p, const CUtensorMap& w0, const CUtensorMap& w1,
+                    const CUtensorMap& x16, int grid, cudaStream_t stream) {
+  using C = lin::Cfg<BN, NA, 2>;
+  auto kern = lin::linear_sk_kernel<T, BN, NA>;
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes),
+               "linear_sk: set max dynamic smem");
+    configured = true;
+  }
+  kern<<<grid, lin::kThreads, C::kSmemBytes, stream>>>(w0, w1, x16, p);
+  launch_check(c.tag ? c.tag : "linear_sk");
+}
+
+template <typename T>
+void launch_sk(int bn, bool dual, const LinearCall& c, const lin::SkParams& p, const CUtensorMap& w0,
+               const CUtensorMap& w1, const CUtensorMap& x16, int grid, cudaStream_t stream) {
+  if (dual) {
+    if (bn == 32) launch_sk_inst<T, 32, 2>(c, p, w0, w1, x16, grid, stream);
+    else if (bn == 64) launch_sk_inst<T, 64, 2>(c, p, w0, w1, x16, grid, stream);
+    else launch_sk_inst<T, 128, 2>(c, p, w0, w1, x16, grid, stream);
+  } else {
+    if (bn == 32) launch_sk_inst<T, 32, 1>(c, p, w0, w1, x16, grid, stream);
+    else if (bn == 64) launch_sk_inst<T, 64, 1>(c, p, w0, w1, x16, grid, stream);
+    else launch_sk_inst<T, 128, 1>(c, p, w0, w1, x16, grid, stream);
+  }
+}
+
+// Decode-time expert GEMM over fixed-capacity groups (linear_sk.cuh).
+void linear_streamk(const LinearCall& c, DType dt, int num_sms, cudaStream_t stream) {
+  const bool dual = c.w1 != nullptr;
+  const int bn = c.bn;
+  if (!c.group_counts || (bn != 32 && bn != 64 && bn != 128) || c.N % lin::BM || c.dyn_groups > 256 || c.k_splits > 1 ||
+      c.nbatch > 1 || !c.sk_ws || !c.sk_flags || c.x_parts != 2 || c.bias || c.row_map || c.act ||
+      (c.out_mode != lin::OUT_T_SPLIT && c.out_mode != lin::OUT_F32))
+    throw std::runtime_error("linear: unsupported device-scheduled grouped problem");
+  lin::SkParams p{};
+  p.K = c.K; p.x_lo_row_off = c.x_lo_row_off; p.out = c.out; p.out_lo = c.out_lo; p.ldo = c.ldo; p.out_mode = c.out_mode;
+  p.counts = c.group_counts; p.groups = c.dyn_groups; p.wpg = c.N / lin::BM; p.cap = c.dyn_cap; p.w_rows = c.N;
+  p.ws = c.sk_ws; p.flags = c.sk_flags;
+  if (c.w_tiled) { p.w0_tiled = (const uint8_t*)c.w0; p.w1_tiled = (const uint8_t*)c.w1; }
+  const long long w_rows = c.w_rows ? c.w_rows : (long long)c.N * c.dyn_groups;
+  CUtensorMap w0 = tmap::make_2d_16bit(c.w0, w_rows, c.K, c.ldw ? c.ldw : c.K, lin::BM, lin::BK);
+  CUtensorMap w1 = dual ? tmap::make_2d_16bit(c.w1, w_rows, c.K, c.ldw ? c.ldw : c.K, lin::BM, lin::BK) : w0;
+  CUtensorMap x16 = tmap::make_2d_16bit(c.x, c.x_rows, c.K, c.ldx ? c.ldx : c.K, 16, lin::BK);
+  if (dt == DType::BF16) launch_sk<__nv_bfloat16>(bn, dual, c, p, w0, w1, x16, num_sms, stream);
+  else launch_sk<__half>(bn, dual, c, p, w0, w1, x16, num_sms, stream);
+}
+
 }  // namespace
 
 int linear_pick_bn(long long m, bool dual) {
@@ -72,6 +123,7 @@ int linear_plan_splits(long long M, int N, int K, int num_sms) {
 void linear(const LinearCall& c, DType dt, int num_sms, cudaStream_t stream) {
   if (c.K % lin::BK != 0) throw std::runtime_error("linear: K must be a multiple of 64, got " + std::to_string(c.K));
   if (c.M <= 0 && !c.tiles && !c.dyn_groups) return;
+  if (c.dyn_groups && c.sk_ws) { linear_streamk(c, dt, num_sms, stream); return; }
   const bool dual = c.w1 != nullptr;
   const int bn = c.bn ? c.bn : linear_pick_bn(c.tiles ? c.tile_rows_hint : c.M, dual);
 
@@ -105,6 +157,10 @@ void linear(const LinearCall& c, DType dt, int num_sms, cudaStream_t stream) {
     p.num_tiles *= p.k_splits;
   }
   if (p.num_tiles <= 0) return;
+  if (c.w_tiled) {
+    if (c.ldw && c.ldw != c.K) throw std::runtime_error("linear: tiled weights have no row pitch");
+    p.w0_tiled = (const uint8_t*)c.w0; p.w1_tiled = (const uint8_t*)c.w1;
+  }
 
   const long long w_rows = c.w_rows ? c.w_rows : c.N;
   CUtensorMap w0 = tmap::make_2d_16bit(c.w0, w_rows, c.K, c.ldw ? c.ldw : c.K, lin::BM, lin::BK);

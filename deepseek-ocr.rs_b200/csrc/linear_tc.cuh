@@ -74,6 +74,11 @@ struct Params {
   int dyn_wpg;     // weight blocks (of 128 rows) per group
   int dyn_cap;
   int dyn_w_rows;
+  // weights pre-tiled for streaming (retile_weights): tile (row block nb, k-block kb) = 16 KB contiguous at
+  // ((nb * K/64 + kb) * 16384), already in the 128B-swizzled shared-memory layout -> one bulk copy per stage that
+  // reads whole DRAM pages.  nullptr = row-major weights through the tensor maps.
+  const uint8_t* w0_tiled;
+  const uint8_t* w1_tiled;
 };
 
 constexpr int BM = 128;  // weight rows per tile (UMMA M)
@@ -246,8 +251,14 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_constant__
           if (p.x_box16) {
             const int nbox = (rows + 15) >> 4;
             ptx::mbar_expect_tx(&full[stage], NA * C::kABytes + NB * nbox * 2048);
+            if (p.w0_tiled) {
+            const size_t woff = ((size_t)(w_row0 / BM) * num_kb + kb) * C::kABytes;
+            ptx::bulk_load(st, p.w0_tiled + woff, C::kABytes, &full[stage]);
+            if (NA == 2) ptx::bulk_load(st + C::kABytes, p.w1_tiled + woff, C::kABytes, &full[stage]);
+          } else {
             ptx::tma_load_2d(st, &tm_w0, &full[stage], kb * BK, w_row0);
             if (NA == 2) ptx::tma_load_2d(st + C::kABytes, &tm_w1, &full[stage], kb * BK, w_row0);
+          }
             for (int b = 0; b < nbox; ++b) {
               ptx::tma_load_2d(st + NA * C::kABytes + b * 2048, &tm_x16, &full[stage], kb * BK, x_row0 + b * 16);
               if (NB == 2)
@@ -258,8 +269,14 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_constant__
             continue;
           }
           ptx::mbar_expect_tx(&full[stage], C::kStageBytes);
-          ptx::tma_load_2d(st, &tm_w0, &full[stage], kb * BK, w_row0);
-          if (NA == 2) ptx::tma_load_2d(st + C::kABytes, &tm_w1, &full[stage], kb * BK, w_row0);
+          if (p.w0_tiled) {
+            const size_t woff = ((size_t)(w_row0 / BM) * num_kb + kb) * C::kABytes;
+            ptx::bulk_load(st, p.w0_tiled + woff, C::kABytes, &full[stage]);
+            if (NA == 2) ptx::bulk_load(st + C::kABytes, p.w1_tiled + woff, C::kABytes, &full[stage]);
+          } else {
+            ptx::tma_load_2d(st, &tm_w0, &full[stage], kb * BK, w_row0);
+            if (NA == 2) ptx::tma_load_2d(st + C::kABytes, &tm_w1, &full[stage], kb * BK, w_row0);
+          }
           if (p.nbatch > 1)
             ptx::tma_load_3d(st + NA * C::kABytes, &tm_x, &full[stage], kb * BK, batch, x_row0);
           else

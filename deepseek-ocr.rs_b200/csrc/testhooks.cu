@@ -122,6 +122,9 @@ extern "C" int dsocr_test_fixedcap_linear(int dtype, int E, int cap, int N, int 
     c.x = dx.p; c.x_rows = (long long)M * x_parts; c.x_parts = x_parts; c.x_lo_row_off = M;
     c.M = M; c.N = N; c.K = K; c.out = dout.p; c.ldo = N; c.out_mode = 2;
     c.dyn_groups = E; c.dyn_cap = cap; c.group_counts = dcounts.as<int>();
+    DevBuf skws(linear_streamk_ws_bytes(sm_count())), skfl((size_t)sm_count() * 8);
+    cuda_check(cudaMemset(skfl.p, 0, (size_t)sm_count() * 8), "memset");
+    c.sk_ws = skws.as<float>(); c.sk_flags = skfl.as<int>();
     c.bn = cap <= 32 ? 32 : (cap <= 64 ? 64 : 128);
     linear(c, dt, sm_count(), 0);
     cuda_check(cudaDeviceSynchronize(), "fixed-capacity grouped linear kernel");

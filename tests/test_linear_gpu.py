@@ -163,16 +163,23 @@ def test_grouped_linear_matches_per_expert(dual):
     assert torch.allclose(y, r, rtol=1e-3, atol=2e-3 * r.abs().max().item())
 
 
-@pytest.mark.parametrize("dual,cap", [(False, 64), (True, 64), (True, 24), (False, 200), (True, 130)])
-def test_fixed_capacity_grouped_linear_device_scheduled(dual, cap):
+@pytest.mark.parametrize("dual,cap,sparse", [(False, 64, False), (True, 64, False), (True, 24, False), (False, 200, False),
+                                             (True, 130, False), (True, 64, True), (False, 8, True)])
+def test_fixed_capacity_grouped_linear_device_scheduled(dual, cap, sparse):
     """Decode-time expert GEMM: units are enumerated on the device from the per-expert counts (empty experts and
-    partially filled segments in any mix); result must equal the per-expert reference, untouched rows stay zero."""
+    partially filled segments in any mix) and their k-blocks are dealt out evenly to the CTAs (stream-K with a
+    fixed-order fix-up); result must equal the per-expert reference, untouched rows stay zero.  (The reuse of
+    the hand-off flags across launches is covered by the decoder tests, which replay the step hundreds of times.)"""
     g = torch.Generator().manual_seed(11 + cap)
     E, N, K = 64, 896 if dual else 1280, 1280 if dual else 896
     counts = torch.randint(0, min(cap, 12) + 1, (E,), generator=g).numpy().astype(np.int32)
     counts[[0, 5, 6, 7, 63]] = 0
     counts[9] = cap
     counts[40] = max(1, cap - 1)
+    if sparse:  # a handful of populated experts: every unit's reduction is split over several CTAs (stream-K)
+        keep = counts[[9, 21, 40]].copy()
+        counts[:] = 0
+        counts[[9, 21, 40]] = np.maximum(keep, 1)
     x = torch.randn(E * cap, K, generator=g)
     w0 = torch.randn(E, N, K, generator=g) * 0.03
     w1 = torch.randn(E, N, K, generator=g) * 0.03 if dual else None
