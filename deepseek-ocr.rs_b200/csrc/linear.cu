@@ -1,10 +1,12 @@
 // Host launcher + instantiations of the tcgen05 linear kernel (linear_tc.cuh).
 #include "linear_tc.cuh"
 #include "linear_sk.cuh"
+#include "linear_pair.cuh"
 #include "kernels.h"
 #include "tmap.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 
@@ -80,6 +82,46 @@ void launch_sk(int bn, bool dual, const LinearCall& c, const lin::SkParams& p, c
   }
 }
 
+// Large-M dense GEMM on CTA pairs (linear_pair.cuh).  Returns false when the problem does not qualify.
+template <typename T>
+void launch_pair(const LinearCall& c, const lin::PairParams& p, const CUtensorMap& w, const CUtensorMap& x, int num_sms,
+                 cudaStream_t stream) {
+  auto kern = lin::linear_pair_kernel<T>;
+  static int max_pairs = 0;  // per instantiation
+  if (!max_pairs) {
+    cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lin::kPairSmemBytes),
+               "linear_pair: set max dynamic smem");
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(num_sms & ~1); cfg.blockDim = dim3(lin::kThreads); cfg.dynamicSmemBytes = lin::kPairSmemBytes;
+    int n = 0;
+    cuda_check(cudaOccupancyMaxActiveClusters(&n, kern, &cfg), "linear_pair: cluster occupancy");
+    if (n < 1) throw std::runtime_error("linear_pair: no CTA pair fits on this device");
+    max_pairs = std::min(n, num_sms / 2);
+  }
+  const int pairs = std::min(max_pairs, p.num_tiles);
+  kern<<<2 * pairs, lin::kThreads, lin::kPairSmemBytes, stream>>>(w, x, p);
+  launch_check(c.tag ? c.tag : "linear_pair");
+}
+
+bool linear_pair(const LinearCall& c, DType dt, int num_sms, cudaStream_t stream) {
+  static const bool off = getenv("DSOCR_NO_PAIR") != nullptr;
+  if (off || c.tiles || c.dyn_groups || c.w1 || c.x_parts != 1 || c.nbatch > 1 || c.k_splits > 1 || c.w_tiled ||
+      c.N % 256 || c.M < 2048 || c.out_mode == lin::OUT_T_SPLIT || c.out_mode == lin::OUT_F32_DUAL ||
+      (c.row_map && c.out_mode != lin::OUT_F32_ADD))
+    return false;
+  lin::PairParams p{};
+  p.M = c.M; p.N = c.N; p.K = c.K; p.bias = c.bias; p.out = c.out; p.ldo = c.ldo; p.row_map = c.row_map;
+  p.act = c.act; p.out_mode = c.out_mode;
+  p.n_w_blocks = c.N / 256;
+  p.num_tiles = p.n_w_blocks * ((c.M + lin::kPairN - 1) / lin::kPairN);
+  const long long w_rows = c.w_rows ? c.w_rows : c.N;
+  CUtensorMap w = tmap::make_2d_16bit(c.w0, w_rows, c.K, c.ldw ? c.ldw : c.K, lin::BM, lin::BK);
+  CUtensorMap x = tmap::make_2d_16bit(c.x, c.x_rows, c.K, c.ldx ? c.ldx : c.K, 128, lin::BK);
+  if (dt == DType::BF16) launch_pair<__nv_bfloat16>(c, p, w, x, num_sms, stream);
+  else launch_pair<__half>(c, p, w, x, num_sms, stream);
+  return true;
+}
+
 // Decode-time expert GEMM over fixed-capacity groups (linear_sk.cuh).
 void linear_streamk(const LinearCall& c, DType dt, int num_sms, cudaStream_t stream) {
   const bool dual = c.w1 != nullptr;
@@ -124,6 +166,7 @@ void linear(const LinearCall& c, DType dt, int num_sms, cudaStream_t stream) {
   if (c.K % lin::BK != 0) throw std::runtime_error("linear: K must be a multiple of 64, got " + std::to_string(c.K));
   if (c.M <= 0 && !c.tiles && !c.dyn_groups) return;
   if (c.dyn_groups && c.sk_ws) { linear_streamk(c, dt, num_sms, stream); return; }
+  if (linear_pair(c, dt, num_sms, stream)) return;
   const bool dual = c.w1 != nullptr;
   const int bn = c.bn ? c.bn : linear_pick_bn(c.tiles ? c.tile_rows_hint : c.M, dual);
 

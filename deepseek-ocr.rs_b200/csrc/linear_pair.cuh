@@ -1,0 +1,207 @@
+// Large-M dense linear layer on CTA pairs (tcgen05 cta_group::2):  out[m, n] = epi( sum_k X[m, k] * W[n, k] + bias[n] )
+//
+// The vision towers run every projection over 10^5 tokens; at that size the one-CTA kernel of linear_tc.cuh is
+// bound by L2 -> shared-memory traffic (48 KB of operands per 128x256x64 MMA block).  Here two CTAs of a cluster
+// (the two SMs of a TPC) share one 256 (weights) x 256 (tokens) output tile: each CTA stages its own 128 weight
+// rows and only HALF of the token tile (32 KB per k-block for the same MMA work), the tensor cores of both SMs read
+// the token halves from both shared memories, and each CTA ends up with its 128 output features x 256 tokens in
+// its own TMEM.  One thread of the leader CTA issues the MMAs for the pair; completion barriers are multicast.
+//
+// Same operand convention and epilogue as linear_tc.cuh (weights = MMA A / TMEM lanes -> one output feature per
+// epilogue thread).  Used for the SAM / CLIP / projector GEMMs (vision/sam.rs:656-701, vision/clip.rs:418-447).
+#pragma once
+#include "linear_tc.cuh"
+
+namespace lin {
+
+struct PairParams {
+  int M, N, K;             // tokens, output features (multiple of 256), reduction (multiple of 64)
+  const float* bias;       // [N] or nullptr
+  void* out;               // [rows, ldo]
+  long long ldo;
+  const int* row_map;      // optional: token row -> output row (-1 = drop); OUT_F32_ADD only
+  int act;                 // Act
+  int out_mode;            // OUT_T, OUT_F32 or OUT_F32_ADD
+  int n_w_blocks;          // N / 256
+  int num_tiles;           // n_w_blocks * ceil(M / 256)
+};
+
+constexpr int kPairN = 256;                        // tokens per tile (MMA N); each CTA loads 128 of them
+constexpr int kPairStageBytes = 2 * BM * BK * 2;   // 128 weight rows + 128 token rows, 64 k each
+constexpr int kPairStages = 6;
+constexpr int kPairSmemBytes = kPairStages * kPairStageBytes + 1024 + 256;
+
+template <typename T>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+linear_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x,
+                   const PairParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kPairStages * kPairStageBytes);
+  uint64_t* full = bars;                    // leader only: both CTAs' tiles of a stage have landed
+  uint64_t* empty = bars + kPairStages;     // per CTA: the pair's MMAs are done with this stage
+  uint64_t* tfull = bars + 2 * kPairStages; // per CTA: accumulator buffer complete
+  uint64_t* tempty = tfull + 2;             // leader only: both CTAs' epilogues drained the buffer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int num_kb = p.K / BK;
+  constexpr int kA = BM * BK * 2;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tm_w);
+    ptx::prefetch_tmap(&tm_x);
+    for (int s = 0; s < kPairStages; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(&tfull[b], 1);
+      ptx::mbar_init(&tempty[b], 2 * kEpiWarps);
+    }
+    ptx::fence_barrier_init();
+  }
+  __syncwarp();
+  if (warp == 1) ptx::tmem_alloc_pair(tmem_slot, 512);
+  ptx::tc_fence_before();
+  ptx::cluster_sync();  // barriers of both CTAs are initialised before any remote arrive / multicast commit
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (each CTA loads its halves)
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = pair; t < p.num_tiles; t += num_pairs) {
+        const int wb = t % p.n_w_blocks, mb = t / p.n_w_blocks;
+        const int w_row0 = wb * 256 + (int)rank * BM;
+        const int x_row0 = mb * kPairN + (int)rank * 128;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* st = smem + stage * kPairStageBytes;
+          if (rank == 0) ptx::mbar_expect_tx(&full[stage], 2 * kPairStageBytes);
+          const uint32_t lead_bar = ptx::mapa(ptx::smem_u32(&full[stage]), 0);
+          ptx::tma_load_2d_pair(st, &tm_w, lead_bar, kb * BK, w_row0);
+          ptx::tma_load_2d_pair(st + kA, &tm_x, lead_bar, kb * BK, x_row0);
+          if (++stage == kPairStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA, one lane)
+    if (rank == 0 && lane == 0) {
+      constexpr uint32_t idesc = ptx::idesc_f16(Elem<T>::kFmt, 256, kPairN);
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int t = pair; t < p.num_tiles; t += num_pairs) {
+        const int buf = it & 1;
+        const uint32_t bphase = (it >> 1) & 1;
+        ++it;
+        ptx::mbar_wait(&tempty[buf], bphase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d0 = tmem_base + buf * kPairN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&full[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + stage * kPairStageBytes);
+          const uint32_t sb = sa + kA;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t ad = ptx::smem_desc_sw128(sa + k * 32, 16, 1024);
+            const uint64_t bd = ptx::smem_desc_sw128(sb + k * 32, 16, 1024);
+            ptx::mma_f16_ss_pair(d0, ad, bd, idesc, (kb | k) ? 1u : 0u);
+          }
+          ptx::mma_commit_pair(&empty[stage], 3);  // frees the stage in both CTAs
+          if (++stage == kPairStages) { stage = 0; phase ^= 1; }
+        }
+        ptx::mma_commit_pair(&tfull[buf], 3);  // accumulators of both CTAs complete
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps (each CTA: its 128 features)
+    const int ew = warp - 2;
+    const int quarter = warp & 3;
+    const int half = ew >> 2;
+    constexpr int kChunks = kPairN / 32;
+    constexpr int kChunksPerHalf = kChunks / 2;
+    int it = 0;
+    for (int t = pair; t < p.num_tiles; t += num_pairs) {
+      const int wb = t % p.n_w_blocks, mb = t / p.n_w_blocks;
+      const int x_row0 = mb * kPairN;
+      const int rows = min(kPairN, p.M - x_row0);
+      const int buf = it & 1;
+      const uint32_t bphase = (it >> 1) & 1;
+      ++it;
+      ptx::mbar_wait(&tfull[buf], bphase);
+      ptx::tc_fence_after();
+      const int n = wb * 256 + (int)rank * BM + quarter * 32 + lane;  // output feature owned by this thread
+      const float bias = p.bias ? p.bias[n] : 0.f;
+      const uint32_t trow = tmem_base + buf * kPairN + ((uint32_t)(quarter * 32) << 16);
+      for (int c = half * kChunksPerHalf; c < (half + 1) * kChunksPerHalf; ++c) {
+        if (c * 32 >= rows) break;  // warp-uniform
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(trow + c * 32, v);
+        long long my_orow = x_row0 + c * 32 + lane;
+        if (p.row_map) my_orow = (c * 32 + lane < rows) ? p.row_map[my_orow] : -1;
+        ptx::tmem_ld_wait();
+        float r[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float tv = __uint_as_float(v[j]) + bias;
+          if (p.act == ACT_GELU_ERF) tv = gelu_erf(tv);
+          else if (p.act == ACT_QUICK_GELU) tv = quick_gelu(tv);
+          r[j] = tv;
+        }
+        const int nvalid = min(32, rows - c * 32);
+        if (p.row_map) {
+          float old[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const long long orow = __shfl_sync(0xffffffffu, my_orow, j);
+            old[j] = (j < nvalid && orow >= 0) ? reinterpret_cast<const float*>(p.out)[orow * p.ldo + n] : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const long long orow = __shfl_sync(0xffffffffu, my_orow, j);
+            if (j < nvalid && orow >= 0) reinterpret_cast<float*>(p.out)[orow * p.ldo + n] = old[j] + r[j];
+          }
+        } else {
+          const long long base = (long long)(x_row0 + c * 32) * p.ldo + n;
+          if (p.out_mode == OUT_F32_ADD) {
+            float* ptr = reinterpret_cast<float*>(p.out) + base;
+            float old[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) old[j] = j < nvalid ? ptr[j * p.ldo] : 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < nvalid) ptr[j * p.ldo] = old[j] + r[j];
+          } else if (p.out_mode == OUT_T) {
+            T* ptr = reinterpret_cast<T*>(p.out) + base;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < nvalid) ptr[j * p.ldo] = Elem<T>::from(r[j]);
+          } else {
+            float* ptr = reinterpret_cast<float*>(p.out) + base;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < nvalid) ptr[j * p.ldo] = r[j];
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) ptx::mbar_arrive(&tempty[buf]);
+        else ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&tempty[buf]), 0));
+      }
+    }
+  }
+
+  // nobody leaves while the partner may still read this CTA's shared memory or signal its barriers
+  __syncwarp();
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  if (warp == 1) ptx::tmem_dealloc_pair(tmem_base, 512);
+}
+
+}  // namespace lin

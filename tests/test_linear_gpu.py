@@ -197,3 +197,43 @@ def test_fixed_capacity_grouped_linear_device_scheduled(dual, cap, sparse):
     assert torch.allclose(y, r, rtol=1e-3, atol=2e-3 * r.abs().max().item())
     for e in range(E):
         assert not y[e * cap + int(counts[e]):(e + 1) * cap].any()
+
+
+# ---- CTA-pair kernel (csrc/linear_pair.cuh): picked for M >= 2048 tokens and N % 256 == 0 ----------------------
+@pytest.mark.parametrize("dtype", [BF16, F16])
+@pytest.mark.parametrize("M,N,K", [(2048, 256, 64), (4173, 768, 768), (2304, 2304, 768), (3001, 1024, 4096)])
+def test_linear_pair_f32_out(dtype, M, N, K):
+    g = torch.Generator().manual_seed(M + N + K)
+    x = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) * 0.05
+    b = torch.randn(N, generator=g)
+    y = run_linear(dtype, x, w, bias=b)
+    r = ref_linear(dtype, x, w, bias=b)
+    assert torch.allclose(y, r, rtol=1e-3, atol=2e-3 * r.abs().max().item()), (y - r).abs().max()
+
+
+@pytest.mark.parametrize("act", [1, 2])
+def test_linear_pair_16bit_out_activations(act):
+    g = torch.Generator().manual_seed(40 + act)
+    x = torch.randn(2500, 768, generator=g)
+    w = torch.randn(3072, 768, generator=g) * 0.04
+    b = torch.randn(3072, generator=g) * 0.1
+    y = run_linear(BF16, x, w, bias=b, act=act, out_mode=0)
+    r = ref_linear(BF16, x, w, bias=b, act=act)
+    assert torch.allclose(y, r, rtol=2 ** -7, atol=1e-2)
+
+
+def test_linear_pair_residual_add_with_row_map():
+    g = torch.Generator().manual_seed(12)
+    M, N, K = 2940, 768, 768   # 15 windows of 14x14 tokens, some of them padding
+    x = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) * 0.03
+    b = torch.randn(N, generator=g)
+    rm = np.full(M, -1, dtype=np.int32)
+    keep = np.random.RandomState(1).permutation(M)[:2500]
+    rm[keep] = np.arange(2500)
+    base = torch.randn(2500, N, generator=g)
+    y = run_linear(BF16, x, w, bias=b, out_mode=3, row_map=rm, out_init=base.numpy(), out_rows=2500)
+    r = base.clone()
+    r[torch.from_numpy(rm[keep]).long()] += ref_linear(BF16, x, w, bias=b)[torch.from_numpy(keep).long()]
+    assert torch.allclose(y, r, rtol=1e-3, atol=5e-3)
