@@ -83,31 +83,43 @@ void launch_sk(int bn, bool dual, const LinearCall& c, const lin::SkParams& p, c
 }
 
 // Large-M dense GEMM on CTA pairs (linear_pair.cuh).  Returns false when the problem does not qualify.
-template <typename T>
-void launch_pair(const LinearCall& c, const lin::PairParams& p, const CUtensorMap& w, const CUtensorMap& x, int num_sms,
-                 cudaStream_t stream) {
-  auto kern = lin::linear_pair_kernel<T>;
+template <typename T, int ACT, int MODE>
+void launch_pair_inst(const LinearCall& c, const lin::PairParams& p, const CUtensorMap& w, const CUtensorMap& x,
+                      int num_sms, cudaStream_t stream) {
+  auto kern = lin::linear_pair_kernel<T, ACT, MODE>;
   static int max_pairs = 0;  // per instantiation
   if (!max_pairs) {
     cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lin::kPairSmemBytes),
                "linear_pair: set max dynamic smem");
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(num_sms & ~1); cfg.blockDim = dim3(lin::kThreads); cfg.dynamicSmemBytes = lin::kPairSmemBytes;
+    cfg.gridDim = dim3(num_sms & ~1); cfg.blockDim = dim3(lin::kPairThreads); cfg.dynamicSmemBytes = lin::kPairSmemBytes;
     int n = 0;
     cuda_check(cudaOccupancyMaxActiveClusters(&n, kern, &cfg), "linear_pair: cluster occupancy");
     if (n < 1) throw std::runtime_error("linear_pair: no CTA pair fits on this device");
     max_pairs = std::min(n, num_sms / 2);
   }
   const int pairs = std::min(max_pairs, p.num_tiles);
-  kern<<<2 * pairs, lin::kThreads, lin::kPairSmemBytes, stream>>>(w, x, p);
+  kern<<<2 * pairs, lin::kPairThreads, lin::kPairSmemBytes, stream>>>(w, x, p);
   launch_check(c.tag ? c.tag : "linear_pair");
+}
+
+template <typename T>
+void launch_pair(const LinearCall& c, const lin::PairParams& p, const CUtensorMap& w, const CUtensorMap& x, int num_sms,
+                 cudaStream_t stream) {
+  if (c.row_map) launch_pair_inst<T, lin::ACT_NONE, lin::kPairMapped>(c, p, w, x, num_sms, stream);
+  else if (c.out_mode == lin::OUT_F32_ADD) launch_pair_inst<T, lin::ACT_NONE, lin::OUT_F32_ADD>(c, p, w, x, num_sms, stream);
+  else if (c.out_mode == lin::OUT_F32) launch_pair_inst<T, lin::ACT_NONE, lin::OUT_F32>(c, p, w, x, num_sms, stream);
+  else if (c.act == lin::ACT_GELU_ERF) launch_pair_inst<T, lin::ACT_GELU_ERF, lin::OUT_T>(c, p, w, x, num_sms, stream);
+  else if (c.act == lin::ACT_QUICK_GELU) launch_pair_inst<T, lin::ACT_QUICK_GELU, lin::OUT_T>(c, p, w, x, num_sms, stream);
+  else launch_pair_inst<T, lin::ACT_NONE, lin::OUT_T>(c, p, w, x, num_sms, stream);
 }
 
 bool linear_pair(const LinearCall& c, DType dt, int num_sms, cudaStream_t stream) {
   static const bool off = getenv("DSOCR_NO_PAIR") != nullptr;
   if (off || c.tiles || c.dyn_groups || c.w1 || c.x_parts != 1 || c.nbatch > 1 || c.k_splits > 1 || c.w_tiled ||
       c.N % 256 || c.M < 2048 || c.out_mode == lin::OUT_T_SPLIT || c.out_mode == lin::OUT_F32_DUAL ||
-      (c.row_map && c.out_mode != lin::OUT_F32_ADD))
+      (c.row_map && (c.out_mode != lin::OUT_F32_ADD || (long long)c.M * c.ldo >= (1LL << 31))) ||
+      (c.act && c.out_mode != lin::OUT_T))
     return false;
   lin::PairParams p{};
   p.M = c.M; p.N = c.N; p.K = c.K; p.bias = c.bias; p.out = c.out; p.ldo = c.ldo; p.row_map = c.row_map;

@@ -30,9 +30,58 @@ constexpr int kPairN = 256;                        // tokens per tile (MMA N); e
 constexpr int kPairStageBytes = 2 * BM * BK * 2;   // 128 weight rows + 128 token rows, 64 k each
 constexpr int kPairStages = 6;
 constexpr int kPairSmemBytes = kPairStages * kPairStageBytes + 1024 + 256;
+constexpr int kPairEpiWarps = 16;                  // 4 per TMEM lane quarter: the epilogue, not the MMA, is the
+constexpr int kPairThreads = 64 + 32 * kPairEpiWarps;  // long pole for K = 768 -> more warps to hide its latencies
+constexpr int kPairChunk = 16;                     // token columns per tcgen05.ld / per store burst
 
-template <typename T>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+// Epilogue variants are compiled out, not branched on per element: ACT (Act) and MODE (Out; kPairMapped = residual
+// add through row_map) are template parameters and full 32-token chunks skip the per-element bounds predicates.
+constexpr int kPairMapped = 100;
+
+template <typename T, int ACT, int MODE, bool FULL>
+__device__ __forceinline__ void pair_store_chunk(const uint32_t (&v)[kPairChunk], float bias, int nvalid,
+                                                 const PairParams& p, long long row0, int n, int my_orow) {
+  float r[kPairChunk];
+#pragma unroll
+  for (int j = 0; j < kPairChunk; ++j) {
+    float tv = __uint_as_float(v[j]) + bias;
+    if (ACT == ACT_GELU_ERF) tv = gelu_erf(tv);
+    else if (ACT == ACT_QUICK_GELU) tv = quick_gelu(tv);
+    r[j] = tv;
+  }
+  if (MODE == kPairMapped) {
+    float* out = reinterpret_cast<float*>(p.out) + n;
+    float old[kPairChunk];
+    int off[kPairChunk];  // element offsets fit 31 bits (checked on the host)
+#pragma unroll
+    for (int j = 0; j < kPairChunk; ++j) {
+      const int orow = __shfl_sync(0xffffffffu, my_orow, j, kPairChunk);
+      off[j] = orow < 0 ? -1 : orow * (int)p.ldo;
+      old[j] = ((FULL || j < nvalid) && orow >= 0) ? out[off[j]] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < kPairChunk; ++j)
+      if ((FULL || j < nvalid) && off[j] >= 0) out[off[j]] = old[j] + r[j];
+  } else if (MODE == OUT_F32_ADD) {
+    float* ptr = reinterpret_cast<float*>(p.out) + row0 * p.ldo + n;
+    float old[kPairChunk];
+#pragma unroll
+    for (int j = 0; j < kPairChunk; ++j) old[j] = (FULL || j < nvalid) ? ptr[j * p.ldo] : 0.f;
+#pragma unroll
+    for (int j = 0; j < kPairChunk; ++j) if (FULL || j < nvalid) ptr[j * p.ldo] = old[j] + r[j];
+  } else if (MODE == OUT_T) {
+    T* ptr = reinterpret_cast<T*>(p.out) + row0 * p.ldo + n;
+#pragma unroll
+    for (int j = 0; j < kPairChunk; ++j) if (FULL || j < nvalid) ptr[j * p.ldo] = Elem<T>::from(r[j]);
+  } else {
+    float* ptr = reinterpret_cast<float*>(p.out) + row0 * p.ldo + n;
+#pragma unroll
+    for (int j = 0; j < kPairChunk; ++j) if (FULL || j < nvalid) ptr[j * p.ldo] = r[j];
+  }
+}
+
+template <typename T, int ACT, int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
 linear_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x,
                    const PairParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -60,7 +109,7 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(&tfull[b], 1);
-      ptx::mbar_init(&tempty[b], 2 * kEpiWarps);
+      ptx::mbar_init(&tempty[b], 2 * kPairEpiWarps);
     }
     ptx::fence_barrier_init();
   }
@@ -123,10 +172,10 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
   } else {
     // ------------------------------------------------------------ epilogue warps (each CTA: its 128 features)
     const int ew = warp - 2;
-    const int quarter = warp & 3;
-    const int half = ew >> 2;
-    constexpr int kChunks = kPairN / 32;
-    constexpr int kChunksPerHalf = kChunks / 2;
+    const int quarter = warp & 3;          // TMEM lane quarter this warp may access
+    const int part = ew >> 2;              // which quarter of the token columns this warp handles
+    constexpr int kChunks = kPairN / kPairChunk;
+    constexpr int kChunksPerPart = kChunks / (kPairEpiWarps / 4);
     int it = 0;
     for (int t = pair; t < p.num_tiles; t += num_pairs) {
       const int wb = t % p.n_w_blocks, mb = t / p.n_w_blocks;
@@ -140,53 +189,24 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
       const int n = wb * 256 + (int)rank * BM + quarter * 32 + lane;  // output feature owned by this thread
       const float bias = p.bias ? p.bias[n] : 0.f;
       const uint32_t trow = tmem_base + buf * kPairN + ((uint32_t)(quarter * 32) << 16);
-      for (int c = half * kChunksPerHalf; c < (half + 1) * kChunksPerHalf; ++c) {
-        if (c * 32 >= rows) break;  // warp-uniform
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(trow + c * 32, v);
-        long long my_orow = x_row0 + c * 32 + lane;
-        if (p.row_map) my_orow = (c * 32 + lane < rows) ? p.row_map[my_orow] : -1;
+      const int c0 = part * kChunksPerPart;
+      // software pipeline: the TMEM load of chunk c + 1 is in flight while chunk c is activated and stored
+      uint32_t v[2][kPairChunk];
+      if (c0 * kPairChunk < rows) ptx::tmem_ld_32x16(trow + c0 * kPairChunk, v[0]);
+#pragma unroll
+      for (int ci = 0; ci < kChunksPerPart; ++ci) {
+        const int c = c0 + ci;
+        if (c * kPairChunk >= rows) break;  // warp-uniform
         ptx::tmem_ld_wait();
-        float r[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float tv = __uint_as_float(v[j]) + bias;
-          if (p.act == ACT_GELU_ERF) tv = gelu_erf(tv);
-          else if (p.act == ACT_QUICK_GELU) tv = quick_gelu(tv);
-          r[j] = tv;
+        if (ci + 1 < kChunksPerPart && (c + 1) * kPairChunk < rows) ptx::tmem_ld_32x16(trow + (c + 1) * kPairChunk, v[(ci + 1) & 1]);
+        int my_orow = 0;
+        if (MODE == kPairMapped) {
+          const int jl = lane & (kPairChunk - 1);
+          my_orow = (c * kPairChunk + jl < rows) ? p.row_map[x_row0 + c * kPairChunk + jl] : -1;
         }
-        const int nvalid = min(32, rows - c * 32);
-        if (p.row_map) {
-          float old[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const long long orow = __shfl_sync(0xffffffffu, my_orow, j);
-            old[j] = (j < nvalid && orow >= 0) ? reinterpret_cast<const float*>(p.out)[orow * p.ldo + n] : 0.f;
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const long long orow = __shfl_sync(0xffffffffu, my_orow, j);
-            if (j < nvalid && orow >= 0) reinterpret_cast<float*>(p.out)[orow * p.ldo + n] = old[j] + r[j];
-          }
-        } else {
-          const long long base = (long long)(x_row0 + c * 32) * p.ldo + n;
-          if (p.out_mode == OUT_F32_ADD) {
-            float* ptr = reinterpret_cast<float*>(p.out) + base;
-            float old[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) old[j] = j < nvalid ? ptr[j * p.ldo] : 0.f;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (j < nvalid) ptr[j * p.ldo] = old[j] + r[j];
-          } else if (p.out_mode == OUT_T) {
-            T* ptr = reinterpret_cast<T*>(p.out) + base;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (j < nvalid) ptr[j * p.ldo] = Elem<T>::from(r[j]);
-          } else {
-            float* ptr = reinterpret_cast<float*>(p.out) + base;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (j < nvalid) ptr[j * p.ldo] = r[j];
-          }
-        }
+        const int nvalid = min(kPairChunk, rows - c * kPairChunk);
+        if (nvalid == kPairChunk) pair_store_chunk<T, ACT, MODE, true>(v[ci & 1], bias, kPairChunk, p, x_row0 + c * kPairChunk, n, my_orow);
+        else pair_store_chunk<T, ACT, MODE, false>(v[ci & 1], bias, nvalid, p, x_row0 + c * kPairChunk, n, my_orow);
       }
       ptx::tc_fence_before();
       __syncwarp();

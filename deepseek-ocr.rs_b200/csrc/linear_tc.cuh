@@ -101,19 +101,25 @@ struct Cfg {
 };
 
 // gelu(x) = 0.5 x (1 + erf(x / sqrt 2)).  erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the
-// 16-bit output rounding): 1 rcp + 1 ex2 + 7 FMA, branch-free.
+// 16-bit output rounding): one MUFU.RCP + one MUFU.EX2 + ~12 FP32 ops, branch-free (the IEEE-rounded __frcp_rn
+// costs a Newton step and a slow-path branch per element and bought nothing at this accuracy).
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float gelu_erf(float x) {
   const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
-  const float e = exp2f(-z * z * 1.4426950408889634f);
+  const float e = ptx::ex2_approx(-z * z * 1.4426950408889634f);
   const float erf_abs = 1.0f - poly * t * e;
   return 0.5f * x * (1.0f + copysignf(erf_abs, x));
 }
-__device__ __forceinline__ float quick_gelu(float x) { return x / (1.0f + __expf(-1.702f * x)); }
+__device__ __forceinline__ float quick_gelu(float x) { return x * rcp_approx(1.0f + ptx::ex2_approx(-2.4554669595930157f * x)); }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 
 template <typename T, int BN, int NA, int NB>
