@@ -279,6 +279,10 @@ def main():
     vs = VisionSettings(base, img, crop)
     params = DecodeParameters(max_new_tokens=args.max_new_tokens, no_repeat_ngram_size=20, eos_token_id=None)
     pages = make_pages(args, rank)
+    # the e2e arm copies every step's pages host -> device inside the timed region: keep them in pinned host memory
+    # (page-locked sources DMA directly; pageable ones are staged through the driver at a third of the rate)
+    pinned = [torch.from_numpy(p).pin_memory() for p in pages]
+    pages = [t.numpy() for t in pinned]
     h2d_bytes = sum(int(p.nbytes) for p in pages)
 
     def sync_all():
@@ -394,7 +398,7 @@ def main():
         "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
         "config": {"workload": workload, "l2": "per-step working set (weights 6.7 GB + KV + activations) exceeds the 126 MB L2",
                    "parallelism": f"pages sharded over {world} GPU(s), no collective"},
-        "e2e": {"value": e2e_val, "unit": "pages/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+        "e2e": {"value": e2e_val, "unit": "pages/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "host_memory": "pinned",
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches_e2e,
         "clocks": clocks,

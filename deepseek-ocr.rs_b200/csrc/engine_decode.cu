@@ -104,7 +104,7 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
       rope_kv(sp_qkv > 1 ? partA : qkv, rope_cos_.as<float>(), rope_sin_.as<float>(), row_page, row_pos, q,
               kcache_[l].p, vcache_[l].p, kv_f16_, rows, heads, smax, sp_qkv, rows * 3 * H, stream_);
       kv_attention(q, kcache_[l].p, vcache_[l].p, kv_f16_, row_page, row_pos, ctx16, rows * H, nullptr, rows, heads, smax, scale,
-                   dt_, stream_);
+                   dt_, stream_, decode_mode ? nullptr : ws("prefill_page_spans", (size_t)2 * n_final * 4).as<int>(), decode_mode ? 0 : n_final);
     }
     {
       LinearCall lc;  // o_proj (+ residual add, fused here or in the following RMSNorm when split)

@@ -134,9 +134,11 @@ void swiglu_reduce(const float* part, int n_splits, long long split_stride, long
 void rope_kv(const float* qkv, const float* cos_t, const float* sin_t, const int* row_page, const int* row_pos,
              float* q_out, void* kc, void* vc, bool kv_f16, long long rows, int heads, int smax, int n_splits,
              long long split_stride, cudaStream_t s);
+// page_spans: optional int[2 * n_pages] workspace; with it a prefill batch (rows > 256, rows ordered by page then
+// position) runs the shared-memory tiled kernel
 void kv_attention(const float* q, const void* kc, const void* vc, bool kv_f16, const int* row_page, const int* row_pos,
                   void* ctx, long long lo_off_elems, float* ctx32, long long rows, int heads, int smax, float scale,
-                  DType dt, cudaStream_t s);
+                  DType dt, cudaStream_t s, int* page_spans = nullptr, int n_pages = 0);
 void moe_router(const float* x, const float* wgt, int* topk_idx, float* topk_w, int* counts, long long rows, int H,
                 int E, int topk, cudaStream_t s);
 void moe_plan(int* counts, int* offsets, int* cursor, LinearTile* tiles1, int* ntiles1, LinearTile* tiles2,

@@ -3,6 +3,8 @@
 // cache, MoE router/top-k, dispatch/combine, n-gram ban + first-index argmax.  f32 math throughout (the
 // reference keeps the whole decoder in f32); 128-bit accesses, warp-shuffle reductions.
 #include "kernels.h"
+
+#include <algorithm>
 #include "ptx.cuh"
 
 #include <cfloat>
@@ -319,6 +321,169 @@ kv_attention_kernel(const float* __restrict__ q, const TKV* __restrict__ kc, con
   if (ctx32) { ctx32[oidx] = o; return; }
   ctx[oidx] = hi;
   ctx[lo_off_elems + oidx] = Elem<T>::from(o - Elem<T>::to(hi));
+}
+
+// Prefill, tiled: one block = 64 consecutive query rows of one page x one head.  Q (pre-scaled), a 32-key K tile
+// and V tile live in shared memory as f32 (rows padded to 132 floats: conflict-free float4 reads); each thread owns
+// a 4x4 register tile of the scores and a 4-row x 16-dim tile of the output, so every shared-memory float4 feeds 8
+// FMAs instead of one key row being re-read from L1 by every query row.  Online softmax per row across the 8 lanes
+// that share it.  Causal: the row at position p attends keys 0..p; key tiles past the block's last row are skipped.
+constexpr int kPfQ = 64, kPfK = 32, kPfLd = 132;
+constexpr int kPfSmemBytes = (kPfQ * kPfLd + 2 * kPfK * kPfLd + kPfQ * (kPfK + 1)) * 4;
+
+__device__ __forceinline__ void stage_row_chunk(const float* g, float* s) {  // 8 floats
+  const float4 a = reinterpret_cast<const float4*>(g)[0], b = reinterpret_cast<const float4*>(g)[1];
+  reinterpret_cast<float4*>(s)[0] = a; reinterpret_cast<float4*>(s)[1] = b;
+}
+__device__ __forceinline__ void stage_row_chunk(const __half* g, float* s) {  // 8 halves -> 8 floats
+  const uint4 t = *reinterpret_cast<const uint4*>(g);
+  const __half2* h = reinterpret_cast<const __half2*>(&t);
+  const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]), f2 = __half22float2(h[2]), f3 = __half22float2(h[3]);
+  reinterpret_cast<float4*>(s)[0] = make_float4(f0.x, f0.y, f1.x, f1.y);
+  reinterpret_cast<float4*>(s)[1] = make_float4(f2.x, f2.y, f3.x, f3.y);
+}
+
+template <typename T, typename TKV>
+__global__ void __launch_bounds__(128)
+kv_attention_prefill_tiled_kernel(const float* __restrict__ q, const TKV* __restrict__ kc, const TKV* __restrict__ vc,
+                                  const int* __restrict__ page_row0, const int* __restrict__ page_len,
+                                  T* __restrict__ ctx, long long lo_off_elems, float* __restrict__ ctx32, int heads,
+                                  int smax, float scale) {
+  constexpr int D = 128;
+  extern __shared__ float pf_smem[];
+  float* Qs = pf_smem;                      // [64][132]
+  float* Ks = Qs + kPfQ * kPfLd;            // [32][132]
+  float* Vs = Ks + kPfK * kPfLd;            // [32][132]
+  float* Ps = Vs + kPfK * kPfLd;            // [64][33]
+  const int page = blockIdx.y, hd = blockIdx.z;
+  const int len = page_len[page];
+  const int q0 = blockIdx.x * kPfQ;
+  if (q0 >= len) return;
+  const int nq = min(kPfQ, len - q0);
+  const long long r0 = (long long)page_row0[page] + q0;
+  const int tid = threadIdx.x;
+  const int tq = tid >> 3, tk = tid & 7;
+  // Q tile, scaled; rows past the page end are zero
+  for (int c = tid; c < kPfQ * (D / 4); c += 128) {
+    const int i = c >> 5, d4 = c & 31;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < nq) {
+      v = reinterpret_cast<const float4*>(q + ((r0 + i) * heads + hd) * D)[d4];
+      v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+    }
+    reinterpret_cast<float4*>(Qs + i * kPfLd)[d4] = v;
+  }
+  const TKV* kbase = kc + ((long long)page * heads + hd) * smax * D;
+  const TKV* vbase = vc + ((long long)page * heads + hd) * smax * D;
+  float m[4], l[4], o[4][16];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    m[a] = -INFINITY; l[a] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o[a][i] = 0.f;
+  }
+  const int kend = q0 + nq;  // keys 0 .. kend-1 are visible to at least one row of this block
+  for (int k0 = 0; k0 < kend; k0 += kPfK) {
+    __syncthreads();  // previous tile fully consumed (also orders the Q stores before the first use)
+    for (int c = tid; c < kPfK * (D / 8); c += 128) {  // 32 rows x 16 chunks of 8
+      const int i = c >> 4, d8 = c & 15;
+      const int pos = min(k0 + i, smax - 1);  // rows past kend are masked below; keep the address in range
+      stage_row_chunk(kbase + (long long)pos * D + d8 * 8, Ks + i * kPfLd + d8 * 8);
+      stage_row_chunk(vbase + (long long)pos * D + d8 * 8, Vs + i * kPfLd + d8 * 8);
+    }
+    __syncthreads();
+    float sc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) sc[a][b] = 0.f;
+#pragma unroll 4
+    for (int d4 = 0; d4 < D / 4; ++d4) {
+      float4 qa[4], kb[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) qa[a] = reinterpret_cast<const float4*>(Qs + (tq + 16 * a) * kPfLd)[d4];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) kb[b] = reinterpret_cast<const float4*>(Ks + (tk + 8 * b) * kPfLd)[d4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+          sc[a][b] += qa[a].x * kb[b].x + qa[a].y * kb[b].y + qa[a].z * kb[b].z + qa[a].w * kb[b].w;
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int qpos = q0 + tq + 16 * a;  // position of this query row
+      float mx = -INFINITY;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        if (k0 + tk + 8 * b > qpos) sc[a][b] = -INFINITY;
+        mx = fmaxf(mx, sc[a][b]);
+      }
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+      const float mn = fmaxf(m[a], mx);
+      const float alpha = (m[a] == -INFINITY) ? 0.f : __expf(m[a] - mn);
+      float ps = 0.f;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const float pe = (sc[a][b] == -INFINITY) ? 0.f : __expf(sc[a][b] - mn);
+        Ps[(tq + 16 * a) * (kPfK + 1) + tk + 8 * b] = pe;
+        ps += pe;
+      }
+      l[a] = l[a] * alpha + ps;  // per-lane partial sum; the 8 lanes of a row are added at the end
+      m[a] = mn;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) o[a][i] *= alpha;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int kk = 0; kk < kPfK; ++kk) {
+      float pa[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) pa[a] = Ps[(tq + 16 * a) * (kPfK + 1) + kk];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 v = reinterpret_cast<const float4*>(Vs + kk * kPfLd + tk * 4 + 32 * j)[0];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          o[a][4 * j] += pa[a] * v.x; o[a][4 * j + 1] += pa[a] * v.y;
+          o[a][4 * j + 2] += pa[a] * v.z; o[a][4 * j + 3] += pa[a] * v.w;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    float lt = l[a];
+    lt += __shfl_xor_sync(0xffffffffu, lt, 1);
+    lt += __shfl_xor_sync(0xffffffffu, lt, 2);
+    lt += __shfl_xor_sync(0xffffffffu, lt, 4);
+    const int i = tq + 16 * a;
+    if (i >= nq) continue;
+    const float inv = 1.f / lt;
+    const long long obase = ((r0 + i) * heads + hd) * D;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float ov[4] = {o[a][4 * j] * inv, o[a][4 * j + 1] * inv, o[a][4 * j + 2] * inv, o[a][4 * j + 3] * inv};
+      const long long oidx = obase + tk * 4 + 32 * j;
+      if (ctx32) { *reinterpret_cast<float4*>(ctx32 + oidx) = make_float4(ov[0], ov[1], ov[2], ov[3]); continue; }
+      uint2 hi, lo;
+      split4<T>(ov, hi, lo);
+      *reinterpret_cast<uint2*>(ctx + oidx) = hi;
+      *reinterpret_cast<uint2*>(ctx + lo_off_elems + oidx) = lo;
+    }
+  }
+}
+
+// first row and length of every page of a prefill batch (rows are ordered by page, then position)
+__global__ void page_spans_kernel(const int* __restrict__ row_page, const int* __restrict__ row_pos, long long rows,
+                                  int* __restrict__ page_row0, int* __restrict__ page_len) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const int p = row_page[r];
+  if (row_pos[r] == 0) page_row0[p] = (int)r;
+  if (r + 1 == rows || row_page[r + 1] != p) page_len[p] = row_pos[r] + 1;
 }
 
 // Prefill variant: one warp per query row (4 rows per block share the K/V rows they read through L1), the
@@ -1204,8 +1369,31 @@ void rope_kv(const float* qkv, const float* cos_t, const float* sin_t, const int
 }
 void kv_attention(const float* q, const void* kc, const void* vc, bool kv_f16, const int* row_page, const int* row_pos,
                   void* ctx, long long lo_off_elems, float* ctx32, long long rows, int heads, int smax, float scale,
-                  DType dt, cudaStream_t s) {
-  if (rows > 256) {  // prefill: warp-per-row variant
+                  DType dt, cudaStream_t s, int* page_spans, int n_pages) {
+  if (rows > 256 && page_spans && n_pages > 0) {  // prefill: 64-query x 32-key shared-memory tiles
+    int* row0 = page_spans;
+    int* plen = page_spans + n_pages;
+    static bool configured = false;
+    if (!configured) {
+      cuda_check(cudaFuncSetAttribute(kv_attention_prefill_tiled_kernel<__half, __half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPfSmemBytes), "prefill attention smem");
+      cuda_check(cudaFuncSetAttribute(kv_attention_prefill_tiled_kernel<__half, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPfSmemBytes), "prefill attention smem");
+      cuda_check(cudaFuncSetAttribute(kv_attention_prefill_tiled_kernel<__nv_bfloat16, __half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPfSmemBytes), "prefill attention smem");
+      cuda_check(cudaFuncSetAttribute(kv_attention_prefill_tiled_kernel<__nv_bfloat16, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPfSmemBytes), "prefill attention smem");
+      configured = true;
+    }
+    page_spans_kernel<<<blocks_for(rows, 256), 256, 0, s>>>(row_page, row_pos, rows, row0, plen);
+    launch_check("page_spans");
+    const long long max_len = std::min<long long>(smax, rows);  // blocks past a page's end exit at once
+    dim3 tgrid((unsigned)((max_len + kPfQ - 1) / kPfQ), (unsigned)n_pages, (unsigned)heads);
+    if (kv_f16) {
+      DISPATCH_T(dt, (kv_attention_prefill_tiled_kernel<T, __half><<<tgrid, 128, kPfSmemBytes, s>>>(q, (const __half*)kc, (const __half*)vc, row0, plen, (T*)ctx, lo_off_elems, ctx32, heads, smax, scale)));
+    } else {
+      DISPATCH_T(dt, (kv_attention_prefill_tiled_kernel<T, float><<<tgrid, 128, kPfSmemBytes, s>>>(q, (const float*)kc, (const float*)vc, row0, plen, (T*)ctx, lo_off_elems, ctx32, heads, smax, scale)));
+    }
+    launch_check("kv_attention");
+    return;
+  }
+  if (rows > 256) {  // prefill without page spans: warp-per-row variant
     dim3 pgrid((unsigned)((rows + 3) / 4), heads);
     if (kv_f16) {
       DISPATCH_T(dt, (kv_attention_prefill_kernel<T, __half><<<pgrid, 128, 0, s>>>(q, (const __half*)kc, (const __half*)vc, row_page, row_pos, (T*)ctx, lo_off_elems, ctx32, rows, heads, smax, scale)));
