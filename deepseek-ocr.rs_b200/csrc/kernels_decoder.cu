@@ -855,7 +855,7 @@ post_attn_kernel(float* __restrict__ x, const float* __restrict__ partials, int 
     const float* wp = wgt + (long long)(ks * kper) * E + e;
     const float* xp = xn_s + ks * kper;
     float acc = 0.f;
-#pragma unroll 8
+#pragma unroll 16  // 16 independent L2 loads in flight per thread: the gate GEMV is latency bound
     for (int k = 0; k < kper; ++k) acc = fmaf(xp[k], wp[(long long)k * E], acc);
     part[ks * E + e] = acc;
   }
@@ -885,6 +885,7 @@ post_attn_kernel(float* __restrict__ x, const float* __restrict__ partials, int 
     sum = warp_sum(sum);
 #pragma unroll
     for (int j = 0; j < PER; ++j) p[j] = (j * 32 + lane < E) ? p[j] / sum : -1.f;
+    int my_e = 0; float my_w = 0.f;
     for (int k = 0; k < topk; ++k) {
       float bv = -1.f; int bi = 1 << 30;
 #pragma unroll
@@ -898,15 +899,17 @@ post_attn_kernel(float* __restrict__ x, const float* __restrict__ partials, int 
         const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
         if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
       }
-      if (lane == 0) {
-        const int pos = bi * cap + atomicAdd(&counts[bi], 1);
-        topk_idx[row * topk + k] = bi;
-        topk_w[row * topk + k] = bv;
-        perm_pos[row * topk + k] = pos;
-        sel_pos[k] = pos;
-      }
+      if (lane == k) { my_e = bi; my_w = bv; }
 #pragma unroll
       for (int j = 0; j < PER; ++j) if (j * 32 + lane == bi) p[j] = -2.f;
+    }
+    // one slot reservation per selected expert, all in flight at once (lane k owns choice k)
+    if (lane < topk) {
+      const int pos = my_e * cap + atomicAdd(&counts[my_e], 1);
+      topk_idx[row * topk + lane] = my_e;
+      topk_w[row * topk + lane] = my_w;
+      perm_pos[row * topk + lane] = pos;
+      sel_pos[lane] = pos;
     }
   }
   __syncthreads();
@@ -926,15 +929,15 @@ post_attn_kernel(float* __restrict__ x, const float* __restrict__ partials, int 
 
 // (3) MoE combine + shared-experts split-K reduce + residual add + the NEXT RMSNorm (next layer's ln1 or the
 // final norm), one 128-thread block per row.
-template <typename T, int MAXS>
-__global__ void __launch_bounds__(128)
+template <typename T, int MAXS, int THREADS, int ITERS>
+__global__ void __launch_bounds__(THREADS)
 combine_norm_kernel(float* __restrict__ x, const float* __restrict__ y, const int* __restrict__ perm_pos,
                     const float* __restrict__ topk_w, int topk, const float* __restrict__ partials, int n_splits,
                     long long split_stride, const float* __restrict__ w_next, T* __restrict__ out16,
                     long long lo_off_elems, int H, float eps, int n_shared, int shared_row0, int cap) {
   const long long row = blockIdx.x;
   const int n4 = H / 4;
-  float4 v[3];
+  float4 v[ITERS];
   float ss = 0.f;
   float wk[8]; int pk[8];
 #pragma unroll
@@ -945,8 +948,8 @@ combine_norm_kernel(float* __restrict__ x, const float* __restrict__ y, const in
     if (k >= topk && k < topk + n_shared) { wk[k] = 1.f; pk[k] = shared_row0 + (k - topk) * cap + (int)row; }
   topk += n_shared;
 #pragma unroll
-  for (int it = 0; it < 3; ++it) {
-    const int i = threadIdx.x + it * 128;
+  for (int it = 0; it < ITERS; ++it) {
+    const int i = threadIdx.x + it * THREADS;
     v[it] = make_float4(0, 0, 0, 0);
     if (i < n4) {
       float4 a = reinterpret_cast<float4*>(x + row * H)[i];
@@ -968,14 +971,17 @@ combine_norm_kernel(float* __restrict__ x, const float* __restrict__ y, const in
       ss += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
     }
   }
-  __shared__ float red[4];
+  __shared__ float red[THREADS / 32];
   ss = warp_sum(ss);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
   __syncthreads();
-  const float inv = rsqrtf((red[0] + red[1] + red[2] + red[3]) / (float)H + eps);
+  float tot = 0.f;
 #pragma unroll
-  for (int it = 0; it < 3; ++it) {
-    const int i = threadIdx.x + it * 128;
+  for (int w = 0; w < THREADS / 32; ++w) tot += red[w];
+  const float inv = rsqrtf(tot / (float)H + eps);
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    const int i = threadIdx.x + it * THREADS;
     if (i < n4) {
       const float4 ww = reinterpret_cast<const float4*>(w_next)[i];
       float o[4] = {v[it].x * inv * ww.x, v[it].y * inv * ww.y, v[it].z * inv * ww.z, v[it].w * inv * ww.w};
@@ -1529,7 +1535,11 @@ void combine_norm(float* x, const float* y, const int* perm_pos, const float* to
                   int n_splits, long long split_stride, const float* w_next, void* out16, long long lo_off_elems,
                   long long rows, int H, float eps, int n_shared, int shared_row0, int cap, DType dt, cudaStream_t s) {
   if (H > 1536 || n_splits > 16 || topk + n_shared > 8) throw std::runtime_error("combine_norm: unsupported shape");
-  DISPATCH_T(dt, (combine_norm_kernel<T, 16><<<(unsigned)rows, 128, 0, s>>>(x, y, perm_pos, topk_w, topk, partials, partials ? n_splits : 0, split_stride, w_next, (T*)out16, lo_off_elems, H, eps, n_shared, shared_row0, cap)));
+  if (!partials && H <= 1280) {  // decode: one float4 per thread, a single round of loads
+    DISPATCH_T(dt, (combine_norm_kernel<T, 1, 320, 1><<<(unsigned)rows, 320, 0, s>>>(x, y, perm_pos, topk_w, topk, nullptr, 0, split_stride, w_next, (T*)out16, lo_off_elems, H, eps, n_shared, shared_row0, cap)));
+  } else {
+    DISPATCH_T(dt, (combine_norm_kernel<T, 16, 128, 3><<<(unsigned)rows, 128, 0, s>>>(x, y, perm_pos, topk_w, topk, partials, partials ? n_splits : 0, split_stride, w_next, (T*)out16, lo_off_elems, H, eps, n_shared, shared_row0, cap)));
+  }
   launch_check("moe_combine_norm");
 }
 
