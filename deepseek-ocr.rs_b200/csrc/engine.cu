@@ -228,6 +228,12 @@ void Engine::load_weights(const std::string& path, const DsqReader* dsq) {
     F32(b.ln1_w, p + "norm1.weight", {D}); F32(b.ln1_b, p + "norm1.bias", {D});
     F32(b.ln2_w, p + "norm2.weight", {D}); F32(b.ln2_b, p + "norm2.bias", {D});
     T16(b.qkv_w, p + "attn.qkv.weight", {3 * D, D}); F32(b.qkv_b, p + "attn.qkv.bias", {3 * D});
+    {
+      std::vector<float> w = to_f32(st.get(p + "attn.qkv.weight")), bq = to_f32(st.get(p + "attn.qkv.bias"));
+      b.q_w_host.assign(w.begin(), w.begin() + (size_t)D * D);
+      for (float& v : b.q_w_host) v = f16_to_32(f32_to_16(v, dt_), dt_);
+      b.q_b_host.assign(bq.begin(), bq.begin() + D);
+    }
     T16(b.proj_w, p + "attn.proj.weight", {D, D}); F32(b.proj_b, p + "attn.proj.bias", {D});
     const std::string m1 = st.has(p + "mlp.fc1.weight") ? "mlp.fc1" : "mlp.lin1";  // sam.rs:897-915
     const std::string m2 = st.has(p + "mlp.fc2.weight") ? "mlp.fc2" : "mlp.lin2";
@@ -528,6 +534,43 @@ const void* Engine::rel_table_for(int layer, int size, int* zhalf) {
   return it->second.p;
 }
 
+// W'[h*2z + n][k] = sum_d tab[n][d] Wq[h*64 + d][k],  b'[h*2z + n] = sum_d tab[n][d] bq[h*64 + d]  (tab rounded to the
+// engine dtype like the table the attention kernel would otherwise multiply with)
+const SamBlockW::RelFused& Engine::rel_fused_for(int layer, int size, int* zhalf) {
+  SamBlockW& b = sam_[layer];
+  const int nr = 2 * size - 1;
+  *zhalf = (nr + 15) / 16 * 16;
+  auto it = b.rel_fused.find(size);
+  if (it != b.rel_fused.end()) return it->second;
+  const int D = cfg_.sam_dim, Hh = cfg_.sam_heads, zw = 2 * (*zhalf);
+  std::vector<float> rh = resize_rel_pos(b.rel_h.data(), b.rel_rows, 64, size);
+  std::vector<float> rw = resize_rel_pos(b.rel_w.data(), b.rel_rows, 64, size);
+  std::vector<float> tab((size_t)zw * 64, 0.f);
+  memcpy(tab.data(), rh.data(), rh.size() * 4);
+  memcpy(tab.data() + (size_t)(*zhalf) * 64, rw.data(), rw.size() * 4);
+  for (float& v : tab) v = f16_to_32(f32_to_16(v, dt_), dt_);
+  std::vector<float> w((size_t)Hh * zw * D, 0.f), bias((size_t)Hh * zw, 0.f);
+  parallel_for((size_t)Hh * zw, [&](size_t r0, size_t r1) {
+    for (size_t r = r0; r < r1; ++r) {
+      const int h = (int)(r / zw), n = (int)(r % zw);
+      float* out = &w[r * D];
+      float bacc = 0.f;
+      for (int d = 0; d < 64; ++d) {
+        const float t = tab[(size_t)n * 64 + d];
+        if (t == 0.f) continue;
+        const float* q = &b.q_w_host[(size_t)(h * 64 + d) * D];
+        for (int k = 0; k < D; ++k) out[k] += t * q[k];
+        bacc += t * b.q_b_host[h * 64 + d];
+      }
+      bias[r] = bacc;
+    }
+  });
+  SamBlockW::RelFused f;
+  upload16_vec(f.w, w, dt_);
+  upload_f32(f.b, bias);
+  return b.rel_fused.emplace(size, std::move(f)).first->second;
+}
+
 // ------------------------------------------------------------------------------------------------ SAM
 void Engine::sam_forward(int Bv, int G, const void* patches16, float* sam_out) {
   const ModelConfig& c = cfg_;
@@ -571,9 +614,16 @@ void Engine::sam_forward(int Bv, int G, const void* patches16, float* sam_out) {
       linear(lc, dt_, num_sms_, stream_);
     }
     int zhalf = 0;
-    const void* table = rel_table_for(i, size, &zhalf);
+    // rel-pos logits Z[row, head, (kh | kw)] straight from the block input (one more GEMM over xn instead of a
+    // K = 64 product per head over the rounded q)
+    const SamBlockW::RelFused& rf = rel_fused_for(i, size, &zhalf);
     float* Z = ws("sam_z32", r * Hh * 2 * zhalf * 4).as<float>();
-    vision_relpos_products(qkv, r, Hh, table, zhalf, Z, dt_, num_sms_, stream_);
+    {
+      LinearCall lc;
+      lc.tag = "sam_relpos_products"; lc.w0 = rf.w.p; lc.x = xn; lc.x_rows = r; lc.M = (int)r; lc.N = Hh * 2 * zhalf; lc.K = D;
+      lc.bias = rf.b.as<float>(); lc.out = Z; lc.ldo = (long long)Hh * 2 * zhalf; lc.out_mode = lin::OUT_F32;
+      linear(lc, dt_, num_sms_, stream_);
+    }
     {
       VAttnCall ac;
       ac.qkv = qkv; ac.rows = r; ac.B = (int)(r / S); ac.S = S; ac.H = Hh; ac.grid = size;

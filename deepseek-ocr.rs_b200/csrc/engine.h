@@ -37,6 +37,10 @@ struct SamBlockW {
   std::vector<float> rel_h, rel_w;  // host copies [rel_rows, 64]
   int rel_rows = 0;
   std::map<int, DevBuf> rel_table;  // token-grid size -> 16-bit [2*zhalf, 64] ([rel_h ; rel_w])
+  // decomposed rel-pos logits as extra output features of the block input: Z = q . tab^T = xn . (tab Wq)^T + tab bq
+  std::vector<float> q_w_host, q_b_host;  // query rows of attn.qkv, values as rounded to the engine dtype: [D, D], [D]
+  struct RelFused { DevBuf w, b; };       // 16-bit [heads*2*zhalf, D], f32 [heads*2*zhalf]
+  std::map<int, RelFused> rel_fused;      // token-grid size -> fused weight
 };
 struct ClipBlockW {
   DevBuf ln1_w, ln1_b, qkv_w, qkv_b, out_w, out_b, ln2_w, ln2_b, fc1_w, fc1_b, fc2_w, fc2_b;
@@ -117,6 +121,7 @@ class Engine {
   const float* sam_pos_for(int g);
   const float* clip_pos_for(int g3);
   const void* rel_table_for(int layer, int size, int* zhalf);
+  const SamBlockW::RelFused& rel_fused_for(int layer, int size, int* zhalf);
   void decoder_forward(float* x, long long rows, const int* row_page, const int* row_pos, int smax,
                        const int* final_rows, int n_final, float* logits, bool decode_mode);
   void record_tap(const std::string& name, const float* dev, size_t n);

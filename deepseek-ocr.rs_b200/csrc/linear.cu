@@ -117,14 +117,14 @@ void launch_pair(const LinearCall& c, const lin::PairParams& p, const CUtensorMa
 bool linear_pair(const LinearCall& c, DType dt, int num_sms, cudaStream_t stream) {
   static const bool off = getenv("DSOCR_NO_PAIR") != nullptr;
   if (off || c.tiles || c.dyn_groups || c.w1 || c.x_parts != 1 || c.nbatch > 1 || c.k_splits > 1 || c.w_tiled ||
-      c.N % 256 || c.M < 2048 || c.out_mode == lin::OUT_T_SPLIT || c.out_mode == lin::OUT_F32_DUAL ||
+      c.N < 256 || c.M < 2048 || c.out_mode == lin::OUT_T_SPLIT || c.out_mode == lin::OUT_F32_DUAL ||
       (c.row_map && (c.out_mode != lin::OUT_F32_ADD || (long long)c.M * c.ldo >= (1LL << 31))) ||
       (c.act && c.out_mode != lin::OUT_T))
     return false;
   lin::PairParams p{};
   p.M = c.M; p.N = c.N; p.K = c.K; p.bias = c.bias; p.out = c.out; p.ldo = c.ldo; p.row_map = c.row_map;
   p.act = c.act; p.out_mode = c.out_mode;
-  p.n_w_blocks = c.N / 256;
+  p.n_w_blocks = (c.N + 255) / 256;
   p.num_tiles = p.n_w_blocks * ((c.M + lin::kPairN - 1) / lin::kPairN);
   const long long w_rows = c.w_rows ? c.w_rows : c.N;
   CUtensorMap w = tmap::make_2d_16bit(c.w0, w_rows, c.K, c.ldw ? c.ldw : c.K, lin::BM, lin::BK);

@@ -15,14 +15,14 @@
 namespace lin {
 
 struct PairParams {
-  int M, N, K;             // tokens, output features (multiple of 256), reduction (multiple of 64)
+  int M, N, K;             // tokens, output features (any; tiles of 256, the tail is not stored), reduction (multiple of 64)
   const float* bias;       // [N] or nullptr
   void* out;               // [rows, ldo]
   long long ldo;
   const int* row_map;      // optional: token row -> output row (-1 = drop); OUT_F32_ADD only
   int act;                 // Act
   int out_mode;            // OUT_T, OUT_F32 or OUT_F32_ADD
-  int n_w_blocks;          // N / 256
+  int n_w_blocks;          // ceil(N / 256)
   int num_tiles;           // n_w_blocks * ceil(M / 256)
 };
 
@@ -41,6 +41,7 @@ constexpr int kPairMapped = 100;
 template <typename T, int ACT, int MODE, bool FULL>
 __device__ __forceinline__ void pair_store_chunk(const uint32_t (&v)[kPairChunk], float bias, int nvalid,
                                                  const PairParams& p, long long row0, int n, int my_orow) {
+  const bool n_ok = n < p.N;  // feature tail of the last 256-block: computed, never stored
   float r[kPairChunk];
 #pragma unroll
   for (int j = 0; j < kPairChunk; ++j) {
@@ -57,11 +58,13 @@ __device__ __forceinline__ void pair_store_chunk(const uint32_t (&v)[kPairChunk]
     for (int j = 0; j < kPairChunk; ++j) {
       const int orow = __shfl_sync(0xffffffffu, my_orow, j, kPairChunk);
       off[j] = orow < 0 ? -1 : orow * (int)p.ldo;
-      old[j] = ((FULL || j < nvalid) && orow >= 0) ? out[off[j]] : 0.f;
+      old[j] = ((FULL || j < nvalid) && orow >= 0 && n_ok) ? out[off[j]] : 0.f;
     }
 #pragma unroll
     for (int j = 0; j < kPairChunk; ++j)
-      if ((FULL || j < nvalid) && off[j] >= 0) out[off[j]] = old[j] + r[j];
+      if ((FULL || j < nvalid) && off[j] >= 0 && n_ok) out[off[j]] = old[j] + r[j];
+  } else if (!n_ok) {
+    return;
   } else if (MODE == OUT_F32_ADD) {
     float* ptr = reinterpret_cast<float*>(p.out) + row0 * p.ldo + n;
     float old[kPairChunk];
@@ -187,7 +190,7 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
       ptx::mbar_wait(&tfull[buf], bphase);
       ptx::tc_fence_after();
       const int n = wb * 256 + (int)rank * BM + quarter * 32 + lane;  // output feature owned by this thread
-      const float bias = p.bias ? p.bias[n] : 0.f;
+      const float bias = (p.bias && n < p.N) ? p.bias[n] : 0.f;
       const uint32_t trow = tmem_base + buf * kPairN + ((uint32_t)(quarter * 32) << 16);
       const int c0 = part * kChunksPerPart;
       // software pipeline: the TMEM load of chunk c + 1 is in flight while chunk c is activated and stored
