@@ -55,7 +55,6 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
     cuda_check(cudaMemsetAsync(counts_layers, 0, (size_t)c.layers * Eg * 4, stream_), "moe counts memset");
     // token tile of the expert GEMMs; the kernel enumerates the non-empty (expert, chunk, block) units itself
     fbn = cap <= 32 ? 32 : (cap <= 64 ? 64 : 128);
-    if (const char* e = getenv("DSOCR_MOE_BN")) fbn = atoi(e);  // experiment switch
     if (!sk_flags_.p) {  // stream-K hand-off flags: zero once, the kernel returns them zeroed
       sk_flags_.alloc((size_t)num_sms_ * 8);
       cuda_check(cudaMemsetAsync(sk_flags_.p, 0, (size_t)num_sms_ * 8, stream_), "stream-K flags");
