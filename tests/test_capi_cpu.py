@@ -70,6 +70,34 @@ def test_preprocess_bit_exact_with_oracle(lib, w, h):
         assert np.array_equal(tiles[i], t)
 
 
+def test_preprocess_mixed_aspect_sweep_covers_every_tile_count(lib):
+    """BASELINE configs[2] sweep: aspect ratios that select every tile count n = 2..9 (preprocess.rs:67-138); grid,
+    token count, global view and every tile of the C++ host path must equal the oracle bit for bit."""
+    from dsocr.engine import VisionSettingsC
+
+    sizes = [(900, 450), (400, 1200), (650, 641), (400, 1600), (2000, 400), (900, 600), (1800, 300), (300, 2100),
+             (2400, 300), (2700, 300)]
+    seen = set()
+    u8 = C.POINTER(C.c_uint8)
+    for w, h in sizes:
+        rng = np.random.RandomState(w * 7 + h)
+        img = rng.randint(0, 256, (h, w, 3), dtype=np.uint8)
+        g = np.empty((1024, 1024, 3), np.uint8)
+        tiles = np.empty((9, 640, 640, 3), np.uint8)
+        n, cw, ch = C.c_int(), C.c_int(), C.c_int()
+        st = lib.dsocr_preprocess(img.ctypes.data_as(u8), w, h, VisionSettingsC(1024, 640, 1), g.ctypes.data_as(u8),
+                                  tiles.ctypes.data_as(u8), C.byref(n), C.byref(cw), C.byref(ch))
+        assert st == 0
+        ref = P.prepare_vision_input(img, 1024, 640, True)
+        assert (cw.value, ch.value) == tuple(ref["crop_shape"]) == P.select_tile_grid(w, h, 640)
+        assert n.value == len(ref["tiles"]) == cw.value * ch.value
+        assert lib.dsocr_image_token_count(1024, 640, 1, cw.value, ch.value) == P.image_token_count(1024, 640, True, ref["crop_shape"])
+        assert np.array_equal(g, ref["global"])
+        assert all(np.array_equal(tiles[i], t) for i, t in enumerate(ref["tiles"]))
+        seen.add(n.value)
+    assert seen == set(range(2, 10))
+
+
 def test_engine_creation_fails_loudly_without_gpu(lib, tmp_path):
     """No CPU fallback: on a box without an sm_100 device load_model must fail with a clear message."""
     import torch

@@ -122,7 +122,9 @@ def test_gpu_preprocess_bit_exact_with_oracle(setup):
 
     cfg, ck, eng, oracle = setup
     rng = np.random.RandomState(1)
-    for (w, h) in [(1654, 2339), (700, 500), (333, 517), (2852, 1756), (640, 640), (100, 80), (1024, 1024)]:
+    # the second half of the list is the mixed-aspect sweep of BASELINE configs[2]: tile counts 2..9
+    for (w, h) in [(1654, 2339), (700, 500), (333, 517), (2852, 1756), (640, 640), (100, 80), (1024, 1024),
+                   (900, 450), (400, 1200), (400, 1600), (2000, 400), (1800, 300), (300, 2100), (2400, 300), (2700, 300)]:
         img = rng.randint(0, 256, (h, w, 3), dtype=np.uint8)
         g, tiles, crop = eng.preprocess_gpu(img, VisionSettings(1024, 640, True))
         ref = P.prepare_vision_input(img, 1024, 640, True)
