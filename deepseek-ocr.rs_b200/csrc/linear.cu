@@ -85,7 +85,7 @@ void launch_sk(int bn, bool dual, const LinearCall& c, const lin::SkParams& p, c
 // Large-M dense GEMM on CTA pairs (linear_pair.cuh).  Returns false when the problem does not qualify.
 template <typename T, int ACT, int MODE>
 void launch_pair_inst(const LinearCall& c, const lin::PairParams& p, const CUtensorMap& w, const CUtensorMap& x,
-                      int num_sms, cudaStream_t stream) {
+                      const CUtensorMap& o, int num_sms, cudaStream_t stream) {
   auto kern = lin::linear_pair_kernel<T, ACT, MODE>;
   static int max_pairs = 0;  // per instantiation
   if (!max_pairs) {
@@ -99,19 +99,19 @@ void launch_pair_inst(const LinearCall& c, const lin::PairParams& p, const CUten
     max_pairs = std::min(n, num_sms / 2);
   }
   const int pairs = std::min(max_pairs, p.num_tiles);
-  kern<<<2 * pairs, lin::kPairThreads, lin::kPairSmemBytes, stream>>>(w, x, p);
+  kern<<<2 * pairs, lin::kPairThreads, lin::kPairSmemBytes, stream>>>(w, x, o, p);
   launch_check(c.tag ? c.tag : "linear_pair");
 }
 
 template <typename T>
-void launch_pair(const LinearCall& c, const lin::PairParams& p, const CUtensorMap& w, const CUtensorMap& x, int num_sms,
-                 cudaStream_t stream) {
-  if (c.row_map) launch_pair_inst<T, lin::ACT_NONE, lin::kPairMapped>(c, p, w, x, num_sms, stream);
-  else if (c.out_mode == lin::OUT_F32_ADD) launch_pair_inst<T, lin::ACT_NONE, lin::OUT_F32_ADD>(c, p, w, x, num_sms, stream);
-  else if (c.out_mode == lin::OUT_F32) launch_pair_inst<T, lin::ACT_NONE, lin::OUT_F32>(c, p, w, x, num_sms, stream);
-  else if (c.act == lin::ACT_GELU_ERF) launch_pair_inst<T, lin::ACT_GELU_ERF, lin::OUT_T>(c, p, w, x, num_sms, stream);
-  else if (c.act == lin::ACT_QUICK_GELU) launch_pair_inst<T, lin::ACT_QUICK_GELU, lin::OUT_T>(c, p, w, x, num_sms, stream);
-  else launch_pair_inst<T, lin::ACT_NONE, lin::OUT_T>(c, p, w, x, num_sms, stream);
+void launch_pair(const LinearCall& c, const lin::PairParams& p, const CUtensorMap& w, const CUtensorMap& x,
+                 const CUtensorMap& o, int num_sms, cudaStream_t stream) {
+  if (c.row_map) launch_pair_inst<T, lin::ACT_NONE, lin::kPairMapped>(c, p, w, x, o, num_sms, stream);
+  else if (c.out_mode == lin::OUT_F32_ADD) launch_pair_inst<T, lin::ACT_NONE, lin::OUT_F32_ADD>(c, p, w, x, o, num_sms, stream);
+  else if (c.out_mode == lin::OUT_F32) launch_pair_inst<T, lin::ACT_NONE, lin::OUT_F32>(c, p, w, x, o, num_sms, stream);
+  else if (c.act == lin::ACT_GELU_ERF) launch_pair_inst<T, lin::ACT_GELU_ERF, lin::OUT_T>(c, p, w, x, o, num_sms, stream);
+  else if (c.act == lin::ACT_QUICK_GELU) launch_pair_inst<T, lin::ACT_QUICK_GELU, lin::OUT_T>(c, p, w, x, o, num_sms, stream);
+  else launch_pair_inst<T, lin::ACT_NONE, lin::OUT_T>(c, p, w, x, o, num_sms, stream);
 }
 
 bool linear_pair(const LinearCall& c, DType dt, int num_sms, cudaStream_t stream) {
@@ -119,7 +119,8 @@ bool linear_pair(const LinearCall& c, DType dt, int num_sms, cudaStream_t stream
   if (off || c.tiles || c.dyn_groups || c.w1 || c.x_parts != 1 || c.nbatch > 1 || c.k_splits > 1 || c.w_tiled ||
       c.N < 256 || c.M < 2048 || c.out_mode == lin::OUT_T_SPLIT || c.out_mode == lin::OUT_F32_DUAL ||
       (c.row_map && (c.out_mode != lin::OUT_F32_ADD || (long long)c.M * c.ldo >= (1LL << 31))) ||
-      (c.act && c.out_mode != lin::OUT_T))
+      (c.act && c.out_mode != lin::OUT_T) ||
+      (c.out_mode == lin::OUT_T && ((c.ldo * 2) % 16 || (reinterpret_cast<uintptr_t>(c.out) & 15))))
     return false;
   lin::PairParams p{};
   p.M = c.M; p.N = c.N; p.K = c.K; p.bias = c.bias; p.out = c.out; p.ldo = c.ldo; p.row_map = c.row_map;
@@ -129,8 +130,12 @@ bool linear_pair(const LinearCall& c, DType dt, int num_sms, cudaStream_t stream
   const long long w_rows = c.w_rows ? c.w_rows : c.N;
   CUtensorMap w = tmap::make_2d_16bit(c.w0, w_rows, c.K, c.ldw ? c.ldw : c.K, lin::BM, lin::BK);
   CUtensorMap x = tmap::make_2d_16bit(c.x, c.x_rows, c.K, c.ldx ? c.ldx : c.K, 128, lin::BK);
-  if (dt == DType::BF16) launch_pair<__nv_bfloat16>(c, p, w, x, num_sms, stream);
-  else launch_pair<__half>(c, p, w, x, num_sms, stream);
+  // 16-bit outputs are written by TMA from a [16 tokens][128 features] staging tile; rows >= M / features >= N clip
+  CUtensorMap o = c.out_mode == lin::OUT_T
+                      ? tmap::make_2d_16bit_store(c.out, c.M, c.N, c.ldo, lin::kPairChunk, lin::BM)
+                      : w;
+  if (dt == DType::BF16) launch_pair<__nv_bfloat16>(c, p, w, x, o, num_sms, stream);
+  else launch_pair<__half>(c, p, w, x, o, num_sms, stream);
   return true;
 }
 

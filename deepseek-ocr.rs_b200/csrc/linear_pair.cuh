@@ -28,8 +28,11 @@ struct PairParams {
 
 constexpr int kPairN = 256;                        // tokens per tile (MMA N); each CTA loads 128 of them
 constexpr int kPairStageBytes = 2 * BM * BK * 2;   // 128 weight rows + 128 token rows, 64 k each
-constexpr int kPairStages = 6;
-constexpr int kPairSmemBytes = kPairStages * kPairStageBytes + 1024 + 256;
+constexpr int kPairStages = 5;
+// 16-bit outputs leave through shared memory + TMA stores: per token-column part two buffers of [16 tokens][128 features]
+constexpr int kPairOutBufBytes = 16 * BM * 2;
+constexpr int kPairOutBytes = 4 * 2 * kPairOutBufBytes;
+constexpr int kPairSmemBytes = kPairStages * kPairStageBytes + kPairOutBytes + 1024 + 256;
 constexpr int kPairEpiWarps = 16;                  // 4 per TMEM lane quarter: the epilogue, not the MMA, is the
 constexpr int kPairThreads = 64 + 32 * kPairEpiWarps;  // long pole for K = 768 -> more warps to hide its latencies
 constexpr int kPairChunk = 16;                     // token columns per tcgen05.ld / per store burst
@@ -86,10 +89,11 @@ __device__ __forceinline__ void pair_store_chunk(const uint32_t (&v)[kPairChunk]
 template <typename T, int ACT, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
 linear_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x,
-                   const PairParams p) {
+                   const __grid_constant__ CUtensorMap tm_out, const PairParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kPairStages * kPairStageBytes);
+  uint8_t* out_stage = smem + kPairStages * kPairStageBytes;  // [4 parts][2][16 tokens][128 features] 16-bit
+  uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + kPairOutBytes);
   uint64_t* full = bars;                    // leader only: both CTAs' tiles of a stage have landed
   uint64_t* empty = bars + kPairStages;     // per CTA: the pair's MMAs are done with this stage
   uint64_t* tfull = bars + 2 * kPairStages; // per CTA: accumulator buffer complete
@@ -106,6 +110,7 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_w);
     ptx::prefetch_tmap(&tm_x);
+    if (MODE == OUT_T) ptx::prefetch_tmap(&tm_out);
     for (int s = 0; s < kPairStages; ++s) {
       ptx::mbar_init(&full[s], 1);
       ptx::mbar_init(&empty[s], 1);
@@ -207,6 +212,28 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
           const int jl = lane & (kPairChunk - 1);
           my_orow = (c * kPairChunk + jl < rows) ? p.row_map[x_row0 + c * kPairChunk + jl] : -1;
         }
+        if (MODE == OUT_T) {
+          // activation + 16-bit conversion into this part's staging buffer, then one TMA store per 16 x 128 tile
+          // (rows past M and features past N are clipped by the tensor map)
+          T* stage = reinterpret_cast<T*>(out_stage + (part * 2 + (ci & 1)) * kPairOutBufBytes) + quarter * 32 + lane;
+#pragma unroll
+          for (int j = 0; j < kPairChunk; ++j) {
+            float tv = __uint_as_float(v[ci & 1][j]) + bias;
+            if (ACT == ACT_GELU_ERF) tv = gelu_erf(tv);
+            else if (ACT == ACT_QUICK_GELU) tv = quick_gelu(tv);
+            stage[j * BM] = Elem<T>::from(tv);
+          }
+          ptx::fence_proxy_async();
+          const bool issuer = (ew & 3) == 0 && lane == 0;
+          if (issuer) ptx::bulk_wait_read_all();  // the previous store (other buffer) has left shared memory
+          ptx::named_bar_sync(1 + part, 128);
+          if (issuer) {
+            ptx::tma_store_2d(&tm_out, out_stage + (part * 2 + (ci & 1)) * kPairOutBufBytes, wb * 256 + (int)rank * BM,
+                              x_row0 + c * kPairChunk);
+            ptx::bulk_commit_group();
+          }
+          continue;
+        }
         const int nvalid = min(kPairChunk, rows - c * kPairChunk);
         if (nvalid == kPairChunk) pair_store_chunk<T, ACT, MODE, true>(v[ci & 1], bias, kPairChunk, p, x_row0 + c * kPairChunk, n, my_orow);
         else pair_store_chunk<T, ACT, MODE, false>(v[ci & 1], bias, nvalid, p, x_row0 + c * kPairChunk, n, my_orow);
@@ -220,6 +247,7 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
     }
   }
 
+  if (MODE == OUT_T && warp >= 2 && ((warp - 2) & 3) == 0 && lane == 0) ptx::bulk_wait_read_all();
   // nobody leaves while the partner may still read this CTA's shared memory or signal its barriers
   __syncwarp();
   ptx::tc_fence_before();

@@ -44,6 +44,23 @@ inline CUtensorMap make_2d_16bit(const void* base, uint64_t rows, uint64_t cols,
   return m;
 }
 
+// 2-D 16-bit row-major tensor for TMA *stores* from an unswizzled shared-memory tile [box_rows][box_cols]
+inline CUtensorMap make_2d_16bit_store(const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                                       uint32_t box_rows, uint32_t box_cols) {
+  CUtensorMap m;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    throw std::runtime_error("cuTensorMapEncodeTiled(store) failed: code " + std::to_string((int)r) + " rows=" +
+                             std::to_string(rows) + " cols=" + std::to_string(cols) + " ld=" + std::to_string(ld_elems));
+  return m;
+}
+
 // 3-D 16-bit tensor [d2, d1, d0] (d0 innermost) with byte strides s1 (dim1) and s2 (dim2).
 inline CUtensorMap make_3d_16bit(const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1_bytes,
                                  uint64_t s2_bytes, uint32_t b0, uint32_t b1, uint32_t b2) {
