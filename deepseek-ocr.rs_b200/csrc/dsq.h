@@ -80,6 +80,46 @@ struct DsqGemvCall {
   const char* tag = "dsq_gemv";
 };
 void dsq_gemv(const DsqGemvCall& c, cudaStream_t stream);
+
+// ---- fused small-batch decode step (dsq_decode.cu)
+// One launch runs up to 3 GEMV jobs.  A job's token rows come in `groups` of `rpg` (<= 4) rows that share one weight
+// matrix (expert = row_expert[group] or 0); x row of (group g, m) = (g*rpg + m) / x_row_div; out row = g*rpg + m.
+// w1 != nullptr: out = silu(x.w0^T) * (x.w1^T).
+struct DsqFusedJob {
+  const QuantWeight* w0 = nullptr;
+  const QuantWeight* w1 = nullptr;
+  const float* x = nullptr;
+  long long ldx = 0;
+  int groups = 1, rpg = 1, x_row_div = 1;
+  const int* row_expert = nullptr;
+  float* out = nullptr;
+  long long ldo = 0;
+};
+// How every block produces its activation rows before the GEMV (all jobs of the launch must then share x and K):
+// x = base + (sum_j wmoe[r*topk+j] * ymoe[r*topk+j] + add1 + add2); block 0 stores x to write_back (a buffer no job reads);
+// with norm_w the rows are RMS-normalised (rms_norm, f32) and scaled by norm_w.
+struct DsqFusedStage {
+  const float* add1 = nullptr;
+  const float* add2 = nullptr;
+  const float* ymoe = nullptr;
+  const float* wmoe = nullptr;
+  int topk = 0;
+  float* write_back = nullptr;
+  const float* norm_w = nullptr;
+  float eps = 0.f;
+};
+void dsq_fused_gemv(const DsqFusedJob* jobs, int njobs, const DsqFusedStage& st, const char* tag, cudaStream_t stream);
+void dsq_router(const float* base, const float* add1, float* xout, const float* w, const float* wgt, float* xn32,
+                int* topk_idx, float* topk_w, long long rows, int H, int E, int topk, float eps, cudaStream_t s);
+void dsq_combine_norm(const float* base, const float* ymoe, const float* wmoe, int topk, const float* add1,
+                      const float* w, float* out, long long rows, int H, float eps, cudaStream_t s);
+int dsq_attn_splits(int smax);
+size_t dsq_attn_ws_floats(long long rows, int heads, int nsplit);
+// counters: int[rows*heads], zero before the first launch (the kernel hands them back zeroed)
+void dsq_attn_split(const float* qkv, const float* cos_t, const float* sin_t, void* kc, void* vc, bool kv_f16,
+                    const int* row_page, const int* row_pos, float* part, int* counters, float* ctx, long long rows,
+                    int heads, int head_dim, int smax, float scale, int nsplit, cudaStream_t s);
+
 // h[i] = silu(g[i]) * u[i]
 void swiglu_f32(const float* g, const float* u, float* h, long long n, cudaStream_t stream);
 

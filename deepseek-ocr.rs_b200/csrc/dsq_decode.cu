@@ -1,0 +1,731 @@
+// Fused small-batch decode step over a DSQ snapshot (BASELINE.json configs[3]: batch-1 q4k / q8_0 decode with long
+// outputs).  The unfused path (decoder_forward_dsq) spends ~18 launches per layer on 6-14 us kernels; at batch 1 the
+// whole quantised model is only ~320 MB per token, so the step is bound by launch count and by how many bytes each
+// launch keeps in flight.  Here a layer is 6 launches:
+//   qkv       : [pending residual adds + RMSNorm(ln1)] staged in shared memory by every block -> q|k|v GEMVs (3 jobs)
+//   attention : RoPE + KV append + split-key attention over the cache, merged by the last block of a (row, head)
+//   o_proj    : GEMV
+//   router    : residual add + RMSNorm(ln2) + gate GEMV + softmax + top-k           (dense layer: folded into gate/up)
+//   gate/up   : routed experts (one job row per (token, slot)) + shared experts, SwiGLU in the epilogue
+//   down      : routed + shared experts; the weighted combine is done by the next layer's qkv staging
+// All activations stay f32 (run_quantized_matmul semantics, quantization.rs:164-185: y = x . dequant(W)^T).
+// GEMV mapping: 8 lanes per output feature (16-byte units of one weight row, 128 contiguous bytes per row and
+// iteration), 4 x R features per warp, the next unit's weight bytes are loaded before the current one is consumed and
+// the first unit before the activations are staged.
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cfloat>
+
+#include "dsq.h"
+#include "kernels.h"
+
+namespace dsocr {
+
+namespace {
+
+constexpr int kThreads = 256, kWarps = 8;
+constexpr int kMaxJobs = 3;
+
+struct Job {
+  const uint8_t* p[2][4];  // planes a..d of w0 (and w1 for the dual gate/up job)
+  int fmt, K, dual, R;
+  long long N;
+  const float* x; long long ldx;
+  int groups, rpg, x_row_div;
+  const int* row_expert;
+  float* out; long long ldo;
+  int block0, fblocks;
+};
+struct Stage {
+  const float* add1; const float* add2;
+  const float* ymoe; const float* wmoe; int topk;
+  float* write_back;
+  const float* norm_w; float eps;
+};
+struct Launch { Job job[kMaxJobs]; int njobs; Stage st; };
+
+// shared-memory index of activation k: 4 floats of padding per 64 keep the 8 lanes of a feature on distinct banks
+__device__ __forceinline__ int xpad(int k) { return k + ((k >> 6) << 2); }
+
+__device__ __forceinline__ uint4 ldg16(const uint8_t* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+template <int FMT> struct Unit;
+template <> struct Unit<8> { uint4 q; __half d; };
+template <> struct Unit<12> { uint4 hdr; uint4 q; };
+template <> struct Unit<14> { uint4 ql; uint4 qh; int8_t s1, s2; __half d; };
+template <> struct Unit<0> { float4 w; };
+
+template <int FMT>
+__device__ __forceinline__ void load_unit(Unit<FMT>& o, const uint8_t* const* pl, long long row, int K, int u) {
+  if constexpr (FMT == 8) {  // planes: qs int8 [rows][K], d f16 [rows][K/32]
+    const int k = u * 16;
+    o.q = ldg16(pl[0] + row * K + k);
+    o.d = reinterpret_cast<const __half*>(pl[1])[row * (K / 32) + (k >> 5)];
+  } else if constexpr (FMT == 12) {  // 144-byte blocks as on disk
+    const int sb = u >> 3, j = u & 7;
+    const uint8_t* blk = pl[0] + (row * (K / 256) + sb) * 144;
+    o.hdr = ldg16(blk);
+    o.q = ldg16(blk + 16 + (j >> 1) * 32 + (j & 1) * 16);
+  } else if constexpr (FMT == 14) {  // planes: ql [rows][K/2], qh [rows][K/4], sc i8 [rows][K/16], d f16 [rows][K/256]
+    const int sb = u >> 3, j = u & 7, half = j >> 2, jj = j & 3, second = jj >> 1, l0 = (jj & 1) * 16;
+    o.ql = ldg16(pl[0] + row * (K / 2) + sb * 128 + half * 64 + second * 32 + l0);
+    o.qh = ldg16(pl[1] + row * (K / 4) + sb * 64 + half * 32 + l0);
+    const int8_t* sc = reinterpret_cast<const int8_t*>(pl[2]) + row * (K / 16) + sb * 16;
+    const int is = half * 8 + (jj & 1) + (second ? 2 : 0);
+    o.s1 = sc[is]; o.s2 = sc[is + 4];
+    o.d = reinterpret_cast<const __half*>(pl[3])[row * (K / 256) + sb];
+  } else {
+    o.w = __ldg(reinterpret_cast<const float4*>(pl[0]) + (row * K) / 4 + u);
+  }
+}
+
+__device__ __forceinline__ void lds16(const float* p, float* v) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 t = reinterpret_cast<const float4*>(p)[i];
+    v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+  }
+}
+
+// contribution of one unit of one weight row to the MT token rows staged in xs (pitch Kp)
+template <int FMT, int MT>
+__device__ __forceinline__ void dot_unit(const Unit<FMT>& w, const float* xs, int Kp, int u, float* acc) {
+  if constexpr (FMT == 8) {
+    const int8_t* qb = reinterpret_cast<const int8_t*>(&w.q);
+    float wq[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) wq[i] = (float)qb[i];
+    const float d = __half2float(w.d);
+    const int xo = xpad(u * 16);
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      float xv[16];
+      lds16(xs + m * Kp + xo, xv);
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) s = fmaf(wq[i], xv[i], s);
+      acc[m] = fmaf(d, s, acc[m]);
+    }
+  } else if constexpr (FMT == 12) {
+    const int sb = u >> 3, j = u & 7, gq = j >> 1, lo = (j & 1) * 16;
+    const int k1 = sb * 256 + gq * 64 + lo, k2 = k1 + 32;
+    const __half2 dd = *reinterpret_cast<const __half2*>(&w.hdr.x);
+    const float d = __low2float(dd), dmin = __high2float(dd);
+    const uint8_t* s = reinterpret_cast<const uint8_t*>(&w.hdr) + 4;
+    int sc1, m1, sc2, m2;  // get_scale_min_k4 for sub-blocks 2*gq and 2*gq + 1
+    {
+      const int j1 = 2 * gq, j2 = 2 * gq + 1;
+      if (j1 < 4) { sc1 = s[j1] & 63; m1 = s[j1 + 4] & 63; }
+      else { sc1 = (s[j1 + 4] & 0xF) | ((s[j1 - 4] >> 6) << 4); m1 = (s[j1 + 4] >> 4) | ((s[j1] >> 6) << 4); }
+      if (j2 < 4) { sc2 = s[j2] & 63; m2 = s[j2 + 4] & 63; }
+      else { sc2 = (s[j2 + 4] & 0xF) | ((s[j2 - 4] >> 6) << 4); m2 = (s[j2 + 4] >> 4) | ((s[j2] >> 6) << 4); }
+    }
+    const uint8_t* qb = reinterpret_cast<const uint8_t*>(&w.q);
+    float w1[16], w2[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { w1[i] = (float)(qb[i] & 0xF); w2[i] = (float)(qb[i] >> 4); }
+    const float ds1 = d * (float)sc1, ds2 = d * (float)sc2, dm1 = dmin * (float)m1, dm2 = dmin * (float)m2;
+    const int xo1 = xpad(k1), xo2 = xpad(k2);
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      float x1[16], x2[16];
+      lds16(xs + m * Kp + xo1, x1);
+      lds16(xs + m * Kp + xo2, x2);
+      float s1 = 0.f, s2 = 0.f, sx1 = 0.f, sx2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        s1 = fmaf(w1[i], x1[i], s1); s2 = fmaf(w2[i], x2[i], s2);
+        sx1 += x1[i]; sx2 += x2[i];
+      }
+      acc[m] += (ds1 * s1 + ds2 * s2) - (dm1 * sx1 + dm2 * sx2);
+    }
+  } else if constexpr (FMT == 14) {
+    const int sb = u >> 3, j = u & 7, half = j >> 2, jj = j & 3, second = jj >> 1, l0 = (jj & 1) * 16;
+    const int kb = sb * 256 + half * 128 + l0;
+    const int k1 = kb + (second ? 32 : 0), k2 = kb + (second ? 96 : 64);
+    const int sh = second ? 2 : 0;
+    const float d = __half2float(w.d);
+    const float d1 = d * (float)w.s1, d2 = d * (float)w.s2;
+    const uint8_t* lb = reinterpret_cast<const uint8_t*>(&w.ql);
+    const uint8_t* hb = reinterpret_cast<const uint8_t*>(&w.qh);
+    float w1[16], w2[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      w1[i] = (float)(((lb[i] & 0xF) | (((hb[i] >> sh) & 3) << 4)) - 32);
+      w2[i] = (float)(((lb[i] >> 4) | (((hb[i] >> (sh + 4)) & 3) << 4)) - 32);
+    }
+    const int xo1 = xpad(k1), xo2 = xpad(k2);
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      float x1[16], x2[16];
+      lds16(xs + m * Kp + xo1, x1);
+      lds16(xs + m * Kp + xo2, x2);
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { s1 = fmaf(w1[i], x1[i], s1); s2 = fmaf(w2[i], x2[i], s2); }
+      acc[m] += d1 * s1 + d2 * s2;
+    }
+  } else {
+    const int xo = xpad(u * 4);
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      const float4 xv = *reinterpret_cast<const float4*>(xs + m * Kp + xo);
+      acc[m] += w.w.x * xv.x + w.w.y * xv.y + w.w.z * xv.z + w.w.w * xv.w;
+    }
+  }
+}
+
+__device__ __forceinline__ void add4(float4& a, const float4 b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+
+template <int FMT, int MT, int R, int NW>
+__device__ __forceinline__ void run_job(const Job& J, const Stage& st, float* xs, float* red, int local) {
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31, grp = lane >> 3, sub = lane & 7;
+  const int K = J.K, Kp = xpad(K), rpg = J.rpg;
+  const int g = local / J.fblocks, fb = local % J.fblocks;
+  const long long n0 = ((long long)(fb * kWarps + warp) * 4 + grp) * R;
+  const long long e = J.row_expert ? J.row_expert[g] : 0;
+  const int units = FMT == 8 ? K / 16 : (FMT == 0 ? K / 4 : K / 32);
+  long long wrow[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) wrow[r] = e * J.N + min(n0 + r, J.N - 1);
+
+  // weight bytes of the first unit are requested before the activations are staged
+  Unit<FMT> cur[NW][R];
+  if (sub < units) {
+#pragma unroll
+    for (int w = 0; w < NW; ++w)
+#pragma unroll
+      for (int r = 0; r < R; ++r) load_unit<FMT>(cur[w][r], J.p[w], wrow[r], K, sub);
+  }
+
+  // ---- stage the token rows of this group: x = base + (sum_j w_j y_j + add1 + add2), optional RMSNorm weight
+  float ss[MT];
+#pragma unroll
+  for (int m = 0; m < MT; ++m) ss[m] = 0.f;
+  const bool wb = st.write_back != nullptr && blockIdx.x == 0;
+  for (int i = t; i < K / 4; i += kThreads) {
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      if (m >= rpg) break;
+      const long long xr = ((long long)g * rpg + m) / J.x_row_div;
+      float4 v = reinterpret_cast<const float4*>(J.x + xr * J.ldx)[i];
+      if (st.ymoe || st.add1 || st.add2) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (st.ymoe) {
+          for (int j = 0; j < st.topk; ++j) {
+            const float wj = st.wmoe[xr * st.topk + j];
+            const float4 y = reinterpret_cast<const float4*>(st.ymoe + (xr * st.topk + j) * K)[i];
+            a.x = fmaf(wj, y.x, a.x); a.y = fmaf(wj, y.y, a.y); a.z = fmaf(wj, y.z, a.z); a.w = fmaf(wj, y.w, a.w);
+          }
+        }
+        if (st.add1) add4(a, reinterpret_cast<const float4*>(st.add1 + xr * K)[i]);
+        if (st.add2) add4(a, reinterpret_cast<const float4*>(st.add2 + xr * K)[i]);
+        add4(v, a);
+      }
+      if (wb) reinterpret_cast<float4*>(st.write_back + xr * K)[i] = v;
+      if (st.norm_w) {
+        ss[m] += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        const float4 nw = reinterpret_cast<const float4*>(st.norm_w)[i];
+        v.x *= nw.x; v.y *= nw.y; v.z *= nw.z; v.w *= nw.w;
+      }
+      *reinterpret_cast<float4*>(xs + m * Kp + xpad(4 * i)) = v;
+    }
+  }
+  if (st.norm_w) {
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      float v = ss[m];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) red[m * kWarps + warp] = v;
+    }
+  }
+  __syncthreads();
+  float rs[MT];
+#pragma unroll
+  for (int m = 0; m < MT; ++m) {
+    rs[m] = 1.f;
+    if (st.norm_w) {
+      float tot = 0.f;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) tot += red[m * kWarps + w];
+      rs[m] = rsqrtf(tot / (float)K + st.eps);
+    }
+  }
+
+  float acc[NW][R][MT];
+#pragma unroll
+  for (int w = 0; w < NW; ++w)
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int m = 0; m < MT; ++m) acc[w][r][m] = 0.f;
+
+  for (int u = sub; u < units; u += 8) {
+    Unit<FMT> nxt[NW][R];
+    const int un = u + 8;
+    if (un < units) {
+#pragma unroll
+      for (int w = 0; w < NW; ++w)
+#pragma unroll
+        for (int r = 0; r < R; ++r) load_unit<FMT>(nxt[w][r], J.p[w], wrow[r], K, un);
+    }
+#pragma unroll
+    for (int w = 0; w < NW; ++w)
+#pragma unroll
+      for (int r = 0; r < R; ++r) dot_unit<FMT, MT>(cur[w][r], xs, Kp, u, acc[w][r]);
+    if (un < units) {
+#pragma unroll
+      for (int w = 0; w < NW; ++w)
+#pragma unroll
+        for (int r = 0; r < R; ++r) cur[w][r] = nxt[w][r];
+    }
+  }
+#pragma unroll
+  for (int w = 0; w < NW; ++w)
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        float v = acc[w][r][m];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        acc[w][r][m] = v;
+      }
+  if (sub == 0) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (n0 + r >= J.N) break;
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        if (m >= rpg) break;
+        float a = acc[0][r][m] * rs[m];
+        if constexpr (NW == 2) {
+          const float b = acc[1][r][m] * rs[m];
+          a = a / (1.f + __expf(-a)) * b;  // SiLU(gate) * up (run_dense_mlp, block.rs:1166-1177)
+        }
+        J.out[((long long)g * rpg + m) * J.ldo + n0 + r] = a;
+      }
+    }
+  }
+}
+
+template <int FMT, int MT>
+__device__ __forceinline__ void run_fmt(const Job& J, const Stage& st, float* xs, float* red, int local) {
+  if (J.dual) run_job<FMT, MT, 1, 2>(J, st, xs, red, local);
+  else if (J.R == 2) run_job<FMT, MT, 2, 1>(J, st, xs, red, local);
+  else run_job<FMT, MT, 1, 1>(J, st, xs, red, local);
+}
+
+template <int MT>
+__global__ void __launch_bounds__(kThreads)
+dsq_fused_gemv_kernel(const __grid_constant__ Launch L) {
+  extern __shared__ __align__(16) float xs[];
+  __shared__ float red[MT * kWarps];
+  int j = 0;
+  for (int i = 1; i < L.njobs; ++i)
+    if ((int)blockIdx.x >= L.job[i].block0) j = i;
+  const Job& J = L.job[j];
+  const int local = (int)blockIdx.x - J.block0;
+  switch (J.fmt) {
+    case 8: run_fmt<8, MT>(J, L.st, xs, red, local); break;
+    case 12: run_fmt<12, MT>(J, L.st, xs, red, local); break;
+    case 14: run_fmt<14, MT>(J, L.st, xs, red, local); break;
+    default: run_fmt<0, MT>(J, L.st, xs, red, local); break;
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// residual add + RMSNorm(ln2) + router (run_moe, block.rs:1263-1301: f32 gate logits -> softmax -> top-k, ties to
+// the lowest index), one block per token row.  Writes the new residual, the normalised row and the choices.
+template <int E>
+__global__ void __launch_bounds__(1024)
+dsq_router_kernel(const float* __restrict__ base, const float* __restrict__ add1, float* __restrict__ xout,
+                  const float* __restrict__ w, const float* __restrict__ wgt, float* __restrict__ xn32,
+                  int* __restrict__ topk_idx, float* __restrict__ topk_w, int H, int topk, float eps) {
+  constexpr int KS = 1024 / E;
+  constexpr int PER = (E + 31) / 32;
+  extern __shared__ float sm[];
+  float* xn_s = sm;      // [H]
+  float* part = sm + H;  // [1024]
+  __shared__ float red[32];
+  const long long row = blockIdx.x;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int n4 = H / 4;
+  float ss = 0.f;
+  for (int i = t; i < n4; i += 1024) {
+    float4 v = reinterpret_cast<const float4*>(base + row * H)[i];
+    add4(v, reinterpret_cast<const float4*>(add1 + row * H)[i]);
+    reinterpret_cast<float4*>(xout + row * H)[i] = v;
+    reinterpret_cast<float4*>(xn_s)[i] = v;
+    ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  ss = warp_sum(ss);
+  if (lane == 0) red[warp] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) tot += red[i];
+  const float inv = rsqrtf(tot / (float)H + eps);
+  for (int i = t; i < n4; i += 1024) {
+    float4 v = reinterpret_cast<float4*>(xn_s)[i];
+    const float4 ww = reinterpret_cast<const float4*>(w)[i];
+    v.x = v.x * inv * ww.x; v.y = v.y * inv * ww.y; v.z = v.z * inv * ww.z; v.w = v.w * inv * ww.w;
+    reinterpret_cast<float4*>(xn_s)[i] = v;
+    reinterpret_cast<float4*>(xn32 + row * H)[i] = v;
+  }
+  __syncthreads();
+  {
+    const int e = t % E, ks = t / E;
+    const int kper = H / KS;
+    const float* wp = wgt + (long long)(ks * kper) * E + e;
+    const float* xp = xn_s + ks * kper;
+    float acc = 0.f;
+#pragma unroll 16
+    for (int k = 0; k < kper; ++k) acc = fmaf(xp[k], wp[(long long)k * E], acc);
+    part[ks * E + e] = acc;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float p[PER];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      const int ee = j * 32 + lane;
+      float s = -INFINITY;
+      if (ee < E) {
+        s = 0.f;
+#pragma unroll
+        for (int q = 0; q < KS; ++q) s += part[q * E + ee];
+      }
+      p[j] = s;
+      mx = fmaxf(mx, s);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      p[j] = (j * 32 + lane < E) ? expf(p[j] - mx) : 0.f;
+      sum += p[j];
+    }
+    sum = warp_sum(sum);
+#pragma unroll
+    for (int j = 0; j < PER; ++j) p[j] = (j * 32 + lane < E) ? p[j] / sum : -1.f;
+    int my_e = 0; float my_w = 0.f;
+    for (int k = 0; k < topk; ++k) {
+      float bv = -1.f; int bi = 1 << 30;
+#pragma unroll
+      for (int j = 0; j < PER; ++j) {
+        const int ee = j * 32 + lane;
+        if (ee < E && (p[j] > bv || (p[j] == bv && ee < bi))) { bv = p[j]; bi = ee; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+      if (lane == k) { my_e = bi; my_w = bv; }
+#pragma unroll
+      for (int j = 0; j < PER; ++j) if (j * 32 + lane == bi) p[j] = -2.f;
+    }
+    if (lane < topk) {
+      topk_idx[row * topk + lane] = my_e;
+      topk_w[row * topk + lane] = my_w;
+    }
+  }
+}
+
+// x = base + (sum_j w_j y_j + add1);  out = RMSNorm(x) * w   (last layer's MoE combine + final norm), block per row
+__global__ void __launch_bounds__(256)
+dsq_combine_norm_kernel(const float* __restrict__ base, const float* __restrict__ ymoe, const float* __restrict__ wmoe,
+                        int topk, const float* __restrict__ add1, const float* __restrict__ w, float* __restrict__ out,
+                        int H, float eps) {
+  extern __shared__ float sm[];  // [H]
+  __shared__ float red[8];
+  const long long row = blockIdx.x;
+  const int t = threadIdx.x;
+  float ss = 0.f;
+  for (int i = t; i < H / 4; i += 256) {
+    float4 v = reinterpret_cast<const float4*>(base + row * H)[i];
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ymoe) {
+      for (int j = 0; j < topk; ++j) {
+        const float wj = wmoe[row * topk + j];
+        const float4 y = reinterpret_cast<const float4*>(ymoe + (row * topk + j) * H)[i];
+        a.x = fmaf(wj, y.x, a.x); a.y = fmaf(wj, y.y, a.y); a.z = fmaf(wj, y.z, a.z); a.w = fmaf(wj, y.w, a.w);
+      }
+    }
+    if (add1) add4(a, reinterpret_cast<const float4*>(add1 + row * H)[i]);
+    add4(v, a);
+    reinterpret_cast<float4*>(sm)[i] = v;
+    ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  ss = warp_sum(ss);
+  if ((t & 31) == 0) red[t >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += red[i];
+  const float inv = rsqrtf(tot / (float)H + eps);
+  for (int i = t; i < H / 4; i += 256) {
+    float4 v = reinterpret_cast<float4*>(sm)[i];
+    const float4 ww = reinterpret_cast<const float4*>(w)[i];
+    v.x = v.x * inv * ww.x; v.y = v.y * inv * ww.y; v.z = v.z * inv * ww.z; v.w = v.w * inv * ww.w;
+    reinterpret_cast<float4*>(out + row * H)[i] = v;
+  }
+}
+
+__device__ __forceinline__ void ld16f(const float* p, float* out) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 t = reinterpret_cast<const float4*>(p)[i];
+    out[4 * i] = t.x; out[4 * i + 1] = t.y; out[4 * i + 2] = t.z; out[4 * i + 3] = t.w;
+  }
+}
+__device__ __forceinline__ void ld16f(const __half* p, float* out) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const uint4 t = reinterpret_cast<const uint4*>(p)[i];
+    const __half2* h = reinterpret_cast<const __half2*>(&t);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); out[8 * i + 2 * j] = f.x; out[8 * i + 2 * j + 1] = f.y; }
+  }
+}
+
+// RoPE + KV append + attention for a handful of query rows (attention_forward, block.rs:446-804, q = 1): the keys of
+// a (row, head) are cut into `nsplit` contiguous ranges, one block each (one block per (row, head) would leave a
+// batch-1 step with 10 blocks streaming the whole cache); each block leaves (max, sum, weighted V) in a workspace and
+// the block that arrives last merges them in split order (deterministic) and resets the arrival counter.
+constexpr int kPartStride = 136;  // m, l, pad, acc[128]
+template <typename TKV>
+__global__ void __launch_bounds__(128)
+dsq_attn_split_kernel(const float* __restrict__ qkv, const float* __restrict__ cos_t, const float* __restrict__ sin_t,
+                      TKV* __restrict__ kc, TKV* __restrict__ vc, const int* __restrict__ row_page,
+                      const int* __restrict__ row_pos, float* __restrict__ part, int* __restrict__ counters,
+                      float* __restrict__ ctx, int heads, int smax, float scale, int nsplit) {
+  constexpr int D = 128;
+  const int rh = blockIdx.x, r = rh / heads, hd = rh % heads, sp = blockIdx.y;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31, grp = lane >> 3, sub = lane & 7;
+  const int pos = row_pos[r], page = row_page[r];
+  TKV* kbase = kc + ((long long)page * heads + hd) * smax * D;
+  TKV* vbase = vc + ((long long)page * heads + hd) * smax * D;
+  __shared__ float q_s[D], knew[D], vnew[D];
+  __shared__ float sm_m[16], sm_l[16], sm_acc[16][D];
+  __shared__ int s_last;
+  const bool tail = sp == nsplit - 1;  // this block also owns the new token
+  const float* base = qkv + (long long)r * 3 * heads * D;
+  if (t < 64) {
+    const float c = cos_t[(long long)pos * 64 + t], sn = sin_t[(long long)pos * 64 + t];
+    const float qlo = base[hd * D + t], qhi = base[hd * D + 64 + t];
+    q_s[t] = (qlo * c - qhi * sn) * scale;
+    q_s[t + 64] = (qhi * c + qlo * sn) * scale;
+    if (tail) {
+      const float klo = base[(heads + hd) * D + t], khi = base[(heads + hd) * D + 64 + t];
+      const TKV k0 = (TKV)(klo * c - khi * sn), k1 = (TKV)(khi * c + klo * sn);
+      kbase[(long long)pos * D + t] = k0;
+      kbase[(long long)pos * D + 64 + t] = k1;
+      knew[t] = (float)k0; knew[t + 64] = (float)k1;  // what later steps read back from the cache
+    }
+  } else if (tail) {
+    const int d = t - 64;
+    const TKV v0 = (TKV)base[(2 * heads + hd) * D + d], v1 = (TKV)base[(2 * heads + hd) * D + 64 + d];
+    vbase[(long long)pos * D + d] = v0;
+    vbase[(long long)pos * D + 64 + d] = v1;
+    vnew[d] = (float)v0; vnew[d + 64] = (float)v1;
+  }
+  __syncthreads();
+  float qv[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) qv[i] = q_s[sub * 16 + i];
+  float m = -INFINITY, l = 0.f, acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  auto fold = [&](float s, const float* vv) {
+    const float mn = fmaxf(m, s);
+    const float a = __expf(m - mn);
+    const float pe = __expf(s - mn);
+    l = l * a + pe;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = acc[i] * a + pe * vv[i];
+    m = mn;
+  };
+  const int chunk = (((pos + nsplit - 1) / nsplit) + 31) & ~31;  // cached keys 0..pos-1, 32 per block iteration
+  const int kb = sp * chunk, ke = min(pos, kb + chunk);
+  const TKV* kr = kbase;
+  const TKV* vr = vbase;
+  for (int ka = kb + warp * 4 + grp; ka < ke; ka += 32) {  // two keys per lane group and iteration
+    const int kb2 = ka + 16;
+    const bool okb = kb2 < ke;
+    float k1[16], v1[16], k2[16], v2[16];
+    ld16f(kr + (long long)ka * D + sub * 16, k1);
+    ld16f(vr + (long long)ka * D + sub * 16, v1);
+    if (okb) { ld16f(kr + (long long)kb2 * D + sub * 16, k2); ld16f(vr + (long long)kb2 * D + sub * 16, v2); }
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s1 += qv[i] * k1[i];
+    if (okb) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) s2 += qv[i] * k2[i];
+    }
+    const unsigned gmask = 0xffu << (grp * 8);  // the 8 lanes of a group share ka
+    s1 += __shfl_xor_sync(gmask, s1, 1); s1 += __shfl_xor_sync(gmask, s1, 2); s1 += __shfl_xor_sync(gmask, s1, 4);
+    s2 += __shfl_xor_sync(gmask, s2, 1); s2 += __shfl_xor_sync(gmask, s2, 2); s2 += __shfl_xor_sync(gmask, s2, 4);
+    fold(s1, v1);
+    if (okb) fold(s2, v2);
+  }
+  if (tail && warp == 0 && grp == 0) {  // the new token itself (key index pos)
+    float sc = 0.f, vv[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { sc += qv[i] * knew[sub * 16 + i]; vv[i] = vnew[sub * 16 + i]; }
+    sc += __shfl_xor_sync(0x000000ffu, sc, 1);
+    sc += __shfl_xor_sync(0x000000ffu, sc, 2);
+    sc += __shfl_xor_sync(0x000000ffu, sc, 4);
+    fold(sc, vv);
+  }
+  const int slot = warp * 4 + grp;
+  if (sub == 0) { sm_m[slot] = m; sm_l[slot] = l; }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) sm_acc[slot][sub * 16 + i] = acc[i];
+  __syncthreads();
+  float gm = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) gm = fmaxf(gm, sm_m[i]);
+  float num = 0.f, den = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float f = sm_m[i] == -INFINITY ? 0.f : __expf(sm_m[i] - gm);
+    num += f * sm_acc[i][t];
+    den += f * sm_l[i];
+  }
+  if (nsplit == 1) {
+    ctx[((long long)r * heads + hd) * D + t] = num / den;
+    return;
+  }
+  float* my = part + ((long long)rh * nsplit + sp) * kPartStride;
+  if (t == 0) { my[0] = gm; my[1] = den; }
+  my[8 + t] = num;
+  __threadfence();
+  __syncthreads();
+  if (t == 0) s_last = atomicAdd(&counters[rh], 1) == nsplit - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const float* all = part + (long long)rh * nsplit * kPartStride;
+  float tm = -INFINITY;
+  for (int s = 0; s < nsplit; ++s) tm = fmaxf(tm, __ldcg(all + s * kPartStride));
+  float tn = 0.f, td = 0.f;
+  for (int s = 0; s < nsplit; ++s) {
+    const float ms = __ldcg(all + s * kPartStride);
+    const float f = ms == -INFINITY ? 0.f : __expf(ms - tm);
+    tn += f * __ldcg(all + s * kPartStride + 8 + t);
+    td += f * __ldcg(all + s * kPartStride + 1);
+  }
+  ctx[((long long)r * heads + hd) * D + t] = tn / td;
+  if (t == 0) counters[rh] = 0;  // ready for the next step (graph replay)
+}
+
+int fmt_code(DsqDType f) {
+  switch (f) {
+    case DsqDType::Q8_0: return 8;
+    case DsqDType::Q4K: return 12;
+    case DsqDType::Q6K: return 14;
+    default: return 0;
+  }
+}
+
+}  // namespace
+
+void dsq_fused_gemv(const DsqFusedJob* jobs, int njobs, const DsqFusedStage& st, const char* tag, cudaStream_t stream) {
+  if (njobs < 1 || njobs > kMaxJobs) throw std::runtime_error("dsq_fused_gemv: 1..3 jobs");
+  Launch L{};
+  L.njobs = njobs;
+  int blocks = 0, max_rpg = 1;
+  size_t smem = 0;
+  for (int i = 0; i < njobs; ++i) {
+    const DsqFusedJob& s = jobs[i];
+    const QuantWeight& w = *s.w0;
+    Job& J = L.job[i];
+    J.fmt = fmt_code(w.fmt); J.K = w.K; J.N = w.N; J.dual = s.w1 ? 1 : 0;
+    const int gran = J.fmt == 8 ? 16 : (J.fmt == 0 ? 4 : 256);
+    if (w.K % gran || w.K % 4) throw std::runtime_error("dsq_fused_gemv: unsupported K for this block format");
+    if (s.w1 && (s.w1->fmt != w.fmt || s.w1->K != w.K || s.w1->N != w.N)) throw std::runtime_error("dsq_fused_gemv: gate/up formats differ");
+    if (s.rpg < 1 || s.rpg > 4 || s.groups < 1) throw std::runtime_error("dsq_fused_gemv: 1..4 rows per group");
+    const QuantWeight* ws[2] = {s.w0, s.w1};
+    for (int k = 0; k < 2; ++k) {
+      if (!ws[k]) continue;
+      J.p[k][0] = (const uint8_t*)ws[k]->a.p; J.p[k][1] = (const uint8_t*)ws[k]->b.p;
+      J.p[k][2] = (const uint8_t*)ws[k]->c.p; J.p[k][3] = (const uint8_t*)ws[k]->d.p;
+    }
+    J.R = (!J.dual && w.N >= 16384) ? 2 : 1;  // wide layers (lm_head): two features per lane share the staged activations
+    J.x = s.x; J.ldx = s.ldx; J.groups = s.groups; J.rpg = s.rpg; J.x_row_div = s.x_row_div < 1 ? 1 : s.x_row_div;
+    J.row_expert = s.row_expert; J.out = s.out; J.ldo = s.ldo;
+    const int per_block = kWarps * 4 * J.R;
+    J.fblocks = (int)((w.N + per_block - 1) / per_block);
+    J.block0 = blocks;
+    blocks += J.fblocks * J.groups;
+    max_rpg = std::max(max_rpg, s.rpg);
+    const size_t kp = (size_t)w.K + ((size_t)w.K >> 6) * 4 + 4;
+    smem = std::max(smem, kp * 4);
+  }
+  L.st.add1 = st.add1; L.st.add2 = st.add2; L.st.ymoe = st.ymoe; L.st.wmoe = st.wmoe; L.st.topk = st.topk;
+  L.st.write_back = st.write_back; L.st.norm_w = st.norm_w; L.st.eps = st.eps;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cuda_check(cudaFuncSetAttribute(dsq_fused_gemv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), "smem attr");
+    cuda_check(cudaFuncSetAttribute(dsq_fused_gemv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), "smem attr");
+    attr_set = true;
+  }
+  if (max_rpg == 1) {
+    dsq_fused_gemv_kernel<1><<<blocks, kThreads, smem, stream>>>(L);
+  } else {
+    if (smem * 4 > 200 * 1024) throw std::runtime_error("dsq_fused_gemv: activation rows do not fit in shared memory");
+    dsq_fused_gemv_kernel<4><<<blocks, kThreads, smem * 4, stream>>>(L);
+  }
+  launch_check(tag);
+}
+
+void dsq_router(const float* base, const float* add1, float* xout, const float* w, const float* wgt, float* xn32,
+                int* topk_idx, float* topk_w, long long rows, int H, int E, int topk, float eps, cudaStream_t s) {
+  const size_t smem = (size_t)(H + 1024) * 4;
+  if (H % 4 || topk > 32) throw std::runtime_error("dsq_router: unsupported shape");
+  if (E == 64 && H % 16 == 0) dsq_router_kernel<64><<<(unsigned)rows, 1024, smem, s>>>(base, add1, xout, w, wgt, xn32, topk_idx, topk_w, H, topk, eps);
+  else if (E == 16 && H % 64 == 0) dsq_router_kernel<16><<<(unsigned)rows, 1024, smem, s>>>(base, add1, xout, w, wgt, xn32, topk_idx, topk_w, H, topk, eps);
+  else throw std::runtime_error("dsq_router: unsupported expert count");
+  launch_check("dsq_router");
+}
+
+void dsq_combine_norm(const float* base, const float* ymoe, const float* wmoe, int topk, const float* add1,
+                      const float* w, float* out, long long rows, int H, float eps, cudaStream_t s) {
+  dsq_combine_norm_kernel<<<(unsigned)rows, 256, (size_t)H * 4, s>>>(base, ymoe, wmoe, topk, add1, w, out, H, eps);
+  launch_check("dsq_combine_norm");
+}
+
+int dsq_attn_splits(int smax) { return std::max(1, std::min(64, (smax + 63) / 64)); }
+size_t dsq_attn_ws_floats(long long rows, int heads, int nsplit) { return (size_t)rows * heads * nsplit * kPartStride; }
+
+void dsq_attn_split(const float* qkv, const float* cos_t, const float* sin_t, void* kc, void* vc, bool kv_f16,
+                    const int* row_page, const int* row_pos, float* part, int* counters, float* ctx, long long rows,
+                    int heads, int head_dim, int smax, float scale, int nsplit, cudaStream_t s) {
+  if (head_dim != 128) throw std::runtime_error("dsq_attn_split: head_dim must be 128");
+  const dim3 grid((unsigned)(rows * heads), (unsigned)nsplit);
+  if (kv_f16)
+    dsq_attn_split_kernel<__half><<<grid, 128, 0, s>>>(qkv, cos_t, sin_t, (__half*)kc, (__half*)vc, row_page, row_pos, part, counters, ctx, heads, smax, scale, nsplit);
+  else
+    dsq_attn_split_kernel<float><<<grid, 128, 0, s>>>(qkv, cos_t, sin_t, (float*)kc, (float*)vc, row_page, row_pos, part, counters, ctx, heads, smax, scale, nsplit);
+  launch_check("dsq_attn_split");
+}
+
+}  // namespace dsocr

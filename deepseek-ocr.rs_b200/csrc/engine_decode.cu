@@ -324,6 +324,94 @@ void Engine::decoder_forward_dsq(float* x, long long rows, const int* row_page, 
   gemv(q_lm_head_, xf, H, logits, c.vocab, n_final, false, "dsq_lm_head");
 }
 
+// Decode step for <= 4 pages over a DSQ snapshot with 6 launches per layer (see dsq_decode.cu).  The residual
+// stream ping-pongs between x (the embedding rows on entry) and x1: a kernel that folds pending adds into the
+// residual while staging its activations writes the sum to the other buffer, which no block of that launch reads.
+void Engine::decoder_step_dsq_fused(float* x, long long rows, const int* row_page, const int* row_pos, int smax, float* logits) {
+  const ModelConfig& c = cfg_;
+  const int H = c.hidden, heads = c.heads, E = c.n_experts, K = c.topk, mi = c.moe_inter;
+  const long long S = (long long)mi * c.n_shared;
+  const float scale = 1.0f / sqrtf((float)c.head_dim());
+  const long long na = rows * K;
+  const int R = (int)rows;
+  float* x1 = ws("dsqf_x1", rows * H * 4).as<float>();
+  float* qkv = ws("dec_qkv32", rows * 3 * H * 4).as<float>();
+  float* ctx = ws("dsq_ctx32", rows * H * 4).as<float>();
+  float* o32 = ws("dsqf_o32", rows * H * 4).as<float>();
+  float* xn = ws("dec_xn32", rows * H * 4).as<float>();
+  float* h = ws("dsqf_h32", rows * std::max<long long>(c.inter, (long long)K * mi) * 4).as<float>();
+  float* hs = ws("dsqf_hs32", rows * S * 4).as<float>();
+  float* y = ws("dsq_y32", na * H * 4).as<float>();
+  float* ysh = ws("dsqf_ysh32", rows * H * 4).as<float>();
+  float* d32 = ws("dsqf_d32", rows * H * 4).as<float>();
+  int* topk_idx = ws("moe_topk_idx", na * 4).as<int>();
+  float* topk_w = ws("moe_topk_w", na * 4).as<float>();
+  const int nsplit = dsq_attn_splits(smax);
+  float* part = ws("dsqf_attn_part", dsq_attn_ws_floats(rows, heads, nsplit) * 4).as<float>();
+  int* counters = ws("dsqf_attn_cnt", (size_t)rows * heads * 4).as<int>();
+
+  float* cur = x;    // residual as of the last kernel that wrote it
+  float* alt = x1;
+  DsqFusedStage pend;  // adds still to be folded into the residual by the next staging kernel
+  for (int l = 0; l < c.layers; ++l) {
+    DecLayerW& L = dec_[l];
+    {  // pending adds + RMSNorm(ln1) + q | k | v
+      DsqFusedStage st = pend;
+      st.write_back = alt; st.norm_w = L.ln1.as<float>(); st.eps = c.rms_eps;
+      DsqFusedJob j[3];
+      const QuantWeight* w[3] = {&L.q_q, &L.q_k, &L.q_v};
+      for (int i = 0; i < 3; ++i) { j[i].w0 = w[i]; j[i].x = cur; j[i].ldx = H; j[i].rpg = R; j[i].out = qkv + (long long)i * H; j[i].ldo = 3 * H; }
+      dsq_fused_gemv(j, 3, st, "dsq_qkv", stream_);
+      std::swap(cur, alt);
+      pend = DsqFusedStage();
+    }
+    dsq_attn_split(qkv, rope_cos_.as<float>(), rope_sin_.as<float>(), kcache_[l].p, vcache_[l].p, kv_f16_, row_page, row_pos,
+                   part, counters, ctx, rows, heads, c.head_dim(), smax, scale, nsplit, stream_);
+    {
+      DsqFusedJob j;
+      j.w0 = &L.q_o; j.x = ctx; j.ldx = H; j.rpg = R; j.out = o32; j.ldo = H;
+      dsq_fused_gemv(&j, 1, DsqFusedStage(), "dsq_o_proj", stream_);
+    }
+    if (!L.moe) {
+      {  // residual + o_proj, RMSNorm(ln2), gate/up + SwiGLU
+        DsqFusedStage st;
+        st.add1 = o32; st.write_back = alt; st.norm_w = L.ln2.as<float>(); st.eps = c.rms_eps;
+        DsqFusedJob j;
+        j.w0 = &L.q_gate; j.w1 = &L.q_up; j.x = cur; j.ldx = H; j.rpg = R; j.out = h; j.ldo = c.inter;
+        dsq_fused_gemv(&j, 1, st, "dsq_dense_gate_up", stream_);
+        std::swap(cur, alt);
+      }
+      DsqFusedJob j;
+      j.w0 = &L.q_down; j.x = h; j.ldx = c.inter; j.rpg = R; j.out = d32; j.ldo = H;
+      dsq_fused_gemv(&j, 1, DsqFusedStage(), "dsq_dense_down", stream_);
+      pend.add1 = d32;
+    } else {
+      dsq_router(cur, o32, alt, L.ln2.as<float>(), L.router_wt.as<float>(), xn, topk_idx, topk_w, rows, H, E, K, c.rms_eps, stream_);
+      std::swap(cur, alt);
+      {  // routed experts (one group per (token, slot)) + shared experts: gate/up + SwiGLU
+        DsqFusedJob j[2];
+        j[0].w0 = &L.q_exp_gate; j[0].w1 = &L.q_exp_up; j[0].x = xn; j[0].ldx = H; j[0].groups = (int)na; j[0].rpg = 1;
+        j[0].x_row_div = K; j[0].row_expert = topk_idx; j[0].out = h; j[0].ldo = mi;
+        j[1].w0 = &L.q_sh_gate; j[1].w1 = &L.q_sh_up; j[1].x = xn; j[1].ldx = H; j[1].rpg = R; j[1].out = hs; j[1].ldo = S;
+        dsq_fused_gemv(j, 2, DsqFusedStage(), "dsq_moe_gate_up", stream_);
+      }
+      {
+        DsqFusedJob j[2];
+        j[0].w0 = &L.q_exp_down; j[0].x = h; j[0].ldx = mi; j[0].groups = (int)na; j[0].rpg = 1; j[0].row_expert = topk_idx;
+        j[0].out = y; j[0].ldo = H;
+        j[1].w0 = &L.q_sh_down; j[1].x = hs; j[1].ldx = S; j[1].rpg = R; j[1].out = ysh; j[1].ldo = H;
+        dsq_fused_gemv(j, 2, DsqFusedStage(), "dsq_moe_down", stream_);
+      }
+      pend.ymoe = y; pend.wmoe = topk_w; pend.topk = K; pend.add1 = ysh;
+    }
+  }
+  // last layer's combine + final RMSNorm once (2020 lm_head blocks would each redo it), then the lm_head GEMV
+  dsq_combine_norm(cur, pend.ymoe, pend.wmoe, pend.topk, pend.add1, final_norm_.as<float>(), xn, rows, H, c.rms_eps, stream_);
+  DsqFusedJob j;
+  j.w0 = &q_lm_head_; j.x = xn; j.ldx = H; j.rpg = R; j.out = logits; j.ldo = c.vocab;
+  dsq_fused_gemv(&j, 1, DsqFusedStage(), "dsq_lm_head", stream_);
+}
+
 void Engine::generate(const GenRequest& rq, int64_t* const* out_tokens, int* n_out) {
   const ModelConfig& c = cfg_;
   const int P = rq.n_pages, H = c.hidden, V = c.vocab;
@@ -461,7 +549,8 @@ void Engine::generate(const GenRequest& rq, int64_t* const* out_tokens, int* n_o
   auto run_step = [&](int step) {
     decode_rows(d_hist, smax, d_hist_len, d_src, d_row_pos, P, stream_);
     embed_gather(d_src, embed_.p, nullptr, x, P, H, dt_, stream_);
-    if (quantized_) decoder_forward_dsq(x, P, d_row_page, d_row_pos, smax, d_row_page, P, logits);
+    if (quantized_ && P <= 4 && dsq_fused_) decoder_step_dsq_fused(x, P, d_row_page, d_row_pos, smax, logits);
+    else if (quantized_) decoder_forward_dsq(x, P, d_row_page, d_row_pos, smax, d_row_page, P, logits);
     else decoder_forward(x, P, d_row_page, d_row_pos, smax, d_row_page /* identity: every row */, P, logits, true);
     copy_logits(step);
     select_token(logits, V, d_hist, smax, d_hist_len, d_gen_count, d_finished, P, ngram, eos, max_new, d_forced, max_new,

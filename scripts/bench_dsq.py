@@ -56,8 +56,10 @@ def main():
     params = DecodeParameters(max_new_tokens=args.tokens, eos_token_id=None)
     eng.generate_batch(ids, masks, rows, DecodeParameters(max_new_tokens=8, eos_token_id=None))  # warm-up
     t0 = time.time()
+    l0 = eng.launch_count()
     out = eng.generate_batch(ids, masks, rows, params)
     wall = time.time() - t0
+    launches = eng.launch_count() - l0
     tm = eng.timings()
     eng.kernel_timing_begin()
     eng.generate_batch(ids, masks, rows, DecodeParameters(max_new_tokens=33, eos_token_id=None))
@@ -69,7 +71,13 @@ def main():
     tok_s = args.pages * (args.tokens - 1) / (tm["decode.iterative"] * 1e-3)
     # algorithmic weight bytes per token: q4k 449 MB, q8_0 610 MB at batch 1
     per_tok = {"q4k": 449e6, "q6k": None, "q8_0": 610e6}[args.primary]
+    # KV bytes read per token at the mean context of the run (f16 cache: K and V, 12 layers)
+    mean_ctx = len(ids[0]) + args.tokens / 2
+    kv_per_tok = 2 * cfg.hidden_size * cfg.num_layers * 2 * mean_ctx
     line = {"config": f"deepseek-ocr-{args.primary} DSQ dequant-fused decode, batch {args.pages}, {args.tokens}-token output, random-init weights",
+            "path": "unfused" if os.environ.get("DSOCR_DSQ_UNFUSED") else "fused step (dsq_decode.cu)",
+            "launches_per_token": round(launches / max(1, args.tokens), 1),
+            "hbm_GBps_weights_plus_kv": ((per_tok + kv_per_tok) * tok_s / args.pages / 1e9) if per_tok else None,
             "decode_tok_s": tok_s, "ms_per_token": tm["decode.iterative"] / (args.tokens - 1), "wall_s": wall,
             "weight_GBps_at_batch1": (per_tok * tok_s / args.pages / 1e9) if per_tok else None,
             "lm_head_gemv": None if lm is None else {"avg_us": lm["ms"] / lm["launches"] * 1e3,

@@ -47,3 +47,58 @@ def test_dsq_decode_matches_dequantised_oracle(primary, name):
         ref = oracle.generate(ids[p], masks[p], None if rows[p] is None else torch.from_numpy(rows[p]), 16, 20, None)
         assert free[p] == ref
     eng.close()
+
+
+@pytest.mark.parametrize("kv_f16", [0, 1])
+def test_dsq_batch1_fused_step_long_context(kv_f16):
+    """Batch-1 decode (the fused 6-launches-per-layer step of dsq_decode.cu, MT = 1 kernels) over enough steps that
+    the split-key attention runs several key ranges per (row, head): teacher-forced logits vs the f32 oracle on the
+    same dequantised weights, then the free-running tokens."""
+    from dsocr.engine import DecodeParameters, load_model
+
+    cfg, ck, d = tiny_model("bf16")
+    snap = os.path.join(d, "model.q4k_b1.dsq")
+    dsq.write_model_snapshot(snap, cfg, ck, dsq.Q4K)
+    oracle = D.DecoderOracle(cfg, dsq.dequantized_checkpoint(snap, ck))
+    eng = load_model(d + "/config.json", d + "/model.safetensors", snap, 0, "bf16")
+    eng.set_option("kv_cache_f16", kv_f16)
+    ids, masks, rows = _prompts(cfg, [33], seed=5)
+    steps = 150
+    g = torch.Generator().manual_seed(9)
+    forced = [torch.randint(2, cfg.vocab_size - 2, (steps,), generator=g).tolist()]
+    params = DecodeParameters(max_new_tokens=steps, eos_token_id=None)
+    sel, logits = eng.generate_forced(ids, masks, rows, params, forced, want_logits=True)
+    ref_logits = []
+    ref_sel = oracle.generate(ids[0], masks[0], torch.from_numpy(rows[0]), steps, 20, None, forced=forced[0], logits_out=ref_logits)
+    err, scale, c = report(f"dsq q4k batch-1 fused step, {steps} forced steps, kv_f16={kv_f16}", torch.from_numpy(logits[0]), torch.stack(ref_logits))
+    assert err <= (4e-3 if kv_f16 else 2e-3) * scale and c > 0.9999
+    if not kv_f16:
+        assert sel[0] == ref_sel
+        free = eng.generate_batch(ids, masks, rows, DecodeParameters(max_new_tokens=48, eos_token_id=None))
+        ref = oracle.generate(ids[0], masks[0], torch.from_numpy(rows[0]), 48, 20, None)
+        assert free[0] == ref
+    eng.close()
+
+
+def test_dsq_fused_step_matches_unfused_path(monkeypatch):
+    """The fused step and the per-linear GEMV path (DSOCR_DSQ_UNFUSED=1) are two schedules of the same f32 math."""
+    from dsocr.engine import DecodeParameters, load_model
+
+    cfg, ck, d = tiny_model("bf16")
+    snap = os.path.join(d, "model.q6k_ab.dsq")
+    dsq.write_model_snapshot(snap, cfg, ck, dsq.Q6K)
+    ids, masks, rows = _prompts(cfg, [12, 30], seed=23)
+    steps = 12
+    g = torch.Generator().manual_seed(2)
+    forced = [torch.randint(2, cfg.vocab_size - 2, (steps,), generator=g).tolist() for _ in ids]
+    params = DecodeParameters(max_new_tokens=steps, eos_token_id=None)
+    out = []
+    for unfused in (False, True):
+        if unfused:
+            monkeypatch.setenv("DSOCR_DSQ_UNFUSED", "1")
+        eng = load_model(d + "/config.json", d + "/model.safetensors", snap, 0, "bf16")
+        out.append(eng.generate_forced(ids, masks, rows, params, forced, want_logits=True)[1])
+        eng.close()
+    for p in range(len(ids)):
+        err, scale, c = report(f"dsq q6k fused vs unfused page {p}", torch.from_numpy(out[0][p]), torch.from_numpy(out[1][p]))
+        assert err <= 1e-4 * scale
