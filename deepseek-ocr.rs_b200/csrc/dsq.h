@@ -109,8 +109,10 @@ struct DsqFusedStage {
   float eps = 0.f;
 };
 void dsq_fused_gemv(const DsqFusedJob* jobs, int njobs, const DsqFusedStage& st, const char* tag, cudaStream_t stream);
+// logits_ws: float[rows*E]; counters: int[rows], zero before the first launch (handed back zeroed)
 void dsq_router(const float* base, const float* add1, float* xout, const float* w, const float* wgt, float* xn32,
-                int* topk_idx, float* topk_w, long long rows, int H, int E, int topk, float eps, cudaStream_t s);
+                float* logits_ws, int* counters, int* topk_idx, float* topk_w, long long rows, int H, int E, int topk,
+                float eps, cudaStream_t s);
 void dsq_combine_norm(const float* base, const float* ymoe, const float* wmoe, int topk, const float* add1,
                       const float* w, float* out, long long rows, int H, float eps, cudaStream_t s);
 int dsq_attn_splits(int smax);

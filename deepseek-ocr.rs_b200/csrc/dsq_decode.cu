@@ -19,6 +19,7 @@
 
 #include "dsq.h"
 #include "kernels.h"
+#include "ptx.cuh"
 
 namespace dsocr {
 
@@ -26,6 +27,7 @@ namespace {
 
 constexpr int kThreads = 256, kWarps = 8;
 constexpr int kMaxJobs = 3;
+constexpr int kMaxSmem = 220 * 1024;
 
 struct Job {
   const uint8_t* p[2][4];  // planes a..d of w0 (and w1 for the dual gate/up job)
@@ -43,40 +45,52 @@ struct Stage {
   float* write_back;
   const float* norm_w; float eps;
 };
-struct Launch { Job job[kMaxJobs]; int njobs; Stage st; };
+struct Launch { Job job[kMaxJobs]; int njobs; int w_off; Stage st; };
 
 // shared-memory index of activation k: 4 floats of padding per 64 keep the 8 lanes of a feature on distinct banks
 __device__ __forceinline__ int xpad(int k) { return k + ((k >> 6) << 2); }
 
-__device__ __forceinline__ uint4 ldg16(const uint8_t* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
-
+// the bytes one lane consumes per step: a 16-byte unit of quants plus its scales
 template <int FMT> struct Unit;
 template <> struct Unit<8> { uint4 q; __half d; };
 template <> struct Unit<12> { uint4 hdr; uint4 q; };
 template <> struct Unit<14> { uint4 ql; uint4 qh; int8_t s1, s2; __half d; };
 template <> struct Unit<0> { float4 w; };
 
+// bytes of one weight row in plane p (the layouts of QuantWeight, dsq.h)
 template <int FMT>
-__device__ __forceinline__ void load_unit(Unit<FMT>& o, const uint8_t* const* pl, long long row, int K, int u) {
+__device__ __host__ __forceinline__ int plane_row_bytes(int K, int p) {
+  if (FMT == 8) return p == 0 ? K : (p == 1 ? K / 16 : 0);
+  if (FMT == 12) return p == 0 ? (K / 256) * 144 : 0;
+  if (FMT == 14) return p == 0 ? K / 2 : (p == 1 ? K / 4 : (p == 2 ? K / 16 : K / 128));
+  return p == 0 ? K * 4 : 0;
+}
+template <int FMT> struct NPlanes { static constexpr int value = FMT == 8 ? 2 : (FMT == 14 ? 4 : 1); };
+
+__device__ __forceinline__ uint4 lds128(const uint8_t* p) { return *reinterpret_cast<const uint4*>(p); }
+
+// unit u of local row `row` from the block's shared-memory slabs pl[0..3] (same layouts as the global planes)
+template <int FMT>
+__device__ __forceinline__ void load_unit(Unit<FMT>& o, const uint8_t* const* pl, int row, int K, int u) {
   if constexpr (FMT == 8) {  // planes: qs int8 [rows][K], d f16 [rows][K/32]
     const int k = u * 16;
-    o.q = ldg16(pl[0] + row * K + k);
+    o.q = lds128(pl[0] + row * K + k);
     o.d = reinterpret_cast<const __half*>(pl[1])[row * (K / 32) + (k >> 5)];
   } else if constexpr (FMT == 12) {  // 144-byte blocks as on disk
     const int sb = u >> 3, j = u & 7;
     const uint8_t* blk = pl[0] + (row * (K / 256) + sb) * 144;
-    o.hdr = ldg16(blk);
-    o.q = ldg16(blk + 16 + (j >> 1) * 32 + (j & 1) * 16);
+    o.hdr = lds128(blk);
+    o.q = lds128(blk + 16 + (j >> 1) * 32 + (j & 1) * 16);
   } else if constexpr (FMT == 14) {  // planes: ql [rows][K/2], qh [rows][K/4], sc i8 [rows][K/16], d f16 [rows][K/256]
     const int sb = u >> 3, j = u & 7, half = j >> 2, jj = j & 3, second = jj >> 1, l0 = (jj & 1) * 16;
-    o.ql = ldg16(pl[0] + row * (K / 2) + sb * 128 + half * 64 + second * 32 + l0);
-    o.qh = ldg16(pl[1] + row * (K / 4) + sb * 64 + half * 32 + l0);
+    o.ql = lds128(pl[0] + row * (K / 2) + sb * 128 + half * 64 + second * 32 + l0);
+    o.qh = lds128(pl[1] + row * (K / 4) + sb * 64 + half * 32 + l0);
     const int8_t* sc = reinterpret_cast<const int8_t*>(pl[2]) + row * (K / 16) + sb * 16;
     const int is = half * 8 + (jj & 1) + (second ? 2 : 0);
     o.s1 = sc[is]; o.s2 = sc[is + 4];
     o.d = reinterpret_cast<const __half*>(pl[3])[row * (K / 256) + sb];
   } else {
-    o.w = __ldg(reinterpret_cast<const float4*>(pl[0]) + (row * K) / 4 + u);
+    o.w = *reinterpret_cast<const float4*>(pl[0] + ((size_t)row * K + (size_t)u * 4) * 4);
   }
 }
 
@@ -88,14 +102,33 @@ __device__ __forceinline__ void lds16(const float* p, float* v) {
   }
 }
 
+// Byte -> float without the conversion unit (I2F runs at a quarter of the FMA rate and would bound the lm_head GEMV):
+// PRMT builds the bit pattern of 2^23 + byte, one FADD removes the offset exactly.
+__device__ __forceinline__ void bytes_to_f32(uint32_t w, float bias, float* out) {
+  out[0] = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440)) - bias;
+  out[1] = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7441)) - bias;
+  out[2] = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7442)) - bias;
+  out[3] = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7443)) - bias;
+}
+constexpr float kMagic = 8388608.f;  // 2^23
+
+// 6-bit scale / min of sub-block jx of a Q4_K super-block (ggml get_scale_min_k4) from the header words
+// (hdr.y|z|w = scales[0..3|4..7|8..11]); shifts instead of byte indexing keep the header in registers.
+__device__ __forceinline__ void q4k_scale_min(const uint4& hdr, int jx, int& sc, int& mn) {
+  const int sh = 8 * (jx & 3);
+  const uint32_t a = (hdr.y >> sh) & 0xFFu, b = (hdr.z >> sh) & 0xFFu, c = (hdr.w >> sh) & 0xFFu;
+  if (jx < 4) { sc = (int)(a & 63u); mn = (int)(b & 63u); }
+  else { sc = (int)((c & 0xFu) | ((a >> 6) << 4)); mn = (int)((c >> 4) | ((b >> 6) << 4)); }
+}
+
 // contribution of one unit of one weight row to the MT token rows staged in xs (pitch Kp)
 template <int FMT, int MT>
 __device__ __forceinline__ void dot_unit(const Unit<FMT>& w, const float* xs, int Kp, int u, float* acc) {
   if constexpr (FMT == 8) {
-    const int8_t* qb = reinterpret_cast<const int8_t*>(&w.q);
+    const uint32_t* qw = reinterpret_cast<const uint32_t*>(&w.q);
     float wq[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) wq[i] = (float)qb[i];
+    for (int i = 0; i < 4; ++i) bytes_to_f32(qw[i] ^ 0x80808080u, kMagic + 128.f, wq + 4 * i);  // int8 + 128 as a byte
     const float d = __half2float(w.d);
     const int xo = xpad(u * 16);
 #pragma unroll
@@ -112,19 +145,16 @@ __device__ __forceinline__ void dot_unit(const Unit<FMT>& w, const float* xs, in
     const int k1 = sb * 256 + gq * 64 + lo, k2 = k1 + 32;
     const __half2 dd = *reinterpret_cast<const __half2*>(&w.hdr.x);
     const float d = __low2float(dd), dmin = __high2float(dd);
-    const uint8_t* s = reinterpret_cast<const uint8_t*>(&w.hdr) + 4;
     int sc1, m1, sc2, m2;  // get_scale_min_k4 for sub-blocks 2*gq and 2*gq + 1
-    {
-      const int j1 = 2 * gq, j2 = 2 * gq + 1;
-      if (j1 < 4) { sc1 = s[j1] & 63; m1 = s[j1 + 4] & 63; }
-      else { sc1 = (s[j1 + 4] & 0xF) | ((s[j1 - 4] >> 6) << 4); m1 = (s[j1 + 4] >> 4) | ((s[j1] >> 6) << 4); }
-      if (j2 < 4) { sc2 = s[j2] & 63; m2 = s[j2 + 4] & 63; }
-      else { sc2 = (s[j2 + 4] & 0xF) | ((s[j2 - 4] >> 6) << 4); m2 = (s[j2 + 4] >> 4) | ((s[j2] >> 6) << 4); }
-    }
-    const uint8_t* qb = reinterpret_cast<const uint8_t*>(&w.q);
+    q4k_scale_min(w.hdr, 2 * gq, sc1, m1);
+    q4k_scale_min(w.hdr, 2 * gq + 1, sc2, m2);
+    const uint32_t* qw = reinterpret_cast<const uint32_t*>(&w.q);
     float w1[16], w2[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { w1[i] = (float)(qb[i] & 0xF); w2[i] = (float)(qb[i] >> 4); }
+    for (int i = 0; i < 4; ++i) {
+      bytes_to_f32(qw[i] & 0x0F0F0F0Fu, kMagic, w1 + 4 * i);
+      bytes_to_f32((qw[i] >> 4) & 0x0F0F0F0Fu, kMagic, w2 + 4 * i);
+    }
     const float ds1 = d * (float)sc1, ds2 = d * (float)sc2, dm1 = dmin * (float)m1, dm2 = dmin * (float)m2;
     const int xo1 = xpad(k1), xo2 = xpad(k2);
 #pragma unroll
@@ -147,13 +177,15 @@ __device__ __forceinline__ void dot_unit(const Unit<FMT>& w, const float* xs, in
     const int sh = second ? 2 : 0;
     const float d = __half2float(w.d);
     const float d1 = d * (float)w.s1, d2 = d * (float)w.s2;
-    const uint8_t* lb = reinterpret_cast<const uint8_t*>(&w.ql);
-    const uint8_t* hb = reinterpret_cast<const uint8_t*>(&w.qh);
+    const uint32_t* lw = reinterpret_cast<const uint32_t*>(&w.ql);
+    const uint32_t* hw = reinterpret_cast<const uint32_t*>(&w.qh);
     float w1[16], w2[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      w1[i] = (float)(((lb[i] & 0xF) | (((hb[i] >> sh) & 3) << 4)) - 32);
-      w2[i] = (float)(((lb[i] >> 4) | (((hb[i] >> (sh + 4)) & 3) << 4)) - 32);
+    for (int i = 0; i < 4; ++i) {  // q = (low nibble | two high bits << 4) - 32, four bytes at a time
+      const uint32_t a = (lw[i] & 0x0F0F0F0Fu) | (((hw[i] >> sh) & 0x03030303u) << 4);
+      const uint32_t b = ((lw[i] >> 4) & 0x0F0F0F0Fu) | (((hw[i] >> (sh + 4)) & 0x03030303u) << 4);
+      bytes_to_f32(a, kMagic + 32.f, w1 + 4 * i);
+      bytes_to_f32(b, kMagic + 32.f, w2 + 4 * i);
     }
     const int xo1 = xpad(k1), xo2 = xpad(k2);
 #pragma unroll
@@ -179,24 +211,49 @@ __device__ __forceinline__ void dot_unit(const Unit<FMT>& w, const float* xs, in
 __device__ __forceinline__ void add4(float4& a, const float4 b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
 
 template <int FMT, int MT, int R, int NW>
-__device__ __forceinline__ void run_job(const Job& J, const Stage& st, float* xs, float* red, int local) {
+__device__ __forceinline__ void run_job(const Job& J, const Stage& st, float* xs, uint8_t* wsm, uint64_t* bar, float* red,
+                                        int local) {
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31, grp = lane >> 3, sub = lane & 7;
+  const int nthreads = blockDim.x, nwarps = nthreads >> 5;
   const int K = J.K, Kp = xpad(K), rpg = J.rpg;
   const int g = local / J.fblocks, fb = local % J.fblocks;
-  const long long n0 = ((long long)(fb * kWarps + warp) * 4 + grp) * R;
+  const int rows_pb = nwarps * 4 * R;                     // weight rows (output features) of a block
+  const long long nb0 = (long long)fb * rows_pb;
+  const int rows_here = (int)min((long long)rows_pb, J.N - nb0);
   const long long e = J.row_expert ? J.row_expert[g] : 0;
   const int units = FMT == 8 ? K / 16 : (FMT == 0 ? K / 4 : K / 32);
-  long long wrow[R];
-#pragma unroll
-  for (int r = 0; r < R; ++r) wrow[r] = e * J.N + min(n0 + r, J.N - 1);
+  constexpr int NP = NPlanes<FMT>::value;
 
-  // weight bytes of the first unit are requested before the activations are staged
-  Unit<FMT> cur[NW][R];
-  if (sub < units) {
+  // ---- the block's weight rows are contiguous in every plane: bulk copies (TMA) bring the whole slab into shared
+  // memory while the threads stage the activations; no registers are tied up by bytes in flight
+  const uint8_t* pl[NW][4];
+  {
+    uint32_t off = 0;
 #pragma unroll
     for (int w = 0; w < NW; ++w)
 #pragma unroll
-      for (int r = 0; r < R; ++r) load_unit<FMT>(cur[w][r], J.p[w], wrow[r], K, sub);
+      for (int p = 0; p < 4; ++p) {
+        pl[w][p] = wsm + off;
+        if (p < NP) off += (uint32_t)rows_pb * plane_row_bytes<FMT>(K, p);
+      }
+    if (t == 0) {
+      ptx::mbar_init(bar, 1);
+      ptx::fence_barrier_init();
+      uint32_t total = 0;
+#pragma unroll
+      for (int p = 0; p < NP; ++p) total += (uint32_t)rows_here * plane_row_bytes<FMT>(K, p);
+      ptx::mbar_expect_tx(bar, total * NW);
+#pragma unroll
+      for (int w = 0; w < NW; ++w)
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+          const uint32_t rb = plane_row_bytes<FMT>(K, p);
+          const uint8_t* src = J.p[w][p] + (size_t)(e * J.N + nb0) * rb;
+          uint8_t* dst = const_cast<uint8_t*>(pl[w][p]);
+          const uint32_t bytes = (uint32_t)rows_here * rb;
+          for (uint32_t o = 0; o < bytes; o += 16384) ptx::bulk_load(dst + o, src + o, min(16384u, bytes - o), bar);
+        }
+    }
   }
 
   // ---- stage the token rows of this group: x = base + (sum_j w_j y_j + add1 + add2), optional RMSNorm weight
@@ -204,7 +261,7 @@ __device__ __forceinline__ void run_job(const Job& J, const Stage& st, float* xs
 #pragma unroll
   for (int m = 0; m < MT; ++m) ss[m] = 0.f;
   const bool wb = st.write_back != nullptr && blockIdx.x == 0;
-  for (int i = t; i < K / 4; i += kThreads) {
+  for (int i = t; i < K / 4; i += nthreads) {
 #pragma unroll
     for (int m = 0; m < MT; ++m) {
       if (m >= rpg) break;
@@ -241,7 +298,7 @@ __device__ __forceinline__ void run_job(const Job& J, const Stage& st, float* xs
       if (lane == 0) red[m * kWarps + warp] = v;
     }
   }
-  __syncthreads();
+  __syncthreads();  // activations staged; the barrier initialised by thread 0 is visible
   float rs[MT];
 #pragma unroll
   for (int m = 0; m < MT; ++m) {
@@ -249,7 +306,7 @@ __device__ __forceinline__ void run_job(const Job& J, const Stage& st, float* xs
     if (st.norm_w) {
       float tot = 0.f;
 #pragma unroll
-      for (int w = 0; w < kWarps; ++w) tot += red[m * kWarps + w];
+      for (int w = 0; w < kWarps; ++w) tot += w < nwarps ? red[m * kWarps + w] : 0.f;
       rs[m] = rsqrtf(tot / (float)K + st.eps);
     }
   }
@@ -262,25 +319,21 @@ __device__ __forceinline__ void run_job(const Job& J, const Stage& st, float* xs
 #pragma unroll
       for (int m = 0; m < MT; ++m) acc[w][r][m] = 0.f;
 
+  const int lr0 = (warp * 4 + grp) * R;  // first local weight row of this lane group
+  int lrow[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) lrow[r] = min(lr0 + r, rows_here - 1);
+  ptx::mbar_wait(bar, 0);  // weight slab landed
+#pragma unroll 2
   for (int u = sub; u < units; u += 8) {
-    Unit<FMT> nxt[NW][R];
-    const int un = u + 8;
-    if (un < units) {
-#pragma unroll
-      for (int w = 0; w < NW; ++w)
-#pragma unroll
-        for (int r = 0; r < R; ++r) load_unit<FMT>(nxt[w][r], J.p[w], wrow[r], K, un);
-    }
 #pragma unroll
     for (int w = 0; w < NW; ++w)
 #pragma unroll
-      for (int r = 0; r < R; ++r) dot_unit<FMT, MT>(cur[w][r], xs, Kp, u, acc[w][r]);
-    if (un < units) {
-#pragma unroll
-      for (int w = 0; w < NW; ++w)
-#pragma unroll
-        for (int r = 0; r < R; ++r) cur[w][r] = nxt[w][r];
-    }
+      for (int r = 0; r < R; ++r) {
+        Unit<FMT> un;
+        load_unit<FMT>(un, pl[w], lrow[r], K, u);
+        dot_unit<FMT, MT>(un, xs, Kp, u, acc[w][r]);
+      }
   }
 #pragma unroll
   for (int w = 0; w < NW; ++w)
@@ -297,7 +350,7 @@ __device__ __forceinline__ void run_job(const Job& J, const Stage& st, float* xs
   if (sub == 0) {
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      if (n0 + r >= J.N) break;
+      if (lr0 + r >= rows_here) break;
 #pragma unroll
       for (int m = 0; m < MT; ++m) {
         if (m >= rpg) break;
@@ -306,35 +359,48 @@ __device__ __forceinline__ void run_job(const Job& J, const Stage& st, float* xs
           const float b = acc[1][r][m] * rs[m];
           a = a / (1.f + __expf(-a)) * b;  // SiLU(gate) * up (run_dense_mlp, block.rs:1166-1177)
         }
-        J.out[((long long)g * rpg + m) * J.ldo + n0 + r] = a;
+        J.out[((long long)g * rpg + m) * J.ldo + nb0 + lr0 + r] = a;
       }
     }
   }
 }
 
 template <int FMT, int MT>
-__device__ __forceinline__ void run_fmt(const Job& J, const Stage& st, float* xs, float* red, int local) {
-  if (J.dual) run_job<FMT, MT, 1, 2>(J, st, xs, red, local);
-  else if (J.R == 2) run_job<FMT, MT, 2, 1>(J, st, xs, red, local);
-  else run_job<FMT, MT, 1, 1>(J, st, xs, red, local);
+__device__ __forceinline__ void run_fmt(const Job& J, const Stage& st, float* xs, uint8_t* wsm, uint64_t* bar, float* red,
+                                        int local) {
+  if (J.dual) run_job<FMT, MT, 1, 2>(J, st, xs, wsm, bar, red, local);
+  else if (J.R == 2) run_job<FMT, MT, 2, 1>(J, st, xs, wsm, bar, red, local);
+  else run_job<FMT, MT, 1, 1>(J, st, xs, wsm, bar, red, local);
 }
 
-template <int MT>
+// One kernel per (format pair, MT): the jobs of a launch use at most two block formats (the routed down projection
+// falls back to Q8_0 because 896 % 256 != 0 while the shared one keeps the K-quant).
+template <int FA, int FB, int MT>
 __global__ void __launch_bounds__(kThreads)
 dsq_fused_gemv_kernel(const __grid_constant__ Launch L) {
-  extern __shared__ __align__(16) float xs[];
+  extern __shared__ __align__(128) float xs[];  // [MT][Kp] activations | weight slabs at byte offset L.w_off
   __shared__ float red[MT * kWarps];
+  __shared__ uint64_t bar;
+  uint8_t* wsm = reinterpret_cast<uint8_t*>(xs) + L.w_off;
   int j = 0;
   for (int i = 1; i < L.njobs; ++i)
     if ((int)blockIdx.x >= L.job[i].block0) j = i;
   const Job& J = L.job[j];
   const int local = (int)blockIdx.x - J.block0;
-  switch (J.fmt) {
-    case 8: run_fmt<8, MT>(J, L.st, xs, red, local); break;
-    case 12: run_fmt<12, MT>(J, L.st, xs, red, local); break;
-    case 14: run_fmt<14, MT>(J, L.st, xs, red, local); break;
-    default: run_fmt<0, MT>(J, L.st, xs, red, local); break;
+  if (FA == FB || J.fmt == FA) run_fmt<FA, MT>(J, L.st, xs, wsm, &bar, red, local);
+  else run_fmt<FB, MT>(J, L.st, xs, wsm, &bar, red, local);
+}
+
+template <int FA, int FB>
+void launch_pair(const Launch& L, int blocks, int threads, size_t smem, int max_rpg, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cuda_check(cudaFuncSetAttribute(dsq_fused_gemv_kernel<FA, FB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem), "smem attr");
+    cuda_check(cudaFuncSetAttribute(dsq_fused_gemv_kernel<FA, FB, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem), "smem attr");
+    attr_set = true;
   }
+  if (max_rpg == 1) dsq_fused_gemv_kernel<FA, FB, 1><<<blocks, threads, smem, stream>>>(L);
+  else dsq_fused_gemv_kernel<FA, FB, 4><<<blocks, threads, smem, stream>>>(L);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -349,26 +415,32 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // residual add + RMSNorm(ln2) + router (run_moe, block.rs:1263-1301: f32 gate logits -> softmax -> top-k, ties to
-// the lowest index), one block per token row.  Writes the new residual, the normalised row and the choices.
-template <int E>
-__global__ void __launch_bounds__(1024)
+// the lowest index).  NB blocks per token row: each normalises the row on its own and computes the logits of E/NB
+// experts (one block pulling the whole 328 KB gate weight through one SM took ~9 us); the block that arrives last
+// does softmax + top-k.  Block 0 writes the new residual and the normalised row.
+template <int E, int NB>
+__global__ void __launch_bounds__(256)
 dsq_router_kernel(const float* __restrict__ base, const float* __restrict__ add1, float* __restrict__ xout,
                   const float* __restrict__ w, const float* __restrict__ wgt, float* __restrict__ xn32,
-                  int* __restrict__ topk_idx, float* __restrict__ topk_w, int H, int topk, float eps) {
-  constexpr int KS = 1024 / E;
+                  float* __restrict__ logits_ws, int* __restrict__ counters, int* __restrict__ topk_idx,
+                  float* __restrict__ topk_w, int H, int topk, float eps) {
+  constexpr int EPB = E / NB;
+  constexpr int KS = 256 / EPB;
   constexpr int PER = (E + 31) / 32;
   extern __shared__ float sm[];
   float* xn_s = sm;      // [H]
-  float* part = sm + H;  // [1024]
-  __shared__ float red[32];
+  float* part = sm + H;  // [256]
+  __shared__ float red[8];
+  __shared__ int s_last;
   const long long row = blockIdx.x;
+  const int blk = blockIdx.y;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int n4 = H / 4;
   float ss = 0.f;
-  for (int i = t; i < n4; i += 1024) {
+  for (int i = t; i < n4; i += 256) {
     float4 v = reinterpret_cast<const float4*>(base + row * H)[i];
     add4(v, reinterpret_cast<const float4*>(add1 + row * H)[i]);
-    reinterpret_cast<float4*>(xout + row * H)[i] = v;
+    if (blk == 0) reinterpret_cast<float4*>(xout + row * H)[i] = v;
     reinterpret_cast<float4*>(xn_s)[i] = v;
     ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
   }
@@ -377,75 +449,80 @@ dsq_router_kernel(const float* __restrict__ base, const float* __restrict__ add1
   __syncthreads();
   float tot = 0.f;
 #pragma unroll
-  for (int i = 0; i < 32; ++i) tot += red[i];
+  for (int i = 0; i < 8; ++i) tot += red[i];
   const float inv = rsqrtf(tot / (float)H + eps);
-  for (int i = t; i < n4; i += 1024) {
+  for (int i = t; i < n4; i += 256) {
     float4 v = reinterpret_cast<float4*>(xn_s)[i];
     const float4 ww = reinterpret_cast<const float4*>(w)[i];
     v.x = v.x * inv * ww.x; v.y = v.y * inv * ww.y; v.z = v.z * inv * ww.z; v.w = v.w * inv * ww.w;
     reinterpret_cast<float4*>(xn_s)[i] = v;
-    reinterpret_cast<float4*>(xn32 + row * H)[i] = v;
+    if (blk == 0) reinterpret_cast<float4*>(xn32 + row * H)[i] = v;
   }
   __syncthreads();
   {
-    const int e = t % E, ks = t / E;
+    const int e = blk * EPB + t % EPB, ks = t / EPB;
     const int kper = H / KS;
     const float* wp = wgt + (long long)(ks * kper) * E + e;
     const float* xp = xn_s + ks * kper;
     float acc = 0.f;
-#pragma unroll 16
+#pragma unroll 20
     for (int k = 0; k < kper; ++k) acc = fmaf(xp[k], wp[(long long)k * E], acc);
-    part[ks * E + e] = acc;
+    part[t] = acc;
   }
   __syncthreads();
-  if (warp == 0) {
-    float p[PER];
-    float mx = -INFINITY;
+  if (t < EPB) {
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < KS; ++q) s += part[q * EPB + t];
+    logits_ws[row * E + blk * EPB + t] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  if (t == 0) s_last = atomicAdd(&counters[row], 1) == NB - 1;
+  __syncthreads();
+  if (!s_last || warp != 0) return;
+  __threadfence();
+  float p[PER];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int ee = j * 32 + lane;
+    p[j] = ee < E ? __ldcg(logits_ws + row * E + ee) : -INFINITY;
+    mx = fmaxf(mx, p[j]);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    p[j] = (j * 32 + lane < E) ? expf(p[j] - mx) : 0.f;
+    sum += p[j];
+  }
+  sum = warp_sum(sum);
+#pragma unroll
+  for (int j = 0; j < PER; ++j) p[j] = (j * 32 + lane < E) ? p[j] / sum : -1.f;
+  int my_e = 0; float my_w = 0.f;
+  for (int k = 0; k < topk; ++k) {
+    float bv = -1.f; int bi = 1 << 30;
 #pragma unroll
     for (int j = 0; j < PER; ++j) {
       const int ee = j * 32 + lane;
-      float s = -INFINITY;
-      if (ee < E) {
-        s = 0.f;
-#pragma unroll
-        for (int q = 0; q < KS; ++q) s += part[q * E + ee];
-      }
-      p[j] = s;
-      mx = fmaxf(mx, s);
+      if (ee < E && (p[j] > bv || (p[j] == bv && ee < bi))) { bv = p[j]; bi = ee; }
     }
-    mx = warp_max(mx);
-    float sum = 0.f;
 #pragma unroll
-    for (int j = 0; j < PER; ++j) {
-      p[j] = (j * 32 + lane < E) ? expf(p[j] - mx) : 0.f;
-      sum += p[j];
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
     }
-    sum = warp_sum(sum);
+    if (lane == k) { my_e = bi; my_w = bv; }
 #pragma unroll
-    for (int j = 0; j < PER; ++j) p[j] = (j * 32 + lane < E) ? p[j] / sum : -1.f;
-    int my_e = 0; float my_w = 0.f;
-    for (int k = 0; k < topk; ++k) {
-      float bv = -1.f; int bi = 1 << 30;
-#pragma unroll
-      for (int j = 0; j < PER; ++j) {
-        const int ee = j * 32 + lane;
-        if (ee < E && (p[j] > bv || (p[j] == bv && ee < bi))) { bv = p[j]; bi = ee; }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-      }
-      if (lane == k) { my_e = bi; my_w = bv; }
-#pragma unroll
-      for (int j = 0; j < PER; ++j) if (j * 32 + lane == bi) p[j] = -2.f;
-    }
-    if (lane < topk) {
-      topk_idx[row * topk + lane] = my_e;
-      topk_w[row * topk + lane] = my_w;
-    }
+    for (int j = 0; j < PER; ++j) if (j * 32 + lane == bi) p[j] = -2.f;
   }
+  if (lane < topk) {
+    topk_idx[row * topk + lane] = my_e;
+    topk_w[row * topk + lane] = my_w;
+  }
+  if (lane == 0) counters[row] = 0;  // ready for the next launch (graph replay)
 }
 
 // x = base + (sum_j w_j y_j + add1);  out = RMSNorm(x) * w   (last layer's MoE combine + final norm), block per row
@@ -672,37 +749,73 @@ void dsq_fused_gemv(const DsqFusedJob* jobs, int njobs, const DsqFusedStage& st,
     J.R = (!J.dual && w.N >= 16384) ? 2 : 1;  // wide layers (lm_head): two features per lane share the staged activations
     J.x = s.x; J.ldx = s.ldx; J.groups = s.groups; J.rpg = s.rpg; J.x_row_div = s.x_row_div < 1 ? 1 : s.x_row_div;
     J.row_expert = s.row_expert; J.out = s.out; J.ldo = s.ldo;
-    const int per_block = kWarps * 4 * J.R;
-    J.fblocks = (int)((w.N + per_block - 1) / per_block);
-    J.block0 = blocks;
-    blocks += J.fblocks * J.groups;
+    J.block0 = 0; J.fblocks = 0;
     max_rpg = std::max(max_rpg, s.rpg);
+    if (w.N % 8) throw std::runtime_error("dsq_fused_gemv: weight rows must be a multiple of 8");
     const size_t kp = (size_t)w.K + ((size_t)w.K >> 6) * 4 + 4;
     smem = std::max(smem, kp * 4);
   }
+  // shared memory: [MT][Kp] activations, then the block's weight slabs (rows_pb rows of every plane, x2 for gate/up)
+  const int MT = max_rpg == 1 ? 1 : 4;
+  const size_t x_bytes = (smem * MT + 127) / 128 * 128;
+  auto row_bytes = [](const Job& J) {
+    size_t rb = 0;
+    for (int p = 0; p < 4; ++p)
+      rb += J.fmt == 8 ? plane_row_bytes<8>(J.K, p) : J.fmt == 12 ? plane_row_bytes<12>(J.K, p)
+          : J.fmt == 14 ? plane_row_bytes<14>(J.K, p) : plane_row_bytes<0>(J.K, p);
+    return rb * (J.dual ? 2 : 1);
+  };
+  // Threads per block (= 8 lanes per weight row): as many as keep two blocks resident per SM, fewer when the launch
+  // would otherwise cover less than two waves of blocks (small projections) or the rows are long (K = 6848).
+  int threads = kThreads;
+  size_t slab = 0;
+  for (;; threads /= 2) {
+    blocks = 0; slab = 0;
+    for (int i = 0; i < njobs; ++i) {
+      Job& J = L.job[i];
+      const int per_block = (threads / 32) * 4 * J.R;
+      J.fblocks = (int)((J.N + per_block - 1) / per_block);
+      J.block0 = blocks;
+      blocks += J.fblocks * J.groups;
+      slab = std::max(slab, row_bytes(J) * per_block);
+    }
+    if (threads == 64) break;  // 8 weight rows per block keep every slab a multiple of 16 bytes
+    if (x_bytes + slab > 110 * 1024) continue;
+    if (blocks >= 296 || threads <= 128) break;
+  }
+  if (x_bytes + slab > (size_t)kMaxSmem) throw std::runtime_error("dsq_fused_gemv: weight rows do not fit in shared memory");
+  L.w_off = (int)x_bytes;
+  smem = x_bytes + slab;
   L.st.add1 = st.add1; L.st.add2 = st.add2; L.st.ymoe = st.ymoe; L.st.wmoe = st.wmoe; L.st.topk = st.topk;
   L.st.write_back = st.write_back; L.st.norm_w = st.norm_w; L.st.eps = st.eps;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cuda_check(cudaFuncSetAttribute(dsq_fused_gemv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), "smem attr");
-    cuda_check(cudaFuncSetAttribute(dsq_fused_gemv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), "smem attr");
-    attr_set = true;
+  int fa = L.job[0].fmt, fb = fa;
+  for (int i = 1; i < njobs; ++i) {
+    if (L.job[i].fmt == fa || L.job[i].fmt == fb) continue;
+    if (fb != fa) throw std::runtime_error("dsq_fused_gemv: more than two block formats in one launch");
+    fb = L.job[i].fmt;
   }
-  if (max_rpg == 1) {
-    dsq_fused_gemv_kernel<1><<<blocks, kThreads, smem, stream>>>(L);
-  } else {
-    if (smem * 4 > 200 * 1024) throw std::runtime_error("dsq_fused_gemv: activation rows do not fit in shared memory");
-    dsq_fused_gemv_kernel<4><<<blocks, kThreads, smem * 4, stream>>>(L);
+  if (fa > fb) std::swap(fa, fb);
+  const int key = fa * 16 + fb;
+  switch (key) {
+    case 8 * 16 + 8: launch_pair<8, 8>(L, blocks, threads, smem, max_rpg, stream); break;
+    case 12 * 16 + 12: launch_pair<12, 12>(L, blocks, threads, smem, max_rpg, stream); break;
+    case 14 * 16 + 14: launch_pair<14, 14>(L, blocks, threads, smem, max_rpg, stream); break;
+    case 0: launch_pair<0, 0>(L, blocks, threads, smem, max_rpg, stream); break;
+    case 8 * 16 + 12: launch_pair<8, 12>(L, blocks, threads, smem, max_rpg, stream); break;
+    case 8 * 16 + 14: launch_pair<8, 14>(L, blocks, threads, smem, max_rpg, stream); break;
+    case 0 * 16 + 8: launch_pair<0, 8>(L, blocks, threads, smem, max_rpg, stream); break;
+    default: throw std::runtime_error("dsq_fused_gemv: unsupported block format pair");
   }
   launch_check(tag);
 }
 
 void dsq_router(const float* base, const float* add1, float* xout, const float* w, const float* wgt, float* xn32,
-                int* topk_idx, float* topk_w, long long rows, int H, int E, int topk, float eps, cudaStream_t s) {
-  const size_t smem = (size_t)(H + 1024) * 4;
-  if (H % 4 || topk > 32) throw std::runtime_error("dsq_router: unsupported shape");
-  if (E == 64 && H % 16 == 0) dsq_router_kernel<64><<<(unsigned)rows, 1024, smem, s>>>(base, add1, xout, w, wgt, xn32, topk_idx, topk_w, H, topk, eps);
-  else if (E == 16 && H % 64 == 0) dsq_router_kernel<16><<<(unsigned)rows, 1024, smem, s>>>(base, add1, xout, w, wgt, xn32, topk_idx, topk_w, H, topk, eps);
+                float* logits_ws, int* counters, int* topk_idx, float* topk_w, long long rows, int H, int E, int topk,
+                float eps, cudaStream_t s) {
+  const size_t smem = (size_t)(H + 256) * 4;
+  if (H % 64 || topk > 32) throw std::runtime_error("dsq_router: unsupported shape");
+  if (E == 64) dsq_router_kernel<64, 16><<<dim3((unsigned)rows, 16), 256, smem, s>>>(base, add1, xout, w, wgt, xn32, logits_ws, counters, topk_idx, topk_w, H, topk, eps);
+  else if (E == 16) dsq_router_kernel<16, 4><<<dim3((unsigned)rows, 4), 256, smem, s>>>(base, add1, xout, w, wgt, xn32, logits_ws, counters, topk_idx, topk_w, H, topk, eps);
   else throw std::runtime_error("dsq_router: unsupported expert count");
   launch_check("dsq_router");
 }

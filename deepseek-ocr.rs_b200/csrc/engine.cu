@@ -459,7 +459,7 @@ DevBuf& Engine::ws(const std::string& name, size_t bytes) {
     cuda_check(cudaStreamSynchronize(stream_), "workspace grow sync");
     b.alloc(bytes + bytes / 8);
     if (name == "dsq_iota") iota_n_ = 0;
-    if (name == "dsqf_attn_cnt") cuda_check(cudaMemset(b.p, 0, b.bytes), "attention counters memset");
+    if (name == "dsqf_attn_cnt" || name == "dsqf_router_cnt") cuda_check(cudaMemset(b.p, 0, b.bytes), "attention counters memset");
   }
   return b;
 }

@@ -349,6 +349,8 @@ void Engine::decoder_step_dsq_fused(float* x, long long rows, const int* row_pag
   const int nsplit = dsq_attn_splits(smax);
   float* part = ws("dsqf_attn_part", dsq_attn_ws_floats(rows, heads, nsplit) * 4).as<float>();
   int* counters = ws("dsqf_attn_cnt", (size_t)rows * heads * 4).as<int>();
+  float* router_ws = ws("dsqf_router_logits", (size_t)rows * E * 4).as<float>();
+  int* router_cnt = ws("dsqf_router_cnt", (size_t)rows * 4).as<int>();
 
   float* cur = x;    // residual as of the last kernel that wrote it
   float* alt = x1;
@@ -386,7 +388,8 @@ void Engine::decoder_step_dsq_fused(float* x, long long rows, const int* row_pag
       dsq_fused_gemv(&j, 1, DsqFusedStage(), "dsq_dense_down", stream_);
       pend.add1 = d32;
     } else {
-      dsq_router(cur, o32, alt, L.ln2.as<float>(), L.router_wt.as<float>(), xn, topk_idx, topk_w, rows, H, E, K, c.rms_eps, stream_);
+      dsq_router(cur, o32, alt, L.ln2.as<float>(), L.router_wt.as<float>(), xn, router_ws, router_cnt, topk_idx, topk_w, rows, H, E, K,
+                 c.rms_eps, stream_);
       std::swap(cur, alt);
       {  // routed experts (one group per (token, slot)) + shared experts: gate/up + SwiGLU
         DsqFusedJob j[2];
