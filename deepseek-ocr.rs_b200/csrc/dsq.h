@@ -92,6 +92,7 @@ struct DsqFusedJob {
   long long ldx = 0;
   int groups = 1, rpg = 1, x_row_div = 1;
   const int* row_expert = nullptr;
+  bool expert_dep = false;  // row_expert is produced by the kernel launched immediately before this one
   float* out = nullptr;
   long long ldo = 0;
 };

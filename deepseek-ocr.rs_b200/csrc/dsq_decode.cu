@@ -16,6 +16,8 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <cstdlib>
+#include <utility>
 
 #include "dsq.h"
 #include "kernels.h"
@@ -36,6 +38,7 @@ struct Job {
   const float* x; long long ldx;
   int groups, rpg, x_row_div;
   const int* row_expert;
+  int expert_dep;  // row_expert is written by the kernel launched just before this one
   float* out; long long ldo;
   int block0, fblocks;
 };
@@ -46,6 +49,25 @@ struct Stage {
   const float* norm_w; float eps;
 };
 struct Launch { Job job[kMaxJobs]; int njobs; int w_off; Stage st; };
+
+// Programmatic dependent launch: a kernel of the step is launched while its predecessor still runs; everything before
+// pdl_wait() may only touch data no kernel of the step writes (weights, tables) or data at least two kernels old.
+// Dependents are released after the wait, so at most two kernels of the chain overlap (main part of N, prologue of N+1).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+template <typename... KArgs, typename... Args>
+void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  static const bool pdl = getenv("DSOCR_DSQ_NO_PDL") == nullptr;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  cuda_check(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...), "cudaLaunchKernelEx");
+}
 
 // shared-memory index of activation k: 4 floats of padding per 64 keep the 8 lanes of a feature on distinct banks
 __device__ __forceinline__ int xpad(int k) { return k + ((k >> 6) << 2); }
@@ -220,7 +242,6 @@ __device__ __forceinline__ void run_job(const Job& J, const Stage& st, float* xs
   const int rows_pb = nwarps * 4 * R;                     // weight rows (output features) of a block
   const long long nb0 = (long long)fb * rows_pb;
   const int rows_here = (int)min((long long)rows_pb, J.N - nb0);
-  const long long e = J.row_expert ? J.row_expert[g] : 0;
   const int units = FMT == 8 ? K / 16 : (FMT == 0 ? K / 4 : K / 32);
   constexpr int NP = NPlanes<FMT>::value;
 
@@ -236,9 +257,8 @@ __device__ __forceinline__ void run_job(const Job& J, const Stage& st, float* xs
         pl[w][p] = wsm + off;
         if (p < NP) off += (uint32_t)rows_pb * plane_row_bytes<FMT>(K, p);
       }
-    if (t == 0) {
-      ptx::mbar_init(bar, 1);
-      ptx::fence_barrier_init();
+    auto issue = [&]() {
+      const long long e = J.row_expert ? J.row_expert[g] : 0;
       uint32_t total = 0;
 #pragma unroll
       for (int p = 0; p < NP; ++p) total += (uint32_t)rows_here * plane_row_bytes<FMT>(K, p);
@@ -253,7 +273,16 @@ __device__ __forceinline__ void run_job(const Job& J, const Stage& st, float* xs
           const uint32_t bytes = (uint32_t)rows_here * rb;
           for (uint32_t o = 0; o < bytes; o += 16384) ptx::bulk_load(dst + o, src + o, min(16384u, bytes - o), bar);
         }
+    };
+    const bool early = !(J.row_expert && J.expert_dep);  // the weight stream does not depend on the predecessor
+    if (t == 0) {
+      ptx::mbar_init(bar, 1);
+      ptx::fence_barrier_init();
+      if (early) issue();
     }
+    pdl_wait();
+    pdl_release();
+    if (t == 0 && !early) issue();
   }
 
   // ---- stage the token rows of this group: x = base + (sum_j w_j y_j + add1 + add2), optional RMSNorm weight
@@ -399,8 +428,8 @@ void launch_pair(const Launch& L, int blocks, int threads, size_t smem, int max_
     cuda_check(cudaFuncSetAttribute(dsq_fused_gemv_kernel<FA, FB, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem), "smem attr");
     attr_set = true;
   }
-  if (max_rpg == 1) dsq_fused_gemv_kernel<FA, FB, 1><<<blocks, threads, smem, stream>>>(L);
-  else dsq_fused_gemv_kernel<FA, FB, 4><<<blocks, threads, smem, stream>>>(L);
+  if (max_rpg == 1) launch_pdl(dsq_fused_gemv_kernel<FA, FB, 1>, dim3(blocks), dim3(threads), smem, stream, L);
+  else launch_pdl(dsq_fused_gemv_kernel<FA, FB, 4>, dim3(blocks), dim3(threads), smem, stream, L);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -436,6 +465,10 @@ dsq_router_kernel(const float* __restrict__ base, const float* __restrict__ add1
   const int blk = blockIdx.y;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int n4 = H / 4;
+  // the gate weight (f32 [H][E], shared by the NB blocks of a row) is pulled towards L2 while o_proj still runs
+  for (int line = blk * 256 + t; line * 32 < H * E; line += NB * 256) prefetch_l2(wgt + (size_t)line * 32);
+  pdl_wait();
+  pdl_release();
   float ss = 0.f;
   for (int i = t; i < n4; i += 256) {
     float4 v = reinterpret_cast<const float4*>(base + row * H)[i];
@@ -534,6 +567,8 @@ dsq_combine_norm_kernel(const float* __restrict__ base, const float* __restrict_
   __shared__ float red[8];
   const long long row = blockIdx.x;
   const int t = threadIdx.x;
+  pdl_wait();
+  pdl_release();
   float ss = 0.f;
   for (int i = t; i < H / 4; i += 256) {
     float4 v = reinterpret_cast<const float4*>(base + row * H)[i];
@@ -603,6 +638,15 @@ dsq_attn_split_kernel(const float* __restrict__ qkv, const float* __restrict__ c
   __shared__ float sm_m[16], sm_l[16], sm_acc[16][D];
   __shared__ int s_last;
   const bool tail = sp == nsplit - 1;  // this block also owns the new token
+  const int chunk = (((pos + nsplit - 1) / nsplit) + 31) & ~31;  // cached keys 0..pos-1, 32 per block iteration
+  const int kb = sp * chunk, ke = min(pos, kb + chunk);
+  // this block's K/V range was written by earlier steps: pull it towards L2 while the qkv projection still runs
+  for (int line = t; line * (128 / (int)sizeof(TKV)) < (ke - kb) * D; line += 128) {
+    prefetch_l2(kbase + (long long)kb * D + (long long)line * (128 / (int)sizeof(TKV)));
+    prefetch_l2(vbase + (long long)kb * D + (long long)line * (128 / (int)sizeof(TKV)));
+  }
+  pdl_wait();
+  pdl_release();
   const float* base = qkv + (long long)r * 3 * heads * D;
   if (t < 64) {
     const float c = cos_t[(long long)pos * 64 + t], sn = sin_t[(long long)pos * 64 + t];
@@ -639,8 +683,6 @@ dsq_attn_split_kernel(const float* __restrict__ qkv, const float* __restrict__ c
     for (int i = 0; i < 16; ++i) acc[i] = acc[i] * a + pe * vv[i];
     m = mn;
   };
-  const int chunk = (((pos + nsplit - 1) / nsplit) + 31) & ~31;  // cached keys 0..pos-1, 32 per block iteration
-  const int kb = sp * chunk, ke = min(pos, kb + chunk);
   const TKV* kr = kbase;
   const TKV* vr = vbase;
   for (int ka = kb + warp * 4 + grp; ka < ke; ka += 32) {  // two keys per lane group and iteration
@@ -748,7 +790,7 @@ void dsq_fused_gemv(const DsqFusedJob* jobs, int njobs, const DsqFusedStage& st,
     }
     J.R = (!J.dual && w.N >= 16384) ? 2 : 1;  // wide layers (lm_head): two features per lane share the staged activations
     J.x = s.x; J.ldx = s.ldx; J.groups = s.groups; J.rpg = s.rpg; J.x_row_div = s.x_row_div < 1 ? 1 : s.x_row_div;
-    J.row_expert = s.row_expert; J.out = s.out; J.ldo = s.ldo;
+    J.row_expert = s.row_expert; J.expert_dep = s.expert_dep ? 1 : 0; J.out = s.out; J.ldo = s.ldo;
     J.block0 = 0; J.fblocks = 0;
     max_rpg = std::max(max_rpg, s.rpg);
     if (w.N % 8) throw std::runtime_error("dsq_fused_gemv: weight rows must be a multiple of 8");
@@ -814,15 +856,15 @@ void dsq_router(const float* base, const float* add1, float* xout, const float* 
                 float eps, cudaStream_t s) {
   const size_t smem = (size_t)(H + 256) * 4;
   if (H % 64 || topk > 32) throw std::runtime_error("dsq_router: unsupported shape");
-  if (E == 64) dsq_router_kernel<64, 16><<<dim3((unsigned)rows, 16), 256, smem, s>>>(base, add1, xout, w, wgt, xn32, logits_ws, counters, topk_idx, topk_w, H, topk, eps);
-  else if (E == 16) dsq_router_kernel<16, 4><<<dim3((unsigned)rows, 4), 256, smem, s>>>(base, add1, xout, w, wgt, xn32, logits_ws, counters, topk_idx, topk_w, H, topk, eps);
+  if (E == 64) launch_pdl(dsq_router_kernel<64, 16>, dim3((unsigned)rows, 16), dim3(256), smem, s, base, add1, xout, w, wgt, xn32, logits_ws, counters, topk_idx, topk_w, H, topk, eps);
+  else if (E == 16) launch_pdl(dsq_router_kernel<16, 4>, dim3((unsigned)rows, 4), dim3(256), smem, s, base, add1, xout, w, wgt, xn32, logits_ws, counters, topk_idx, topk_w, H, topk, eps);
   else throw std::runtime_error("dsq_router: unsupported expert count");
   launch_check("dsq_router");
 }
 
 void dsq_combine_norm(const float* base, const float* ymoe, const float* wmoe, int topk, const float* add1,
                       const float* w, float* out, long long rows, int H, float eps, cudaStream_t s) {
-  dsq_combine_norm_kernel<<<(unsigned)rows, 256, (size_t)H * 4, s>>>(base, ymoe, wmoe, topk, add1, w, out, H, eps);
+  launch_pdl(dsq_combine_norm_kernel, dim3((unsigned)rows), dim3(256), (size_t)H * 4, s, base, ymoe, wmoe, topk, add1, w, out, H, eps);
   launch_check("dsq_combine_norm");
 }
 
@@ -835,9 +877,9 @@ void dsq_attn_split(const float* qkv, const float* cos_t, const float* sin_t, vo
   if (head_dim != 128) throw std::runtime_error("dsq_attn_split: head_dim must be 128");
   const dim3 grid((unsigned)(rows * heads), (unsigned)nsplit);
   if (kv_f16)
-    dsq_attn_split_kernel<__half><<<grid, 128, 0, s>>>(qkv, cos_t, sin_t, (__half*)kc, (__half*)vc, row_page, row_pos, part, counters, ctx, heads, smax, scale, nsplit);
+    launch_pdl(dsq_attn_split_kernel<__half>, grid, dim3(128), 0, s, qkv, cos_t, sin_t, (__half*)kc, (__half*)vc, row_page, row_pos, part, counters, ctx, heads, smax, scale, nsplit);
   else
-    dsq_attn_split_kernel<float><<<grid, 128, 0, s>>>(qkv, cos_t, sin_t, (float*)kc, (float*)vc, row_page, row_pos, part, counters, ctx, heads, smax, scale, nsplit);
+    launch_pdl(dsq_attn_split_kernel<float>, grid, dim3(128), 0, s, qkv, cos_t, sin_t, (float*)kc, (float*)vc, row_page, row_pos, part, counters, ctx, heads, smax, scale, nsplit);
   launch_check("dsq_attn_split");
 }
 

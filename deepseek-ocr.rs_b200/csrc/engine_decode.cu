@@ -394,7 +394,7 @@ void Engine::decoder_step_dsq_fused(float* x, long long rows, const int* row_pag
       {  // routed experts (one group per (token, slot)) + shared experts: gate/up + SwiGLU
         DsqFusedJob j[2];
         j[0].w0 = &L.q_exp_gate; j[0].w1 = &L.q_exp_up; j[0].x = xn; j[0].ldx = H; j[0].groups = (int)na; j[0].rpg = 1;
-        j[0].x_row_div = K; j[0].row_expert = topk_idx; j[0].out = h; j[0].ldo = mi;
+        j[0].x_row_div = K; j[0].row_expert = topk_idx; j[0].expert_dep = true; j[0].out = h; j[0].ldo = mi;
         j[1].w0 = &L.q_sh_gate; j[1].w1 = &L.q_sh_up; j[1].x = xn; j[1].ldx = H; j[1].rpg = R; j[1].out = hs; j[1].ldo = S;
         dsq_fused_gemv(j, 2, DsqFusedStage(), "dsq_moe_gate_up", stream_);
       }
