@@ -33,7 +33,7 @@ constexpr int kMaxSmem = 220 * 1024;
 
 struct Job {
   const uint8_t* p[2][4];  // planes a..d of w0 (and w1 for the dual gate/up job)
-  int fmt, K, dual, R;
+  int fmt, K, dual, R, lpr;
   long long N;
   const float* x; long long ldx;
   int groups, rpg, x_row_div;
@@ -133,6 +133,15 @@ __device__ __forceinline__ void bytes_to_f32(uint32_t w, float bias, float* out)
   out[3] = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7443)) - bias;
 }
 constexpr float kMagic = 8388608.f;  // 2^23
+// Small unsigned values (4 or 6 bits, one per byte): PRMT drops the byte into mantissa bits 16..23 of 128.0f, giving
+// 128 + v exactly with no further instruction; the offset leaves through the per-segment activation sums
+// (sum (128 + v_i) x_i - 128 sum x_i), which the K-quant min term needs anyway.
+__device__ __forceinline__ void small_to_f32_plus128(uint32_t w, float* out) {
+  out[0] = __uint_as_float(__byte_perm(w, 0x43000000u, 0x7044));
+  out[1] = __uint_as_float(__byte_perm(w, 0x43000000u, 0x7144));
+  out[2] = __uint_as_float(__byte_perm(w, 0x43000000u, 0x7244));
+  out[3] = __uint_as_float(__byte_perm(w, 0x43000000u, 0x7344));
+}
 
 // 6-bit scale / min of sub-block jx of a Q4_K super-block (ggml get_scale_min_k4) from the header words
 // (hdr.y|z|w = scales[0..3|4..7|8..11]); shifts instead of byte indexing keep the header in registers.
@@ -145,7 +154,7 @@ __device__ __forceinline__ void q4k_scale_min(const uint4& hdr, int jx, int& sc,
 
 // contribution of one unit of one weight row to the MT token rows staged in xs (pitch Kp)
 template <int FMT, int MT>
-__device__ __forceinline__ void dot_unit(const Unit<FMT>& w, const float* xs, int Kp, int u, float* acc) {
+__device__ __forceinline__ void dot_unit(const Unit<FMT>& w, const float* xs, int Kp, const float* xsum, int Sp, int u, float* acc) {
   if constexpr (FMT == 8) {
     const uint32_t* qw = reinterpret_cast<const uint32_t*>(&w.q);
     float wq[16];
@@ -171,26 +180,25 @@ __device__ __forceinline__ void dot_unit(const Unit<FMT>& w, const float* xs, in
     q4k_scale_min(w.hdr, 2 * gq, sc1, m1);
     q4k_scale_min(w.hdr, 2 * gq + 1, sc2, m2);
     const uint32_t* qw = reinterpret_cast<const uint32_t*>(&w.q);
-    float w1[16], w2[16];
+    float w1[16], w2[16];  // 128 + nibble
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      bytes_to_f32(qw[i] & 0x0F0F0F0Fu, kMagic, w1 + 4 * i);
-      bytes_to_f32((qw[i] >> 4) & 0x0F0F0F0Fu, kMagic, w2 + 4 * i);
+      small_to_f32_plus128(qw[i] & 0x0F0F0F0Fu, w1 + 4 * i);
+      small_to_f32_plus128((qw[i] >> 4) & 0x0F0F0F0Fu, w2 + 4 * i);
     }
-    const float ds1 = d * (float)sc1, ds2 = d * (float)sc2, dm1 = dmin * (float)m1, dm2 = dmin * (float)m2;
+    const float ds1 = d * (float)sc1, ds2 = d * (float)sc2;
+    const float c1 = 128.f * ds1 + dmin * (float)m1, c2 = 128.f * ds2 + dmin * (float)m2;
     const int xo1 = xpad(k1), xo2 = xpad(k2);
 #pragma unroll
     for (int m = 0; m < MT; ++m) {
       float x1[16], x2[16];
       lds16(xs + m * Kp + xo1, x1);
       lds16(xs + m * Kp + xo2, x2);
-      float s1 = 0.f, s2 = 0.f, sx1 = 0.f, sx2 = 0.f;
+      const float sx1 = xsum[m * Sp + (k1 >> 4)], sx2 = xsum[m * Sp + (k2 >> 4)];
+      float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        s1 = fmaf(w1[i], x1[i], s1); s2 = fmaf(w2[i], x2[i], s2);
-        sx1 += x1[i]; sx2 += x2[i];
-      }
-      acc[m] += (ds1 * s1 + ds2 * s2) - (dm1 * sx1 + dm2 * sx2);
+      for (int i = 0; i < 16; ++i) { s1 = fmaf(w1[i], x1[i], s1); s2 = fmaf(w2[i], x2[i], s2); }
+      acc[m] += (ds1 * s1 + ds2 * s2) - (c1 * sx1 + c2 * sx2);
     }
   } else if constexpr (FMT == 14) {
     const int sb = u >> 3, j = u & 7, half = j >> 2, jj = j & 3, second = jj >> 1, l0 = (jj & 1) * 16;
@@ -201,13 +209,13 @@ __device__ __forceinline__ void dot_unit(const Unit<FMT>& w, const float* xs, in
     const float d1 = d * (float)w.s1, d2 = d * (float)w.s2;
     const uint32_t* lw = reinterpret_cast<const uint32_t*>(&w.ql);
     const uint32_t* hw = reinterpret_cast<const uint32_t*>(&w.qh);
-    float w1[16], w2[16];
+    float w1[16], w2[16];  // 128 + (low nibble | two high bits << 4); the stored value is that minus 32
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {  // q = (low nibble | two high bits << 4) - 32, four bytes at a time
+    for (int i = 0; i < 4; ++i) {
       const uint32_t a = (lw[i] & 0x0F0F0F0Fu) | (((hw[i] >> sh) & 0x03030303u) << 4);
       const uint32_t b = ((lw[i] >> 4) & 0x0F0F0F0Fu) | (((hw[i] >> (sh + 4)) & 0x03030303u) << 4);
-      bytes_to_f32(a, kMagic + 32.f, w1 + 4 * i);
-      bytes_to_f32(b, kMagic + 32.f, w2 + 4 * i);
+      small_to_f32_plus128(a, w1 + 4 * i);
+      small_to_f32_plus128(b, w2 + 4 * i);
     }
     const int xo1 = xpad(k1), xo2 = xpad(k2);
 #pragma unroll
@@ -215,10 +223,11 @@ __device__ __forceinline__ void dot_unit(const Unit<FMT>& w, const float* xs, in
       float x1[16], x2[16];
       lds16(xs + m * Kp + xo1, x1);
       lds16(xs + m * Kp + xo2, x2);
+      const float sx1 = xsum[m * Sp + (k1 >> 4)], sx2 = xsum[m * Sp + (k2 >> 4)];
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll
       for (int i = 0; i < 16; ++i) { s1 = fmaf(w1[i], x1[i], s1); s2 = fmaf(w2[i], x2[i], s2); }
-      acc[m] += d1 * s1 + d2 * s2;
+      acc[m] += d1 * (s1 - 160.f * sx1) + d2 * (s2 - 160.f * sx2);
     }
   } else {
     const int xo = xpad(u * 4);
@@ -232,14 +241,17 @@ __device__ __forceinline__ void dot_unit(const Unit<FMT>& w, const float* xs, in
 
 __device__ __forceinline__ void add4(float4& a, const float4 b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
 
-template <int FMT, int MT, int R, int NW>
+// LPR = lanes per weight row: 8 for the wide lm_head (few shuffles, R = 2 rows share the staged activations), 32 for the
+// small projections of a batch-1 step (4x the warps and a quarter of the serial work per lane).
+template <int FMT, int MT, int R, int NW, int LPR>
 __device__ __forceinline__ void run_job(const Job& J, const Stage& st, float* xs, uint8_t* wsm, uint64_t* bar, float* red,
                                         int local) {
-  const int t = threadIdx.x, warp = t >> 5, lane = t & 31, grp = lane >> 3, sub = lane & 7;
+  constexpr int RPW = 32 / LPR;  // weight-row groups per warp
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31, grp = lane / LPR, sub = lane % LPR;
   const int nthreads = blockDim.x, nwarps = nthreads >> 5;
   const int K = J.K, Kp = xpad(K), rpg = J.rpg;
   const int g = local / J.fblocks, fb = local % J.fblocks;
-  const int rows_pb = nwarps * 4 * R;                     // weight rows (output features) of a block
+  const int rows_pb = nwarps * RPW * R;                   // weight rows (output features) of a block
   const long long nb0 = (long long)fb * rows_pb;
   const int rows_here = (int)min((long long)rows_pb, J.N - nb0);
   const int units = FMT == 8 ? K / 16 : (FMT == 0 ? K / 4 : K / 32);
@@ -290,32 +302,51 @@ __device__ __forceinline__ void run_job(const Job& J, const Stage& st, float* xs
 #pragma unroll
   for (int m = 0; m < MT; ++m) ss[m] = 0.f;
   const bool wb = st.write_back != nullptr && blockIdx.x == 0;
-  for (int i = t; i < K / 4; i += nthreads) {
+  const int n4 = K / 4, Sp = K / 16;
+  float* xsum = xs + MT * Kp;  // [MT][K/16] sums of the staged activations over 16-element segments
+  for (int i0 = 0; i0 < n4; i0 += nthreads) {  // whole warps iterate together (segment sums use shuffles)
+    const int i = i0 + t;
+    const bool in = i < n4;
 #pragma unroll
     for (int m = 0; m < MT; ++m) {
       if (m >= rpg) break;
       const long long xr = ((long long)g * rpg + m) / J.x_row_div;
-      float4 v = reinterpret_cast<const float4*>(J.x + xr * J.ldx)[i];
-      if (st.ymoe || st.add1 || st.add2) {
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (st.ymoe) {
-          for (int j = 0; j < st.topk; ++j) {
-            const float wj = st.wmoe[xr * st.topk + j];
-            const float4 y = reinterpret_cast<const float4*>(st.ymoe + (xr * st.topk + j) * K)[i];
-            a.x = fmaf(wj, y.x, a.x); a.y = fmaf(wj, y.y, a.y); a.z = fmaf(wj, y.z, a.z); a.w = fmaf(wj, y.w, a.w);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (in) {
+        v = reinterpret_cast<const float4*>(J.x + xr * J.ldx)[i];
+        if (st.ymoe || st.add1 || st.add2) {
+          float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (st.ymoe) {
+            float wj[8]; float4 y[8];  // all expert rows are requested before the first one is consumed
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const bool on = j < st.topk;
+              wj[j] = on ? st.wmoe[xr * st.topk + j] : 0.f;
+              y[j] = on ? reinterpret_cast<const float4*>(st.ymoe + (xr * st.topk + j) * K)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              a.x = fmaf(wj[j], y[j].x, a.x); a.y = fmaf(wj[j], y[j].y, a.y); a.z = fmaf(wj[j], y[j].z, a.z); a.w = fmaf(wj[j], y[j].w, a.w);
+            }
           }
+          if (st.add1) add4(a, reinterpret_cast<const float4*>(st.add1 + xr * K)[i]);
+          if (st.add2) add4(a, reinterpret_cast<const float4*>(st.add2 + xr * K)[i]);
+          add4(v, a);
         }
-        if (st.add1) add4(a, reinterpret_cast<const float4*>(st.add1 + xr * K)[i]);
-        if (st.add2) add4(a, reinterpret_cast<const float4*>(st.add2 + xr * K)[i]);
-        add4(v, a);
+        if (wb) reinterpret_cast<float4*>(st.write_back + xr * K)[i] = v;
+        if (st.norm_w) {
+          ss[m] += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+          const float4 nw = reinterpret_cast<const float4*>(st.norm_w)[i];
+          v.x *= nw.x; v.y *= nw.y; v.z *= nw.z; v.w *= nw.w;
+        }
+        *reinterpret_cast<float4*>(xs + m * Kp + xpad(4 * i)) = v;
       }
-      if (wb) reinterpret_cast<float4*>(st.write_back + xr * K)[i] = v;
-      if (st.norm_w) {
-        ss[m] += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-        const float4 nw = reinterpret_cast<const float4*>(st.norm_w)[i];
-        v.x *= nw.x; v.y *= nw.y; v.z *= nw.z; v.w *= nw.w;
+      if constexpr (FMT == 12 || FMT == 14) {
+        float sg = (v.x + v.y) + (v.z + v.w);
+        sg += __shfl_xor_sync(0xffffffffu, sg, 1);
+        sg += __shfl_xor_sync(0xffffffffu, sg, 2);
+        if (in && (i & 3) == 0) xsum[m * Sp + (i >> 2)] = sg;
       }
-      *reinterpret_cast<float4*>(xs + m * Kp + xpad(4 * i)) = v;
     }
   }
   if (st.norm_w) {
@@ -348,20 +379,20 @@ __device__ __forceinline__ void run_job(const Job& J, const Stage& st, float* xs
 #pragma unroll
       for (int m = 0; m < MT; ++m) acc[w][r][m] = 0.f;
 
-  const int lr0 = (warp * 4 + grp) * R;  // first local weight row of this lane group
+  const int lr0 = (warp * RPW + grp) * R;  // first local weight row of this lane group
   int lrow[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) lrow[r] = min(lr0 + r, rows_here - 1);
   ptx::mbar_wait(bar, 0);  // weight slab landed
 #pragma unroll 2
-  for (int u = sub; u < units; u += 8) {
+  for (int u = sub; u < units; u += LPR) {
 #pragma unroll
     for (int w = 0; w < NW; ++w)
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         Unit<FMT> un;
         load_unit<FMT>(un, pl[w], lrow[r], K, u);
-        dot_unit<FMT, MT>(un, xs, Kp, u, acc[w][r]);
+        dot_unit<FMT, MT>(un, xs, Kp, xsum, Sp, u, acc[w][r]);
       }
   }
 #pragma unroll
@@ -371,9 +402,8 @@ __device__ __forceinline__ void run_job(const Job& J, const Stage& st, float* xs
 #pragma unroll
       for (int m = 0; m < MT; ++m) {
         float v = acc[w][r][m];
-        v += __shfl_xor_sync(0xffffffffu, v, 1);
-        v += __shfl_xor_sync(0xffffffffu, v, 2);
-        v += __shfl_xor_sync(0xffffffffu, v, 4);
+#pragma unroll
+        for (int o = 1; o < LPR; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         acc[w][r][m] = v;
       }
   if (sub == 0) {
@@ -397,9 +427,10 @@ __device__ __forceinline__ void run_job(const Job& J, const Stage& st, float* xs
 template <int FMT, int MT>
 __device__ __forceinline__ void run_fmt(const Job& J, const Stage& st, float* xs, uint8_t* wsm, uint64_t* bar, float* red,
                                         int local) {
-  if (J.dual) run_job<FMT, MT, 1, 2>(J, st, xs, wsm, bar, red, local);
-  else if (J.R == 2) run_job<FMT, MT, 2, 1>(J, st, xs, wsm, bar, red, local);
-  else run_job<FMT, MT, 1, 1>(J, st, xs, wsm, bar, red, local);
+  if (J.R == 2) run_job<FMT, MT, 2, 1, 8>(J, st, xs, wsm, bar, red, local);
+  else if (J.lpr == 8) { if (J.dual) run_job<FMT, MT, 1, 2, 8>(J, st, xs, wsm, bar, red, local); else run_job<FMT, MT, 1, 1, 8>(J, st, xs, wsm, bar, red, local); }
+  else if (J.lpr == 16) { if (J.dual) run_job<FMT, MT, 1, 2, 16>(J, st, xs, wsm, bar, red, local); else run_job<FMT, MT, 1, 1, 16>(J, st, xs, wsm, bar, red, local); }
+  else { if (J.dual) run_job<FMT, MT, 1, 2, 32>(J, st, xs, wsm, bar, red, local); else run_job<FMT, MT, 1, 1, 32>(J, st, xs, wsm, bar, red, local); }
 }
 
 // One kernel per (format pair, MT): the jobs of a launch use at most two block formats (the routed down projection
@@ -574,10 +605,16 @@ dsq_combine_norm_kernel(const float* __restrict__ base, const float* __restrict_
     float4 v = reinterpret_cast<const float4*>(base + row * H)[i];
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
     if (ymoe) {
-      for (int j = 0; j < topk; ++j) {
-        const float wj = wmoe[row * topk + j];
-        const float4 y = reinterpret_cast<const float4*>(ymoe + (row * topk + j) * H)[i];
-        a.x = fmaf(wj, y.x, a.x); a.y = fmaf(wj, y.y, a.y); a.z = fmaf(wj, y.z, a.z); a.w = fmaf(wj, y.w, a.w);
+      float wj[8]; float4 y[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const bool on = j < topk;
+        wj[j] = on ? wmoe[row * topk + j] : 0.f;
+        y[j] = on ? reinterpret_cast<const float4*>(ymoe + (row * topk + j) * H)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        a.x = fmaf(wj[j], y[j].x, a.x); a.y = fmaf(wj[j], y[j].y, a.y); a.z = fmaf(wj[j], y[j].z, a.z); a.w = fmaf(wj[j], y[j].w, a.w);
       }
     }
     if (add1) add4(a, reinterpret_cast<const float4*>(add1 + row * H)[i]);
@@ -743,14 +780,27 @@ dsq_attn_split_kernel(const float* __restrict__ qkv, const float* __restrict__ c
   if (!s_last) return;
   __threadfence();
   const float* all = part + (long long)rh * nsplit * kPartStride;
+  // merge in split order: the per-split (max, sum) pairs meet in shared memory first, then every thread sums its own
+  // output dimension with the loads of 8 splits in flight at a time
+  float* mm = &sm_acc[0][0];      // [nsplit] max   (the per-block merge above is done with sm_acc)
+  float* dd = &sm_acc[1][0];      // [nsplit] sum
+  if (t < nsplit) { mm[t] = __ldcg(all + t * kPartStride); dd[t] = __ldcg(all + t * kPartStride + 1); }
+  __syncthreads();
   float tm = -INFINITY;
-  for (int s = 0; s < nsplit; ++s) tm = fmaxf(tm, __ldcg(all + s * kPartStride));
+  for (int s = 0; s < nsplit; ++s) tm = fmaxf(tm, mm[s]);
   float tn = 0.f, td = 0.f;
-  for (int s = 0; s < nsplit; ++s) {
-    const float ms = __ldcg(all + s * kPartStride);
-    const float f = ms == -INFINITY ? 0.f : __expf(ms - tm);
-    tn += f * __ldcg(all + s * kPartStride + 8 + t);
-    td += f * __ldcg(all + s * kPartStride + 1);
+  for (int s0 = 0; s0 < nsplit; s0 += 8) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = s0 + i < nsplit ? __ldcg(all + (s0 + i) * kPartStride + 8 + t) : 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (s0 + i < nsplit) {
+        const float f = mm[s0 + i] == -INFINITY ? 0.f : __expf(mm[s0 + i] - tm);
+        tn += f * v[i];
+        td += f * dd[s0 + i];
+      }
+    }
   }
   ctx[((long long)r * heads + hd) * D + t] = tn / td;
   if (t == 0) counters[rh] = 0;  // ready for the next step (graph replay)
@@ -788,13 +838,19 @@ void dsq_fused_gemv(const DsqFusedJob* jobs, int njobs, const DsqFusedStage& st,
       J.p[k][0] = (const uint8_t*)ws[k]->a.p; J.p[k][1] = (const uint8_t*)ws[k]->b.p;
       J.p[k][2] = (const uint8_t*)ws[k]->c.p; J.p[k][3] = (const uint8_t*)ws[k]->d.p;
     }
-    J.R = (!J.dual && w.N >= 16384) ? 2 : 1;  // wide layers (lm_head): two features per lane share the staged activations
+    J.R = (!J.dual && w.N >= 16384 && w.N % 64 == 0) ? 2 : 1;  // wide layers (lm_head): 8 lanes per row, two rows per lane group
+    // lanes per weight row: the K-quants have 40 units per 1280-wide row (8 lanes: 5 steps each, no idle lanes),
+    // Q8_0 has 80 (16 lanes: 5 steps; measured 1821 vs 1670 tok/s with 32); DSOCR_DSQ_LPR_K / DSOCR_DSQ_LPR_8 override for experiments
+    static const int lpr_k = getenv("DSOCR_DSQ_LPR_K") ? atoi(getenv("DSOCR_DSQ_LPR_K")) : 8;
+    static const int lpr_8 = getenv("DSOCR_DSQ_LPR_8") ? atoi(getenv("DSOCR_DSQ_LPR_8")) : 16;
+    J.lpr = J.R == 2 ? 8 : ((J.fmt == 12 || J.fmt == 14) ? lpr_k : lpr_8);
+    if (J.lpr != 8 && J.lpr != 16 && J.lpr != 32) throw std::runtime_error("dsq_fused_gemv: lanes per row must be 8, 16 or 32");
     J.x = s.x; J.ldx = s.ldx; J.groups = s.groups; J.rpg = s.rpg; J.x_row_div = s.x_row_div < 1 ? 1 : s.x_row_div;
     J.row_expert = s.row_expert; J.expert_dep = s.expert_dep ? 1 : 0; J.out = s.out; J.ldo = s.ldo;
     J.block0 = 0; J.fblocks = 0;
     max_rpg = std::max(max_rpg, s.rpg);
     if (w.N % 8) throw std::runtime_error("dsq_fused_gemv: weight rows must be a multiple of 8");
-    const size_t kp = (size_t)w.K + ((size_t)w.K >> 6) * 4 + 4;
+    const size_t kp = (size_t)w.K + ((size_t)w.K >> 6) * 4 + 4 + (size_t)w.K / 16;  // padded row + its segment sums
     smem = std::max(smem, kp * 4);
   }
   // shared memory: [MT][Kp] activations, then the block's weight slabs (rows_pb rows of every plane, x2 for gate/up)
@@ -807,23 +863,18 @@ void dsq_fused_gemv(const DsqFusedJob* jobs, int njobs, const DsqFusedStage& st,
           : J.fmt == 14 ? plane_row_bytes<14>(J.K, p) : plane_row_bytes<0>(J.K, p);
     return rb * (J.dual ? 2 : 1);
   };
-  // Threads per block (= 8 lanes per weight row): as many as keep two blocks resident per SM, fewer when the launch
-  // would otherwise cover less than two waves of blocks (small projections) or the rows are long (K = 6848).
-  int threads = kThreads;
+  // Weight rows per 256-thread block: 8 (one warp per row) or 64 (lm_head: 8 lanes per row, 2 rows per lane group).
+  const int threads = kThreads;
   size_t slab = 0;
-  for (;; threads /= 2) {
-    blocks = 0; slab = 0;
-    for (int i = 0; i < njobs; ++i) {
-      Job& J = L.job[i];
-      const int per_block = (threads / 32) * 4 * J.R;
-      J.fblocks = (int)((J.N + per_block - 1) / per_block);
-      J.block0 = blocks;
-      blocks += J.fblocks * J.groups;
-      slab = std::max(slab, row_bytes(J) * per_block);
-    }
-    if (threads == 64) break;  // 8 weight rows per block keep every slab a multiple of 16 bytes
-    if (x_bytes + slab > 110 * 1024) continue;
-    if (blocks >= 296 || threads <= 128) break;
+  blocks = 0;
+  for (int i = 0; i < njobs; ++i) {
+    Job& J = L.job[i];
+    while (J.lpr < 32 && x_bytes + row_bytes(J) * (threads / 32) * (32 / J.lpr) * J.R > 110 * 1024) J.lpr *= 2;  // long rows (K = 6848)
+    const int per_block = (threads / 32) * (32 / J.lpr) * J.R;
+    J.fblocks = (int)((J.N + per_block - 1) / per_block);
+    J.block0 = blocks;
+    blocks += J.fblocks * J.groups;
+    slab = std::max(slab, row_bytes(J) * per_block);
   }
   if (x_bytes + slab > (size_t)kMaxSmem) throw std::runtime_error("dsq_fused_gemv: weight rows do not fit in shared memory");
   L.w_off = (int)x_bytes;
@@ -868,7 +919,7 @@ void dsq_combine_norm(const float* base, const float* ymoe, const float* wmoe, i
   launch_check("dsq_combine_norm");
 }
 
-int dsq_attn_splits(int smax) { return std::max(1, std::min(64, (smax + 63) / 64)); }
+int dsq_attn_splits(int smax) { return std::max(1, std::min(32, (smax + 127) / 128)); }
 size_t dsq_attn_ws_floats(long long rows, int heads, int nsplit) { return (size_t)rows * heads * nsplit * kPartStride; }
 
 void dsq_attn_split(const float* qkv, const float* cos_t, const float* sin_t, void* kc, void* vc, bool kv_f16,
