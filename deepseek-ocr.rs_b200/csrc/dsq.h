@@ -85,9 +85,19 @@ void dsq_gemv(const DsqGemvCall& c, cudaStream_t stream);
 // One launch runs up to 3 GEMV jobs.  A job's token rows come in `groups` of `rpg` (<= 4) rows that share one weight
 // matrix (expert = row_expert[group] or 0); x row of (group g, m) = (g*rpg + m) / x_row_div; out row = g*rpg + m.
 // w1 != nullptr: out = silu(x.w0^T) * (x.w1^T).
+// Weight matrix of a job: a DSQ QuantWeight, or a 16-bit matrix in the engine's pre-tiled streaming layout
+// (retile_weights: 128x64 tiles of 16 KB, rows 128-byte swizzled) - the float engine's decoder weights.
+struct FusedWeight {
+  int fmt = -1;  // 8 / 12 / 14 / 0 (f32): QuantWeight planes; 16 / 17: tiled f16 / bf16
+  long long N = 0;
+  int K = 0;
+  const void* p[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool valid() const { return fmt >= 0; }
+};
+FusedWeight fused_weight(const QuantWeight& w);
+FusedWeight fused_weight_tiled16(const void* tiled, long long N, int K, bool bf16);
 struct DsqFusedJob {
-  const QuantWeight* w0 = nullptr;
-  const QuantWeight* w1 = nullptr;
+  FusedWeight w0, w1;
   const float* x = nullptr;
   long long ldx = 0;
   int groups = 1, rpg = 1, x_row_div = 1;

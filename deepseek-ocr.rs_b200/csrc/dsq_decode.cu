@@ -78,6 +78,8 @@ template <> struct Unit<8> { uint4 q; __half d; };
 template <> struct Unit<12> { uint4 hdr; uint4 q; };
 template <> struct Unit<14> { uint4 ql; uint4 qh; int8_t s1, s2; __half d; };
 template <> struct Unit<0> { float4 w; };
+template <> struct Unit<16> { uint4 w; };  // 8 f16 weights
+template <> struct Unit<17> { uint4 w; };  // 8 bf16 weights
 
 // bytes of one weight row in plane p (the layouts of QuantWeight, dsq.h)
 template <int FMT>
@@ -85,6 +87,7 @@ __device__ __host__ __forceinline__ int plane_row_bytes(int K, int p) {
   if (FMT == 8) return p == 0 ? K : (p == 1 ? K / 16 : 0);
   if (FMT == 12) return p == 0 ? (K / 256) * 144 : 0;
   if (FMT == 14) return p == 0 ? K / 2 : (p == 1 ? K / 4 : (p == 2 ? K / 16 : K / 128));
+  if (FMT == 16 || FMT == 17) return p == 0 ? K * 2 : 0;
   return p == 0 ? K * 4 : 0;
 }
 template <int FMT> struct NPlanes { static constexpr int value = FMT == 8 ? 2 : (FMT == 14 ? 4 : 1); };
@@ -93,7 +96,7 @@ __device__ __forceinline__ uint4 lds128(const uint8_t* p) { return *reinterpret_
 
 // unit u of local row `row` from the block's shared-memory slabs pl[0..3] (same layouts as the global planes)
 template <int FMT>
-__device__ __forceinline__ void load_unit(Unit<FMT>& o, const uint8_t* const* pl, int row, int K, int u) {
+__device__ __forceinline__ void load_unit(Unit<FMT>& o, const uint8_t* const* pl, int row, int K, int u, int rows_pb) {
   if constexpr (FMT == 8) {  // planes: qs int8 [rows][K], d f16 [rows][K/32]
     const int k = u * 16;
     o.q = lds128(pl[0] + row * K + k);
@@ -111,6 +114,11 @@ __device__ __forceinline__ void load_unit(Unit<FMT>& o, const uint8_t* const* pl
     const int is = half * 8 + (jj & 1) + (second ? 2 : 0);
     o.s1 = sc[is]; o.s2 = sc[is + 4];
     o.d = reinterpret_cast<const __half*>(pl[3])[row * (K / 256) + sb];
+  } else if constexpr (FMT == 16 || FMT == 17) {
+    // slab = [k-block][row][128 B]; the 16-byte chunk q of a row sits at position q ^ (row & 7) (128B swizzle of the
+    // tiled layout; the block's first row is a multiple of 8)
+    const int kb = u >> 3, q = u & 7;
+    o.w = lds128(pl[0] + ((size_t)kb * rows_pb + row) * 128 + ((q ^ (row & 7)) << 4));
   } else {
     o.w = *reinterpret_cast<const float4*>(pl[0] + ((size_t)row * K + (size_t)u * 4) * 4);
   }
@@ -229,6 +237,28 @@ __device__ __forceinline__ void dot_unit(const Unit<FMT>& w, const float* xs, in
       for (int i = 0; i < 16; ++i) { s1 = fmaf(w1[i], x1[i], s1); s2 = fmaf(w2[i], x2[i], s2); }
       acc[m] += d1 * (s1 - 160.f * sx1) + d2 * (s2 - 160.f * sx2);
     }
+  } else if constexpr (FMT == 16 || FMT == 17) {
+    const uint32_t* ww = reinterpret_cast<const uint32_t*>(&w.w);
+    float wf[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if constexpr (FMT == 16) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&ww[i]));
+        wf[2 * i] = f.x; wf[2 * i + 1] = f.y;
+      } else {
+        wf[2 * i] = __uint_as_float(ww[i] << 16); wf[2 * i + 1] = __uint_as_float(ww[i] & 0xFFFF0000u);
+      }
+    }
+    const int xo = xpad(u * 8);
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      const float4 a = *reinterpret_cast<const float4*>(xs + m * Kp + xo);
+      const float4 b = *reinterpret_cast<const float4*>(xs + m * Kp + xo + 4);
+      float s0 = wf[0] * a.x;
+      s0 = fmaf(wf[1], a.y, s0); s0 = fmaf(wf[2], a.z, s0); s0 = fmaf(wf[3], a.w, s0);
+      s0 = fmaf(wf[4], b.x, s0); s0 = fmaf(wf[5], b.y, s0); s0 = fmaf(wf[6], b.z, s0); s0 = fmaf(wf[7], b.w, s0);
+      acc[m] += s0;
+    }
   } else {
     const int xo = xpad(u * 4);
 #pragma unroll
@@ -254,7 +284,7 @@ __device__ __forceinline__ void run_job(const Job& J, const Stage& st, float* xs
   const int rows_pb = nwarps * RPW * R;                   // weight rows (output features) of a block
   const long long nb0 = (long long)fb * rows_pb;
   const int rows_here = (int)min((long long)rows_pb, J.N - nb0);
-  const int units = FMT == 8 ? K / 16 : (FMT == 0 ? K / 4 : K / 32);
+  const int units = FMT == 8 ? K / 16 : (FMT == 0 ? K / 4 : ((FMT == 16 || FMT == 17) ? K / 8 : K / 32));
   constexpr int NP = NPlanes<FMT>::value;
 
   // ---- the block's weight rows are contiguous in every plane: bulk copies (TMA) bring the whole slab into shared
@@ -271,6 +301,19 @@ __device__ __forceinline__ void run_job(const Job& J, const Stage& st, float* xs
       }
     auto issue = [&]() {
       const long long e = J.row_expert ? J.row_expert[g] : 0;
+      if constexpr (FMT == 16 || FMT == 17) {  // one copy per 64-wide k-block: rows_here x 128 B contiguous inside a tile
+        const long long grow = e * J.N + nb0;
+        const int num_kb = K / 64;
+        ptx::mbar_expect_tx(bar, (uint32_t)rows_here * (uint32_t)K * 2u * NW);
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+          const uint8_t* src = J.p[w][0] + ((size_t)(grow >> 7) * num_kb) * 16384 + (size_t)(grow & 127) * 128;
+          uint8_t* dst = const_cast<uint8_t*>(pl[w][0]);
+          for (int kb = 0; kb < num_kb; ++kb)
+            ptx::bulk_load(dst + (size_t)kb * rows_pb * 128, src + (size_t)kb * 16384, (uint32_t)rows_here * 128u, bar);
+        }
+        return;
+      }
       uint32_t total = 0;
 #pragma unroll
       for (int p = 0; p < NP; ++p) total += (uint32_t)rows_here * plane_row_bytes<FMT>(K, p);
@@ -391,7 +434,7 @@ __device__ __forceinline__ void run_job(const Job& J, const Stage& st, float* xs
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         Unit<FMT> un;
-        load_unit<FMT>(un, pl[w], lrow[r], K, u);
+        load_unit<FMT>(un, pl[w], lrow[r], K, u, rows_pb);
         dot_unit<FMT, MT>(un, xs, Kp, xsum, Sp, u, acc[w][r]);
       }
   }
@@ -427,10 +470,12 @@ __device__ __forceinline__ void run_job(const Job& J, const Stage& st, float* xs
 template <int FMT, int MT>
 __device__ __forceinline__ void run_fmt(const Job& J, const Stage& st, float* xs, uint8_t* wsm, uint64_t* bar, float* red,
                                         int local) {
+  // lanes per weight row: the K-quants have 40 16-byte units per 1280-wide row (8 lanes: 5 steps each, no idle lane),
+  // Q8_0 has 80 (16 lanes: 5 steps; 1821 vs 1670 tok/s with 32), 16-bit rows 160 (32 lanes: 5 steps)
+  constexpr int LPR = (FMT == 12 || FMT == 14) ? 8 : ((FMT == 16 || FMT == 17) ? 32 : 16);
   if (J.R == 2) run_job<FMT, MT, 2, 1, 8>(J, st, xs, wsm, bar, red, local);
-  else if (J.lpr == 8) { if (J.dual) run_job<FMT, MT, 1, 2, 8>(J, st, xs, wsm, bar, red, local); else run_job<FMT, MT, 1, 1, 8>(J, st, xs, wsm, bar, red, local); }
-  else if (J.lpr == 16) { if (J.dual) run_job<FMT, MT, 1, 2, 16>(J, st, xs, wsm, bar, red, local); else run_job<FMT, MT, 1, 1, 16>(J, st, xs, wsm, bar, red, local); }
-  else { if (J.dual) run_job<FMT, MT, 1, 2, 32>(J, st, xs, wsm, bar, red, local); else run_job<FMT, MT, 1, 1, 32>(J, st, xs, wsm, bar, red, local); }
+  else if (J.dual) run_job<FMT, MT, 1, 2, LPR>(J, st, xs, wsm, bar, red, local);
+  else run_job<FMT, MT, 1, 1, LPR>(J, st, xs, wsm, bar, red, local);
 }
 
 // One kernel per (format pair, MT): the jobs of a launch use at most two block formats (the routed down projection
@@ -806,14 +851,27 @@ dsq_attn_split_kernel(const float* __restrict__ qkv, const float* __restrict__ c
   if (t == 0) counters[rh] = 0;  // ready for the next step (graph replay)
 }
 
-int fmt_code(DsqDType f) {
-  switch (f) {
-    case DsqDType::Q8_0: return 8;
-    case DsqDType::Q4K: return 12;
-    case DsqDType::Q6K: return 14;
-    default: return 0;
+}  // namespace
+
+FusedWeight fused_weight(const QuantWeight& w) {
+  FusedWeight f;
+  switch (w.fmt) {
+    case DsqDType::Q8_0: f.fmt = 8; break;
+    case DsqDType::Q4K: f.fmt = 12; break;
+    case DsqDType::Q6K: f.fmt = 14; break;
+    default: f.fmt = 0; break;
   }
+  f.N = w.N; f.K = w.K;
+  f.p[0] = w.a.p; f.p[1] = w.b.p; f.p[2] = w.c.p; f.p[3] = w.d.p;
+  return f;
 }
+FusedWeight fused_weight_tiled16(const void* tiled, long long N, int K, bool bf16) {
+  FusedWeight f;
+  f.fmt = bf16 ? 17 : 16; f.N = N; f.K = K; f.p[0] = tiled;
+  return f;
+}
+
+namespace {
 
 }  // namespace
 
@@ -825,26 +883,16 @@ void dsq_fused_gemv(const DsqFusedJob* jobs, int njobs, const DsqFusedStage& st,
   size_t smem = 0;
   for (int i = 0; i < njobs; ++i) {
     const DsqFusedJob& s = jobs[i];
-    const QuantWeight& w = *s.w0;
+    const FusedWeight& w = s.w0;
     Job& J = L.job[i];
-    J.fmt = fmt_code(w.fmt); J.K = w.K; J.N = w.N; J.dual = s.w1 ? 1 : 0;
-    const int gran = J.fmt == 8 ? 16 : (J.fmt == 0 ? 4 : 256);
-    if (w.K % gran || w.K % 4) throw std::runtime_error("dsq_fused_gemv: unsupported K for this block format");
-    if (s.w1 && (s.w1->fmt != w.fmt || s.w1->K != w.K || s.w1->N != w.N)) throw std::runtime_error("dsq_fused_gemv: gate/up formats differ");
+    J.fmt = w.fmt; J.K = w.K; J.N = w.N; J.dual = s.w1.valid() ? 1 : 0;
+    const int gran = J.fmt == 8 ? 32 : (J.fmt == 0 ? 16 : (J.fmt >= 16 ? 64 : 256));
+    if (!w.valid() || w.K % gran) throw std::runtime_error("dsq_fused_gemv: unsupported K for this weight format");
+    if (J.dual && (s.w1.fmt != w.fmt || s.w1.K != w.K || s.w1.N != w.N)) throw std::runtime_error("dsq_fused_gemv: gate/up formats differ");
     if (s.rpg < 1 || s.rpg > 4 || s.groups < 1) throw std::runtime_error("dsq_fused_gemv: 1..4 rows per group");
-    const QuantWeight* ws[2] = {s.w0, s.w1};
-    for (int k = 0; k < 2; ++k) {
-      if (!ws[k]) continue;
-      J.p[k][0] = (const uint8_t*)ws[k]->a.p; J.p[k][1] = (const uint8_t*)ws[k]->b.p;
-      J.p[k][2] = (const uint8_t*)ws[k]->c.p; J.p[k][3] = (const uint8_t*)ws[k]->d.p;
-    }
+    for (int q = 0; q < 4; ++q) { J.p[0][q] = (const uint8_t*)w.p[q]; J.p[1][q] = (const uint8_t*)s.w1.p[q]; }
     J.R = (!J.dual && w.N >= 16384 && w.N % 64 == 0) ? 2 : 1;  // wide layers (lm_head): 8 lanes per row, two rows per lane group
-    // lanes per weight row: the K-quants have 40 units per 1280-wide row (8 lanes: 5 steps each, no idle lanes),
-    // Q8_0 has 80 (16 lanes: 5 steps; measured 1821 vs 1670 tok/s with 32); DSOCR_DSQ_LPR_K / DSOCR_DSQ_LPR_8 override for experiments
-    static const int lpr_k = getenv("DSOCR_DSQ_LPR_K") ? atoi(getenv("DSOCR_DSQ_LPR_K")) : 8;
-    static const int lpr_8 = getenv("DSOCR_DSQ_LPR_8") ? atoi(getenv("DSOCR_DSQ_LPR_8")) : 16;
-    J.lpr = J.R == 2 ? 8 : ((J.fmt == 12 || J.fmt == 14) ? lpr_k : lpr_8);
-    if (J.lpr != 8 && J.lpr != 16 && J.lpr != 32) throw std::runtime_error("dsq_fused_gemv: lanes per row must be 8, 16 or 32");
+    J.lpr = J.R == 2 ? 8 : ((J.fmt == 12 || J.fmt == 14) ? 8 : (J.fmt >= 16 ? 32 : 16));  // == run_fmt's LPR
     J.x = s.x; J.ldx = s.ldx; J.groups = s.groups; J.rpg = s.rpg; J.x_row_div = s.x_row_div < 1 ? 1 : s.x_row_div;
     J.row_expert = s.row_expert; J.expert_dep = s.expert_dep ? 1 : 0; J.out = s.out; J.ldo = s.ldo;
     J.block0 = 0; J.fblocks = 0;
@@ -860,21 +908,27 @@ void dsq_fused_gemv(const DsqFusedJob* jobs, int njobs, const DsqFusedStage& st,
     size_t rb = 0;
     for (int p = 0; p < 4; ++p)
       rb += J.fmt == 8 ? plane_row_bytes<8>(J.K, p) : J.fmt == 12 ? plane_row_bytes<12>(J.K, p)
-          : J.fmt == 14 ? plane_row_bytes<14>(J.K, p) : plane_row_bytes<0>(J.K, p);
+          : J.fmt == 14 ? plane_row_bytes<14>(J.K, p) : J.fmt >= 16 ? plane_row_bytes<16>(J.K, p) : plane_row_bytes<0>(J.K, p);
     return rb * (J.dual ? 2 : 1);
   };
   // Weight rows per 256-thread block: 8 (one warp per row) or 64 (lm_head: 8 lanes per row, 2 rows per lane group).
-  const int threads = kThreads;
+  int threads = kThreads;
+  for (int i = 0; i < njobs; ++i)
+    if (L.job[i].R == 2 && L.job[i].fmt >= 16) threads = 128;  // 16-bit lm_head: 32 rows (80 KB) per block, two blocks per SM
   size_t slab = 0;
-  blocks = 0;
-  for (int i = 0; i < njobs; ++i) {
-    Job& J = L.job[i];
-    while (J.lpr < 32 && x_bytes + row_bytes(J) * (threads / 32) * (32 / J.lpr) * J.R > 110 * 1024) J.lpr *= 2;  // long rows (K = 6848)
-    const int per_block = (threads / 32) * (32 / J.lpr) * J.R;
-    J.fblocks = (int)((J.N + per_block - 1) / per_block);
-    J.block0 = blocks;
-    blocks += J.fblocks * J.groups;
-    slab = std::max(slab, row_bytes(J) * per_block);
+  for (;; threads /= 2) {  // long rows (K = 6848) with 4 token rows staged: fewer weight rows per block
+    slab = 0; blocks = 0;
+    int min_rows = 1 << 30;
+    for (int i = 0; i < njobs; ++i) {
+      Job& J = L.job[i];
+      const int per_block = (threads / 32) * (32 / J.lpr) * J.R;
+      J.fblocks = (int)((J.N + per_block - 1) / per_block);
+      J.block0 = blocks;
+      blocks += J.fblocks * J.groups;
+      slab = std::max(slab, row_bytes(J) * per_block);
+      min_rows = std::min(min_rows, per_block);
+    }
+    if (x_bytes + slab <= (size_t)kMaxSmem || min_rows < 16) break;  // a block keeps >= 8 rows (slab alignment, swizzle phase)
   }
   if (x_bytes + slab > (size_t)kMaxSmem) throw std::runtime_error("dsq_fused_gemv: weight rows do not fit in shared memory");
   L.w_off = (int)x_bytes;
@@ -897,6 +951,8 @@ void dsq_fused_gemv(const DsqFusedJob* jobs, int njobs, const DsqFusedStage& st,
     case 8 * 16 + 12: launch_pair<8, 12>(L, blocks, threads, smem, max_rpg, stream); break;
     case 8 * 16 + 14: launch_pair<8, 14>(L, blocks, threads, smem, max_rpg, stream); break;
     case 0 * 16 + 8: launch_pair<0, 8>(L, blocks, threads, smem, max_rpg, stream); break;
+    case 16 * 16 + 16: launch_pair<16, 16>(L, blocks, threads, smem, max_rpg, stream); break;
+    case 17 * 16 + 17: launch_pair<17, 17>(L, blocks, threads, smem, max_rpg, stream); break;
     default: throw std::runtime_error("dsq_fused_gemv: unsupported block format pair");
   }
   launch_check(tag);

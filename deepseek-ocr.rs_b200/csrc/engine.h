@@ -112,8 +112,8 @@ class Engine {
   void load_weights(const std::string& path, const DsqReader* dsq);
   void decoder_forward_dsq(float* x, long long rows, const int* row_page, const int* row_pos, int smax,
                            const int* final_rows, int n_final, float* logits);
-  // one decode step for <= 4 pages with 6 launches per layer (dsq_decode.cu)
-  void decoder_step_dsq_fused(float* x, long long rows, const int* row_page, const int* row_pos, int smax, float* logits);
+  // one decode step for <= 4 pages with 6 launches per layer (dsq_decode.cu), DSQ snapshot or 16-bit weights
+  void decoder_step_fused_small(float* x, long long rows, const int* row_page, const int* row_pos, int smax, float* logits);
  public:
   bool quantized() const { return quantized_; }
  private:
@@ -147,7 +147,8 @@ class Engine {
   bool streamk_ = getenv("DSOCR_NO_STREAMK") == nullptr;  // A/B switch: balanced static units instead
   DevBuf sk_ws_, sk_flags_;  // stream-K partial slots + hand-off flags of the decode-time expert GEMMs
   bool quantized_ = false;
-  bool dsq_fused_ = getenv("DSOCR_DSQ_UNFUSED") == nullptr;  // A/B switch: the unfused per-linear GEMV path
+  // A/B switch: decode steps of <= 4 pages through the batched kernels (float engine) / per-linear GEMVs (DSQ)
+  bool small_fused_ = getenv("DSOCR_DSQ_UNFUSED") == nullptr && getenv("DSOCR_NO_SMALL_FUSED") == nullptr;
   QuantWeight q_lm_head_;
   long long iota_n_ = 0;
   std::map<std::string, std::vector<float>> taps_;

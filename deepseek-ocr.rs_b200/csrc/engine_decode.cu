@@ -324,16 +324,21 @@ void Engine::decoder_forward_dsq(float* x, long long rows, const int* row_page, 
   gemv(q_lm_head_, xf, H, logits, c.vocab, n_final, false, "dsq_lm_head");
 }
 
-// Decode step for <= 4 pages over a DSQ snapshot with 6 launches per layer (see dsq_decode.cu).  The residual
-// stream ping-pongs between x (the embedding rows on entry) and x1: a kernel that folds pending adds into the
-// residual while staging its activations writes the sum to the other buffer, which no block of that launch reads.
-void Engine::decoder_step_dsq_fused(float* x, long long rows, const int* row_page, const int* row_pos, int smax, float* logits) {
+// Decode step for <= 4 pages with 6 launches per layer (see dsq_decode.cu): f32 activations against either the DSQ
+// snapshot's quantised blocks or the float engine's pre-tiled 16-bit weights.  The residual stream ping-pongs between
+// x (the embedding rows on entry) and x1: a kernel that folds pending adds into the residual while staging its
+// activations writes the sum to the other buffer, which no block of that launch reads.
+void Engine::decoder_step_fused_small(float* x, long long rows, const int* row_page, const int* row_pos, int smax, float* logits) {
   const ModelConfig& c = cfg_;
   const int H = c.hidden, heads = c.heads, E = c.n_experts, K = c.topk, mi = c.moe_inter;
   const long long S = (long long)mi * c.n_shared;
   const float scale = 1.0f / sqrtf((float)c.head_dim());
   const long long na = rows * K;
   const int R = (int)rows;
+  const bool bf = dt_ == DType::BF16;
+  auto W = [&](const QuantWeight& q, const DevBuf& t, long long N, int Kin) {
+    return quantized_ ? fused_weight(q) : fused_weight_tiled16(t.p, N, Kin, bf);
+  };
   float* x1 = ws("dsqf_x1", rows * H * 4).as<float>();
   float* qkv = ws("dec_qkv32", rows * 3 * H * 4).as<float>();
   float* ctx = ws("dsq_ctx32", rows * H * 4).as<float>();
@@ -361,9 +366,16 @@ void Engine::decoder_step_dsq_fused(float* x, long long rows, const int* row_pag
       DsqFusedStage st = pend;
       st.write_back = alt; st.norm_w = L.ln1.as<float>(); st.eps = c.rms_eps;
       DsqFusedJob j[3];
-      const QuantWeight* w[3] = {&L.q_q, &L.q_k, &L.q_v};
-      for (int i = 0; i < 3; ++i) { j[i].w0 = w[i]; j[i].x = cur; j[i].ldx = H; j[i].rpg = R; j[i].out = qkv + (long long)i * H; j[i].ldo = 3 * H; }
-      dsq_fused_gemv(j, 3, st, "dsq_qkv", stream_);
+      int nj = 1;
+      if (quantized_) {
+        const QuantWeight* w[3] = {&L.q_q, &L.q_k, &L.q_v};
+        for (int i = 0; i < 3; ++i) { j[i].w0 = fused_weight(*w[i]); j[i].out = qkv + (long long)i * H; }
+        nj = 3;
+      } else {
+        j[0].w0 = fused_weight_tiled16(L.qkv_w.p, 3 * H, H, bf); j[0].out = qkv;
+      }
+      for (int i = 0; i < nj; ++i) { j[i].x = cur; j[i].ldx = H; j[i].rpg = R; j[i].ldo = 3 * H; }
+      dsq_fused_gemv(j, nj, st, "fs_qkv", stream_);
       std::swap(cur, alt);
       pend = DsqFusedStage();
     }
@@ -371,21 +383,22 @@ void Engine::decoder_step_dsq_fused(float* x, long long rows, const int* row_pag
                    part, counters, ctx, rows, heads, c.head_dim(), smax, scale, nsplit, stream_);
     {
       DsqFusedJob j;
-      j.w0 = &L.q_o; j.x = ctx; j.ldx = H; j.rpg = R; j.out = o32; j.ldo = H;
-      dsq_fused_gemv(&j, 1, DsqFusedStage(), "dsq_o_proj", stream_);
+      j.w0 = W(L.q_o, L.o_w, H, H); j.x = ctx; j.ldx = H; j.rpg = R; j.out = o32; j.ldo = H;
+      dsq_fused_gemv(&j, 1, DsqFusedStage(), "fs_o_proj", stream_);
     }
     if (!L.moe) {
       {  // residual + o_proj, RMSNorm(ln2), gate/up + SwiGLU
         DsqFusedStage st;
         st.add1 = o32; st.write_back = alt; st.norm_w = L.ln2.as<float>(); st.eps = c.rms_eps;
         DsqFusedJob j;
-        j.w0 = &L.q_gate; j.w1 = &L.q_up; j.x = cur; j.ldx = H; j.rpg = R; j.out = h; j.ldo = c.inter;
-        dsq_fused_gemv(&j, 1, st, "dsq_dense_gate_up", stream_);
+        j.w0 = W(L.q_gate, L.gate_w, c.inter, H); j.w1 = W(L.q_up, L.up_w, c.inter, H);
+        j.x = cur; j.ldx = H; j.rpg = R; j.out = h; j.ldo = c.inter;
+        dsq_fused_gemv(&j, 1, st, "fs_dense_gate_up", stream_);
         std::swap(cur, alt);
       }
       DsqFusedJob j;
-      j.w0 = &L.q_down; j.x = h; j.ldx = c.inter; j.rpg = R; j.out = d32; j.ldo = H;
-      dsq_fused_gemv(&j, 1, DsqFusedStage(), "dsq_dense_down", stream_);
+      j.w0 = W(L.q_down, L.down_w, H, c.inter); j.x = h; j.ldx = c.inter; j.rpg = R; j.out = d32; j.ldo = H;
+      dsq_fused_gemv(&j, 1, DsqFusedStage(), "fs_dense_down", stream_);
       pend.add1 = d32;
     } else {
       dsq_router(cur, o32, alt, L.ln2.as<float>(), L.router_wt.as<float>(), xn, router_ws, router_cnt, topk_idx, topk_w, rows, H, E, K,
@@ -393,26 +406,28 @@ void Engine::decoder_step_dsq_fused(float* x, long long rows, const int* row_pag
       std::swap(cur, alt);
       {  // routed experts (one group per (token, slot)) + shared experts: gate/up + SwiGLU
         DsqFusedJob j[2];
-        j[0].w0 = &L.q_exp_gate; j[0].w1 = &L.q_exp_up; j[0].x = xn; j[0].ldx = H; j[0].groups = (int)na; j[0].rpg = 1;
+        j[0].w0 = W(L.q_exp_gate, L.exp_gate, mi, H); j[0].w1 = W(L.q_exp_up, L.exp_up, mi, H);
+        j[0].x = xn; j[0].ldx = H; j[0].groups = (int)na; j[0].rpg = 1;
         j[0].x_row_div = K; j[0].row_expert = topk_idx; j[0].expert_dep = true; j[0].out = h; j[0].ldo = mi;
-        j[1].w0 = &L.q_sh_gate; j[1].w1 = &L.q_sh_up; j[1].x = xn; j[1].ldx = H; j[1].rpg = R; j[1].out = hs; j[1].ldo = S;
-        dsq_fused_gemv(j, 2, DsqFusedStage(), "dsq_moe_gate_up", stream_);
+        j[1].w0 = W(L.q_sh_gate, L.sh_gate, S, H); j[1].w1 = W(L.q_sh_up, L.sh_up, S, H);
+        j[1].x = xn; j[1].ldx = H; j[1].rpg = R; j[1].out = hs; j[1].ldo = S;
+        dsq_fused_gemv(j, 2, DsqFusedStage(), "fs_moe_gate_up", stream_);
       }
       {
         DsqFusedJob j[2];
-        j[0].w0 = &L.q_exp_down; j[0].x = h; j[0].ldx = mi; j[0].groups = (int)na; j[0].rpg = 1; j[0].row_expert = topk_idx;
-        j[0].out = y; j[0].ldo = H;
-        j[1].w0 = &L.q_sh_down; j[1].x = hs; j[1].ldx = S; j[1].rpg = R; j[1].out = ysh; j[1].ldo = H;
-        dsq_fused_gemv(j, 2, DsqFusedStage(), "dsq_moe_down", stream_);
+        j[0].w0 = W(L.q_exp_down, L.exp_down, H, mi); j[0].x = h; j[0].ldx = mi; j[0].groups = (int)na; j[0].rpg = 1;
+        j[0].row_expert = topk_idx; j[0].out = y; j[0].ldo = H;
+        j[1].w0 = W(L.q_sh_down, L.sh_down, H, (int)S); j[1].x = hs; j[1].ldx = S; j[1].rpg = R; j[1].out = ysh; j[1].ldo = H;
+        dsq_fused_gemv(j, 2, DsqFusedStage(), "fs_moe_down", stream_);
       }
       pend.ymoe = y; pend.wmoe = topk_w; pend.topk = K; pend.add1 = ysh;
     }
   }
-  // last layer's combine + final RMSNorm once (2020 lm_head blocks would each redo it), then the lm_head GEMV
+  // last layer's combine + final RMSNorm once (the lm_head blocks would each redo it), then the lm_head GEMV
   dsq_combine_norm(cur, pend.ymoe, pend.wmoe, pend.topk, pend.add1, final_norm_.as<float>(), xn, rows, H, c.rms_eps, stream_);
   DsqFusedJob j;
-  j.w0 = &q_lm_head_; j.x = xn; j.ldx = H; j.rpg = R; j.out = logits; j.ldo = c.vocab;
-  dsq_fused_gemv(&j, 1, DsqFusedStage(), "dsq_lm_head", stream_);
+  j.w0 = W(q_lm_head_, lm_head_, c.vocab, H); j.x = xn; j.ldx = H; j.rpg = R; j.out = logits; j.ldo = c.vocab;
+  dsq_fused_gemv(&j, 1, DsqFusedStage(), "fs_lm_head", stream_);
 }
 
 void Engine::generate(const GenRequest& rq, int64_t* const* out_tokens, int* n_out) {
@@ -552,7 +567,7 @@ void Engine::generate(const GenRequest& rq, int64_t* const* out_tokens, int* n_o
   auto run_step = [&](int step) {
     decode_rows(d_hist, smax, d_hist_len, d_src, d_row_pos, P, stream_);
     embed_gather(d_src, embed_.p, nullptr, x, P, H, dt_, stream_);
-    if (quantized_ && P <= 4 && dsq_fused_) decoder_step_dsq_fused(x, P, d_row_page, d_row_pos, smax, logits);
+    if (P <= 4 && small_fused_ && (quantized_ || w_tiled_) && !record_taps_) decoder_step_fused_small(x, P, d_row_page, d_row_pos, smax, logits);
     else if (quantized_) decoder_forward_dsq(x, P, d_row_page, d_row_pos, smax, d_row_page, P, logits);
     else decoder_forward(x, P, d_row_page, d_row_pos, smax, d_row_page /* identity: every row */, P, logits, true);
     copy_logits(step);

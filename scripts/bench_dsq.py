@@ -22,7 +22,8 @@ import torch  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--primary", default="q4k", choices=["q4k", "q6k", "q8_0"])
+    ap.add_argument("--primary", default="q4k", choices=["q4k", "q6k", "q8_0", "float"],
+                    help="snapshot format, or `float`: the 16-bit engine without a snapshot (batch-1 decode of configs[1]/[2])")
     ap.add_argument("--tokens", type=int, default=256)
     ap.add_argument("--pages", type=int, default=1)
     ap.add_argument("--config", default="full", choices=["full", "tiny"])
@@ -34,9 +35,11 @@ def main():
     class A: pass
     a = A(); a.config = args.config; a.dtype = args.dtype
     cfg, ckdir = B.ensure_checkpoint(a, 0)
-    primary = {"q4k": dsq.Q4K, "q6k": dsq.Q6K, "q8_0": dsq.Q8_0}[args.primary]
+    primary = {"q4k": dsq.Q4K, "q6k": dsq.Q6K, "q8_0": dsq.Q8_0, "float": None}[args.primary]
     snap = ckdir / f"model.{args.primary}.dsq"
-    if not snap.exists():
+    if primary is None:
+        snap = None
+    elif not snap.exists():
         t0 = time.time()
         ck = OC.load_checkpoint(str(ckdir / "model.safetensors"))
         dsq.write_model_snapshot(str(snap), cfg, ck, primary)
@@ -45,7 +48,7 @@ def main():
     from dsocr.engine import DecodeParameters, load_model
 
     t0 = time.time()
-    eng = load_model(str(ckdir / "config.json"), str(ckdir / "model.safetensors"), str(snap), 0, args.dtype)
+    eng = load_model(str(ckdir / "config.json"), str(ckdir / "model.safetensors"), None if snap is None else str(snap), 0, args.dtype)
     print(f"[dsq] engine load {time.time() - t0:.1f}s", file=sys.stderr)
     eng.set_option("kv_cache_f16", 1)
     g = torch.Generator().manual_seed(0)
@@ -66,16 +69,16 @@ def main():
     kt = [r for r in eng.kernel_timing_end() if r["name"].startswith("decode/")]
     kt.sort(key=lambda r: -r["ms"])
     H, V = cfg.hidden_size, cfg.vocab_size
-    bytes_lm = V * H * 34 / 32
-    lm = next((r for r in kt if r["name"].endswith("dsq_lm_head")), None)
+    bytes_lm = V * H * (2 if args.primary == "float" else 34 / 32)
+    lm = next((r for r in kt if r["name"].endswith("fs_lm_head")), None)
     tok_s = args.pages * (args.tokens - 1) / (tm["decode.iterative"] * 1e-3)
     # algorithmic weight bytes per token: q4k 449 MB, q8_0 610 MB at batch 1
-    per_tok = {"q4k": 449e6, "q6k": None, "q8_0": 610e6}[args.primary]
+    per_tok = {"q4k": 449e6, "q6k": None, "q8_0": 610e6, "float": 1148e6}[args.primary]
     # KV bytes read per token at the mean context of the run (f16 cache: K and V, 12 layers)
     mean_ctx = len(ids[0]) + args.tokens / 2
     kv_per_tok = 2 * cfg.hidden_size * cfg.num_layers * 2 * mean_ctx
-    line = {"config": f"deepseek-ocr-{args.primary} DSQ dequant-fused decode, batch {args.pages}, {args.tokens}-token output, random-init weights",
-            "path": "unfused" if os.environ.get("DSOCR_DSQ_UNFUSED") else "fused step (dsq_decode.cu)",
+    line = {"config": f"deepseek-ocr-{args.primary} ({args.dtype} engine) decode, batch {args.pages}, {args.tokens}-token output, random-init weights",
+            "path": "batched kernels / per-linear GEMVs" if (os.environ.get("DSOCR_DSQ_UNFUSED") or os.environ.get("DSOCR_NO_SMALL_FUSED")) else "fused small-batch step (dsq_decode.cu)",
             "launches_per_token": round(launches / max(1, args.tokens), 1),
             "hbm_GBps_weights_plus_kv": ((per_tok + kv_per_tok) * tok_s / args.pages / 1e9) if per_tok else None,
             "decode_tok_s": tok_s, "ms_per_token": tm["decode.iterative"] / (args.tokens - 1), "wall_s": wall,
