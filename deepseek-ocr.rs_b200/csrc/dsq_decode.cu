@@ -930,7 +930,21 @@ void dsq_fused_gemv(const DsqFusedJob* jobs, int njobs, const DsqFusedStage& st,
     }
     if (x_bytes + slab <= (size_t)kMaxSmem || min_rows < 16) break;  // a block keeps >= 8 rows (slab alignment, swizzle phase)
   }
-  if (x_bytes + slab > (size_t)kMaxSmem) throw std::runtime_error("dsq_fused_gemv: weight rows do not fit in shared memory");
+  if (x_bytes + slab > (size_t)kMaxSmem) {
+    // long rows (the dense down projection, K = 6848) with several token rows staged: one launch per token row
+    const bool plain = !st.add1 && !st.add2 && !st.ymoe && !st.write_back && !st.norm_w;
+    if (njobs == 1 && jobs[0].groups == 1 && jobs[0].rpg > 1 && jobs[0].x_row_div <= 1 && !jobs[0].row_expert && plain) {
+      for (int m = 0; m < jobs[0].rpg; ++m) {
+        DsqFusedJob one = jobs[0];
+        one.rpg = 1;
+        one.x = jobs[0].x + (long long)m * jobs[0].ldx;
+        one.out = jobs[0].out + (long long)m * jobs[0].ldo;
+        dsq_fused_gemv(&one, 1, st, tag, stream);
+      }
+      return;
+    }
+    throw std::runtime_error("dsq_fused_gemv: weight rows do not fit in shared memory");
+  }
   L.w_off = (int)x_bytes;
   smem = x_bytes + slab;
   L.st.add1 = st.add1; L.st.add2 = st.add2; L.st.ymoe = st.ymoe; L.st.wmoe = st.wmoe; L.st.topk = st.topk;
