@@ -161,3 +161,31 @@ def test_large_prefill_batch_paths(setup):
     for p in range(len(ids)):
         ref = oracle.generate(ids[p], masks[p], torch.from_numpy(rows[p]), 6, 20, None)
         assert got[p] == ref
+
+
+@pytest.mark.parametrize("n_pages", [1, 2])
+def test_small_batch_fused_step_f16_engine(n_pages):
+    """Decode steps of <= 4 pages run the fused small-batch step (dsq_decode.cu) on the engine's pre-tiled 16-bit
+    weights with f32 activations; here with an f16 checkpoint/engine (the bf16 engine is covered by the tests above,
+    whose batches are <= 4 pages).  Teacher-forced logits and free-running tokens against the f32 oracle."""
+    from dsocr.engine import DecodeParameters, load_model
+
+    cfg, ck, d = tiny_model("f16")
+    eng = load_model(d + "/config.json", d + "/model.safetensors", None, 0, "f16")
+    oracle = D.DecoderOracle(cfg, ck)
+    ids, masks, rows = _prompts(cfg, [29, 3][:n_pages], seed=31)
+    steps = 20
+    g = torch.Generator().manual_seed(13)
+    forced = [torch.randint(2, cfg.vocab_size - 2, (steps,), generator=g).tolist() for _ in ids]
+    params = DecodeParameters(max_new_tokens=steps, no_repeat_ngram_size=20, eos_token_id=None)
+    sel, logits = eng.generate_forced(ids, masks, rows, params, forced, want_logits=True)
+    free = eng.generate_batch(ids, masks, rows, DecodeParameters(max_new_tokens=24, no_repeat_ngram_size=20, eos_token_id=None))
+    for p in range(len(ids)):
+        ref_logits = []
+        rt = None if rows[p] is None else torch.from_numpy(rows[p])
+        ref_sel = oracle.generate(ids[p], masks[p], rt, steps, 20, None, forced=forced[p], logits_out=ref_logits)
+        err, scale, c = report(f"f16 engine, {n_pages} page(s), fused small-batch step, page {p}", torch.from_numpy(logits[p]), torch.stack(ref_logits))
+        assert err <= 2e-3 * scale and c > 0.999999
+        assert sel[p] == ref_sel
+        assert free[p] == oracle.generate(ids[p], masks[p], rt, 24, 20, None)
+    eng.close()
