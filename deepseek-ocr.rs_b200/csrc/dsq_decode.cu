@@ -280,7 +280,8 @@ __device__ __forceinline__ void run_job(const Job& J, const Stage& st, float* xs
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31, grp = lane / LPR, sub = lane % LPR;
   const int nthreads = blockDim.x, nwarps = nthreads >> 5;
   const int K = J.K, Kp = xpad(K), rpg = J.rpg;
-  const int g = local / J.fblocks, fb = local % J.fblocks;
+  // (integer division by a run-time value costs ~25 instructions; most jobs have one group)
+  const int g = J.groups == 1 ? 0 : local / J.fblocks, fb = local - g * J.fblocks;
   const int rows_pb = nwarps * RPW * R;                   // weight rows (output features) of a block
   const long long nb0 = (long long)fb * rows_pb;
   const int rows_here = (int)min((long long)rows_pb, J.N - nb0);
@@ -353,7 +354,7 @@ __device__ __forceinline__ void run_job(const Job& J, const Stage& st, float* xs
 #pragma unroll
     for (int m = 0; m < MT; ++m) {
       if (m >= rpg) break;
-      const long long xr = ((long long)g * rpg + m) / J.x_row_div;
+      const long long xr = J.x_row_div == 1 ? (long long)g * rpg + m : ((long long)g * rpg + m) / J.x_row_div;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (in) {
         v = reinterpret_cast<const float4*>(J.x + xr * J.ldx)[i];
@@ -427,7 +428,9 @@ __device__ __forceinline__ void run_job(const Job& J, const Stage& st, float* xs
 #pragma unroll
   for (int r = 0; r < R; ++r) lrow[r] = min(lr0 + r, rows_here - 1);
   ptx::mbar_wait(bar, 0);  // weight slab landed
-#pragma unroll 2
+  // not unrolled: a step's kernels run for a few microseconds each and ncu attributes ~49 % of their stall samples to
+  // instruction fetch (stall_no_inst); the executed path is kept short instead
+#pragma unroll 1
   for (int u = sub; u < units; u += LPR) {
 #pragma unroll
     for (int w = 0; w < NW; ++w)
