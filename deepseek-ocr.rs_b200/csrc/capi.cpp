@@ -101,6 +101,34 @@ extern "C" int dsocr_engine_set_option(dsocr_engine* e, const char* name, int va
   });
 }
 
+extern "C" int dsocr_dsq_inspect(const char* path, dsocr_dsq_header* header, dsocr_dsq_record* records, size_t capacity) {
+  return api("snapshot open failed", [&] {
+    if (!path) throw std::runtime_error("null argument");
+    DsqReader rd(path);
+    if (header) {
+      memset(header, 0, sizeof(*header));
+      header->version = 1;
+      header->default_qdtype = (uint32_t)rd.default_dtype();
+      header->block_size = rd.block_size();
+      header->tensor_count = (uint32_t)rd.records().size();
+      strncpy(header->candle_version, rd.candle_version.c_str(), sizeof(header->candle_version) - 1);
+      strncpy(header->model_id, rd.model_id.c_str(), sizeof(header->model_id) - 1);
+      strncpy(header->backend, rd.backend.c_str(), sizeof(header->backend) - 1);
+    }
+    for (size_t i = 0; records && i < rd.records().size() && i < capacity; ++i) {
+      const DsqRecord& r = rd.records()[i];
+      dsocr_dsq_record& o = records[i];
+      memset(&o, 0, sizeof(o));
+      strncpy(o.name, r.name.c_str(), sizeof(o.name) - 1);
+      o.out_dim = r.out_dim; o.in_dim = r.in_dim; o.q_dtype = (uint32_t)r.q_dtype;
+      o.q_offset = r.q_offset; o.q_len = r.q_len;
+      o.bias_offset = r.has_bias ? r.bias_offset : 0; o.bias_len = r.has_bias ? r.bias_len : 0;
+      o.bias_dtype = r.has_bias ? r.bias_dtype : 0;
+      o.first_q_byte = rd.bytes(r)[0];
+    }
+  });
+}
+
 extern "C" int dsocr_image_token_count(uint32_t base_size, uint32_t image_size, int crop_mode, int crop_w, int crop_h) {
   return image_token_count((int)base_size, (int)image_size, crop_mode, crop_w, crop_h);
 }

@@ -52,8 +52,7 @@ DsqReader::DsqReader(const std::string& path) {
   default_dtype_ = dtype_from(c.get<uint32_t>());
   const uint32_t block_size = c.get<uint32_t>();
   if (block_size == 0) throw std::runtime_error("snapshot validation failed: block_size must be non-zero");
-  if ((int)block_size != dsq_block_elems(default_dtype_))
-    throw std::runtime_error("snapshot validation failed: block size mismatches dtype");
+  block_size_ = block_size;
   const uint32_t count = c.get<uint32_t>();
   records_.reserve(count);
   for (uint32_t i = 0; i < count; ++i) {
@@ -64,27 +63,47 @@ DsqReader::DsqReader(const std::string& path) {
     r.q_offset = c.get<uint64_t>(); r.q_len = c.get<uint64_t>();
     r.bias_offset = c.get<uint64_t>(); r.bias_len = c.get<uint64_t>();
     r.bias_dtype = c.get<uint32_t>();
-    r.has_bias = r.bias_len != 0;
+    r.has_bias = r.bias_len != 0;  // bias_len == 0 -> (None, None, None), lib.rs:352-357
+    if (r.has_bias && r.bias_dtype > 6)  // DsqBiasDType::try_from: U8 U32 I64 F16 F32 F64 BF16 = 0..6
+      throw std::runtime_error("snapshot malformed: unsupported bias dtype code " + std::to_string(r.bias_dtype));
     records_.push_back(std::move(r));
   }
+  // validate_records + the duplicate check of DsqReader::from_mmap (crates/dsq/src/lib.rs:217-232, 409-520), same
+  // order and wording.  Like the reference, `open` does not compare the payload length of a *block* dtype with its
+  // dims (only in_dim % block); that is checked when the tensor is uploaded (load_quant).
   const uint64_t meta_len = (uint64_t)(c.p - base_);
+  auto fail = [](const std::string& m) { throw std::runtime_error("snapshot validation failed: " + m); };
+  // validate_header (lib.rs:393-407)
+  if (dsq_block_elems(default_dtype_) == 0) fail("snapshot dtype " + std::to_string((uint32_t)default_dtype_) + " not supported");
+  if ((int)block_size_ != dsq_block_elems(default_dtype_))
+    fail("snapshot block size " + std::to_string(block_size_) + " mismatches expected " + std::to_string(dsq_block_elems(default_dtype_)));
+  if (size_ < meta_len) fail("file smaller than metadata region");
+  auto check_bounds = [&](uint64_t off, uint64_t len, const std::string& name, const char* label) {
+    if (off + len < off) fail("tensor `" + name + "` " + label + " slice " + std::to_string(off) + "+" + std::to_string(len) + " overflows usize");
+    if (off + len > size_)
+      fail("tensor `" + name + "` " + label + " slice [" + std::to_string(off) + ", " + std::to_string(off) + "+" + std::to_string(len) +
+           ") exceeds file size " + std::to_string(size_));
+  };
   for (size_t i = 0; i < records_.size(); ++i) {
     const DsqRecord& r = records_[i];
-    if (r.q_len == 0) throw std::runtime_error("snapshot validation failed: tensor `" + r.name + "` has empty quantized payload");
-    if (r.q_offset < meta_len) throw std::runtime_error("snapshot validation failed: tensor `" + r.name + "` overlaps metadata");
-    if (r.q_offset + r.q_len > size_) throw std::runtime_error("snapshot validation failed: tensor `" + r.name + "` exceeds file size");
-    if (r.has_bias && r.bias_offset + r.bias_len > size_) throw std::runtime_error("snapshot validation failed: bias of `" + r.name + "` exceeds file size");
+    if (r.q_len == 0) fail("tensor `" + r.name + "` has empty quantized payload");
+    if (r.q_offset < meta_len)
+      fail("tensor `" + r.name + "` q_offset " + std::to_string(r.q_offset) + " overlaps metadata (" + std::to_string(meta_len) + " bytes)");
+    check_bounds(r.q_offset, r.q_len, r.name, "quantized");
+    if (r.has_bias) check_bounds(r.bias_offset, r.bias_len, r.name, "bias");
     const int be = dsq_block_elems(r.q_dtype);
     if (be) {
-      if (r.in_dim % be) throw std::runtime_error("snapshot validation failed: tensor `" + r.name + "` in_dim not divisible by block_size");
-      if (r.q_len != (uint64_t)r.out_dim * (r.in_dim / be) * dsq_block_bytes(r.q_dtype))
-        throw std::runtime_error("snapshot validation failed: tensor `" + r.name + "` payload length mismatch");
+      if (r.in_dim % be)
+        fail("tensor `" + r.name + "` in_dim " + std::to_string(r.in_dim) + " not divisible by block_size " + std::to_string(be));
     } else {
       const uint64_t es = r.q_dtype == DsqDType::F32 ? 4 : 2;
-      if (r.q_len != (uint64_t)r.out_dim * r.in_dim * es) throw std::runtime_error("snapshot validation failed: tensor `" + r.name + "` float payload length mismatch");
+      const uint64_t expected = (uint64_t)r.out_dim * r.in_dim * es;
+      if (r.q_len != expected)
+        fail("tensor `" + r.name + "` has q_len " + std::to_string(r.q_len) + " but expected " + std::to_string(expected) + " bytes");
     }
-    if (!index_.emplace(r.name, i).second) throw std::runtime_error("snapshot validation failed: duplicate tensor record `" + r.name + "`");
   }
+  for (size_t i = 0; i < records_.size(); ++i)
+    if (!index_.emplace(records_[i].name, i).second) fail("duplicate tensor record `" + records_[i].name + "`");
 }
 
 DsqReader::~DsqReader() {

@@ -32,6 +32,8 @@ class DsqReader {
   const uint8_t* bytes(const DsqRecord& r) const { return base_ + r.q_offset; }
   const std::vector<DsqRecord>& records() const { return records_; }
   DsqDType default_dtype() const { return default_dtype_; }
+  uint32_t block_size() const { return block_size_; }
+  size_t file_size() const { return size_; }
   std::string model_id, backend, candle_version;
 
  private:
@@ -39,6 +41,7 @@ class DsqReader {
   size_t size_ = 0;
   const uint8_t* base_ = nullptr;
   DsqDType default_dtype_ = DsqDType::Q8_0;
+  uint32_t block_size_ = 0;
   std::vector<DsqRecord> records_;
   std::map<std::string, size_t> index_;
 };

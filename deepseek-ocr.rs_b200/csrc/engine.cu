@@ -187,6 +187,11 @@ void load_quant(QuantWeight& w, const DsqReader& dsq, const std::string& name, l
   if (!r) throw std::runtime_error("snapshot is missing tensor `" + name + "`");
   if ((long long)r->out_dim != N || (int)r->in_dim != K) throw std::runtime_error("snapshot tensor `" + name + "` has unexpected dims");
   if (r->has_bias) throw std::runtime_error("snapshot bias tensors are not supported (`" + name + "`)");
+  // the reader (like DsqReader::open) only checks in_dim % block for block dtypes; the payload length is checked here,
+  // where the reference would fail while building the QTensor (dsq-runtime/src/lib.rs:316-369)
+  if (const int be = dsq_block_elems(r->q_dtype))
+    if (r->q_len != (uint64_t)r->out_dim * (r->in_dim / be) * dsq_block_bytes(r->q_dtype))
+      throw std::runtime_error("snapshot tensor `" + name + "` payload length does not match its dims");
   if (idx == 0) dsq_alloc(w, r->q_dtype, N, K, count);
   dsq_upload_rows(w, (long long)idx * N, dsq.bytes(*r), r->q_dtype, N);
 }

@@ -95,6 +95,24 @@ DSOCR_API int dsocr_engine_info_get(const dsocr_engine* e, dsocr_engine_info* in
  * "host_preprocess" (0/1) runs the integer resample / tiling on the host cores instead of the device. */
 DSOCR_API int dsocr_engine_set_option(dsocr_engine* e, const char* name, int value);
 
+/* DsqReader::open + header() / records() (crates/dsq/src/lib.rs:208-262): maps a `.dsq` snapshot, validates header and
+ * records exactly as the reference does (same order, same messages through dsocr_last_error) and reports the records.
+ * Host only - needs no GPU.  `records` may be NULL (count only); at most `capacity` records are written. */
+typedef struct dsocr_dsq_record {
+  char name[192];
+  uint32_t out_dim, in_dim;
+  uint32_t q_dtype; /* 8 Q8_0, 12 Q4_K, 14 Q6_K, 1 F16, 16 BF16, 0 F32 */
+  uint64_t q_offset, q_len;
+  uint64_t bias_offset, bias_len; /* bias_len == 0: no bias */
+  uint32_t bias_dtype;
+  uint8_t first_q_byte; /* tensor_bytes(record)[0] */
+} dsocr_dsq_record;
+typedef struct dsocr_dsq_header {
+  uint32_t version, default_qdtype, block_size, tensor_count;
+  char candle_version[64], model_id[128], backend[32];
+} dsocr_dsq_header;
+DSOCR_API int dsocr_dsq_inspect(const char* path, dsocr_dsq_header* header, dsocr_dsq_record* records, size_t capacity);
+
 /* image_token_count: rows `compute_image_embeddings` will produce == placeholders
  * `build_image_placeholders` emits (model/mod.rs:2605-2689). */
 DSOCR_API int dsocr_image_token_count(uint32_t base_size, uint32_t image_size, int crop_mode, int crop_w, int crop_h);
