@@ -129,6 +129,53 @@ extern "C" int dsocr_dsq_inspect(const char* path, dsocr_dsq_header* header, dso
   });
 }
 
+struct dsocr_dsq_writer { std::unique_ptr<DsqWriter> impl; };
+
+static DsqDType writer_dtype(uint32_t v) {
+  switch (v) {
+    case 0: case 1: case 8: case 12: case 14: case 16: return static_cast<DsqDType>(v);
+    default: throw std::runtime_error("unsupported tensor dtype code " + std::to_string(v));
+  }
+}
+
+extern "C" int dsocr_dsq_writer_create(const char* path, const char* candle_version, const char* model_id, const char* backend,
+                                       uint32_t default_qdtype, dsocr_dsq_writer** out) {
+  return api("snapshot writer", [&] {
+    if (!path || !out) throw std::runtime_error("null argument");
+    auto h = std::make_unique<dsocr_dsq_writer>();
+    h->impl = std::make_unique<DsqWriter>(path, candle_version ? candle_version : "", model_id ? model_id : "",
+                                          backend ? backend : "", writer_dtype(default_qdtype));
+    *out = h.release();
+  });
+}
+
+extern "C" int dsocr_dsq_writer_add_tensor(dsocr_dsq_writer* w, const char* name, uint32_t out_dim, uint32_t in_dim, uint32_t q_dtype,
+                                           const float* weights, const float* bias) {
+  return api("snapshot writer", [&] {
+    if (!w || !w->impl || !name || !weights) throw std::runtime_error("null argument");
+    w->impl->add_tensor_f32(name, out_dim, in_dim, writer_dtype(q_dtype), weights, bias);
+  });
+}
+
+extern "C" int dsocr_dsq_writer_add_quantized_bytes(dsocr_dsq_writer* w, const char* name, uint32_t out_dim, uint32_t in_dim,
+                                                    uint32_t q_dtype, const uint8_t* qbytes, size_t q_len, const float* bias) {
+  return api("snapshot writer", [&] {
+    if (!w || !w->impl || !name || !qbytes) throw std::runtime_error("null argument");
+    w->impl->add_quantized_bytes(name, out_dim, in_dim, writer_dtype(q_dtype), qbytes, q_len, bias);
+  });
+}
+
+extern "C" int dsocr_dsq_writer_finalize(dsocr_dsq_writer* w) {
+  const int st = api("snapshot writer", [&] {
+    if (!w || !w->impl) throw std::runtime_error("null argument");
+    w->impl->finalize();
+  });
+  delete w;
+  return st;
+}
+
+extern "C" void dsocr_dsq_writer_destroy(dsocr_dsq_writer* w) { delete w; }
+
 extern "C" int dsocr_image_token_count(uint32_t base_size, uint32_t image_size, int crop_mode, int crop_w, int crop_h) {
   return image_token_count((int)base_size, (int)image_size, crop_mode, crop_w, crop_h);
 }

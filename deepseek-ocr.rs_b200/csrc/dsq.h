@@ -46,6 +46,35 @@ class DsqReader {
   std::map<std::string, size_t> index_;
 };
 
+// DsqWriter (crates/dsq-writer/src/lib.rs:93-527): collects tensors and emits header | records | payload.  Host only.
+class DsqWriter {
+ public:
+  DsqWriter(const std::string& path, const std::string& candle_version, const std::string& model_id, const std::string& backend,
+            DsqDType default_dtype);
+  // quantise (Q8_0 / Q4_K / Q6_K) or convert (F32 / F16 / BF16) a row-major f32 matrix [out_dim, in_dim]; bias: out_dim f32 or null
+  void add_tensor_f32(const std::string& name, uint32_t out_dim, uint32_t in_dim, DsqDType dt, const float* w, const float* bias);
+  // blocks quantised elsewhere (add_quantized_bytes, :366-409)
+  void add_quantized_bytes(const std::string& name, uint32_t out_dim, uint32_t in_dim, DsqDType dt, const uint8_t* q, size_t q_len,
+                           const float* bias);
+  void finalize();
+  const std::string& path() const { return path_; }
+
+ private:
+  struct Pending {
+    std::string name;
+    uint32_t out_dim = 0, in_dim = 0;
+    DsqDType dtype = DsqDType::Q8_0;
+    uint64_t q_offset = 0, q_len = 0, bias_offset = 0, bias_len = 0;
+    bool has_bias = false;
+  };
+  void check_new(const std::string& name, DsqDType dt, uint32_t in_dim) const;
+  void append(const std::string& name, uint32_t out_dim, uint32_t in_dim, DsqDType dt, const uint8_t* q, size_t q_len, const float* bias);
+  std::string path_, candle_version_, model_id_, backend_;
+  DsqDType default_dtype_;
+  std::vector<uint8_t> payload_;
+  std::vector<Pending> records_;
+};
+
 inline int dsq_block_elems(DsqDType t) { return t == DsqDType::Q8_0 ? 32 : (t == DsqDType::Q4K || t == DsqDType::Q6K) ? 256 : 0; }
 inline int dsq_block_bytes(DsqDType t) { return t == DsqDType::Q8_0 ? 34 : t == DsqDType::Q4K ? 144 : t == DsqDType::Q6K ? 210 : 0; }
 

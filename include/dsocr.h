@@ -113,6 +113,21 @@ typedef struct dsocr_dsq_header {
 } dsocr_dsq_header;
 DSOCR_API int dsocr_dsq_inspect(const char* path, dsocr_dsq_header* header, dsocr_dsq_record* records, size_t capacity);
 
+/* DsqWriter (crates/dsq-writer/src/lib.rs:93-527), host only: `create` (the path gets the `.dsq` extension, as
+ * Path::with_extension does), `add_tensor` quantises a row-major f32 [out_dim, in_dim] matrix to q_dtype (8 Q8_0 with the
+ * reference's quantize_q8_0; 12 / 14 Q4_K / Q6_K with ggml-style reference quantisers - valid blocks, not byte-pinned to
+ * candle's from_float; 0 / 1 / 16 float payloads), `add_quantized_bytes` == the reference method of that name,
+ * `finalize` writes the file and frees the handle.  bias: out_dim f32 values or NULL. */
+typedef struct dsocr_dsq_writer dsocr_dsq_writer;
+DSOCR_API int dsocr_dsq_writer_create(const char* path, const char* candle_version, const char* model_id, const char* backend,
+                                      uint32_t default_qdtype, dsocr_dsq_writer** out);
+DSOCR_API int dsocr_dsq_writer_add_tensor(dsocr_dsq_writer* w, const char* name, uint32_t out_dim, uint32_t in_dim, uint32_t q_dtype,
+                                          const float* weights, const float* bias);
+DSOCR_API int dsocr_dsq_writer_add_quantized_bytes(dsocr_dsq_writer* w, const char* name, uint32_t out_dim, uint32_t in_dim,
+                                                   uint32_t q_dtype, const uint8_t* qbytes, size_t q_len, const float* bias);
+DSOCR_API int dsocr_dsq_writer_finalize(dsocr_dsq_writer* w);
+DSOCR_API void dsocr_dsq_writer_destroy(dsocr_dsq_writer* w);
+
 /* image_token_count: rows `compute_image_embeddings` will produce == placeholders
  * `build_image_placeholders` emits (model/mod.rs:2605-2689). */
 DSOCR_API int dsocr_image_token_count(uint32_t base_size, uint32_t image_size, int crop_mode, int crop_w, int crop_h);
