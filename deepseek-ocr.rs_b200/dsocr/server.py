@@ -1,0 +1,218 @@
+"""OpenAI-compatible `/v1/chat/completions` (+ `/v1/models`, `/v1/health`) on top of the batcher: the routes of
+crates/server/src/routes.rs:33-222 with the message handling of generation.rs:169-300 (latest user message plus the
+system messages before it; content parts are flattened in reverse order, images become `<image>` placeholders; only
+`data:` URLs carry images here - this box has no egress for http(s) ones) and the SSE chunks of stream.rs:160-370
+(`chat.completion.chunk`: a role chunk, UTF-8-safe content deltas from DeltaTracker, a `finish_reason: "stop"` chunk with
+usage, `[DONE]`).  Unlike the reference, concurrent requests do not queue on an engine mutex: they are batched."""
+from __future__ import annotations
+
+import asyncio
+import base64
+import io
+import json
+import time
+import uuid
+from typing import Any, Callable, Dict, List, Optional, Tuple
+
+import numpy as np
+from fastapi import FastAPI, Request
+from fastapi.responses import JSONResponse, StreamingResponse
+
+from .batcher import PageBatcher, PageRequest
+from .report import split_prompt_on_image, tokenize_segments
+from .streaming import DeltaTracker
+
+MISSING_IMAGE = ("⚠️ **Image Required**\n\n- This OCR backend expects at least one `<image>` placeholder or attached image.\n"
+                 "- Please include `input_image` / `image_url`, or add `<image>` inside the prompt.\n\n---\n\n"
+                 "⚠️ **需要图像输入**\n\n- 当前 OCR 模型需要至少一个 `<image>` 占位符或实际图片。\n"
+                 "- 请在请求中附带 `input_image`/`image_url`，或在 prompt 中插入 `<image>`。")
+EOS_TEXT = "<｜end▁of▁sentence｜>"
+
+
+class BadRequest(Exception):
+    pass
+
+
+def load_image(url: str) -> np.ndarray:
+    from PIL import Image
+
+    if url.startswith("data:"):
+        meta, sep, payload = url[5:].partition(",")
+        if not sep:
+            raise BadRequest("invalid data URL")
+        if not meta.endswith(";base64"):
+            raise BadRequest("data URLs must specify base64 encoding")
+        try:
+            raw = base64.b64decode(payload, validate=True)
+            return np.asarray(Image.open(io.BytesIO(raw)).convert("RGB"))
+        except Exception as ex:
+            raise BadRequest(f"failed to decode inline image: {ex}")
+    if url.startswith("http://") or url.startswith("https://"):
+        raise BadRequest("remote image URLs are not reachable from this server (no egress); send a data: URL")
+    raise BadRequest("only data: URIs or http(s) image URLs are supported")
+
+
+def flatten_content(content: Any) -> Tuple[str, List[np.ndarray]]:
+    """generation.rs:246-268."""
+    if content is None:
+        return "", []
+    if isinstance(content, str):
+        return content.strip(), []
+    buf, images = "", []
+    for part in reversed(content):
+        kind = part.get("type")
+        if kind in ("image_url", "input_image"):
+            spec = part.get("image_url")
+            buf += "<image>"
+            images.append(load_image(spec if isinstance(spec, str) else (spec or {}).get("url", "")))
+        elif kind in ("text", "input_text"):
+            if buf:
+                buf += "\n"
+            buf += part.get("text", "")
+        else:
+            raise BadRequest(f"unsupported content part type `{kind}`")
+    return buf.strip(), images
+
+
+def convert_messages(messages: List[Dict[str, Any]]) -> Tuple[str, List[np.ndarray]]:
+    """generation.rs:181-243: only one round of prompt is kept (the model is not trained for dialogue)."""
+    idx = None
+    for i, m in enumerate(messages):
+        if str(m.get("role", "")).lower() == "user":
+            idx = i
+    if idx is None:
+        raise BadRequest("request must include at least one user message")
+    sections, images = [], []
+    for m in messages[:idx]:
+        if str(m.get("role", "")).lower() != "system":
+            continue
+        text, imgs = flatten_content(m.get("content"))
+        if text:
+            sections.append(text)
+        images += imgs
+    text, imgs = flatten_content(messages[idx].get("content"))
+    if text:
+        sections.append(text)
+    images += imgs
+    if not sections and not images:
+        raise BadRequest("user content must include text or images")
+    return "\n\n".join(sections).strip(), images
+
+
+def create_app(batcher: PageBatcher, tokenizer: Any, image_token_id: int, model_id: str = "deepseek-ocr",
+               vision: Tuple[int, int, bool] = (1024, 640, True), max_new_tokens: int = 512, no_repeat_ngram_size: int = 20):
+    app = FastAPI(title="dsocr-b200")
+
+    def decode_text(ids: List[int]) -> str:
+        return tokenizer.decode(ids, skip_special_tokens=False) if ids else ""
+
+    def final_text(ids: List[int]) -> str:
+        return decode_text(ids).replace("\r\n", "\n").replace(EOS_TEXT, "").strip()  # normalize_text (inference.rs:228-233)
+
+    @app.get("/v1/health")
+    def health():
+        return {"status": "ok"}
+
+    @app.get("/v1/models")
+    def models():
+        return {"object": "list", "data": [{"id": model_id, "object": "model", "created": 0, "owned_by": "dsocr-b200"}]}
+
+    def chat_body(text: str, prompt_tokens: int, completion_tokens: int):
+        return {"id": f"chatcmpl-{uuid.uuid4()}", "object": "chat.completion", "created": int(time.time()), "model": model_id,
+                "choices": [{"index": 0, "message": {"role": "assistant", "content": text}, "finish_reason": "stop"}],
+                "usage": {"prompt_tokens": prompt_tokens, "completion_tokens": completion_tokens,
+                          "total_tokens": prompt_tokens + completion_tokens}}
+
+    @app.post("/v1/chat/completions")
+    async def chat(request: Request):
+        try:
+            req = await request.json()
+        except Exception:
+            return JSONResponse({"error": {"message": "invalid JSON body", "type": "invalid_request_error"}}, status_code=400)
+        if req.get("model") not in (None, "", model_id):
+            return JSONResponse({"error": {"message": f"requested model `{req.get('model')}` is not available", "type": "invalid_request_error"}},
+                                status_code=400)
+        try:
+            prompt, images = convert_messages(req.get("messages") or [])
+        except BadRequest as ex:
+            return JSONResponse({"error": {"message": str(ex), "type": "invalid_request_error"}}, status_code=400)
+        stream = bool(req.get("stream"))
+        created, cid = int(time.time()), f"chatcmpl-{uuid.uuid4()}"
+
+        def chunk(delta: Dict[str, Any], finish: Optional[str], usage: Optional[Dict[str, int]] = None) -> str:
+            body = {"id": cid, "object": "chat.completion.chunk", "created": created, "model": model_id,
+                    "choices": [{"index": 0, "delta": delta, "finish_reason": finish}]}
+            if usage is not None:
+                body["usage"] = usage
+            return f"data: {json.dumps(body, ensure_ascii=False)}\n\n"
+
+        if "<image>" not in prompt:  # prompt_missing_image (routes.rs:241-247)
+            if not stream:
+                return chat_body(MISSING_IMAGE, 0, 0)
+
+            async def fallback():
+                yield chunk({"role": "assistant"}, None)
+                yield chunk({"content": MISSING_IMAGE}, None)
+                yield chunk({}, "stop", {"prompt_tokens": 0, "completion_tokens": 0, "total_tokens": 0})
+                yield "data: [DONE]\n\n"
+            return StreamingResponse(fallback(), media_type="text/event-stream")
+
+        pieces = split_prompt_on_image(prompt)
+        if len(pieces) - 1 != len(images) or len(images) != 1:
+            # the wording the reference's server maps to HTTP 400 (generation.rs:111-115)
+            return JSONResponse({"error": {"message": f"prompt formatting failed: prompt/image embedding mismatch: {len(pieces) - 1} "
+                                                      f"<image> placeholders, {len(images)} images (one image per request is served)",
+                                           "type": "invalid_request_error"}}, status_code=400)
+        segs = tokenize_segments(tokenizer, pieces)
+        budget = int(req.get("max_tokens") or max_new_tokens)
+        ngram = int(req["no_repeat_ngram_size"]) if req.get("no_repeat_ngram_size") is not None else no_repeat_ngram_size
+        params = (budget, ngram, 1)
+        loop = asyncio.get_running_loop()
+        events: "asyncio.Queue[Tuple[int, List[int]]]" = asyncio.Queue()
+
+        def on_tokens(count: int, tokens: List[int]):  # called on the batcher thread
+            loop.call_soon_threadsafe(events.put_nowait, (count, list(tokens)))
+
+        pr = PageRequest(page=images[0], seg0=tuple(segs[0]), seg1=tuple(segs[1]), image_token_id=image_token_id, vision=vision,
+                         params=params, on_tokens=on_tokens if stream else None)
+        fut = asyncio.wrap_future(batcher.submit(pr))
+        if not stream:
+            try:
+                out = await fut
+            except Exception as ex:
+                code = 400 if "prompt formatting failed" in str(ex) or "embedding mismatch" in str(ex) else 500
+                return JSONResponse({"error": {"message": str(ex), "type": "server_error" if code == 500 else "invalid_request_error"}},
+                                    status_code=code)
+            return chat_body(final_text(out.generated_tokens), out.prompt_tokens, out.response_tokens)
+
+        async def sse():
+            tracker = DeltaTracker()
+            yield chunk({"role": "assistant"}, None)
+            while True:
+                getter = asyncio.ensure_future(events.get())
+                done, _ = await asyncio.wait({getter, fut}, return_when=asyncio.FIRST_COMPLETED)
+                if getter in done:
+                    _, toks = getter.result()
+                    delta = tracker.advance(decode_text(toks), False)
+                    if delta:
+                        yield chunk({"content": delta}, None)
+                    continue
+                getter.cancel()
+                break
+            try:
+                out = fut.result()
+            except Exception as ex:
+                yield chunk({}, "error")
+                yield "data: [DONE]\n\n"
+                return
+            while not events.empty():  # tokens delivered between the last wake-up and completion
+                events.get_nowait()
+            delta = tracker.advance(final_text(out.generated_tokens), True)
+            if delta:
+                yield chunk({"content": delta}, None)
+            yield chunk({}, "stop", {"prompt_tokens": out.prompt_tokens, "completion_tokens": out.response_tokens,
+                                     "total_tokens": out.prompt_tokens + out.response_tokens})
+            yield "data: [DONE]\n\n"
+        return StreamingResponse(sse(), media_type="text/event-stream")
+
+    return app
