@@ -111,7 +111,7 @@ def test_writes_float_payloads(lib, tmp_path):
 
 
 def test_q8_quantiser_bit_exact_with_golden_gguf(lib, tmp_path):
-    z = np.load("tests/golden/dsq_blocks.npz")
+    z = np.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "dsq_blocks.npz"))
     h = _writer(lib, tmp_path / "g")
     assert _add(lib, h, "w", z["q8_weight"], Q8_0) == 0
     assert lib.dsocr_dsq_writer_finalize(h) == 0
