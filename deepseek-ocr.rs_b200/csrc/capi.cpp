@@ -6,6 +6,8 @@
 #include <thread>
 
 #include "dsocr.h"
+#include "dsocr_test.h"
+#include "dsq_dequant.h"
 #include "engine.h"
 #include "hostmath.h"
 
@@ -126,6 +128,33 @@ extern "C" int dsocr_dsq_inspect(const char* path, dsocr_dsq_header* header, dso
       o.bias_dtype = r.has_bias ? r.bias_dtype : 0;
       o.first_q_byte = rd.bytes(r)[0];
     }
+  });
+}
+
+extern "C" int dsocr_test_dsq_dequant64(uint32_t q_dtype, const uint8_t* blocks, int rows, int K, float* out) {
+  return api("", [&] {
+    if (!blocks || !out || rows <= 0) throw std::runtime_error("null argument");
+    const DsqDType dt = static_cast<DsqDType>(q_dtype);
+    const int be = dsq_block_elems(dt);
+    if (!be || K % be || K % 64) throw std::runtime_error("K must be a multiple of the block size and of 64");
+    // the plane split of dsq_upload_rows, kept on the host
+    std::vector<uint8_t> a, b, c, d;
+    const size_t nb = (size_t)rows * (K / be);
+    if (dt == DsqDType::Q8_0) {
+      a.resize((size_t)rows * K); b.resize(nb * 2);
+      for (size_t i = 0; i < nb; ++i) { memcpy(&b[2 * i], blocks + i * 34, 2); memcpy(&a[32 * i], blocks + i * 34 + 2, 32); }
+    } else if (dt == DsqDType::Q4K) {
+      a.assign(blocks, blocks + nb * 144);
+    } else {
+      a.resize(nb * 128); b.resize(nb * 64); c.resize(nb * 16); d.resize(nb * 2);
+      for (size_t i = 0; i < nb; ++i) {
+        const uint8_t* blk = blocks + i * 210;
+        memcpy(&a[128 * i], blk, 128); memcpy(&b[64 * i], blk + 128, 64); memcpy(&c[16 * i], blk + 192, 16); memcpy(&d[2 * i], blk + 208, 2);
+      }
+    }
+    const DsqPlanes pl{a.data(), b.data(), c.data(), d.data()};
+    for (int r = 0; r < rows; ++r)
+      for (int kb = 0; kb < K / 64; ++kb) dsq_dequant64((int)q_dtype, pl, r, K, kb, out + (size_t)r * K + (size_t)kb * 64);
   });
 }
 

@@ -34,6 +34,11 @@ DSOCR_API int dsocr_test_fixedcap_linear(int dtype, int E, int cap, int N, int K
 DSOCR_API int dsocr_test_vision_attention(int dtype, int B, int S, int H, const float* qkv, int grid, const float* rel_h,
                                           const float* rel_w, int rel_rows, float* out);
 
+/* Host-only: repacks on-disk ggml blocks (rows x K/blk blocks of q_dtype 8 / 12 / 14) into the device plane layouts and
+ * dequantises every 64-wide k-block with dsq_dequant64 (csrc/dsq_dequant.h), the routine the dequant-fused GEMM's
+ * producer threads run.  out[rows, K] f32. */
+DSOCR_API int dsocr_test_dsq_dequant64(uint32_t q_dtype, const uint8_t* blocks, int rows, int K, float* out);
+
 #ifdef __cplusplus
 }
 #endif
