@@ -29,21 +29,18 @@ def main():
     ap.add_argument("--config", default="full", choices=["full", "tiny"])
     ap.add_argument("--dtype", default="bf16")
     args = ap.parse_args()
-    import bench as B
-    from oracle import config as OC, dsq
+    import bench as B  # random-init checkpoint generator shared with bench.py
+    from dsocr.export import export_snapshot
 
     class A: pass
     a = A(); a.config = args.config; a.dtype = args.dtype
     cfg, ckdir = B.ensure_checkpoint(a, 0)
-    primary = {"q4k": dsq.Q4K, "q6k": dsq.Q6K, "q8_0": dsq.Q8_0, "float": None}[args.primary]
-    snap = ckdir / f"model.{args.primary}.dsq"
-    if primary is None:
+    snap = ckdir / f"model.{args.primary}.lib.dsq"
+    if args.primary == "float":
         snap = None
     elif not snap.exists():
-        t0 = time.time()
-        ck = OC.load_checkpoint(str(ckdir / "model.safetensors"))
-        dsq.write_model_snapshot(str(snap), cfg, ck, primary)
-        del ck
+        t0 = time.time()  # the library's own exporter (dsocr_dsq_writer_*): adapter tensor list + dtype fallback chain
+        export_snapshot(str(ckdir / "config.json"), str(ckdir / "model.safetensors"), str(snap), args.primary)
         print(f"[dsq] wrote {snap} ({snap.stat().st_size / 1e9:.2f} GB) in {time.time() - t0:.1f}s", file=sys.stderr)
     from dsocr.engine import DecodeParameters, load_model
 
