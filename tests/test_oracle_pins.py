@@ -253,3 +253,56 @@ def test_dsq_dtype_assignment_follows_exporter():
     assert dsq.choose_dtype("lm_head.weight", 1280, dsq.Q4K) == dsq.Q8_0
     assert dsq.choose_dtype("lm_head.weight", 1280, dsq.Q8_0) == dsq.Q8_0
     assert dsq.choose_dtype("x", 1792, dsq.Q6K) == dsq.Q6K
+
+
+# --- KV-cache bookkeeping and padding mask: the reference's own unit tests ------------------------------
+def _chunk(batch, heads, seq, dim):
+    from oracle.cache import KvCacheChunk
+
+    return KvCacheChunk(torch.zeros(batch, heads, dim, seq), torch.zeros(batch, heads, seq, dim))
+
+
+def test_lengths_to_padding_mask_builds_expected():
+    """crates/infer-deepseek/tests/transformer_block.rs:59-67."""
+    from oracle.cache import lengths_to_padding_mask
+
+    m = lengths_to_padding_mask([2, 4], 4)
+    assert m[0].tolist() == [1.0, 1.0, 0.0, 0.0] and m[1].tolist() == [1.0, 1.0, 1.0, 1.0]
+    with pytest.raises(ValueError, match="exceeds sequence dimension"):
+        lengths_to_padding_mask([5], 4)
+
+
+def test_layer_cache_auto_resizes_and_rejects_incompatible_dimensions():
+    """transformer_cache.rs:20-47."""
+    from oracle.cache import LayerKvCache
+
+    cache = LayerKvCache()
+    cache.append_chunk(1, _chunk(1, 2, 3, 4))
+    assert len(cache) == 2 and cache.get(0) is None and cache.get(1).seq_len() == 3 and cache.seq_len() == 3
+    cache = LayerKvCache(1)
+    cache.append_chunk(0, _chunk(1, 2, 3, 4))
+    with pytest.raises(ValueError, match="chunk heads"):
+        cache.append_chunk(0, _chunk(1, 3, 1, 4))
+
+
+def test_dynamic_cache_tracks_sequence_growth_and_guard_clears():
+    """transformer_cache.rs:49-101."""
+    from oracle.cache import DynamicCache
+
+    cache = DynamicCache(3)
+    cache.append(0, _chunk(1, 2, 3, 4))
+    cache.append(1, _chunk(1, 2, 3, 4))
+    assert cache.seq_len() == 3
+    cache.append(0, _chunk(1, 2, 1, 4))
+    assert cache.seq_len() == 4
+    with pytest.raises(ValueError, match="seq_len decreased"):
+        cache.append(2, _chunk(1, 2, 2, 4))
+    cache.append(1, _chunk(1, 2, 1, 4))
+    assert cache.seq_len() == 4
+    assert cache.get(0).key_view().shape == (1, 2, 4, 4) and cache.get(0).value_view().shape == (1, 2, 4, 4)
+    cache = DynamicCache(1)
+    flag = []
+    with cache.prompt_guard(reset=lambda: flag.append(True)) as c:
+        c.append(0, _chunk(1, 2, 3, 4))
+        assert c.seq_len() == 3
+    assert cache.seq_len() is None and all(e is None for e in cache.layers.entries) and flag == [True]
