@@ -110,3 +110,29 @@ def test_engine_creation_fails_loudly_without_gpu(lib, tmp_path):
     lib.dsocr_last_error.restype = C.c_char_p
     msg = lib.dsocr_last_error().decode()
     assert "load_model" in msg and ("CUDA" in msg or "cuda" in msg or "device" in msg), msg
+
+
+def test_preprocess_property_random_shapes_bit_exact_with_oracle(lib):
+    """Seeded random sizes incl. the edges the reference handles specially: 1-pixel sides, sides just below / above the
+    640 tile (no-tile rule, preprocess.rs:72-80), extreme aspect ratios (ratio search clamps at 9 tiles), upscales."""
+    from dsocr.engine import VisionSettingsC
+
+    rng = np.random.RandomState(2026)
+    shapes = [(1, 1), (1, 700), (700, 1), (639, 640), (640, 641), (641, 641), (3000, 90), (90, 2000), (17, 23)]
+    shapes += [(int(rng.randint(2, 1500)), int(rng.randint(2, 1500))) for _ in range(12)]
+    u8 = C.POINTER(C.c_uint8)
+    for w, h in shapes:
+        img = rng.randint(0, 256, (h, w, 3), dtype=np.uint8)
+        for base, tile, crop in ((1024, 640, 1), (640, 640, 0)):
+            gsz = base if crop else tile
+            g = np.empty((gsz, gsz, 3), np.uint8)
+            tiles = np.empty((9, tile, tile, 3), np.uint8)
+            n, cw, ch = C.c_int(), C.c_int(), C.c_int()
+            st = lib.dsocr_preprocess(img.ctypes.data_as(u8), w, h, VisionSettingsC(base, tile, crop), g.ctypes.data_as(u8),
+                                      tiles.ctypes.data_as(u8), C.byref(n), C.byref(cw), C.byref(ch))
+            assert st == 0, (w, h, lib.dsocr_last_error().decode())
+            ref = P.prepare_vision_input(img, base, tile, bool(crop))
+            assert (cw.value, ch.value) == tuple(ref["crop_shape"] or (1, 1)) and n.value == len(ref["tiles"]), (w, h, crop)
+            assert np.array_equal(g, ref["global"]), (w, h, crop)
+            for i, t in enumerate(ref["tiles"]):
+                assert np.array_equal(tiles[i], t), (w, h, i)
