@@ -1,4 +1,4 @@
-"""OpenAI-compatible `/v1/chat/completions` (+ `/v1/models`, `/v1/health`) on top of the batcher: the routes of
+"""OpenAI-compatible `/v1/chat/completions` and `/v1/responses` (+ `/v1/models`, `/v1/health`) on top of the batcher: the routes of
 crates/server/src/routes.rs:33-222 with the message handling of generation.rs:169-300 (latest user message plus the
 system messages before it; content parts are flattened in reverse order, images become `<image>` placeholders; only
 `data:` URLs carry images here - this box has no egress for http(s) ones) and the SSE chunks of stream.rs:160-370
@@ -117,54 +117,112 @@ def create_app(batcher: PageBatcher, tokenizer: Any, image_token_id: int, model_
     def models():
         return {"object": "list", "data": [{"id": model_id, "object": "model", "created": 0, "owned_by": "dsocr-b200"}]}
 
-    def chat_body(text: str, prompt_tokens: int, completion_tokens: int):
-        return {"id": f"chatcmpl-{uuid.uuid4()}", "object": "chat.completion", "created": int(time.time()), "model": model_id,
-                "choices": [{"index": 0, "message": {"role": "assistant", "content": text}, "finish_reason": "stop"}],
-                "usage": {"prompt_tokens": prompt_tokens, "completion_tokens": completion_tokens,
-                          "total_tokens": prompt_tokens + completion_tokens}}
+    def sse(obj: Dict[str, Any]) -> str:
+        return f"data: {json.dumps(obj, ensure_ascii=False)}\n\n"
 
-    @app.post("/v1/chat/completions")
-    async def chat(request: Request):
+    class ChatShape:
+        """`/v1/chat/completions` bodies and chunks (routes.rs:142-222, stream.rs StreamKind::Chat)."""
+        messages_key = "messages"
+
+        def __init__(self):
+            self.id, self.created = f"chatcmpl-{uuid.uuid4()}", int(time.time())
+
+        def budget(self, req):
+            return req.get("max_tokens")
+
+        def body(self, text, p, c):
+            return {"id": self.id, "object": "chat.completion", "created": self.created, "model": model_id,
+                    "choices": [{"index": 0, "message": {"role": "assistant", "content": text}, "finish_reason": "stop"}],
+                    "usage": {"prompt_tokens": p, "completion_tokens": c, "total_tokens": p + c}}
+
+        def _chunk(self, delta, finish, usage=None):
+            o = {"id": self.id, "object": "chat.completion.chunk", "created": self.created, "model": model_id,
+                 "choices": [{"index": 0, "delta": delta, "finish_reason": finish}]}
+            if usage is not None:
+                o["usage"] = usage
+            return sse(o)
+
+        def initial(self):
+            return self._chunk({"role": "assistant"}, None)
+
+        def delta(self, text):
+            return self._chunk({"content": text}, None)
+
+        def final(self, text, p, c):
+            return self._chunk({}, "stop", {"prompt_tokens": p, "completion_tokens": c, "total_tokens": p + c})
+
+        def error(self):
+            return self._chunk({}, "error")
+
+    class ResponsesShape:
+        """`/v1/responses` bodies and events (routes.rs:54-140, stream.rs StreamKind::Responses)."""
+        messages_key = "input"
+
+        def __init__(self):
+            self.id, self.out_id, self.created = f"resp-{uuid.uuid4()}", f"msg-{uuid.uuid4()}", int(time.time())
+
+        def budget(self, req):
+            return req.get("max_output_tokens") or req.get("max_tokens")
+
+        def _head(self):
+            return {"id": self.id, "object": "response", "created": self.created, "model": model_id}
+
+        def _output(self, text):
+            return [{"id": self.out_id, "type": "message", "role": "assistant", "content": [{"type": "output_text", "text": text}]}]
+
+        def body(self, text, p, c):
+            return {**self._head(), "output": self._output(text),
+                    "usage": {"prompt_tokens": p, "completion_tokens": c, "total_tokens": p + c}}
+
+        def initial(self):
+            return sse({"type": "response.created", "response": self._head()})
+
+        def delta(self, text):
+            return sse({"type": "response.output_text.delta", "response": self._head(), "output_id": self.out_id, "output_index": 0,
+                        "delta": text})
+
+        def final(self, text, p, c):
+            return sse({"type": "response.completed", "response": {**self._head(), "output": self._output(text),
+                                                                   "usage": {"input_tokens": p, "output_tokens": c, "total_tokens": p + c}}})
+
+        def error(self):
+            return sse({"type": "response.error", "response": self._head()})
+
+    def bad(message: str, code: int = 400):
+        return JSONResponse({"error": {"message": message, "type": "invalid_request_error" if code == 400 else "server_error"}},
+                            status_code=code)
+
+    async def generate(request: Request, shape):
         try:
             req = await request.json()
         except Exception:
-            return JSONResponse({"error": {"message": "invalid JSON body", "type": "invalid_request_error"}}, status_code=400)
+            return bad("invalid JSON body")
         if req.get("model") not in (None, "", model_id):
-            return JSONResponse({"error": {"message": f"requested model `{req.get('model')}` is not available", "type": "invalid_request_error"}},
-                                status_code=400)
+            return bad(f"requested model `{req.get('model')}` is not available")
         try:
-            prompt, images = convert_messages(req.get("messages") or [])
+            prompt, images = convert_messages(req.get(shape.messages_key) or [])
         except BadRequest as ex:
-            return JSONResponse({"error": {"message": str(ex), "type": "invalid_request_error"}}, status_code=400)
+            return bad(str(ex))
         stream = bool(req.get("stream"))
-        created, cid = int(time.time()), f"chatcmpl-{uuid.uuid4()}"
-
-        def chunk(delta: Dict[str, Any], finish: Optional[str], usage: Optional[Dict[str, int]] = None) -> str:
-            body = {"id": cid, "object": "chat.completion.chunk", "created": created, "model": model_id,
-                    "choices": [{"index": 0, "delta": delta, "finish_reason": finish}]}
-            if usage is not None:
-                body["usage"] = usage
-            return f"data: {json.dumps(body, ensure_ascii=False)}\n\n"
 
         if "<image>" not in prompt:  # prompt_missing_image (routes.rs:241-247)
             if not stream:
-                return chat_body(MISSING_IMAGE, 0, 0)
+                return shape.body(MISSING_IMAGE, 0, 0)
 
             async def fallback():
-                yield chunk({"role": "assistant"}, None)
-                yield chunk({"content": MISSING_IMAGE}, None)
-                yield chunk({}, "stop", {"prompt_tokens": 0, "completion_tokens": 0, "total_tokens": 0})
+                yield shape.initial()
+                yield shape.delta(MISSING_IMAGE)
+                yield shape.final(MISSING_IMAGE, 0, 0)
                 yield "data: [DONE]\n\n"
             return StreamingResponse(fallback(), media_type="text/event-stream")
 
         pieces = split_prompt_on_image(prompt)
         if len(pieces) - 1 != len(images) or len(images) != 1:
             # the wording the reference's server maps to HTTP 400 (generation.rs:111-115)
-            return JSONResponse({"error": {"message": f"prompt formatting failed: prompt/image embedding mismatch: {len(pieces) - 1} "
-                                                      f"<image> placeholders, {len(images)} images (one image per request is served)",
-                                           "type": "invalid_request_error"}}, status_code=400)
+            return bad(f"prompt formatting failed: prompt/image embedding mismatch: {len(pieces) - 1} <image> placeholders, "
+                       f"{len(images)} images (one image per request is served)")
         segs = tokenize_segments(tokenizer, pieces)
-        budget = int(req.get("max_tokens") or max_new_tokens)
+        budget = int(shape.budget(req) or max_new_tokens)
         ngram = int(req["no_repeat_ngram_size"]) if req.get("no_repeat_ngram_size") is not None else no_repeat_ngram_size
         params = (budget, ngram, 1)
         loop = asyncio.get_running_loop()
@@ -180,14 +238,13 @@ def create_app(batcher: PageBatcher, tokenizer: Any, image_token_id: int, model_
             try:
                 out = await fut
             except Exception as ex:
-                code = 400 if "prompt formatting failed" in str(ex) or "embedding mismatch" in str(ex) else 500
-                return JSONResponse({"error": {"message": str(ex), "type": "server_error" if code == 500 else "invalid_request_error"}},
-                                    status_code=code)
-            return chat_body(final_text(out.generated_tokens), out.prompt_tokens, out.response_tokens)
+                client_fault = "prompt formatting failed" in str(ex) or "embedding mismatch" in str(ex)
+                return bad(str(ex), 400 if client_fault else 500)
+            return shape.body(final_text(out.generated_tokens), out.prompt_tokens, out.response_tokens)
 
-        async def sse():
+        async def events_stream():
             tracker = DeltaTracker()
-            yield chunk({"role": "assistant"}, None)
+            yield shape.initial()
             while True:
                 getter = asyncio.ensure_future(events.get())
                 done, _ = await asyncio.wait({getter, fut}, return_when=asyncio.FIRST_COMPLETED)
@@ -195,24 +252,30 @@ def create_app(batcher: PageBatcher, tokenizer: Any, image_token_id: int, model_
                     _, toks = getter.result()
                     delta = tracker.advance(decode_text(toks), False)
                     if delta:
-                        yield chunk({"content": delta}, None)
+                        yield shape.delta(delta)
                     continue
                 getter.cancel()
                 break
             try:
                 out = fut.result()
-            except Exception as ex:
-                yield chunk({}, "error")
+            except Exception:
+                yield shape.error()
                 yield "data: [DONE]\n\n"
                 return
-            while not events.empty():  # tokens delivered between the last wake-up and completion
-                events.get_nowait()
-            delta = tracker.advance(final_text(out.generated_tokens), True)
+            text = final_text(out.generated_tokens)
+            delta = tracker.advance(text, True)  # whatever was still held back (and the normalisation of the tail)
             if delta:
-                yield chunk({"content": delta}, None)
-            yield chunk({}, "stop", {"prompt_tokens": out.prompt_tokens, "completion_tokens": out.response_tokens,
-                                     "total_tokens": out.prompt_tokens + out.response_tokens})
+                yield shape.delta(delta)
+            yield shape.final(text, out.prompt_tokens, out.response_tokens)
             yield "data: [DONE]\n\n"
-        return StreamingResponse(sse(), media_type="text/event-stream")
+        return StreamingResponse(events_stream(), media_type="text/event-stream")
+
+    @app.post("/v1/chat/completions")
+    async def chat(request: Request):
+        return await generate(request, ChatShape())
+
+    @app.post("/v1/responses")
+    async def responses(request: Request):
+        return await generate(request, ResponsesShape())
 
     return app

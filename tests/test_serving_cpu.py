@@ -196,3 +196,33 @@ def test_chat_streaming_emits_role_deltas_stop_and_done():
     assert text == "".join(chr(0x4E00 + i) for i in (1, 2, 3)) and "�" not in text
     assert chunks[-1]["choices"][0]["finish_reason"] == "stop" and chunks[-1]["usage"]["total_tokens"] == 284
     b.close()
+
+
+def test_responses_route_json_and_stream():
+    import json as _json
+
+    from dsocr.engine import DecodeOutcome
+
+    def run(batch):
+        for r in batch:
+            if r.on_tokens:
+                r.on_tokens(2, [4, 5])
+                time.sleep(0.02)
+        return [DecodeOutcome(281, 2, [4, 5]) for _ in batch]
+
+    client, b = _client(run)
+    body = {"model": "deepseek-ocr", "max_output_tokens": 16, "input": [{"role": "user", "content": [
+        {"type": "input_text", "text": "Free OCR."}, {"type": "input_image", "image_url": _png_data_url()}]}]}
+    d = client.post("/v1/responses", json=body).json()
+    text = "".join(chr(0x4E00 + i) for i in (4, 5))
+    assert d["object"] == "response" and d["output"][0]["content"] == [{"type": "output_text", "text": text}]
+    assert d["usage"] == {"prompt_tokens": 281, "completion_tokens": 2, "total_tokens": 283}
+    with client.stream("POST", "/v1/responses", json={**body, "stream": True}) as r:
+        lines = [l for l in r.iter_lines() if l.startswith("data: ")]
+    assert lines[-1] == "data: [DONE]"
+    ev = [_json.loads(l[6:]) for l in lines[:-1]]
+    assert ev[0]["type"] == "response.created" and ev[-1]["type"] == "response.completed"
+    assert "".join(e["delta"] for e in ev if e["type"] == "response.output_text.delta") == text
+    assert ev[-1]["response"]["usage"] == {"input_tokens": 281, "output_tokens": 2, "total_tokens": 283}
+    assert ev[-1]["response"]["output"][0]["content"][0]["text"] == text
+    b.close()
