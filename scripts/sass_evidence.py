@@ -39,7 +39,8 @@ def main():
     names = demangle(list(counts))
     print("kernel," + ",".join(k.replace(".*", "x") for k in KEYS))
     for fn, c in counts.items():
-        short = re.sub(r"\(.*", "", names.get(fn, fn)).replace("dsocr::", "").replace("(anonymous namespace)::", "").replace("void ", "")
+        full = names.get(fn, fn).replace("(anonymous namespace)::", "").replace("dsocr::", "").replace("void ", "")
+        short = re.sub(r"\(.*", "", full)
         print('"' + short + '",' + ",".join(str(c[k]) for k in KEYS))
 
 
