@@ -19,6 +19,7 @@
 #include <fstream>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "dsq.h"
@@ -32,21 +33,21 @@ float f16_val(uint16_t u) { __half h; memcpy(&h, &u, 2); return __half2float(h);
 uint16_t bf16_bits(float v) { __nv_bfloat16 h = __float2bfloat16_rn(v); uint16_t u; memcpy(&u, &h, 2); return u; }
 int nearest_int(float v) { return (int)lrintf(v); }  // ggml nearest_int: round half to even
 
-void quantize_q8_0(const float* w, size_t rows, size_t cols, std::vector<uint8_t>& out) {
-  out.reserve(out.size() + rows * (cols / 32) * 34);
+void quantize_q8_0(const float* w, size_t rows, size_t cols, uint8_t* dst) {
   for (size_t b = 0; b < rows * cols / 32; ++b) {
     const float* x = w + b * 32;
+    uint8_t* o = dst + b * 34;
     float amax = 0.f;
     for (int i = 0; i < 32; ++i) amax = std::max(amax, fabsf(x[i]));
     const float scale = amax > 0.f ? amax / 127.0f : 0.f;
     const uint16_t d = f16_bits(scale);
-    out.push_back((uint8_t)(d & 0xFF)); out.push_back((uint8_t)(d >> 8));
-    if (scale == 0.f) { out.insert(out.end(), 32, 0); continue; }
+    o[0] = (uint8_t)(d & 0xFF); o[1] = (uint8_t)(d >> 8);
+    if (scale == 0.f) { memset(o + 2, 0, 32); continue; }
     const float inv = 1.0f / scale;
     for (int i = 0; i < 32; ++i) {
       float q = roundf(x[i] * inv);  // f32::round: half away from zero
       q = std::min(127.f, std::max(-128.f, q));
-      out.push_back((uint8_t)(int8_t)(int)q);
+      o[2 + i] = (uint8_t)(int8_t)(int)q;
     }
   }
 }
@@ -116,8 +117,7 @@ void scale_min_k4(int j, const uint8_t* q, uint8_t* d, uint8_t* m) {  // ggml ge
   else { *d = (q[j + 4] & 0xF) | ((q[j - 4] >> 6) << 4); *m = (q[j + 4] >> 4) | ((q[j] >> 6) << 4); }
 }
 
-void quantize_q4k(const float* w, size_t rows, size_t cols, std::vector<uint8_t>& out) {
-  out.reserve(out.size() + rows * (cols / 256) * 144);
+void quantize_q4k(const float* w, size_t rows, size_t cols, uint8_t* dst) {
   for (size_t b = 0; b < rows * cols / 256; ++b) {
     const float* x = w + b * 256;
     uint8_t L[256]; float mins[8], scales[8];
@@ -150,12 +150,11 @@ void quantize_q4k(const float* w, size_t rows, size_t cols, std::vector<uint8_t>
     uint8_t* q = blk + 16;
     for (int g = 0; g < 4; ++g)
       for (int l = 0; l < 32; ++l) q[32 * g + l] = L[64 * g + l] | (uint8_t)(L[64 * g + 32 + l] << 4);
-    out.insert(out.end(), blk, blk + 144);
+    memcpy(dst + b * 144, blk, 144);
   }
 }
 
-void quantize_q6k(const float* w, size_t rows, size_t cols, std::vector<uint8_t>& out) {
-  out.reserve(out.size() + rows * (cols / 256) * 210);
+void quantize_q6k(const float* w, size_t rows, size_t cols, uint8_t* dst) {
   for (size_t b = 0; b < rows * cols / 256; ++b) {
     const float* x = w + b * 256;
     int8_t L[256]; float scales[16];
@@ -165,7 +164,7 @@ void quantize_q6k(const float* w, size_t rows, size_t cols, std::vector<uint8_t>
       if (fabsf(scales[ib]) > max_abs) { max_abs = fabsf(scales[ib]); max_scale = scales[ib]; }
     }
     uint8_t blk[210] = {0};
-    if (max_abs == 0.f) { out.insert(out.end(), blk, blk + 210); continue; }  // all-zero block
+    if (max_abs == 0.f) { memcpy(dst + b * 210, blk, 210); continue; }  // all-zero block
     const float iscale = -128.f / max_scale;
     const uint16_t d16 = f16_bits(1.f / iscale);
     memcpy(blk + 208, &d16, 2);
@@ -186,7 +185,7 @@ void quantize_q6k(const float* w, size_t rows, size_t cols, std::vector<uint8_t>
         ql[64 * half + 32 + l] = (q2 & 0xF) | (uint8_t)((q4 & 0xF) << 4);
         qh[32 * half + l] = (uint8_t)((q1 >> 4) | ((q2 >> 4) << 2) | ((q3 >> 4) << 4) | ((q4 >> 4) << 6));
       }
-    out.insert(out.end(), blk, blk + 210);
+    memcpy(dst + b * 210, blk, 210);
   }
 }
 
@@ -232,13 +231,39 @@ void DsqWriter::add_tensor_f32(const std::string& name, uint32_t out_dim, uint32
   check_new(name, dt, in_dim);
   const size_t n = (size_t)out_dim * in_dim;
   std::vector<uint8_t> q;
-  switch (dt) {
-    case DsqDType::Q8_0: quantize_q8_0(w, out_dim, in_dim, q); break;
-    case DsqDType::Q4K: quantize_q4k(w, out_dim, in_dim, q); break;
-    case DsqDType::Q6K: quantize_q6k(w, out_dim, in_dim, q); break;
-    case DsqDType::F32: q.resize(n * 4); memcpy(q.data(), w, n * 4); break;
-    case DsqDType::F16: q.resize(n * 2); for (size_t i = 0; i < n; ++i) { const uint16_t u = f16_bits(w[i]); memcpy(&q[2 * i], &u, 2); } break;
-    case DsqDType::BF16: q.resize(n * 2); for (size_t i = 0; i < n; ++i) { const uint16_t u = bf16_bits(w[i]); memcpy(&q[2 * i], &u, 2); } break;
+  const int be = dsq_block_elems(dt);
+  if (be) {
+    // rows are independent: quantise row ranges on the host cores (the output offset of a row is known up front, so the
+    // bytes do not depend on the thread count)
+    const size_t row_bytes = (size_t)(in_dim / be) * dsq_block_bytes(dt);
+    q.resize((size_t)out_dim * row_bytes);
+    const size_t want = std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 32);
+    const size_t nthreads = n < (1u << 18) ? 1 : std::min<size_t>(want, out_dim);
+    auto work = [&](size_t r0, size_t r1) {
+      const float* src = w + r0 * in_dim;
+      uint8_t* dst = q.data() + r0 * row_bytes;
+      if (dt == DsqDType::Q8_0) quantize_q8_0(src, r1 - r0, in_dim, dst);
+      else if (dt == DsqDType::Q4K) quantize_q4k(src, r1 - r0, in_dim, dst);
+      else quantize_q6k(src, r1 - r0, in_dim, dst);
+    };
+    if (nthreads <= 1) work(0, out_dim);
+    else {
+      std::vector<std::thread> th;
+      const size_t chunk = (out_dim + nthreads - 1) / nthreads;
+      for (size_t t = 0; t < nthreads; ++t) {
+        const size_t r0 = t * chunk, r1 = std::min<size_t>(out_dim, r0 + chunk);
+        if (r0 < r1) th.emplace_back(work, r0, r1);
+      }
+      for (auto& t : th) t.join();
+    }
+  } else if (dt == DsqDType::F32) {
+    q.resize(n * 4); memcpy(q.data(), w, n * 4);
+  } else if (dt == DsqDType::F16) {
+    q.resize(n * 2);
+    for (size_t i = 0; i < n; ++i) { const uint16_t u = f16_bits(w[i]); memcpy(&q[2 * i], &u, 2); }
+  } else {
+    q.resize(n * 2);
+    for (size_t i = 0; i < n; ++i) { const uint16_t u = bf16_bits(w[i]); memcpy(&q[2 * i], &u, 2); }
   }
   append(name, out_dim, in_dim, dt, q.data(), q.size(), bias);
 }
