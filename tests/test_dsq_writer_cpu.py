@@ -152,3 +152,36 @@ def test_file_is_byte_identical_to_the_oracle_writer(lib, tmp_path):
     assert lib.dsocr_dsq_writer_add_quantized_bytes(h, b"b.weight", 2, 256, Q4K, qb.ctypes.data_as(C.POINTER(C.c_uint8)), len(q2), None) == 0
     assert lib.dsocr_dsq_writer_finalize(h) == 0
     assert (tmp_path / "mine.dsq").read_bytes() == ref.read_bytes()
+
+
+def test_writer_reader_roundtrip_random_tensor_sets(lib, tmp_path):
+    """Seeded random snapshots (mixed dtypes, odd names, with / without bias): what the library writes, the library's
+    reader and the oracle's reader both list, and the dequantised payload stays within the format's error of the input."""
+    rng = np.random.RandomState(77)
+    for case in range(6):
+        h = _writer(lib, tmp_path / f"rt{case}", default=[Q8_0, Q4K, Q6K][case % 3])
+        want = []
+        for t in range(int(rng.randint(1, 6))):
+            dt = [Q8_0, Q4K, Q6K, F32, F16, BF16][int(rng.randint(0, 6))]
+            blk = {Q8_0: 32, Q4K: 256, Q6K: 256}.get(dt, 1)
+            out_dim, in_dim = int(rng.randint(1, 9)) * 8, int(rng.randint(1, 4)) * blk * (1 if blk > 1 else 8)
+            w = (rng.randn(out_dim, in_dim) * 10 ** rng.uniform(-3, 1)).astype(np.float32)
+            bias = rng.randn(out_dim).astype(np.float32) if rng.rand() < 0.5 else None
+            name = f"model.layers.{t}.weird name/{case}.weight"
+            assert _add(lib, h, name, w, dt, bias) == 0, lib.dsocr_last_error().decode()
+            want.append((name, dt, w, bias))
+        assert lib.dsocr_dsq_writer_finalize(h) == 0
+        path = tmp_path / f"rt{case}.dsq"
+        hdr, recs = _inspect(lib, path, cap=8)
+        assert hdr.tensor_count == len(want)
+        _, orecs, data = dsq.read_snapshot(str(path))
+        for i, (name, dt, w, bias) in enumerate(want):
+            r, o = recs[i], orecs[name]
+            assert r.name.decode() == name and (r.q_dtype, r.out_dim, r.in_dim) == (dt, w.shape[0], w.shape[1]) == (o.q_dtype, o.out_dim, o.in_dim)
+            assert (r.bias_len != 0) == (bias is not None)
+            if bias is not None:
+                assert np.array_equal(np.frombuffer(data[r.bias_offset:r.bias_offset + r.bias_len], np.float32), bias)
+            deq = dsq.dequantize(data[r.q_offset:r.q_offset + r.q_len], dt, w.shape[0], w.shape[1])
+            tol = {Q8_0: 0.01, Q4K: 0.12, Q6K: 0.04, F32: 0.0, F16: 1e-3, BF16: 8e-3}[dt]
+            err = np.abs(deq - w).max() / max(1e-30, np.abs(w).max())
+            assert err <= tol, (name, dt, err)
