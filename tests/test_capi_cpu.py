@@ -136,3 +136,27 @@ def test_preprocess_property_random_shapes_bit_exact_with_oracle(lib):
             assert np.array_equal(g, ref["global"]), (w, h, crop)
             for i, t in enumerate(ref["tiles"]):
                 assert np.array_equal(tiles[i], t), (w, h, i)
+
+
+def test_plain_c_consumer_builds_links_and_runs(lib, tmp_path):
+    """examples/c_consumer.c: the boundary is usable from C99 with nothing but include/dsocr.h and -ldsocr (what a cgo /
+    Rust FFI binding needs); its host-only calls run here, engine creation fails loudly without a GPU."""
+    import shutil
+    import subprocess
+
+    from dsocr.binding import LIB_PATH
+
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    exe = tmp_path / "c_consumer"
+    cmd = ["gcc", "-std=c99", "-Wall", "-Werror", "-I", str(ROOT / "include"), str(ROOT / "examples" / "c_consumer.c"), "-L",
+           str(LIB_PATH.parent), "-ldsocr", f"-Wl,-rpath,{LIB_PATH.parent}", "-o", str(exe)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe), str(tmp_path / "snap")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "snapshot: 1 tensor(s), `linear.weight` [2, 32] dtype 8, 68 payload bytes, 8 bias bytes" in r.stdout
+    assert "A4 page: grid 2x3, 6 tiles, 903 image tokens" in r.stdout
+    import torch
+    if not torch.cuda.is_available():
+        assert "engine_create failed as expected" in r.stdout
