@@ -6,8 +6,8 @@ same `--output-json` (crates/cli/src/debug.rs:100-157) and `--bench-output` (cra
 the reference's strict token gate and perf tables can consume the run unchanged.
 
 What stays on the host exactly as in the reference: image decode (PIL instead of the `image` crate), the tokenizer
-(`tokenizers` JSON file), `normalize_text`.  Prompt templates (crates/core conversation rendering) are out of scope:
---prompt is taken as the already rendered prompt, which is what the benchsuite passes (`rendered_prompt`).
+(`tokenizers` JSON file), `normalize_text`.  --prompt is rendered through --template (dsocr/conversation.py == crates/core/src/conversation; the default `plain`
+leaves the benchsuite's already rendered prompt unchanged apart from trimming).
 Offline (no tokenizer file): --prompt-ids '[[ids before <image>], [ids after]]' replaces --prompt / --tokenizer."""
 from __future__ import annotations
 
@@ -22,6 +22,7 @@ sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "deepseek-ocr.rs_b200"))
 
 from dsocr import report  # noqa: E402
+from dsocr.conversation import render_prompt  # noqa: E402
 
 EOS_TEXT = "<｜end▁of▁sentence｜>"
 
@@ -100,6 +101,11 @@ def resolve_prompt(args, tokenizer):
         raise SystemExit("one of --prompt, --prompt-file or --prompt-ids is required")
     if tokenizer is None:
         raise SystemExit("--tokenizer is required to encode --prompt")
+    user = text
+    try:
+        text = render_prompt(args.template, "", text)  # crates/cli/src/app.rs:135
+    except ValueError as ex:
+        raise SystemExit(f"prompt formatting failed: {ex}")
     pieces = report.split_prompt_on_image(text)
     n_images = len(args.images)
     if len(pieces) - 1 != n_images:
@@ -109,7 +115,7 @@ def resolve_prompt(args, tokenizer):
     image_id = args.image_token_id if args.image_token_id is not None else tokenizer.token_to_id("<image>")
     if image_id is None:
         raise SystemExit("tokenizer has no <image> token")
-    return text, text, report.tokenize_segments(tokenizer, pieces), int(image_id)
+    return user, text, report.tokenize_segments(tokenizer, pieces), int(image_id)
 
 
 def run(args) -> int:

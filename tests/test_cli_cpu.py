@@ -97,3 +97,31 @@ def test_run_writes_reference_schema_files(tmp_path, monkeypatch):
         r = RustDecodeOutput.from_payload(o, token_field="tokens")
         assert r.tokens == [11, 12, 13] and r.generated_len == 3
         assert StageTotals.from_payload(b).stage_ms("decode.iterative") == 2.0
+
+
+def test_conversation_templates():
+    """crates/core/tests/conversation_templates.rs:3-18 + render_prompt (inference.rs:212-225)."""
+    from dsocr.conversation import get_conv_template, render_prompt
+
+    conv = get_conv_template("deepseek")
+    for i, m in enumerate(["Hello!", "Hi! This is Tony.", "Who are you?", "I am a helpful assistant.", "How are you?", None]):
+        conv.append_message(conv.roles[i % 2], m)
+    prompt = conv.get_prompt()
+    assert "Hello!" in prompt and "<｜end▁of▁sentence｜>" in prompt
+    assert prompt.startswith("<|User|>: Hello!\n\n<|Assistant|>: Hi! This is Tony.<｜end▁of▁sentence｜>") and prompt.endswith("<|Assistant|>:")
+    assert get_conv_template("deepseek").messages == []             # registry hands out copies
+    assert render_prompt("plain", "", "<image>\nFree OCR. ") == "<image>\nFree OCR."
+    assert render_prompt("deepseek", "", "<image>\nFree OCR.") == "User: <image>\nFree OCR.\n\nAssistant:"
+    assert render_prompt("alignment", "", "anything") == "<image>\n"
+    assert get_conv_template("nope") is None
+    with pytest.raises(ValueError, match="unknown conversation template"):
+        render_prompt("nope", "", "x")
+
+
+def test_cli_renders_prompt_through_template():
+    p = cli.build_parser()
+    a = p.parse_args(["--image", "x.png", "--prompt", "  <image>\nFree OCR.  ", "--template", "plain"])
+    user, rendered, segs, _ = cli.resolve_prompt(a, Tok())
+    assert user == "  <image>\nFree OCR.  " and rendered == "<image>\nFree OCR." and segs == [[], [104, 104]]
+    with pytest.raises(SystemExit, match="unknown conversation template"):
+        cli.resolve_prompt(p.parse_args(["--image", "x.png", "--prompt", "<image>", "--template", "nope"]), Tok())
