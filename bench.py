@@ -1,14 +1,16 @@
 #!/usr/bin/env python
 """Throughput benchmark of the DeepSeek-OCR per-page forward path on B200 (see BASELINE.json).
 
-One "step" = one pass of the whole hot path over a batch of synthetic pages:
-   host RGB8 pages -> integer preprocess -> H2D -> SAM + CLIP + projector -> prompt build -> prefill ->
+One "step" = one pass of the whole hot path over the page set:
+   host RGB8 pages -> H2D -> integer resample / tiling -> SAM + CLIP + projector -> prompt build -> prefill ->
    greedy decode (no-repeat-ngram 20) to the token budget -> D2H of the generated ids.
-Workload at N=1: BASELINE.json configs[1]: fp16, Base mode 1024x1024, batch of 64 synthetic pages, 512-token
-budget, random-init weights of the exact architecture (no checkpoint offline).
+Default workload = BASELINE.json configs[2], the configuration the metric is quoted on: bf16, Gundam dynamic tiling
+(A4 pages 1654x2339 -> 6 local 640x640 crops + the 1024x1024 global view, 903 image tokens), ONE fixed set of 1024
+synthetic pages sharded round-robin over the N GPUs (strong scaling, no data-path collective), 512-token budget,
+random-init weights of the exact architecture (no checkpoint offline).  `--mode base` = configs[1] (Base 1024x1024).
 
-  value : pages/s with the (already resized) page views resident in HBM when the timed region starts
-  e2e   : pages/s through the public C-ABI call `dsocr_decode_pages` with HOST page buffers (H2D of the
+  value : pages/s with the (already resized / tiled) page views resident in HBM when the timed region starts
+  e2e   : pages/s through the public C-ABI call `dsocr_decode_pages` with pinned HOST page buffers (H2D of the
           pages and D2H of the tokens inside the timed region)
   roofline / cpu_baseline : see DESIGN.md "Measurement"
 
@@ -45,17 +47,26 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--pages", type=int, default=64, help="pages per GPU per step")
+    ap.add_argument("--pages", type=int, default=0, help="pages in the whole job (default: 1024 Gundam / 64 Base), sharded over the GPUs")
+    ap.add_argument("--batch", type=int, default=256, help="pages decoded in lock-step per group on one GPU")
     ap.add_argument("--max-new-tokens", type=int, default=512)
-    ap.add_argument("--mode", default="base", choices=["base", "gundam"])
-    ap.add_argument("--dtype", default="f16", choices=["f16", "bf16"])
+    ap.add_argument("--mode", default="gundam", choices=["base", "gundam"])
+    ap.add_argument("--dtype", default="", choices=["", "f16", "bf16"], help="default: bf16 Gundam / f16 Base (BASELINE.json)")
     ap.add_argument("--config", default="full", choices=["full", "tiny"])
-    ap.add_argument("--cpu-tokens", type=int, default=24, help="decode tokens in the CPU-baseline sample")
+    ap.add_argument("--cpu-tokens", type=int, default=64, help="decode tokens in the CPU-baseline sample")
+    ap.add_argument("--agree-pages", type=int, default=4, help="pages of the GPU batch compared token by token with the CPU oracle")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the f32-KV / batch-1 / CUPTI side measurements")
     ap.add_argument("--profile-json", default="", help="write the per-kernel timing breakdown here")
     ap.add_argument("--kv-cache", default="f16", choices=["f32", "f16"],
-                    help="KV cache storage: f16 (matches the fp16 config; token-exact on the fixtures) or f32 (the reference's choice)")
-    return ap.parse_args()
+                    help="KV cache storage of the headline run: f16 (half the decode-attention bytes; token agreement with the f32 "
+                         "oracle is reported) or f32 (the reference's choice; its number is printed beside the headline)")
+    a = ap.parse_args()
+    if not a.dtype:
+        a.dtype = "bf16" if a.mode == "gundam" else "f16"
+    if a.pages <= 0:
+        a.pages = 1024 if a.mode == "gundam" else 64
+    return a
 
 
 def checkpoint_dir(args) -> Path:
@@ -82,11 +93,24 @@ def ensure_checkpoint(args, rank: int):
     return cfg, d
 
 
-def make_pages(args, rank: int):
+def _page(job):
     from oracle import preprocess as P
 
+    w, h, seed = job
+    return P.synthetic_page(w, h, seed=seed)
+
+
+def make_pages(args, indices, workers: int):
+    """Synthetic document pages (SURVEY.md 8d generator), page i seeded with i.  Generated on forked worker processes
+    BEFORE anything touches CUDA (70 ms per A4 page on one core)."""
     w, h = (1024, 1024) if args.mode == "base" else (1654, 2339)
-    return [P.synthetic_page(w, h, seed=rank * 100000 + i) for i in range(args.pages)]
+    jobs = [(w, h, int(i)) for i in indices]
+    if workers <= 1 or len(jobs) < 16:
+        return [_page(j) for j in jobs]
+    import multiprocessing as mp
+
+    with mp.get_context("fork").Pool(workers) as pool:
+        return pool.map(_page, jobs, chunksize=8)
 
 
 class ClockSampler:
@@ -135,16 +159,19 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------- CPU baseline
-def cpu_reference_sample(args, cfg, ckdir: Path, page: np.ndarray, max_new: int) -> dict:
+def cpu_reference_sample(args, cfg, ckdir: Path, page: np.ndarray, max_new: int, n_tok: int, oracles=None) -> dict:
     """The oracle (CPU restatement of the reference algorithm, f32, torch/MKL threads = all host cores) on ONE
-    page: preprocess + vision + prefill + `cpu_tokens` decode steps; the token loop is extrapolated linearly to
+    page: preprocess + vision + prefill + `n_tok` decode steps; the token loop is extrapolated linearly to
     the full budget (per-step cost is dominated by the fixed 574 M active parameters)."""
     import torch
     from oracle import config as OC, decoder as D, preprocess as P, vision as V
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    ck = OC.load_checkpoint(str(ckdir / "model.safetensors"))
+    if oracles is None:
+        ck = OC.load_checkpoint(str(ckdir / "model.safetensors"))
+        oracles = (V.VisionOracle(cfg, ck), D.DecoderOracle(cfg, ck))
+    vo, do = oracles
     t = {}
     t0 = time.perf_counter()
     base, img = (1024, 1024) if args.mode == "base" else (1024, 640)
@@ -152,14 +179,12 @@ def cpu_reference_sample(args, cfg, ckdir: Path, page: np.ndarray, max_new: int)
     g = torch.from_numpy(P.image_to_tensor(vi["global"]))
     tiles = torch.from_numpy(np.stack([P.image_to_tensor(x) for x in vi["tiles"]])) if vi["tiles"] else None
     t["vision.prepare_inputs"] = time.perf_counter() - t0
-    vo = V.VisionOracle(cfg, ck)
     t0 = time.perf_counter()
     with torch.no_grad():
         rows = vo.encode(g, tiles, vi["crop_shape"])
     t["vision.compute_embeddings"] = time.perf_counter() - t0
-    do = D.DecoderOracle(cfg, ck)
     ids, mask = D.build_prompt_tokens([[], prompt_tail(cfg)], [rows.shape[0]], cfg)
-    n_tok = min(args.cpu_tokens, max_new)
+    n_tok = min(n_tok, max_new)
     marks = []
     t0 = time.perf_counter()
     with torch.no_grad():
@@ -170,21 +195,24 @@ def cpu_reference_sample(args, cfg, ckdir: Path, page: np.ndarray, max_new: int)
     t["decode.iterative"] = per_tok * (max_new - 1)
     page_s = sum(t.values())
     return {"pages_per_s": 1.0 / page_s, "seconds_per_page": page_s, "stages_s": t, "cores": cores,
-            "cpu_decode_tok_s": 1.0 / per_tok, "sample_tokens": n_tok, "sample_wall_s": total + t["vision.compute_embeddings"],
-            "first_tokens": toks[:8]}
+            "cpu_decode_tok_s": 1.0 / per_tok, "sample_tokens": n_tok,
+            "sample_wall_s": total + t["vision.compute_embeddings"] + t["vision.prepare_inputs"],
+            "tokens": toks, "oracles": oracles}
 
 
 # ------------------------------------------------------------------------------------------- roofline
-def kernel_model(cfg, name: str, args, pages: int, hbm_gbs: float, tf_peak: float, active_experts: float | None = None) -> dict | None:
-    """Algorithmic bytes / flops of one launch of a named kernel (DESIGN.md 'Kernels')."""
+def kernel_model(cfg, name: str, args, B: int, views: dict, ctx_mean: float, hbm_gbs: float, tf_peak: float,
+                 active_experts: float | None = None, launches: int = 1) -> dict | None:
+    """Algorithmic bytes / flops of an AVERAGE launch of a named kernel (DESIGN.md 'Kernels').
+    B = pages per decode step; views = {'global': (n, T), 'local': (n, T)} of the profiled pass."""
     H, V, E, mi, K = cfg.hidden_size, cfg.vocab_size, cfg.n_routed_experts, cfg.moe_intermediate_size, cfg.num_experts_per_tok
     S = mi * cfg.n_shared_experts
-    B = pages
     # routed-expert weight segments one launch really streams: measured (dsocr_moe_stats) when available
     Ea = active_experts if active_experts else min(E, B * K)
     phase, _, k = name.partition("/")
     if phase == "decode":
         act = lambda kk, nn, parts=2: B * kk * 2 * parts + B * nn * 4  # noqa: E731
+        kvb = 2 if args.kv_cache == "f16" else 4
         table = {
             "lm_head": V * H * 2 + act(H, V),
             "dec_qkv": 3 * H * H * 2 + act(H, 3 * H),
@@ -196,19 +224,23 @@ def kernel_model(cfg, name: str, args, pages: int, hbm_gbs: float, tf_peak: floa
             "moe_expert_down": (Ea + cfg.n_shared_experts) * H * mi * 2 + B * (K + cfg.n_shared_experts) * (mi * 4 + H * 4),
             "moe_shared_gate_up": 2 * S * H * 2 + act(H, S),
             "moe_shared_down": H * S * 2 + act(S, H),
+            # cached K and V rows of every (page, head) read once + the step's q/k/v row and the output row
+            "rope_attn_decode": B * (2 * ctx_mean * H * kvb + 3 * H * 4 + 2 * H * 2),
         }
         if k in table:
             return {"bound": "hbm", "bytes": float(table[k]), "peak": hbm_gbs, "unit": "GB/s"}
     if phase == "vision":
-        g = 64 if args.mode == "base" else 64
-        T = g * g
-        flops = {
-            "sam_qkv": 2 * T * 768 * 2304, "sam_proj": 2 * T * 768 * 768, "sam_fc1_gelu": 2 * T * 768 * 3072,
-            "sam_fc2": 2 * T * 3072 * 768, "sam_global_attention": 4 * T * T * 64 * 12,
-            "clip_fc1_quickgelu": 2 * 257 * 1024 * 4096, "clip_fc2": 2 * 257 * 1024 * 4096, "clip_qkv": 2 * 257 * 1024 * 3072,
+        (ng, Tg), (nl, Tl) = views["global"], views["local"]
+        T = ng * Tg + nl * Tl                      # SAM tokens of the pass
+        Tc = ng * (Tg // 16 + 1) + nl * (Tl // 16 + 1)   # CLIP tokens (incl. cls)
+        glob_layers = 4
+        total = {
+            "sam_qkv": 12 * 2 * T * 768 * 2304, "sam_proj": 12 * 2 * T * 768 * 768, "sam_fc1_gelu": 12 * 2 * T * 768 * 3072,
+            "sam_fc2": 12 * 2 * T * 3072 * 768, "sam_global_attention": glob_layers * 4 * (ng * Tg * Tg + nl * Tl * Tl) * 64 * 12,
+            "clip_fc1_quickgelu": 24 * 2 * Tc * 1024 * 4096, "clip_fc2": 24 * 2 * Tc * 1024 * 4096, "clip_qkv": 24 * 2 * Tc * 1024 * 3072,
         }
-        if k in flops:
-            return {"bound": "tensor", "flops": float(flops[k]) * B, "peak": tf_peak, "unit": "TFLOP/s"}
+        if k in total:
+            return {"bound": "tensor", "flops": float(total[k]) / max(1, launches), "peak": tf_peak, "unit": "TFLOP/s"}
     return None
 
 
@@ -226,8 +258,8 @@ def main():
     tf_sustained = float(peaks.get("bf16_tflops_sustained", 1400.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
     base, img, crop = (1024, 1024, False) if args.mode == "base" else (1024, 640, True)
-    workload = (f"deepseek-ocr {args.dtype} {'Base 1024x1024' if args.mode == 'base' else 'Gundam A4 1654x2339'}, "
-                f"batch of {args.pages} synthetic pages per GPU, {args.max_new_tokens}-token budget, greedy, "
+    workload = (f"deepseek-ocr {args.dtype} {'Base 1024x1024' if args.mode == 'base' else 'Gundam A4 1654x2339 (6 x 640 crops + 1024 global)'}, "
+                f"{args.pages} synthetic pages sharded over the GPUs, {args.max_new_tokens}-token budget, greedy, "
                 f"no_repeat_ngram_size=20, {args.kv_cache} KV cache, random-init weights ({args.config} architecture)")
 
     if args.impl == "reference":
@@ -235,10 +267,11 @@ def main():
         if rank != 0:
             return
         cfg, ckdir = ensure_checkpoint(args, 0)
-        page = make_pages(args, 0)[0]
-        vals = []
+        page = make_pages(args, [0], 1)[0]
+        vals, oracles = [], None
         for _ in range(max(1, min(args.steps, 2))):
-            r = cpu_reference_sample(args, cfg, ckdir, page, args.max_new_tokens)
+            r = cpu_reference_sample(args, cfg, ckdir, page, args.max_new_tokens, min(args.cpu_tokens, 32), oracles)
+            oracles = r.pop("oracles")
             vals.append(r)
         best = max(vals, key=lambda r: r["pages_per_s"])
         sample = (f"1 page through the f32 torch-CPU oracle: preprocess + vision + prefill + {best['sample_tokens']} decode "
@@ -246,7 +279,7 @@ def main():
         line = {
             "impl": "reference", "metric": "pages/sec/box", "value": best["pages_per_s"], "unit": "pages/s",
             "n_gpus": args.gpus, "steps": len(vals), "warmup": 0, "ms_per_step": best["seconds_per_page"] * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload},
             "cpu_baseline": {"value": best["pages_per_s"], "unit": "pages/s", "cores": best["cores"], "kind": "port",
                              "sample": sample, "stages_s": best["stages_s"], "decode_tok_s": best["cpu_decode_tok_s"]},
@@ -254,6 +287,15 @@ def main():
         }
         print(json.dumps(line))
         return
+
+    # ---- this rank's shard of the fixed page set (pages are independent: round-robin, no data-path collective)
+    from dsocr.sharding import shard_indices
+
+    mine = shard_indices(args.pages, rank, world)
+    t0 = time.time()
+    pages = make_pages(args, mine, max(1, min(16, (os.cpu_count() or 1) // max(1, world))))
+    if rank == 0:
+        print(f"[bench] {len(pages)} pages per rank generated in {time.time() - t0:.1f}s", file=sys.stderr)
 
     import torch
     import torch.distributed as dist
@@ -276,9 +318,9 @@ def main():
     stream = torch.cuda.Stream()  # a capturable (non-default) stream that torch events can bracket
     eng.set_stream(stream.cuda_stream)
     eng.set_option("kv_cache_f16", 1 if args.kv_cache == "f16" else 0)
+    eng.set_option("decode_batch", args.batch)
     vs = VisionSettings(base, img, crop)
     params = DecodeParameters(max_new_tokens=args.max_new_tokens, no_repeat_ngram_size=20, eos_token_id=None)
-    pages = make_pages(args, rank)
     # the e2e arm copies every step's pages host -> device inside the timed region: keep them in pinned host memory
     # (page-locked sources DMA directly; pageable ones are staged through the driver at a third of the rate)
     pinned = [torch.from_numpy(p).pin_memory() for p in pages]
@@ -325,11 +367,26 @@ def main():
     gen_tokens = sum(o.response_tokens for o in outs_res)
     d2h_bytes = gen_tokens * 8
 
-    # one extra step with per-kernel CUDA-event timing for the roofline / breakdown (not part of the timed value)
+    # ---- side measurements on ONE lock-step group of this rank's pages (not part of the timed value)
+    sub = pages[: min(len(pages), args.batch)]
+    nsub = len(sub)
+    eng.stage_pages(sub, vs)
+    kv_compare = None
+    if not args.no_extras:
+        res = {}
+        for kv in ("f16", "f32"):
+            eng.set_option("kv_cache_f16", 1 if kv == "f16" else 0)
+            step_resident()  # sizes the KV workspaces of this mode
+            ms, _ = timed(step_resident, 1)
+            res[kv] = {"pages_per_s_per_gpu": nsub / (ms * 1e-3), "ms": ms, "decode_ms": eng.timings()["decode.iterative"]}
+        eng.set_option("kv_cache_f16", 1 if args.kv_cache == "f16" else 0)
+        kv_compare = {"pages": nsub, "note": "one lock-step group on one GPU, views resident; the reference stores KV in f32 (model/mod.rs:82-88)", **res}
+
+    # one extra pass with per-kernel CUDA-event timing for the roofline / breakdown
     eng.set_option("moe_stats", 1)
     eng.moe_stats()
     eng.kernel_timing_begin()
-    step_resident()
+    outs_sub = step_resident()
     kt = eng.kernel_timing_end()
     seg, nsteps = eng.moe_stats()
     eng.set_option("moe_stats", 0)
@@ -338,81 +395,97 @@ def main():
     kt.sort(key=lambda r: -r["ms"])
     total_kernel_ms = sum(r["ms"] for r in kt)
     if args.profile_json and rank == 0:
-        Path(args.profile_json).write_text(json.dumps({"kernels": kt, "total_ms": total_kernel_ms, "stage_ms": stage_ms}, indent=1))
+        Path(args.profile_json).write_text(json.dumps({"kernels": kt, "total_ms": total_kernel_ms, "stage_ms": eng.timings(),
+                                                       "pages": nsub}, indent=1))
+    prompt_len = outs_sub[0].prompt_tokens
+    gen_mean = float(np.mean([o.response_tokens for o in outs_sub]))
+    ctx_mean = prompt_len + max(0.0, gen_mean - 1) / 2.0
+    n_tiles = 0 if args.mode == "base" else 6
+    views = {"global": (nsub, 4096), "local": (nsub * n_tiles, 1600)}
 
-    # the same step once more as it really runs (CUDA-graph replay), kernel durations from CUPTI activity records:
+    # the same pass once more as it really runs (CUDA-graph replay), kernel durations from CUPTI activity records:
     # the per-launch events above serialise the step and add the host launch gap to short kernels
     cupti = {}
-    try:
-        from torch.profiler import ProfilerActivity, profile
-        with profile(activities=[ProfilerActivity.CUDA]) as prof:
-            step_resident()
-            torch.cuda.synchronize()
-        for e in prof.events():
-            if e.device_type == torch.autograd.DeviceType.CUDA:
-                a = cupti.setdefault(e.name, [0.0, 0])
-                a[0] += e.time_range.end - e.time_range.start
-                a[1] += 1
-    except Exception as ex:  # diagnostics only
-        print(f"[bench] CUPTI pass skipped: {ex}", file=sys.stderr)
+    if not args.no_extras:
+        try:
+            from torch.profiler import ProfilerActivity, profile
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                step_resident()
+                torch.cuda.synchronize()
+            for e in prof.events():
+                if e.device_type == torch.autograd.DeviceType.CUDA:
+                    a = cupti.setdefault(e.name, [0.0, 0])
+                    a[0] += e.time_range.end - e.time_range.start
+                    a[1] += 1
+        except Exception as ex:  # diagnostics only
+            print(f"[bench] CUPTI pass skipped: {ex}", file=sys.stderr)
     cupti_match = {"decode/moe_expert_gate_up": ("linear_sk_kernel", ", 2>"), "decode/moe_expert_down": ("linear_sk_kernel", ", 1>"),
                    "decode/rope_attn_decode": ("rope_attn_decode", "")}
+    traffic_db = {}
+    try:
+        traffic_db = json.loads((ROOT / "profiles" / "roofline_traffic.json").read_text())
+    except Exception:
+        pass
 
-    roof = None
+    roof, roofs = None, []
     for r in kt:
-        m = kernel_model(cfg, r["name"], args, args.pages, hbm_peak, tf_sustained, active_experts)
+        m = kernel_model(cfg, r["name"], args, nsub, views, ctx_mean, hbm_peak, tf_sustained, active_experts, r["launches"])
         if m is None:
             continue
         avg_s = r["ms"] / r["launches"] * 1e-3
-        if m["bound"] == "hbm":
-            ach = m["bytes"] / avg_s / 1e9
-        else:
-            ach = m["flops"] / avg_s / 1e12
-        roof = {"kernel": r["name"], "bound": m["bound"], "achieved": ach, "peak": m["peak"], "unit": m["unit"],
-                "frac": ach / m["peak"], "traffic": None, "launches_per_step": r["launches"],
-                "avg_launch_us": avg_s * 1e6,
-                "active_experts_per_layer": active_experts, "share_of_step": r["ms"] / total_kernel_ms, "peak_source": peak_src,
-                "timed": "CUDA events after every launch on the engine stream, one extra profiled step"}
+        ach = (m["bytes"] / avg_s / 1e9) if m["bound"] == "hbm" else (m["flops"] / avg_s / 1e12)
+        tr = traffic_db.get(f"{args.mode}/{r['name']}") or traffic_db.get(r["name"])
+        entry = {"kernel": r["name"], "bound": m["bound"], "achieved": ach, "peak": m["peak"], "unit": m["unit"],
+                 "frac": ach / m["peak"], "traffic": tr.get("dram_bytes_per_launch") if tr else None,
+                 "traffic_source": tr.get("source") if tr else None,
+                 "algorithmic_per_launch": m.get("bytes", m.get("flops")), "launches_per_pass": r["launches"],
+                 "avg_launch_us": avg_s * 1e6, "share_of_pass": r["ms"] / total_kernel_ms}
         if r["name"] in cupti_match and cupti:
             a, b = cupti_match[r["name"]]
             us = [v for k, v in cupti.items() if a in k and (not b or k.split("(")[0].rstrip().endswith(b))]
             if us:
                 avg_us = sum(v[0] for v in us) / max(1, sum(v[1] for v in us))
                 ach_g = (m["bytes"] if m["bound"] == "hbm" else m["flops"] * 1e-3) / (avg_us * 1e-6) / 1e9
-                roof.update({"achieved_graph": ach_g, "frac_graph": ach_g / m["peak"], "avg_kernel_us_graph": avg_us,
-                             "timed_graph": "CUPTI kernel records (torch.profiler) of one more step running as the "
-                                            "production CUDA-graph replay"})
-        break
+                entry.update({"achieved_graph": ach_g, "frac_graph": ach_g / m["peak"], "avg_kernel_us_graph": avg_us})
+        roofs.append(entry)
+    if roofs:
+        roof = dict(roofs[0])  # the dominant kernel (largest share of the pass) that has a closed-form model
+        roof.update({"active_experts_per_layer": active_experts, "mean_context": ctx_mean, "pages_per_decode_step": nsub,
+                     "peak_source": peak_src,
+                     "timed": "CUDA events after every launch on the engine stream, one extra profiled pass over one lock-step group; "
+                              "achieved_graph = CUPTI kernel records of the same pass replayed as the production CUDA graph"})
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    pages_total = args.pages * world * args.steps
+    pages_total = args.pages * args.steps
     value = pages_total / (ms_res * 1e-3)
     e2e_val = pages_total / (ms_e2e * 1e-3)
     line = {
         "metric": "pages/sec/box", "value": value, "unit": "pages/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
         "config": {"workload": workload, "l2": "per-step working set (weights 6.7 GB + KV + activations) exceeds the 126 MB L2",
-                   "parallelism": f"pages sharded over {world} GPU(s), no collective"},
-        "e2e": {"value": e2e_val, "unit": "pages/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "host_memory": "pinned",
-                "ms_per_step": ms_e2e / args.steps},
+                   "parallelism": f"one fixed set of {args.pages} pages sharded round-robin over {world} GPU(s), "
+                                  f"{args.batch} pages per lock-step decode group, no collective"},
+        "e2e": {"value": e2e_val, "unit": "pages/s", "h2d_bytes_per_step": h2d_bytes * world, "d2h_bytes_per_step": d2h_bytes * world,
+                "host_memory": "pinned", "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches_e2e,
         "clocks": clocks,
         "decode_tok_s_per_gpu": gen_tokens / max(1e-9, stage_ms["decode.iterative"] * 1e-3),
         "stage_ms": stage_ms,
-        "top_kernels": [{"name": r["name"], "ms": round(r["ms"], 3), "launches": r["launches"]} for r in kt[:12]],
+        "kv_cache_compare": kv_compare,
+        "top_kernels": [{"name": r["name"], "ms": round(r["ms"], 3), "launches": r["launches"]} for r in kt[:14]],
         "roofline": roof,
+        "roofline_others": [{k: e[k] for k in ("kernel", "bound", "achieved", "frac", "share_of_pass", "avg_launch_us")} for e in roofs[1:8]],
     }
-    if world == 1:
+    if world == 1 and not args.no_extras:
         # BASELINE's second metric (decode tok/s per GPU) in the reference's own shape: one page per call.  Outside the
         # timed region; steps of <= 4 pages run the fused small-batch decode step (csrc/dsq_decode.cu).
         try:
-            import numpy as np
-            n_img = 273
+            n_img = 903 if args.mode == "gundam" else 273
             ids1 = [0] + [cfg.image_token_id] * n_img + prompt_tail(cfg)
             mask1 = [0] + [1] * n_img + [0] * len(prompt_tail(cfg))
             rows1 = (np.random.default_rng(0).standard_normal((n_img, cfg.hidden_size)) * 0.7).astype(np.float32)
@@ -427,16 +500,27 @@ def main():
             line["decode_batch1"] = {"error": str(ex)}
     if world == 1 and not args.no_cpu_baseline:
         try:
-            r = cpu_reference_sample(args, cfg, ckdir, pages[0], args.max_new_tokens)
+            r = cpu_reference_sample(args, cfg, ckdir, pages[0], args.max_new_tokens, args.cpu_tokens)
+            oracles = r.pop("oracles")
             line["cpu_baseline"] = {
                 "value": r["pages_per_s"], "unit": "pages/s", "cores": r["cores"], "kind": "port",
                 "sample": (f"1 page through the f32 torch-CPU oracle: preprocess + vision + prefill + {r['sample_tokens']} "
                            f"decode steps ({r['sample_wall_s']:.1f} s of CPU work), token loop extrapolated linearly to "
                            f"{args.max_new_tokens} tokens"),
                 "stages_s": r["stages_s"], "decode_tok_s": r["cpu_decode_tok_s"]}
-            # token agreement of the GPU batch's page 0 with the oracle over the sampled prefix
-            n = len(r["first_tokens"])
-            line["token_agreement_page0_first_tokens"] = sum(int(a == b) for a, b in zip(outs_res[0].generated_tokens[:n], r["first_tokens"])) / max(1, n)
+            # token agreement of pages of the timed GPU run (end-to-end call, the headline KV mode) with the f32 oracle
+            agree, total, per_page = 0, 0, []
+            refs = [r["tokens"]]
+            for i in range(1, min(args.agree_pages, len(pages))):
+                refs.append(cpu_reference_sample(args, cfg, ckdir, pages[i], args.max_new_tokens, args.cpu_tokens, oracles)["tokens"])
+            for i, ref in enumerate(refs):
+                got = outs[i].generated_tokens[: len(ref)]
+                a = sum(int(x == y) for x, y in zip(got, ref))
+                per_page.append(a / max(1, len(ref)))
+                agree += a; total += len(ref)
+            line["token_agreement"] = {"pages": len(refs), "tokens_per_page": len(refs[0]), "agreement": agree / max(1, total),
+                                       "per_page": per_page, "against": "f32 CPU oracle, same pages, free-running greedy",
+                                       "gpu_run": f"timed end-to-end call, {args.kv_cache} KV cache"}
         except Exception as ex:  # the baseline must never take the GPU number down with it
             line["cpu_baseline"] = {"value": None, "unit": "pages/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"failed: {ex}"}

@@ -10,6 +10,7 @@
 #include "dsq_dequant.h"
 #include "engine.h"
 #include "hostmath.h"
+#include "sampler.h"
 
 using namespace dsocr;
 
@@ -27,6 +28,7 @@ struct dsocr_engine {
   std::map<std::pair<int, int>, DevCoef> coefs;
   DevBuf pages_raw, horiz;
   bool host_preprocess = false;
+  int decode_batch = 256;  // requests decoded in lock-step per group
 };
 
 namespace {
@@ -99,6 +101,7 @@ extern "C" int dsocr_engine_set_option(dsocr_engine* e, const char* name, int va
     else if (n == "kv_cache_f16") e->impl->set_kv_f16(value != 0);
     else if (n == "moe_stats") e->impl->set_moe_stats(value != 0);
     else if (n == "host_preprocess") e->host_preprocess = value != 0;
+    else if (n == "decode_batch") { if (value < 1) throw std::runtime_error("decode_batch must be >= 1"); e->decode_batch = value; }
     else throw std::runtime_error("unknown option `" + n + "`");
   });
 }
@@ -155,6 +158,36 @@ extern "C" int dsocr_test_dsq_dequant64(uint32_t q_dtype, const uint8_t* blocks,
     const DsqPlanes pl{a.data(), b.data(), c.data(), d.data()};
     for (int r = 0; r < rows; ++r)
       for (int kb = 0; kb < K / 64; ++kb) dsq_dequant64((int)q_dtype, pl, r, K, kb, out + (size_t)r * K + (size_t)kb * 64);
+  });
+}
+
+extern "C" int dsocr_test_chacha_words(const uint8_t* key32, int rounds, int n, uint32_t* out) {
+  return api("", [&] {
+    if (!key32 || !out || n < 0) throw std::runtime_error("null argument");
+    StdRng rng(key32, rounds);
+    for (int i = 0; i < n; ++i) out[i] = rng.next_u32();
+  });
+}
+
+extern "C" int dsocr_test_stdrng_u64(uint64_t seed, int n, uint64_t* out) {
+  return api("", [&] {
+    if (!out || n < 0) throw std::runtime_error("null argument");
+    StdRng rng(seed);
+    for (int i = 0; i < n; ++i) out[i] = rng.next_u64();
+  });
+}
+
+extern "C" int dsocr_test_select_tokens(const float* logits, size_t vocab, int n_steps, const dsocr_decode_params* params,
+                                        const int64_t* context, size_t n_context, int64_t* out) {
+  return api("", [&] {
+    if (!logits || !params || !out || (!context && n_context)) throw std::runtime_error("null argument");
+    const SamplingParams sp = sampling_params_of(*params);
+    StdRng rng = params->has_seed ? StdRng(params->seed) : StdRng::from_entropy();
+    std::vector<int64_t> ctx(context, context + n_context);
+    for (int s = 0; s < n_steps; ++s) {
+      out[s] = select_token_id(logits + (size_t)s * vocab, vocab, sp, ctx.data(), ctx.size(), rng);
+      ctx.push_back(out[s]);
+    }
   });
 }
 
@@ -494,47 +527,110 @@ void stage_pages(dsocr_engine* e, int n_pages, const uint8_t* const* rgb, const 
   en.timings.prepare = now_ms() - t0;
 }
 
-void decode_staged(dsocr_engine* e, const int64_t* seg0, int n_seg0, const int64_t* seg1, int n_seg1,
-                   int64_t image_token_id, const dsocr_decode_params* params, dsocr_token_cb cb, void* user,
-                   int64_t* const* out_tokens, int* n_out, int* prompt_tokens, std::string& stage) {
+// One request = the reference's `decode(prompt, images)` (model/mod.rs:2370-2454): n_images staged views in a row and
+// n_images + 1 already-tokenised text segments around the <image> slots.
+struct RequestSpec {
+  int n_images = 0;
+  std::vector<const int64_t*> seg;
+  std::vector<int> seg_len;
+};
+
+// Requests [r0, r1) of a staged set: vision tower over their images, prompt build, generate.
+void decode_request_group(dsocr_engine* e, const std::vector<RequestSpec>& reqs, int r0, int r1, int img0, size_t tile0,
+                          int64_t image_token_id, const dsocr_decode_params* params, dsocr_token_cb cb, void* user,
+                          int64_t* const* out_tokens, int* n_out, int* prompt_tokens, std::string& stage, Timings& total) {
   Engine& en = *e->impl;
   auto& sg = e->staged;
-  const int n_pages = sg.n_pages;
-  if (n_pages <= 0) throw std::runtime_error("no pages staged");
+  const int n_req = r1 - r0;
+  int n_images = 0;
+  for (int r = r0; r < r1; ++r) n_images += reqs[r].n_images;
   const dsocr_vision_settings vs = sg.vs;
   const int G = vs.crop_mode ? (int)vs.base_size : (int)vs.image_size, P = (int)vs.image_size;
-  // ---- compute_image_embeddings
+  const size_t gbytes = (size_t)G * G * 3, tbytes = (size_t)P * P * 3;
+  // ---- compute_image_embeddings (model/mod.rs:2494-2534): nothing to do for text-only prompts
   stage = "image embedding failed";
   const double t1 = now_ms();
-  std::vector<Engine::PageViews> pages(n_pages);
-  for (int p = 0; p < n_pages; ++p) { pages[p].n_tiles = sg.ntiles[p]; pages[p].crop_w = sg.cw[p]; pages[p].crop_h = sg.ch[p]; }
   std::vector<int> counts;
-  const float* rows = en.vision_encode(n_pages, sg.globals.p, false, G, sg.tiles.p, false, P, pages, &counts);
-  cuda_check(cudaStreamSynchronize(en.stream()), "vision sync");
-  en.timings.vision = now_ms() - t1;
-  // ---- build_prompt_tokens (model/mod.rs:2536-2603): BOS + seg0 + <image> x n + seg1
+  const float* rows = nullptr;
+  if (n_images > 0) {
+    std::vector<Engine::PageViews> pages(n_images);
+    for (int p = 0; p < n_images; ++p) { pages[p].n_tiles = sg.ntiles[img0 + p]; pages[p].crop_w = sg.cw[img0 + p]; pages[p].crop_h = sg.ch[img0 + p]; }
+    rows = en.vision_encode(n_images, sg.globals.as<uint8_t>() + gbytes * img0, false, G, sg.tiles.as<uint8_t>() + tbytes * tile0,
+                            false, P, pages, &counts);
+    cuda_check(cudaStreamSynchronize(en.stream()), "vision sync");
+  }
+  total.vision += now_ms() - t1;
+  // ---- build_prompt_tokens (model/mod.rs:2536-2603): BOS + seg[0] + <image> x n_0 + seg[1] + ...
   stage = "prompt formatting failed";
-  std::vector<std::vector<int64_t>> ids(n_pages);
-  std::vector<std::vector<uint8_t>> masks(n_pages);
-  std::vector<const int64_t*> idp(n_pages);
-  std::vector<const uint8_t*> mp(n_pages);
-  std::vector<int> nt(n_pages);
-  for (int p = 0; p < n_pages; ++p) {
-    const int expect = image_token_count((int)vs.base_size, (int)vs.image_size, vs.crop_mode, sg.cw[p], sg.ch[p]);
-    if (expect != counts[p])
-      throw std::runtime_error("placeholder count " + std::to_string(expect) + " does not match expected " + std::to_string(counts[p]));
-    ids[p].push_back(0); masks[p].push_back(0);  // bos_id = 0 (model/mod.rs:2547)
-    for (int i = 0; i < n_seg0; ++i) { ids[p].push_back(seg0[i]); masks[p].push_back(0); }
-    for (int i = 0; i < counts[p]; ++i) { ids[p].push_back(image_token_id); masks[p].push_back(1); }
-    for (int i = 0; i < n_seg1; ++i) { ids[p].push_back(seg1[i]); masks[p].push_back(0); }
-    idp[p] = ids[p].data(); mp[p] = masks[p].data(); nt[p] = (int)ids[p].size();
-    if (prompt_tokens) prompt_tokens[p] = nt[p];
+  std::vector<std::vector<int64_t>> ids(n_req);
+  std::vector<std::vector<uint8_t>> masks(n_req);
+  std::vector<const int64_t*> idp(n_req);
+  std::vector<const uint8_t*> mp(n_req);
+  std::vector<int> nt(n_req), n_img_rows(n_req, 0);
+  int img = 0;
+  for (int r = 0; r < n_req; ++r) {
+    const RequestSpec& rq = reqs[r0 + r];
+    const int slots = std::max(0, (int)rq.seg.size() - 1);
+    if (slots != rq.n_images)
+      throw std::runtime_error("prompt/image embedding mismatch: " + std::to_string(slots) + " slots vs " +
+                               std::to_string(rq.n_images) + " embeddings");
+    ids[r].push_back(0); masks[r].push_back(0);  // bos_id = 0 (model/mod.rs:2547)
+    for (size_t sidx = 0; sidx < rq.seg.size(); ++sidx) {
+      for (int i = 0; i < rq.seg_len[sidx]; ++i) { ids[r].push_back(rq.seg[sidx][i]); masks[r].push_back(0); }
+      if ((int)sidx < rq.n_images) {
+        const int expect = image_token_count((int)vs.base_size, (int)vs.image_size, vs.crop_mode, sg.cw[img0 + img], sg.ch[img0 + img]);
+        if (expect != counts[img])
+          throw std::runtime_error("placeholder count " + std::to_string(expect) + " does not match expected " + std::to_string(counts[img]));
+        for (int i = 0; i < counts[img]; ++i) { ids[r].push_back(image_token_id); masks[r].push_back(1); }
+        n_img_rows[r] += counts[img];
+        ++img;
+      }
+    }
+    idp[r] = ids[r].data(); mp[r] = masks[r].data(); nt[r] = (int)ids[r].size();
+    if (prompt_tokens) prompt_tokens[r0 + r] = nt[r];
   }
   stage = "";
   Engine::GenRequest rq;
-  rq.n_pages = n_pages; rq.input_ids = idp.data(); rq.mask = mp.data(); rq.n_tokens = nt.data();
-  rq.image_rows_dev = rows; rq.n_image_rows = counts.data(); rq.params = *params; rq.cb = cb; rq.user = user;
-  en.generate(rq, out_tokens, n_out);
+  rq.n_pages = n_req; rq.input_ids = idp.data(); rq.mask = mp.data(); rq.n_tokens = nt.data();
+  rq.image_rows_dev = rows; rq.n_image_rows = n_img_rows.data(); rq.params = *params; rq.cb = cb; rq.user = user;
+  rq.page_offset = r0;
+  en.generate(rq, out_tokens + r0, n_out + r0);
+  total.prefill += en.timings.prefill; total.iterative += en.timings.iterative; total.generate += en.timings.generate;
+}
+
+// All requests of a staged set, `decode_batch` requests per lock-step group (option "decode_batch", default 256): the
+// decode step's weight traffic is shared by the pages of a group, its KV / activation workspaces grow with the group.
+void decode_staged_requests(dsocr_engine* e, const std::vector<RequestSpec>& reqs, int64_t image_token_id,
+                            const dsocr_decode_params* params, dsocr_token_cb cb, void* user, int64_t* const* out_tokens,
+                            int* n_out, int* prompt_tokens, std::string& stage) {
+  Engine& en = *e->impl;
+  auto& sg = e->staged;
+  const int n_req = (int)reqs.size();
+  int n_images = 0;
+  for (const auto& r : reqs) n_images += r.n_images;
+  if (n_images != sg.n_pages) throw std::runtime_error("staged views do not match the requests' image lists");
+  Timings total;
+  total.prepare = en.timings.prepare;
+  const int group = std::max(1, e->decode_batch);
+  int img0 = 0;
+  size_t tile0 = 0;
+  for (int r0 = 0; r0 < n_req; r0 += group) {
+    const int r1 = std::min(n_req, r0 + group);
+    decode_request_group(e, reqs, r0, r1, img0, tile0, image_token_id, params, cb, user, out_tokens, n_out, prompt_tokens, stage, total);
+    for (int r = r0; r < r1; ++r)
+      for (int i = 0; i < reqs[r].n_images; ++i) tile0 += sg.ntiles[img0++];
+  }
+  en.timings = total;
+}
+
+void decode_staged(dsocr_engine* e, const int64_t* seg0, int n_seg0, const int64_t* seg1, int n_seg1,
+                   int64_t image_token_id, const dsocr_decode_params* params, dsocr_token_cb cb, void* user,
+                   int64_t* const* out_tokens, int* n_out, int* prompt_tokens, std::string& stage) {
+  if (e->staged.n_pages <= 0) throw std::runtime_error("no pages staged");
+  RequestSpec one;
+  one.n_images = 1; one.seg = {seg0, seg1}; one.seg_len = {n_seg0, n_seg1};
+  std::vector<RequestSpec> reqs(e->staged.n_pages, one);
+  decode_staged_requests(e, reqs, image_token_id, params, cb, user, out_tokens, n_out, prompt_tokens, stage);
 }
 }  // namespace
 
@@ -570,6 +666,33 @@ extern "C" int dsocr_decode_pages(dsocr_engine* e, int n_pages, const uint8_t* c
       if (!params) throw std::runtime_error("null decode params");
       stage_pages(e, n_pages, rgb, widths, heights, vs);
       decode_staged(e, seg0, n_seg0, seg1, n_seg1, image_token_id, params, cb, user, out_tokens, n_out, prompt_tokens, stage);
+    } catch (const std::exception& ex) {
+      throw std::runtime_error(stage.empty() ? std::string(ex.what()) : stage + ": " + ex.what());
+    }
+  });
+}
+
+extern "C" int dsocr_decode_requests(dsocr_engine* e, int n_requests, const dsocr_request* requests, dsocr_vision_settings vs,
+                                     int64_t image_token_id, const dsocr_decode_params* params, dsocr_token_cb cb, void* user,
+                                     int64_t* const* out_tokens, int* n_out, int* prompt_tokens) {
+  std::string stage = "vision input failed";
+  return api("", [&] {
+    try {
+      bind(e);
+      if (!params || (!requests && n_requests > 0)) throw std::runtime_error("null argument");
+      std::vector<RequestSpec> reqs(n_requests);
+      std::vector<const uint8_t*> rgb;
+      std::vector<int> ws, hs;
+      for (int r = 0; r < n_requests; ++r) {
+        const dsocr_request& q = requests[r];
+        if (q.n_images < 0 || q.n_segments < 0) throw std::runtime_error("negative count in request");
+        reqs[r].n_images = q.n_images;
+        for (int i = 0; i < q.n_images; ++i) { rgb.push_back(q.rgb[i]); ws.push_back(q.widths[i]); hs.push_back(q.heights[i]); }
+        for (int i = 0; i < q.n_segments; ++i) { reqs[r].seg.push_back(q.segments[i]); reqs[r].seg_len.push_back(q.segment_lens[i]); }
+      }
+      if (!rgb.empty()) stage_pages(e, (int)rgb.size(), rgb.data(), ws.data(), hs.data(), vs);
+      else { e->staged.n_pages = 0; e->staged.vs = vs; e->impl->timings.prepare = 0; }
+      decode_staged_requests(e, reqs, image_token_id, params, cb, user, out_tokens, n_out, prompt_tokens, stage);
     } catch (const std::exception& ex) {
       throw std::runtime_error(stage.empty() ? std::string(ex.what()) : stage + ": " + ex.what());
     }

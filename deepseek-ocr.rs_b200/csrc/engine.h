@@ -89,6 +89,7 @@ class Engine {
     float* const* logits_out = nullptr;
     dsocr_token_cb cb = nullptr;
     void* user = nullptr;
+    int page_offset = 0;  // added to the page index the callback reports (calls that are one group of a larger batch)
   };
   void generate(const GenRequest& rq, int64_t* const* out_tokens, int* n_out);
 
@@ -171,6 +172,11 @@ class Engine {
 
   std::map<std::string, DevBuf> ws_;
   std::vector<DevBuf> kcache_, vcache_;
+  // KV cache of page p of the current pass lives at page (kv_page_base_ + p) of the call's cache (chunked prefill)
+  size_t kv_page_bytes_ = 0;
+  int kv_page_base_ = 0;
+  void* kc_ptr(int l) const { return (char*)kcache_[l].p + (size_t)kv_page_base_ * kv_page_bytes_; }
+  void* vc_ptr(int l) const { return (char*)vcache_[l].p + (size_t)kv_page_base_ * kv_page_bytes_; }
 };
 
 }  // namespace dsocr

@@ -5,6 +5,7 @@
 
 #include "engine.h"
 #include "linear_tc.cuh"
+#include "sampler.h"
 
 namespace dsocr {
 
@@ -98,11 +99,11 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
     }
     if (fused) {
       rope_attn_decode(sp_qkv > 1 ? partA : qkv, sp_qkv, rows * 3 * H, rope_cos_.as<float>(), rope_sin_.as<float>(),
-                       kcache_[l].p, vcache_[l].p, kv_f16_, row_page, row_pos, ctx16, rows * H, rows, heads, smax, scale, dt_, stream_);
+                       kc_ptr(l), vc_ptr(l), kv_f16_, row_page, row_pos, ctx16, rows * H, rows, heads, smax, scale, dt_, stream_);
     } else {
       rope_kv(sp_qkv > 1 ? partA : qkv, rope_cos_.as<float>(), rope_sin_.as<float>(), row_page, row_pos, q,
-              kcache_[l].p, vcache_[l].p, kv_f16_, rows, heads, smax, sp_qkv, rows * 3 * H, stream_);
-      kv_attention(q, kcache_[l].p, vcache_[l].p, kv_f16_, row_page, row_pos, ctx16, rows * H, nullptr, rows, heads, smax, scale,
+              kc_ptr(l), vc_ptr(l), kv_f16_, rows, heads, smax, sp_qkv, rows * 3 * H, stream_);
+      kv_attention(q, kc_ptr(l), vc_ptr(l), kv_f16_, row_page, row_pos, ctx16, rows * H, nullptr, rows, heads, smax, scale,
                    dt_, stream_, decode_mode ? nullptr : ws("prefill_page_spans", (size_t)2 * n_final * 4).as<int>(), decode_mode ? 0 : n_final);
     }
     {
@@ -294,9 +295,9 @@ void Engine::decoder_forward_dsq(float* x, long long rows, const int* row_page, 
     gemv(L.q_q, xn, H, qkv, 3 * H, rows, false, "dsq_q_proj");
     gemv(L.q_k, xn, H, qkv + H, 3 * H, rows, false, "dsq_k_proj");
     gemv(L.q_v, xn, H, qkv + 2 * H, 3 * H, rows, false, "dsq_v_proj");
-    rope_kv(qkv, rope_cos_.as<float>(), rope_sin_.as<float>(), row_page, row_pos, q, kcache_[l].p, vcache_[l].p, kv_f16_,
+    rope_kv(qkv, rope_cos_.as<float>(), rope_sin_.as<float>(), row_page, row_pos, q, kc_ptr(l), vc_ptr(l), kv_f16_,
             rows, heads, smax, 1, 0, stream_);
-    kv_attention(q, kcache_[l].p, vcache_[l].p, kv_f16_, row_page, row_pos, nullptr, 0, ctx, rows, heads, smax, scale, dt_, stream_);
+    kv_attention(q, kc_ptr(l), vc_ptr(l), kv_f16_, row_page, row_pos, nullptr, 0, ctx, rows, heads, smax, scale, dt_, stream_);
     gemv(L.q_o, ctx, H, x, H, rows, true, "dsq_o_proj");
     rmsnorm_split(x, L.ln2.as<float>(), xn16, rows * H, xn, nullptr, rows, H, c.rms_eps, nullptr, 0, 0, dt_, stream_);
     if (!L.moe) {
@@ -379,7 +380,7 @@ void Engine::decoder_step_fused_small(float* x, long long rows, const int* row_p
       std::swap(cur, alt);
       pend = DsqFusedStage();
     }
-    dsq_attn_split(qkv, rope_cos_.as<float>(), rope_sin_.as<float>(), kcache_[l].p, vcache_[l].p, kv_f16_, row_page, row_pos,
+    dsq_attn_split(qkv, rope_cos_.as<float>(), rope_sin_.as<float>(), kc_ptr(l), vc_ptr(l), kv_f16_, row_page, row_pos,
                    part, counters, ctx, rows, heads, c.head_dim(), smax, scale, nsplit, stream_);
     {
       DsqFusedJob j;
@@ -434,10 +435,10 @@ void Engine::generate(const GenRequest& rq, int64_t* const* out_tokens, int* n_o
   const ModelConfig& c = cfg_;
   const int P = rq.n_pages, H = c.hidden, V = c.vocab;
   if (P <= 0) return;
-  if (rq.params.do_sample) throw std::runtime_error("sampling is not supported on the device path (greedy only)");
-  if (rq.params.repetition_penalty != 0.f && fabsf(rq.params.repetition_penalty - 1.0f) > 1e-6f)
-    throw std::runtime_error("repetition_penalty != 1.0 is not supported");
   const bool forced = rq.forced != nullptr;
+  // sampling.rs:62: sampling needs do_sample and temperature > 0, everything else is the (device) argmax path
+  const bool host_sample = !forced && rq.params.do_sample && rq.params.temperature > 0.0;
+  const float penalty = rq.params.repetition_penalty;
   const int max_new = forced ? rq.n_forced_steps : (int)rq.params.max_new_tokens;
   for (int p = 0; p < P; ++p) n_out[p] = 0;
   if (max_new == 0) return;  // model/mod.rs:1889-1897
@@ -453,15 +454,23 @@ void Engine::generate(const GenRequest& rq, int64_t* const* out_tokens, int* n_o
   const int smax = (max_T + max_new + 15) / 16 * 16;
   if (smax > rope_len_) throw std::runtime_error("sequence length exceeds max_position_embeddings");
   std::vector<int> src(total_rows), row_page(total_rows), row_pos(total_rows), last_rows(P), hist((size_t)P * smax, 0), hist_len(P);
+  // The prompts are prefilled in chunks of whole pages (<= kPrefillRows rows each, so the activation workspaces stay
+  // bounded however many pages a call carries); row_page / last_rows are relative to the chunk a page belongs to.
+  constexpr long long kPrefillRows = 32768;
+  struct Chunk { int page0, n_pages; long long row0, rows; };
+  std::vector<Chunk> chunks;
   {
     long long r = 0, img_base = 0;
     for (int p = 0; p < P; ++p) {
+      if (chunks.empty() || chunks.back().rows + rq.n_tokens[p] > kPrefillRows) chunks.push_back({p, 0, r, 0});
+      Chunk& ch = chunks.back();
+      ch.n_pages++; ch.rows += rq.n_tokens[p];
       int img_used = 0;
       for (int t = 0; t < rq.n_tokens[p]; ++t, ++r) {
         const int64_t id = rq.input_ids[p][t];
         if (id < 0 || id >= V) throw std::runtime_error("token id out of range");
         hist[(size_t)p * smax + t] = (int)id;
-        row_page[r] = p; row_pos[r] = t;
+        row_page[r] = p - ch.page0; row_pos[r] = t;
         if (rq.mask && rq.mask[p] && rq.mask[p][t]) src[r] = -(int)(img_base + img_used++) - 1;
         else src[r] = (int)id;
       }
@@ -469,7 +478,7 @@ void Engine::generate(const GenRequest& rq, int64_t* const* out_tokens, int* n_o
         throw std::runtime_error("image embeddings provide " + std::to_string(rq.n_image_rows[p]) +
                                  " tokens but mask requires " + std::to_string(img_used));
       img_base += rq.n_image_rows[p];
-      last_rows[p] = (int)r - 1;
+      last_rows[p] = (int)(r - ch.row0) - 1;
       hist_len[p] = rq.n_tokens[p];
     }
   }
@@ -488,7 +497,11 @@ void Engine::generate(const GenRequest& rq, int64_t* const* out_tokens, int* n_o
   const size_t kv_bytes = (size_t)P * c.heads * smax * c.head_dim() * (kv_f16_ ? 2 : 4);
   kcache_.resize(c.layers); vcache_.resize(c.layers);
   for (int l = 0; l < c.layers; ++l) { kcache_[l].ensure(kv_bytes); vcache_[l].ensure(kv_bytes); }
+  kv_page_bytes_ = (size_t)c.heads * smax * c.head_dim() * (kv_f16_ ? 2 : 4);
+  kv_page_base_ = 0;
 
+  long long max_chunk_rows = P;
+  for (const Chunk& ch : chunks) max_chunk_rows = std::max(max_chunk_rows, ch.rows);
   const long long max_rows = std::max<long long>(total_rows, P);
   int* d_src = ws("gen_src", max_rows * 4).as<int>();
   int* d_row_page = ws("gen_row_page", max_rows * 4).as<int>();
@@ -497,7 +510,7 @@ void Engine::generate(const GenRequest& rq, int64_t* const* out_tokens, int* n_o
   int* d_hist = ws("gen_hist", (size_t)P * smax * 4).as<int>();
   int* d_state = ws("gen_state", (size_t)P * 3 * 4).as<int>();  // hist_len | gen_count | finished
   int* d_hist_len = d_state, *d_gen_count = d_state + P, *d_finished = d_state + 2 * P;
-  float* x = ws("gen_x32", max_rows * H * 4).as<float>();
+  float* x = ws("gen_x32", max_chunk_rows * H * 4).as<float>();
   float* logits = ws("gen_logits32", (size_t)P * V * 4).as<float>();
   float* sel_scratch = ws("gen_select_scratch", (size_t)P * kSelectScratchPerPage * 4).as<float>();
   cuda_check(cudaMemsetAsync(sel_scratch, 0, (size_t)P * kSelectScratchPerPage * 4, stream_), "select scratch memset");
@@ -531,19 +544,60 @@ void Engine::generate(const GenRequest& rq, int64_t* const* out_tokens, int* n_o
 
   // ---- prefill (model/mod.rs:1925-1947)
   kernel_timing_phase("prefill/");
-  embed_gather(d_src, embed_.p, img_rows, x, total_rows, H, dt_, stream_);
-  if (quantized_) decoder_forward_dsq(x, total_rows, d_row_page, d_row_pos, smax, d_last, P, logits);
-  else decoder_forward(x, total_rows, d_row_page, d_row_pos, smax, d_last, P, logits, false);
+  for (const Chunk& ch : chunks) {
+    kv_page_base_ = ch.page0;
+    embed_gather(d_src + ch.row0, embed_.p, img_rows, x, ch.rows, H, dt_, stream_);
+    if (quantized_) decoder_forward_dsq(x, ch.rows, d_row_page + ch.row0, d_row_pos + ch.row0, smax, d_last + ch.page0, ch.n_pages, logits + (size_t)ch.page0 * V);
+    else decoder_forward(x, ch.rows, d_row_page + ch.row0, d_row_pos + ch.row0, smax, d_last + ch.page0, ch.n_pages, logits + (size_t)ch.page0 * V, false);
+  }
+  kv_page_base_ = 0;
   copy_logits(0);
-  select_token(logits, V, d_hist, smax, d_hist_len, d_gen_count, d_finished, P, ngram, eos, max_new, d_forced, max_new,
-               d_selected, max_new, sel_scratch, stream_);
+  // host sampling state (do_sample): one RNG per page, seeded like the reference's single-page call (model/mod.rs:1917)
+  const SamplingParams sp = sampling_params_of(rq.params);
+  std::vector<StdRng> rngs;
+  std::vector<std::vector<int64_t>> ctxs;
+  std::vector<int> h_chosen, h_count, h_done;
+  std::vector<float> h_rows;
+  int* d_chosen = nullptr;
+  if (host_sample) {
+    for (int p = 0; p < P; ++p) {
+      rngs.push_back(rq.params.has_seed ? StdRng(rq.params.seed) : StdRng::from_entropy());
+      ctxs.emplace_back(rq.input_ids[p], rq.input_ids[p] + rq.n_tokens[p]);
+    }
+    h_chosen.assign(P, 0); h_count.assign(P, 0); h_done.assign(P, 0);
+    h_rows.resize((size_t)P * V);
+    d_chosen = ws("gen_chosen", (size_t)P * 4).as<int>();
+  }
+  auto select = [&]() {
+    if (!host_sample) {
+      select_token(logits, V, d_hist, smax, d_hist_len, d_gen_count, d_finished, P, ngram, penalty, eos, max_new, d_forced,
+                   max_new, d_selected, max_new, sel_scratch, stream_);
+      return;
+    }
+    cuda_check(cudaMemcpyAsync(h_rows.data(), logits, h_rows.size() * 4, cudaMemcpyDeviceToHost, stream_), "logits D2H");
+    cuda_check(cudaStreamSynchronize(stream_), "logits sync");
+    for (int p = 0; p < P; ++p) {
+      if (h_done[p]) continue;
+      const int64_t t = select_token_id(h_rows.data() + (size_t)p * V, (size_t)V, sp, ctxs[p].data(), ctxs[p].size(), rngs[p]);
+      h_chosen[p] = (int)t;
+      if (eos >= 0 && t == eos) { h_done[p] = 1; continue; }
+      ctxs[p].push_back(t);
+      if (++h_count[p] >= max_new) h_done[p] = 1;
+    }
+    cuda_check(cudaMemcpyAsync(d_chosen, h_chosen.data(), (size_t)P * 4, cudaMemcpyHostToDevice, stream_), "chosen H2D");
+    append_tokens(d_chosen, d_hist, smax, d_hist_len, d_gen_count, d_finished, P, eos, max_new, stream_);
+    cuda_check(cudaStreamSynchronize(stream_), "chosen sync");  // h_chosen is reused by the next step
+  };
+  select();
   cuda_check(cudaEventRecord(ev1, stream_), "event");
 
   // ---- token loop (model/mod.rs:1977-2034): every page advances one token per step
   std::vector<int> page_ids(P), fin(P), h_hist, h_len(P), delivered(P, 0);
   for (int p = 0; p < P; ++p) page_ids[p] = p;
   up(d_row_page, page_ids);
-  const int sync_every = rq.cb ? 4 : 16;
+  // with a callback every step is followed by a sync so that tokens are delivered one at a time, in the order the
+  // reference's loop would (model/mod.rs:1978-1982); without one the "all pages finished" test runs every 16 steps
+  const int sync_every = (rq.cb || host_sample) ? 1 : 16;
   auto deliver = [&]() {  // streaming callback: (count, all generated ids) after every accepted token
     if (!rq.cb) return;
     h_hist.resize((size_t)P * smax);
@@ -555,7 +609,7 @@ void Engine::generate(const GenRequest& rq, int64_t* const* out_tokens, int* n_o
       for (int cnt = delivered[p] + 1; cnt <= gen; ++cnt) {
         toks.resize(cnt);
         for (int i = 0; i < cnt; ++i) toks[i] = h_hist[(size_t)p * smax + rq.n_tokens[p] + i];
-        rq.cb(rq.user, p, (size_t)cnt, toks.data());
+        rq.cb(rq.user, p + rq.page_offset, (size_t)cnt, toks.data());
       }
       delivered[p] = std::max(delivered[p], gen);
     }
@@ -571,10 +625,9 @@ void Engine::generate(const GenRequest& rq, int64_t* const* out_tokens, int* n_o
     else if (quantized_) decoder_forward_dsq(x, P, d_row_page, d_row_pos, smax, d_row_page, P, logits);
     else decoder_forward(x, P, d_row_page, d_row_pos, smax, d_row_page /* identity: every row */, P, logits, true);
     copy_logits(step);
-    select_token(logits, V, d_hist, smax, d_hist_len, d_gen_count, d_finished, P, ngram, eos, max_new, d_forced, max_new,
-                 d_selected, max_new, sel_scratch, stream_);
+    select();
   };
-  bool use_graph = !kernel_timing_enabled() && !rq.logits_out && !record_taps_ && !getenv("DSOCR_NO_GRAPH");
+  bool use_graph = !kernel_timing_enabled() && !rq.logits_out && !record_taps_ && !host_sample && !getenv("DSOCR_NO_GRAPH");
   if (use_graph && (stream_ == nullptr || stream_ == cudaStreamLegacy || stream_ == cudaStreamPerThread))
     use_graph = false;  // the default streams cannot be captured
   cudaGraph_t graph = nullptr;

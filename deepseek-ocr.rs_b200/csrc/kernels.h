@@ -149,9 +149,12 @@ void moe_dispatch(const int* topk_idx, const int* offsets, int* cursor, const vo
 void moe_combine(const float* y, const int* perm_pos, const float* topk_w, float* x, long long rows, int topk, int H,
                  const float* partials, int n_splits, long long split_stride, cudaStream_t s);
 void select_token(const float* logits, int V, int* hist, int hist_stride, int* hist_len, int* gen_count, int* finished,
-                  int n_pages, int ngram, int eos, int max_new, const int* forced, int forced_stride,
+                  int n_pages, int ngram, float penalty, int eos, int max_new, const int* forced, int forced_stride,
                   int* selected_out, int selected_stride, float* scratch, cudaStream_t s);
-constexpr int kSelectScratchPerPage = 16 * 2 + 1;  // 32-bit words of select_token scratch per page
+constexpr int kSelectScratchPerPage = 16 * 3 * 2 + 1;  // 32-bit words of select_token scratch per page
+// host-selected tokens (sampling path): same bookkeeping as select_token's tail (append / EOS freeze / budget)
+void append_tokens(const int* chosen, int* hist, int hist_stride, int* hist_len, int* gen_count, int* finished, int n_pages,
+                   int eos, int max_new, cudaStream_t s);
 bool kernel_timing_enabled();
 void decode_rows(const int* hist, int hist_stride, const int* hist_len, int* src, int* row_pos, int n_pages,
                  cudaStream_t s);

@@ -1190,22 +1190,44 @@ __global__ void swiglu_reduce_kernel(const float* __restrict__ part, int n_split
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Token selection (crates/core/src/sampling.rs:34-158, greedy path): ban every token that would complete
-// an n-gram already present in the page's context (prompt + generated), then first-index argmax over the
-// finite logits.  One block per page.  The new token is appended to the history; pages that emitted EOS
-// (or reached their budget) are frozen.
-constexpr int kSelChunks = 16;   // vocabulary chunks (blocks) per page
+// Token selection (crates/core/src/sampling.rs:34-158, greedy path): repetition penalty over the distinct tokens
+// of the context (:120-139), ban of every token that would complete an n-gram already present in the page's
+// context (prompt + generated, :141-158), then first-index argmax over the finite values with the reference's
+// fall-backs (filtered -> penalised -> raw logits -> 0, :86-95).  kSelChunks blocks per page, each owning one
+// slice of the vocabulary: the banned / seen sets are bitmaps of that slice in shared memory, so there is no
+// cap on the number of bans (the reference's sets are unbounded HashSets).  The block that finishes last
+// reduces the slice winners, appends the new token to the history and freezes pages that emitted EOS (or
+// reached their budget).
+constexpr int kSelChunks = 16;   // vocabulary slices (blocks) per page
 constexpr int kSelThreads = 256;
+struct SelBest {
+  float v; int i;
+  __device__ void init() { v = -INFINITY; i = INT_MAX; }
+  __device__ void take(float ov, int oi) { if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; } }
+};
+__device__ __forceinline__ SelBest sel_block_reduce(SelBest b, float* s_val, int* s_idx) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, b.v, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, b.i, o);
+    b.take(ov, oi);
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) { s_val[threadIdx.x >> 5] = b.v; s_idx[threadIdx.x >> 5] = b.i; }
+  __syncthreads();
+  if (threadIdx.x == 0)
+    for (int w = 1; w < kSelThreads / 32; ++w) b.take(s_val[w], s_idx[w]);
+  return b;  // valid in thread 0
+}
 __global__ void __launch_bounds__(kSelThreads)
 select_token_kernel(const float* __restrict__ logits, int V, int* __restrict__ hist, int hist_stride,
                     int* __restrict__ hist_len, int* __restrict__ gen_count, int* __restrict__ finished, int ngram,
-                    int eos, int max_new, const int* __restrict__ forced, int forced_stride,
+                    float penalty, int eos, int max_new, const int* __restrict__ forced, int forced_stride,
                     int* __restrict__ selected_out, int selected_stride, float* __restrict__ part_val,
-                    int* __restrict__ part_idx, int* __restrict__ tickets) {
+                    int* __restrict__ part_idx, int* __restrict__ tickets, int per, int words) {
   const int page = blockIdx.y;
   const int chunk = blockIdx.x;
-  __shared__ int s_ban[64];
-  __shared__ int s_nban;
+  extern __shared__ unsigned s_bits[];  // [words] banned | [words] seen, bit t - c0
   __shared__ float s_val[kSelThreads / 32];
   __shared__ int s_idx[kSelThreads / 32];
   __shared__ int s_last;
@@ -1213,7 +1235,10 @@ select_token_kernel(const float* __restrict__ logits, int V, int* __restrict__ h
   const int step = gen_count[page];  // tokens accepted so far == index of this selection (graph-replay safe)
   int* h = hist + (long long)page * hist_stride;
   const int L = hist_len[page];
-  if (threadIdx.x == 0) s_nban = 0;
+  const int c0 = chunk * per, c1 = min(V, c0 + per);
+  unsigned* s_ban = s_bits;
+  unsigned* s_seen = s_bits + words;
+  for (int i = threadIdx.x; i < 2 * words; i += blockDim.x) s_bits[i] = 0u;
   __syncthreads();
   if (ngram > 1 && L >= ngram - 1) {
     const int pre = ngram - 1;
@@ -1221,17 +1246,22 @@ select_token_kernel(const float* __restrict__ logits, int V, int* __restrict__ h
       bool eq = true;
       for (int j = 0; j < pre && eq; ++j) eq = h[i + j] == h[L - pre + j];
       if (eq) {
-        const int slot = atomicAdd(&s_nban, 1);
-        if (slot < 64) s_ban[slot] = h[i + pre];
+        const int t = h[i + pre];
+        if (t >= c0 && t < c1) atomicOr(&s_ban[(t - c0) >> 5], 1u << ((t - c0) & 31));
       }
     }
   }
+  const bool use_pen = penalty > 0.f && fabsf(penalty - 1.0f) > FLT_EPSILON;  // sampling.rs:121-123
+  if (use_pen) {
+    for (int i = threadIdx.x; i < L; i += blockDim.x) {
+      const int t = h[i];
+      if (t >= c0 && t < c1) atomicOr(&s_seen[(t - c0) >> 5], 1u << ((t - c0) & 31));
+    }
+  }
   __syncthreads();
-  const int nban = min(s_nban, 64);
   const float* lg = logits + (long long)page * V;
-  const int per = ((V + kSelChunks - 1) / kSelChunks + 3) & ~3;  // chunk length, multiple of 4
-  const int c0 = chunk * per, c1 = min(V, c0 + per);
-  float bv = -INFINITY; int bi = INT_MAX;
+  SelBest bf, ba, br;  // best of: filtered (penalised + bans) | adjusted (penalised) | raw logits
+  bf.init(); ba.init(); br.init();
   for (int i = c0 + threadIdx.x * 4; i < c1; i += kSelThreads * 4) {
     float v4[4];
     if (i + 3 < c1 && ((reinterpret_cast<uintptr_t>(lg + i) & 15) == 0)) {
@@ -1239,45 +1269,49 @@ select_token_kernel(const float* __restrict__ logits, int V, int* __restrict__ h
       v4[0] = t.x; v4[1] = t.y; v4[2] = t.z; v4[3] = t.w;
     } else {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) v4[k] = (i + k < c1) ? lg[i + k] : -INFINITY;
+      for (int k = 0; k < 4; ++k) v4[k] = (i + k < c1) ? lg[i + k] : NAN;
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const float v = v4[k];
-      if (!(fabsf(v) <= FLT_MAX)) continue;  // skip NaN / inf like the reference's is_finite filter
-      bool banned = false;
-      for (int b = 0; b < nban; ++b) banned |= (s_ban[b] == i + k);
-      if (!banned && v > bv) { bv = v; bi = i + k; }  // ascending scan keeps the first index per thread
+      const float raw = v4[k];
+      const int t = i + k, bit = t - c0;
+      if (t >= c1) continue;
+      // ascending scan + strict > keeps the first index per thread; non-finite values are skipped like the
+      // reference's is_finite filter (sampling.rs:104-118)
+      if (fabsf(raw) <= FLT_MAX && raw > br.v) { br.v = raw; br.i = t; }
+      float adj = raw;
+      if (use_pen && ((s_seen[bit >> 5] >> (bit & 31)) & 1u)) adj = raw > 0.f ? __fdiv_rn(raw, penalty) : raw * penalty;
+      if (!(fabsf(adj) <= FLT_MAX)) continue;
+      if (adj > ba.v) { ba.v = adj; ba.i = t; }
+      if (!((s_ban[bit >> 5] >> (bit & 31)) & 1u) && adj > bf.v) { bf.v = adj; bf.i = t; }
     }
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-  }
-  if ((threadIdx.x & 31) == 0) { s_val[threadIdx.x >> 5] = bv; s_idx[threadIdx.x >> 5] = bi; }
-  __syncthreads();
+  bf = sel_block_reduce(bf, s_val, s_idx);
+  ba = sel_block_reduce(ba, s_val, s_idx);
+  br = sel_block_reduce(br, s_val, s_idx);
   if (threadIdx.x == 0) {
-    for (int w = 1; w < kSelThreads / 32; ++w)
-      if (s_val[w] > bv || (s_val[w] == bv && s_idx[w] < bi)) { bv = s_val[w]; bi = s_idx[w]; }
-    part_val[page * kSelChunks + chunk] = bv;
-    part_idx[page * kSelChunks + chunk] = bi;
+    const int o = (page * kSelChunks + chunk) * 3;
+    part_val[o] = bf.v; part_idx[o] = bf.i;
+    part_val[o + 1] = ba.v; part_idx[o + 1] = ba.i;
+    part_val[o + 2] = br.v; part_idx[o + 2] = br.i;
     __threadfence();
     s_last = atomicAdd(&tickets[page], 1) == kSelChunks - 1;
   }
   __syncthreads();
   if (!s_last || threadIdx.x != 0) return;
-  // last block of this page: reduce the chunk winners and do the bookkeeping
+  // last block of this page: reduce the slice winners and do the bookkeeping
   __threadfence();
   tickets[page] = 0;
-  bv = -INFINITY; bi = INT_MAX;
-  for (int c = 0; c < kSelChunks; ++c) {
-    const float v = reinterpret_cast<volatile float*>(part_val)[page * kSelChunks + c];
-    const int ix = reinterpret_cast<volatile int*>(part_idx)[page * kSelChunks + c];
-    if (v > bv || (v == bv && ix < bi)) { bv = v; bi = ix; }
-  }
-  int tok = bi == INT_MAX ? 0 : bi;
+  SelBest best[3];
+  for (int q = 0; q < 3; ++q) best[q].init();
+  for (int c = 0; c < kSelChunks; ++c)
+    for (int q = 0; q < 3; ++q) {
+      const int o = (page * kSelChunks + c) * 3 + q;
+      best[q].take(reinterpret_cast<volatile float*>(part_val)[o], reinterpret_cast<volatile int*>(part_idx)[o]);
+    }
+  int tok = 0;
+  for (int q = 2; q >= 0; --q)
+    if (best[q].i != INT_MAX) tok = best[q].i;  // filtered, else penalised, else raw, else 0
   if (selected_out) selected_out[(long long)page * selected_stride + step] = tok;
   if (forced) {
     tok = forced[(long long)page * forced_stride + step];
@@ -1290,6 +1324,22 @@ select_token_kernel(const float* __restrict__ logits, int V, int* __restrict__ h
   const int g = gen_count[page] + 1;
   gen_count[page] = g;
   if (g >= max_new) finished[page] = 1;
+}
+
+// Tokens chosen on the host (sampling path): append / EOS freeze / budget exactly like select_token_kernel's tail.
+__global__ void append_tokens_kernel(const int* __restrict__ chosen, int* __restrict__ hist, int hist_stride,
+                                     int* __restrict__ hist_len, int* __restrict__ gen_count, int* __restrict__ finished,
+                                     int n_pages, int eos, int max_new) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pages || finished[p]) return;
+  const int tok = chosen[p];
+  if (eos >= 0 && tok == eos) { finished[p] = 1; return; }
+  const int L = hist_len[p];
+  hist[(long long)p * hist_stride + L] = tok;
+  hist_len[p] = L + 1;
+  const int g = gen_count[p] + 1;
+  gen_count[p] = g;
+  if (g >= max_new) finished[p] = 1;
 }
 
 // Decode-step bookkeeping: for every page, the row of the next forward is its last history token at
@@ -1464,16 +1514,27 @@ void swiglu_reduce(const float* part, int n_splits, long long split_stride, long
   launch_check("swiglu_reduce");
 }
 void select_token(const float* logits, int V, int* hist, int hist_stride, int* hist_len, int* gen_count, int* finished,
-                  int n_pages, int ngram, int eos, int max_new, const int* forced, int forced_stride,
+                  int n_pages, int ngram, float penalty, int eos, int max_new, const int* forced, int forced_stride,
                   int* selected_out, int selected_stride, float* scratch, cudaStream_t s) {
-  // scratch: [n_pages*16] f32 values | [n_pages*16] i32 indices | [n_pages] i32 tickets (zero-initialised)
+  // scratch: [n_pages*16*3] f32 values | [n_pages*16*3] i32 indices | [n_pages] i32 tickets (zero-initialised)
   float* part_val = scratch;
-  int* part_idx = reinterpret_cast<int*>(scratch + (size_t)n_pages * kSelChunks);
-  int* tickets = part_idx + (size_t)n_pages * kSelChunks;
-  select_token_kernel<<<dim3(kSelChunks, n_pages), kSelThreads, 0, s>>>(logits, V, hist, hist_stride, hist_len, gen_count,
-                                                                      finished, ngram, eos, max_new, forced, forced_stride,
-                                                                      selected_out, selected_stride, part_val, part_idx, tickets);
+  int* part_idx = reinterpret_cast<int*>(scratch + (size_t)n_pages * kSelChunks * 3);
+  int* tickets = part_idx + (size_t)n_pages * kSelChunks * 3;
+  const int per = ((V + kSelChunks - 1) / kSelChunks + 3) & ~3;  // slice length, multiple of 4
+  const int words = (per + 31) / 32;
+  const size_t smem = (size_t)2 * words * 4;
+  if (smem > 48 * 1024) throw std::runtime_error("select_token: vocabulary too large for the per-slice bitmaps");
+  select_token_kernel<<<dim3(kSelChunks, n_pages), kSelThreads, smem, s>>>(logits, V, hist, hist_stride, hist_len, gen_count,
+                                                                         finished, ngram, penalty, eos, max_new, forced,
+                                                                         forced_stride, selected_out, selected_stride,
+                                                                         part_val, part_idx, tickets, per, words);
   launch_check("select_token");
+}
+void append_tokens(const int* chosen, int* hist, int hist_stride, int* hist_len, int* gen_count, int* finished, int n_pages,
+                   int eos, int max_new, cudaStream_t s) {
+  append_tokens_kernel<<<blocks_for(n_pages, 128), 128, 0, s>>>(chosen, hist, hist_stride, hist_len, gen_count, finished,
+                                                               n_pages, eos, max_new);
+  launch_check("append_tokens");
 }
 void decode_rows(const int* hist, int hist_stride, const int* hist_len, int* src, int* row_pos, int n_pages,
                  cudaStream_t s) {

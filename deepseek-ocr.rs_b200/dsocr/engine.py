@@ -24,7 +24,15 @@ class VisionSettingsC(C.Structure):
 
 class DecodeParamsC(C.Structure):
     _fields_ = [("max_new_tokens", C.c_uint32), ("do_sample", C.c_int32), ("repetition_penalty", C.c_float),
-                ("no_repeat_ngram_size", C.c_uint32), ("eos_token_id", C.c_int64), ("use_cache", C.c_int32)]
+                ("no_repeat_ngram_size", C.c_uint32), ("eos_token_id", C.c_int64), ("use_cache", C.c_int32),
+                ("has_seed", C.c_int32), ("temperature", C.c_double), ("top_p", C.c_double), ("top_k", C.c_uint32),
+                ("reserved_", C.c_uint32), ("seed", C.c_uint64)]
+
+
+class RequestC(C.Structure):
+    _fields_ = [("n_images", C.c_int32), ("rgb", C.POINTER(C.POINTER(C.c_uint8))), ("widths", C.POINTER(C.c_int32)),
+                ("heights", C.POINTER(C.c_int32)), ("n_segments", C.c_int32),
+                ("segments", C.POINTER(C.POINTER(C.c_int64))), ("segment_lens", C.POINTER(C.c_int32))]
 
 
 class EngineInfoC(C.Structure):
@@ -54,11 +62,17 @@ class DecodeParameters:  # crates/core/src/inference.rs:18-34, defaults :66-78
     no_repeat_ngram_size: Optional[int] = 20
     eos_token_id: Optional[int] = 1
     use_cache: bool = True
+    temperature: float = 0.0
+    top_p: Optional[float] = 1.0
+    top_k: Optional[int] = None
+    seed: Optional[int] = None
 
     def c(self) -> DecodeParamsC:
         return DecodeParamsC(self.max_new_tokens, 1 if self.do_sample else 0, self.repetition_penalty,
                              self.no_repeat_ngram_size or 0, -1 if self.eos_token_id is None else self.eos_token_id,
-                             1 if self.use_cache else 0)
+                             1 if self.use_cache else 0, 0 if self.seed is None else 1, float(self.temperature),
+                             -1.0 if self.top_p is None else float(self.top_p), int(self.top_k or 0), 0,
+                             int(self.seed or 0))
 
 
 @dataclass
@@ -250,6 +264,33 @@ class OcrEngine:
                                            _ptr_array(outs, C.c_int64), n_out, n_prompt), "decode")
         return [DecodeOutcome(n_prompt[i], n_out[i], outs[i][: n_out[i]].tolist()) for i in range(n)]
 
+
+    def decode_requests(self, requests: Sequence[tuple], vs: VisionSettings, image_token_id: int,
+                        params: DecodeParameters, callback=None) -> List[DecodeOutcome]:
+        """`OcrEngine::decode` for a batch of requests; request = (images: list of RGB8 arrays, segments: list of
+        token-id lists around the <image> slots, len(images) + 1 of them)."""
+        n = len(requests)
+        reqs = (RequestC * n)()
+        keep = []
+        for r, (images, segments) in enumerate(requests):
+            imgs = [np.ascontiguousarray(p, dtype=np.uint8) for p in images]
+            segs = [np.asarray(x, dtype=np.int64) for x in segments]
+            ws = (C.c_int32 * max(1, len(imgs)))(*[p.shape[1] for p in imgs])
+            hs = (C.c_int32 * max(1, len(imgs)))(*[p.shape[0] for p in imgs])
+            lens = (C.c_int32 * max(1, len(segs)))(*[len(x) for x in segs])
+            ip, sp = _ptr_array(imgs, C.c_uint8), _ptr_array(segs, C.c_int64)
+            keep.append((imgs, segs, ws, hs, lens, ip, sp))
+            reqs[r] = RequestC(len(imgs), C.cast(ip, C.POINTER(C.POINTER(C.c_uint8))), ws, hs, len(segs),
+                               C.cast(sp, C.POINTER(C.POINTER(C.c_int64))), lens)
+        outs = [np.zeros(max(1, params.max_new_tokens), dtype=np.int64) for _ in range(n)]
+        n_out = (C.c_int * n)()
+        n_prompt = (C.c_int * n)()
+        cb = TOKEN_CB(lambda user, page, count, toks: callback(page, count, [toks[i] for i in range(count)])) if callback else None
+        p = params.c()
+        check(self._lib.dsocr_decode_requests(self._h, n, reqs, vs.c(), C.c_int64(image_token_id), C.byref(p),
+                                              cb if cb else C.cast(None, TOKEN_CB), None, _ptr_array(outs, C.c_int64),
+                                              n_out, n_prompt), "decode")
+        return [DecodeOutcome(n_prompt[i], n_out[i], outs[i][: n_out[i]].tolist()) for i in range(n)]
 
     # -- staged variant (device-resident pages) ---------------------------------------------------
     def stage_pages(self, pages_rgb: Sequence[np.ndarray], vs: VisionSettings):

@@ -54,20 +54,31 @@ typedef struct dsocr_vision_settings {
   int32_t crop_mode;   /* 1    */
 } dsocr_vision_settings;
 
-/* DecodeParameters (crates/core/src/inference.rs:18-34, defaults :66-78).  Only greedy decoding is
- * implemented on the device (do_sample must be 0; the reference's CLI/server default). */
+/* DecodeParameters (crates/core/src/inference.rs:18-34, defaults :66-78).  Greedy selection (do_sample == 0 or
+ * temperature <= 0: sampling.rs:62 falls through to the argmax) runs on the device, including the repetition
+ * penalty and the no-repeat-n-gram ban.  With do_sample != 0 and temperature > 0 every step's logits rows are copied
+ * to the host and crates/core/src/sampling.rs:34-96 is restated there (temperature, top-k, top-p, StdRng seeded with
+ * `seed`: ChaCha12 + WeightedIndex, the draw sequence of rand 0.8); each page of a batched call owns an RNG seeded
+ * like the reference's single-page call. */
 typedef struct dsocr_decode_params {
   uint32_t max_new_tokens;       /* 512 */
   int32_t do_sample;             /* 0 */
-  float repetition_penalty;      /* 1.0 (only 1.0 is supported) */
+  float repetition_penalty;      /* 1.0; <= 0 or within f32 epsilon of 1 disables (sampling.rs:121-123) */
   uint32_t no_repeat_ngram_size; /* 20; 0 or 1 disables */
   int64_t eos_token_id;          /* < 0 disables EOS stopping */
-  int32_t use_cache;             /* 1 */
+  int32_t use_cache;             /* 1 (0 is accepted: the cached path computes the same tokens) */
+  int32_t has_seed;              /* 0: seed from the OS entropy source, like StdRng::from_entropy */
+  double temperature;            /* 0.0 */
+  double top_p;                  /* Option<f64>: < 0 = None; only values in [0, 1) filter (sampling.rs:74) */
+  uint32_t top_k;                /* Option<usize>: 0 = None */
+  uint32_t reserved_;
+  uint64_t seed;
 } dsocr_decode_params;
 
 /* Progress callback == the reference's `stream: Option<&dyn Fn(usize, &[i64])>` (inference.rs:205-207):
  * invoked synchronously on the calling thread after every accepted token with (count, all generated ids).
- * `page` is the index inside a batched call (0 for single-page calls). */
+ * `page` is the index inside a batched call (0 for single-page calls).  When a callback is set the decode loop
+ * synchronises after every step, so each page's callbacks arrive one token at a time as in model/mod.rs:1978-1982. */
 typedef void (*dsocr_token_cb)(void* user, int32_t page, size_t count, const int64_t* tokens);
 
 typedef struct dsocr_engine_info {
@@ -92,7 +103,9 @@ DSOCR_API int dsocr_engine_info_get(const dsocr_engine* e, dsocr_engine_info* in
 /* Engine options: "record_taps" (0/1) keeps host copies of the debug-trace taps of the next vision call;
  * "kv_cache_f16" (0/1) stores the KV cache in f16 instead of the reference's f32 (model/mod.rs:82-88): half the
  * decode-attention bytes, K/V rounded to 11 bits (off by default; parity numbers are quoted for both);
- * "host_preprocess" (0/1) runs the integer resample / tiling on the host cores instead of the device. */
+ * "host_preprocess" (0/1) runs the integer resample / tiling on the host cores instead of the device;
+ * "decode_batch" (n >= 1, default 256): dsocr_decode_pages / _staged / _requests split their pages into lock-step groups
+ * of at most n (vision + prefill + token loop per group); results do not depend on it. */
 DSOCR_API int dsocr_engine_set_option(dsocr_engine* e, const char* name, int value);
 
 /* DsqReader::open + header() / records() (crates/dsq/src/lib.rs:208-262): maps a `.dsq` snapshot, validates header and
@@ -187,13 +200,33 @@ DSOCR_API int dsocr_generate_forced(dsocr_engine* e, int n_pages, const int64_t*
 
 /* OcrEngine::decode minus tokenizer (model/mod.rs:2370-2454): RGB8 pages -> preprocess -> vision ->
  * build_prompt_tokens (:2536-2603; text segments are passed already tokenised: the tokenizer stays in the
- * host language) -> generate.  prompt_segments: n_segments id arrays around the single <image> slot
- * (n_segments == 2).  This is the end-to-end call the throughput benchmark times. */
+ * host language) -> generate.  One image per page with the text segments seg0 / seg1 around its single <image> slot
+ * (dsocr_decode_requests takes any number of images per prompt).  This is the end-to-end call the throughput
+ * benchmark times. */
 DSOCR_API int dsocr_decode_pages(dsocr_engine* e, int n_pages, const uint8_t* const* rgb, const int* widths,
                                  const int* heights, dsocr_vision_settings vs, const int64_t* seg0, int n_seg0,
                                  const int64_t* seg1, int n_seg1, int64_t image_token_id,
                                  const dsocr_decode_params* params, dsocr_token_cb cb, void* user,
                                  int64_t* const* out_tokens, int* n_out, int* prompt_tokens);
+
+/* OcrEngine::decode (model/mod.rs:2370-2454) in full generality, for a batch of independent requests: request r has
+ * images[n_images] (prepare_vision_inputs :2457-2492 maps over them; 0 images = text-only prompt, the vision tower is
+ * skipped) and the n_segments = n_images + 1 text segments of `prompt.split("<image>")` (:2551), already tokenised.
+ * Slot i receives the placeholders / embedding rows of image i (:2573-2592).  A segment count that does not match
+ * fails with "prompt formatting failed: prompt/image embedding mismatch: S slots vs N embeddings" (DSOCR_ERR_MISMATCH).
+ * Outputs are indexed by request; the callback's `page` is the request index. */
+typedef struct dsocr_request {
+  int32_t n_images;
+  const uint8_t* const* rgb;    /* [n_images] RGB8 HWC */
+  const int32_t* widths;        /* [n_images] */
+  const int32_t* heights;       /* [n_images] */
+  int32_t n_segments;
+  const int64_t* const* segments; /* [n_segments] token ids of each text segment (may be empty) */
+  const int32_t* segment_lens;    /* [n_segments] */
+} dsocr_request;
+DSOCR_API int dsocr_decode_requests(dsocr_engine* e, int n_requests, const dsocr_request* requests, dsocr_vision_settings vs,
+                                    int64_t image_token_id, const dsocr_decode_params* params, dsocr_token_cb cb, void* user,
+                                    int64_t* const* out_tokens, int* n_out, int* prompt_tokens);
 
 /* The two halves of dsocr_decode_pages, for callers that keep pages resident on the device:
  * dsocr_stage_pages = host integer preprocessing + host->device copy of the RGB8 views (engine-owned);

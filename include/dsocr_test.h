@@ -39,6 +39,16 @@ DSOCR_API int dsocr_test_vision_attention(int dtype, int B, int S, int H, const 
  * producer threads run.  out[rows, K] f32. */
 DSOCR_API int dsocr_test_dsq_dequant64(uint32_t q_dtype, const uint8_t* blocks, int rows, int K, float* out);
 
+/* Host-only hooks of the sampling path (csrc/sampler.cpp; sampling.rs:34-96 + rand 0.8 StdRng).
+ * dsocr_test_chacha_words: first n keystream words of the block RNG for a 32-byte key and a round count (12 = StdRng);
+ * dsocr_test_stdrng_u64: first n next_u64() draws of StdRng::seed_from_u64(seed);
+ * dsocr_test_select_tokens: n_steps calls of select_token_id on logits[step] with one RNG made from params
+ * (seeded or from entropy) and a context that grows by the selected token after every call, as generate does. */
+DSOCR_API int dsocr_test_chacha_words(const uint8_t* key32, int rounds, int n, uint32_t* out);
+DSOCR_API int dsocr_test_stdrng_u64(uint64_t seed, int n, uint64_t* out);
+DSOCR_API int dsocr_test_select_tokens(const float* logits, size_t vocab, int n_steps, const dsocr_decode_params* params,
+                                       const int64_t* context, size_t n_context, int64_t* out);
+
 #ifdef __cplusplus
 }
 #endif
