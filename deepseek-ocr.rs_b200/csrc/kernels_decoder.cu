@@ -387,9 +387,16 @@ kv_attention_prefill_tiled_kernel(const float* __restrict__ q, const TKV* __rest
     __syncthreads();  // previous tile fully consumed (also orders the Q stores before the first use)
     for (int c = tid; c < kPfK * (D / 8); c += 128) {  // 32 rows x 16 chunks of 8
       const int i = c >> 4, d8 = c & 15;
-      const int pos = min(k0 + i, smax - 1);  // rows past kend are masked below; keep the address in range
-      stage_row_chunk(kbase + (long long)pos * D + d8 * 8, Ks + i * kPfLd + d8 * 8);
-      stage_row_chunk(vbase + (long long)pos * D + d8 * 8, Vs + i * kPfLd + d8 * 8);
+      if (k0 + i < kend) {
+        stage_row_chunk(kbase + (long long)(k0 + i) * D + d8 * 8, Ks + i * kPfLd + d8 * 8);
+        stage_row_chunk(vbase + (long long)(k0 + i) * D + d8 * 8, Vs + i * kPfLd + d8 * 8);
+      } else {
+        // cache rows past the block's last position were never written by this call: stale bytes there may decode to
+        // Inf / NaN, and a masked probability of 0 times NaN would still poison the output row
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        reinterpret_cast<float4*>(Ks + i * kPfLd + d8 * 8)[0] = z; reinterpret_cast<float4*>(Ks + i * kPfLd + d8 * 8)[1] = z;
+        reinterpret_cast<float4*>(Vs + i * kPfLd + d8 * 8)[0] = z; reinterpret_cast<float4*>(Vs + i * kPfLd + d8 * 8)[1] = z;
+      }
     }
     __syncthreads();
     float sc[4][4];
