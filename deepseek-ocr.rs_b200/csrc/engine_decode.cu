@@ -41,7 +41,7 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
   LinearTile* tiles1 = ws("moe_tiles1", (size_t)max_chunks * (mi / 128) * sizeof(LinearTile)).as<LinearTile>();
   LinearTile* tiles2 = ws("moe_tiles2", (size_t)max_chunks * (H / 128) * sizeof(LinearTile)).as<LinearTile>();
   // decode mode: every expert owns a fixed-capacity segment of `cap` rows (a token picks an expert at most once)
-  const bool fused = decode_mode && rows <= 256;
+  const bool fused = decode_mode && rows <= fused_max_rows_;
   const long long cap = rows;
   const int Eg = E + c.n_shared;  // decode: routed experts + the shared experts as extra groups of the grouped GEMMs
   const long long perm_rows = fused ? std::max<long long>(n_assign, (long long)Eg * cap) : n_assign;

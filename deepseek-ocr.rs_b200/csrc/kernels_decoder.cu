@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include "ptx.cuh"
+#include "attention_prefill_tc.cuh"
 
 #include <cfloat>
 #include <cstdlib>
@@ -1433,9 +1434,33 @@ void rope_kv(const float* qkv, const float* cos_t, const float* sin_t, const int
 void kv_attention(const float* q, const void* kc, const void* vc, bool kv_f16, const int* row_page, const int* row_pos,
                   void* ctx, long long lo_off_elems, float* ctx32, long long rows, int heads, int smax, float scale,
                   DType dt, cudaStream_t s, int* page_spans, int n_pages) {
-  if (rows > 256 && page_spans && n_pages > 0) {  // prefill: 64-query x 32-key shared-memory tiles
+  if (rows > 256 && page_spans && n_pages > 0) {
     int* row0 = page_spans;
     int* plen = page_spans + n_pages;
+    page_spans_kernel<<<blocks_for(rows, 256), 256, 0, s>>>(row_page, row_pos, rows, row0, plen);
+    launch_check("page_spans");
+    static const bool simt = getenv("DSOCR_PREFILL_SIMT") != nullptr;  // A/B switch: the f32 shared-memory-tile kernel
+    if (!simt && !ctx32) {  // prefill on the tensor cores: 128 queries x 64-key blocks, hi/lo split f16 operands
+      const long long max_len = std::min<long long>(smax, rows);
+      dim3 pgrid((unsigned)((max_len + pattn::BQ - 1) / pattn::BQ), (unsigned)n_pages, (unsigned)heads);
+      const float scale_log2 = scale * 1.4426950408889634f;
+      if (kv_f16) {
+        DISPATCH_T(dt, {
+          auto kern = pattn::pattn_kernel<T, __half>;
+          cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pattn::Cfg<1>::kSmemBytes), "prefill attention smem");
+          kern<<<pgrid, pattn::kThreads, pattn::Cfg<1>::kSmemBytes, s>>>(q, (const __half*)kc, (const __half*)vc, row0, plen, (T*)ctx, lo_off_elems, heads, smax, scale_log2);
+        });
+      } else {
+        DISPATCH_T(dt, {
+          auto kern = pattn::pattn_kernel<T, float>;
+          cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pattn::Cfg<2>::kSmemBytes), "prefill attention smem");
+          kern<<<pgrid, pattn::kThreads, pattn::Cfg<2>::kSmemBytes, s>>>(q, (const float*)kc, (const float*)vc, row0, plen, (T*)ctx, lo_off_elems, heads, smax, scale_log2);
+        });
+      }
+      launch_check("kv_attention");
+      return;
+    }
+    // 64-query x 32-key shared-memory tiles, f32 FMA
     static bool configured = false;
     if (!configured) {
       cuda_check(cudaFuncSetAttribute(kv_attention_prefill_tiled_kernel<__half, __half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPfSmemBytes), "prefill attention smem");
@@ -1444,8 +1469,6 @@ void kv_attention(const float* q, const void* kc, const void* vc, bool kv_f16, c
       cuda_check(cudaFuncSetAttribute(kv_attention_prefill_tiled_kernel<__nv_bfloat16, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPfSmemBytes), "prefill attention smem");
       configured = true;
     }
-    page_spans_kernel<<<blocks_for(rows, 256), 256, 0, s>>>(row_page, row_pos, rows, row0, plen);
-    launch_check("page_spans");
     const long long max_len = std::min<long long>(smax, rows);  // blocks past a page's end exit at once
     dim3 tgrid((unsigned)((max_len + kPfQ - 1) / kPfQ), (unsigned)n_pages, (unsigned)heads);
     if (kv_f16) {

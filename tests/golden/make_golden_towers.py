@@ -217,5 +217,5 @@ if __name__ == "__main__":
     run(cfg, OC.random_checkpoint(cfg, seed=1234, storage=torch.bfloat16), store=True)
     if a.full:
         cfg = OC.full_config()
-        cfg.vocab_size = 4096  # the lm_head / embedding width is not what this compares
+        cfg.vocab_size, cfg.image_token_id = 4096, 4095  # the lm_head / embedding width is not what this compares
         run(cfg, OC.random_checkpoint(cfg, seed=1234, storage=torch.bfloat16), store=False)
