@@ -48,7 +48,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pages", type=int, default=0, help="pages in the whole job (default: 1024 Gundam / 64 Base), sharded over the GPUs")
-    ap.add_argument("--batch", type=int, default=256, help="pages decoded in lock-step per group on one GPU")
+    ap.add_argument("--batch", type=int, default=512, help="pages decoded in lock-step per group on one GPU")
     ap.add_argument("--max-new-tokens", type=int, default=512)
     ap.add_argument("--mode", default="gundam", choices=["base", "gundam"])
     ap.add_argument("--dtype", default="", choices=["", "f16", "bf16"], help="default: bf16 Gundam / f16 Base (BASELINE.json)")

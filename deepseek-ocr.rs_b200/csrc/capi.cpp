@@ -28,7 +28,7 @@ struct dsocr_engine {
   std::map<std::pair<int, int>, DevCoef> coefs;
   DevBuf pages_raw, horiz;
   bool host_preprocess = false;
-  int decode_batch = 256;  // requests decoded in lock-step per group
+  int decode_batch = 512;  // requests decoded in lock-step per group
 };
 
 namespace {
@@ -598,7 +598,7 @@ void decode_request_group(dsocr_engine* e, const std::vector<RequestSpec>& reqs,
   total.prefill += en.timings.prefill; total.iterative += en.timings.iterative; total.generate += en.timings.generate;
 }
 
-// All requests of a staged set, `decode_batch` requests per lock-step group (option "decode_batch", default 256): the
+// All requests of a staged set, `decode_batch` requests per lock-step group (option "decode_batch", default 512): the
 // decode step's weight traffic is shared by the pages of a group, its KV / activation workspaces grow with the group.
 void decode_staged_requests(dsocr_engine* e, const std::vector<RequestSpec>& reqs, int64_t image_token_id,
                             const dsocr_decode_params* params, dsocr_token_cb cb, void* user, int64_t* const* out_tokens,

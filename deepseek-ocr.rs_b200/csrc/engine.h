@@ -147,7 +147,7 @@ class Engine {
   void retile_inplace(DevBuf& w, long long n, int k);
   bool streamk_ = getenv("DSOCR_NO_STREAMK") == nullptr;  // A/B switch: balanced static units instead
   // largest decode batch (pages per step) that takes the fused decode schedule (post_attn / stream-K experts / combine_norm)
-  int fused_max_rows_ = getenv("DSOCR_FUSED_MAX_ROWS") ? atoi(getenv("DSOCR_FUSED_MAX_ROWS")) : 256;
+  int fused_max_rows_ = getenv("DSOCR_FUSED_MAX_ROWS") ? atoi(getenv("DSOCR_FUSED_MAX_ROWS")) : 1024;
   DevBuf sk_ws_, sk_flags_;  // stream-K partial slots + hand-off flags of the decode-time expert GEMMs
   bool quantized_ = false;
   // A/B switch: decode steps of <= 4 pages through the batched kernels (float engine) / per-linear GEMVs (DSQ)

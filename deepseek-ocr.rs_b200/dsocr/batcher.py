@@ -2,8 +2,8 @@
 behind `Arc<Mutex<..>>` and every `/v1/chat/completions` call runs `decode` under that lock (server/src/state.rs:210-224,
 generation.rs:84-103), because `generate` is batch-1.  This engine decodes many pages in lock step, so concurrent requests
 are collected for a few milliseconds and run as one batch; tokens stream back per request through the engine's per-page
-callback.  Requests are only batched together when they agree on everything one engine call shares (vision settings,
-decode parameters, prompt token segments)."""
+callback.  Requests are only batched together when they agree on what one engine call shares (vision settings, decode
+parameters, the <image> token id); prompts and image counts may differ per request (dsocr_decode_requests)."""
 from __future__ import annotations
 
 import queue
@@ -16,18 +16,27 @@ from typing import Any, Callable, List, Optional, Sequence, Tuple
 
 @dataclass
 class PageRequest:
-    page: Any                                  # RGB8 H x W x 3
-    seg0: Tuple[int, ...]                      # prompt token ids before <image>
-    seg1: Tuple[int, ...]                      # ... and after
+    page: Any                                  # RGB8 H x W x 3 (the first image; None for a text-only prompt)
+    seg0: Tuple[int, ...]                      # prompt token ids before the first <image>
+    seg1: Tuple[int, ...]                      # ... and after it
     image_token_id: int
     vision: Tuple[int, int, bool]              # base_size, image_size, crop_mode
-    params: Tuple                              # hashable decode parameters (max_new_tokens, ngram, eos, ...)
-    on_tokens: Optional[Callable[[int, List[int]], None]] = None   # (count, all generated ids) after every sync point
+    params: Tuple                              # hashable decode parameters (max_new_tokens, ngram, eos, sampling ...)
+    on_tokens: Optional[Callable[[int, List[int]], None]] = None   # (count, all generated ids) after every accepted token
+    more: Tuple = ()                           # further (image, token ids after its <image>) pairs of a multi-image prompt
     future: Future = field(default_factory=Future)
     enqueued: float = field(default_factory=time.perf_counter)
 
     def key(self):
-        return (self.seg0, self.seg1, self.image_token_id, self.vision, self.params)
+        return (self.image_token_id, self.vision, self.params)
+
+    def images(self) -> list:
+        return ([] if self.page is None else [self.page]) + [m[0] for m in self.more]
+
+    def segments(self) -> list:
+        if self.page is None:
+            return [list(self.seg0)]
+        return [list(self.seg0), list(self.seg1)] + [list(m[1]) for m in self.more]
 
 
 class PageBatcher:
@@ -65,6 +74,10 @@ class PageBatcher:
                     continue
                 return
             batch, skipped = [first], []
+            # compatible requests that an earlier round had to set aside join this batch first
+            for item in self._held:
+                (batch if item.key() == first.key() and len(batch) < self.max_batch else skipped).append(item)
+            self._held = []
             deadline = time.perf_counter() + self.max_wait
             stop = False
             while len(batch) < self.max_batch:
@@ -94,8 +107,8 @@ class PageBatcher:
 
 
 def engine_runner(engine, make_params, make_vision) -> Callable[[List[PageRequest]], Sequence[Any]]:
-    """run_batch over a dsocr.engine.OcrEngine: one `decode_pages` call per batch; the per-page callback of the engine
-    (count, all generated ids) is routed to the request that owns the page."""
+    """run_batch over a dsocr.engine.OcrEngine: one `decode_requests` call per batch; the per-request callback of the
+    engine (count, all generated ids) is routed to the request that owns it."""
     def run(batch: List[PageRequest]):
         first = batch[0]
 
@@ -105,6 +118,6 @@ def engine_runner(engine, make_params, make_vision) -> Callable[[List[PageReques
                 r.on_tokens(count, tokens)
 
         want_cb = any(r.on_tokens is not None for r in batch)
-        return engine.decode_pages([r.page for r in batch], make_vision(first.vision), list(first.seg0), list(first.seg1),
-                                   first.image_token_id, make_params(first.params), cb if want_cb else None)
+        return engine.decode_requests([(r.images(), r.segments()) for r in batch], make_vision(first.vision),
+                                      first.image_token_id, make_params(first.params), cb if want_cb else None)
     return run

@@ -99,8 +99,18 @@ def convert_messages(messages: List[Dict[str, Any]]) -> Tuple[str, List[np.ndarr
     return "\n\n".join(sections).strip(), images
 
 
+def params_from_tuple(p: Tuple):
+    """The hashable decode-parameter tuple a request carries through the batcher -> dsocr.engine.DecodeParameters."""
+    from .engine import DecodeParameters
+
+    budget, ngram, eos, do_sample, temperature, top_p, top_k, penalty, seed = p
+    return DecodeParameters(max_new_tokens=budget, no_repeat_ngram_size=ngram or None, eos_token_id=eos, do_sample=do_sample,
+                            temperature=temperature, top_p=top_p, top_k=top_k, repetition_penalty=penalty, seed=seed)
+
+
 def create_app(batcher: PageBatcher, tokenizer: Any, image_token_id: int, model_id: str = "deepseek-ocr",
-               vision: Tuple[int, int, bool] = (1024, 640, True), max_new_tokens: int = 512, no_repeat_ngram_size: int = 20):
+               vision: Tuple[int, int, bool] = (1024, 640, True), max_new_tokens: int = 512, no_repeat_ngram_size: int = 20,
+               max_budget: int = 8192 - 1024):
     app = FastAPI(title="dsocr-b200")
 
     def decode_text(ids: List[int]) -> str:
@@ -217,14 +227,27 @@ def create_app(batcher: PageBatcher, tokenizer: Any, image_token_id: int, model_
             return StreamingResponse(fallback(), media_type="text/event-stream")
 
         pieces = split_prompt_on_image(prompt)
-        if len(pieces) - 1 != len(images) or len(images) != 1:
-            # the wording the reference's server maps to HTTP 400 (generation.rs:111-115)
-            return bad(f"prompt formatting failed: prompt/image embedding mismatch: {len(pieces) - 1} <image> placeholders, "
-                       f"{len(images)} images (one image per request is served)")
+        if len(pieces) - 1 != len(images):
+            # the wording the reference's server maps to HTTP 400 (generation.rs:111-115, model/mod.rs:2550-2555)
+            return bad(f"prompt formatting failed: prompt/image embedding mismatch: {len(pieces) - 1} slots vs "
+                       f"{len(images)} embeddings")
         segs = tokenize_segments(tokenizer, pieces)
-        budget = int(shape.budget(req) or max_new_tokens)
-        ngram = int(req["no_repeat_ngram_size"]) if req.get("no_repeat_ngram_size") is not None else no_repeat_ngram_size
-        params = (budget, ngram, 1)
+        try:
+            # the budget is clamped to what the server allows (a larger one would only fail later against the position table)
+            budget = max(0, min(int(shape.budget(req) or max_new_tokens), max_budget))
+            ngram = int(req["no_repeat_ngram_size"]) if req.get("no_repeat_ngram_size") is not None else no_repeat_ngram_size
+            if ngram < 0 or ngram > 4096:
+                return bad("no_repeat_ngram_size must be between 0 and 4096")
+            # DecodeParameters of the request (routes.rs / generation.rs forward them unchanged): greedy unless do_sample
+            temperature = float(req.get("temperature") or 0.0)
+            do_sample = bool(req.get("do_sample", False))
+            top_p = float(req["top_p"]) if req.get("top_p") is not None else 1.0
+            top_k = int(req["top_k"]) if req.get("top_k") is not None else None
+            penalty = float(req.get("repetition_penalty") or 1.0)
+            seed = int(req["seed"]) if req.get("seed") is not None else None
+        except (TypeError, ValueError) as ex:
+            return bad(f"invalid generation parameter: {ex}")
+        params = (budget, ngram, 1, do_sample, temperature, top_p, top_k, penalty, seed)
         loop = asyncio.get_running_loop()
         events: "asyncio.Queue[Tuple[int, List[int]]]" = asyncio.Queue()
 
@@ -232,7 +255,8 @@ def create_app(batcher: PageBatcher, tokenizer: Any, image_token_id: int, model_
             loop.call_soon_threadsafe(events.put_nowait, (count, list(tokens)))
 
         pr = PageRequest(page=images[0], seg0=tuple(segs[0]), seg1=tuple(segs[1]), image_token_id=image_token_id, vision=vision,
-                         params=params, on_tokens=on_tokens if stream else None)
+                         params=params, on_tokens=on_tokens if stream else None,
+                         more=tuple((images[i], tuple(segs[i + 1])) for i in range(1, len(images))))
         fut = asyncio.wrap_future(batcher.submit(pr))
         if not stream:
             try:

@@ -104,7 +104,7 @@ DSOCR_API int dsocr_engine_info_get(const dsocr_engine* e, dsocr_engine_info* in
  * "kv_cache_f16" (0/1) stores the KV cache in f16 instead of the reference's f32 (model/mod.rs:82-88): half the
  * decode-attention bytes, K/V rounded to 11 bits (off by default; parity numbers are quoted for both);
  * "host_preprocess" (0/1) runs the integer resample / tiling on the host cores instead of the device;
- * "decode_batch" (n >= 1, default 256): dsocr_decode_pages / _staged / _requests split their pages into lock-step groups
+ * "decode_batch" (n >= 1, default 512): dsocr_decode_pages / _staged / _requests split their pages into lock-step groups
  * of at most n (vision + prefill + token loop per group); results do not depend on it. */
 DSOCR_API int dsocr_engine_set_option(dsocr_engine* e, const char* name, int value);
 

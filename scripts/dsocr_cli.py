@@ -66,6 +66,7 @@ def build_parser() -> argparse.ArgumentParser:
     ap.add_argument("--prompt-file")
     ap.add_argument("--prompt-ids", help="JSON [[ids...], [ids...]]: token ids of the text before / after <image> (offline use)")
     ap.add_argument("--image-token-id", type=int, help="id of <image> when no tokenizer file is given")
+    ap.add_argument("--eos-token-id", type=int, default=1, help="config.json eos_token_id (1 for the released checkpoint)")
     ap.add_argument("--image", dest="images", action="append", default=[])
     ap.add_argument("--bench", action="store_true")
     ap.add_argument("--bench-output")
@@ -87,12 +88,13 @@ def resolve_prompt(args, tokenizer):
     """-> (user prompt, rendered prompt, [ids before image, ids after image], image token id)."""
     if args.prompt_ids:
         segs = json.loads(args.prompt_ids)
-        if not (isinstance(segs, list) and len(segs) == 2):
-            raise SystemExit("--prompt-ids needs exactly two id lists (before and after <image>)")
+        if not (isinstance(segs, list) and len(segs) == len(args.images) + 1):
+            raise SystemExit("prompt formatting failed: prompt/image embedding mismatch: --prompt-ids needs one id list more "
+                             "than there are --image arguments (the text around every <image> slot)")
         if args.image_token_id is None:
             raise SystemExit("--prompt-ids needs --image-token-id")
         text = args.prompt or ""
-        return text, text, [list(map(int, segs[0])), list(map(int, segs[1]))], args.image_token_id
+        return text, text, [list(map(int, x)) for x in segs], args.image_token_id
     if args.prompt_file:
         text = Path(args.prompt_file).read_text()
     elif args.prompt is not None:
@@ -126,10 +128,6 @@ def run(args) -> int:
 
     if args.model != "deepseek-ocr":
         raise SystemExit(f"model `{args.model}` is not served by this engine (deepseek-ocr only)")
-    if args.do_sample:
-        raise SystemExit("sampling is not supported on the device path (greedy only)")
-    if len(args.images) != 1:
-        raise SystemExit("exactly one --image per call is supported (pages are batched through the library API, not the CLI)")
     if not args.model_config or not args.weights:
         raise SystemExit("--model-config and --weights are required")
     tokenizer = None
@@ -140,15 +138,17 @@ def run(args) -> int:
     t0 = time.perf_counter()
     user_prompt, rendered, segs, image_id = resolve_prompt(args, tokenizer)
     rec.record(report.STAGE_PROMPT, time.perf_counter() - t0)
-    page = np.asarray(Image.open(args.images[0]).convert("RGB"))  # DynamicImage::to_rgb8 drops alpha
+    pages = [np.asarray(Image.open(p).convert("RGB")) for p in args.images]  # DynamicImage::to_rgb8 drops alpha
 
     t0 = time.perf_counter()
     eng = load_model(args.model_config, args.weights, args.snapshot, device_ordinal(args.device), args.dtype)
     rec.record(report.STAGE_LOAD, time.perf_counter() - t0)
-    params = DecodeParameters(max_new_tokens=args.max_new_tokens, do_sample=False, repetition_penalty=args.repetition_penalty,
-                              no_repeat_ngram_size=args.no_repeat_ngram_size or None, eos_token_id=1, use_cache=not args.no_cache)
+    params = DecodeParameters(max_new_tokens=args.max_new_tokens, do_sample=args.do_sample, temperature=args.temperature or 0.0,
+                              top_p=args.top_p, top_k=args.top_k, seed=args.seed, repetition_penalty=args.repetition_penalty,
+                              no_repeat_ngram_size=args.no_repeat_ngram_size or None, eos_token_id=args.eos_token_id,
+                              use_cache=not args.no_cache)
     vs = VisionSettings(args.base_size, args.image_size, args.crop_mode)
-    out = eng.decode_pages([page], vs, segs[0], segs[1], image_id, params)[0]
+    out = eng.decode_requests([(pages, segs)], vs, image_id, params)[0]
     report.record_engine_timings(rec, eng.timings(), out.prompt_tokens, out.response_tokens)
     eng.close()
 

@@ -34,7 +34,7 @@ def main(argv=None) -> int:
 
     from dsocr.batcher import PageBatcher, engine_runner
     from dsocr.engine import DecodeParameters, VisionSettings, load_model
-    from dsocr.server import create_app
+    from dsocr.server import create_app, params_from_tuple
 
     tok = Tokenizer.from_file(a.tokenizer)
     image_id = tok.token_to_id("<image>")
@@ -43,8 +43,7 @@ def main(argv=None) -> int:
     ordinal = int(a.device.split(":", 1)[1]) if ":" in a.device else 0
     eng = load_model(a.model_config, a.weights, a.snapshot, ordinal, a.dtype)
     eng.set_option("kv_cache_f16", 1)
-    run = engine_runner(eng, lambda p: DecodeParameters(max_new_tokens=p[0], no_repeat_ngram_size=p[1] or None, eos_token_id=p[2]),
-                        lambda v: VisionSettings(*v))
+    run = engine_runner(eng, params_from_tuple, lambda v: VisionSettings(*v))
     batcher = PageBatcher(run, max_batch=a.max_batch, max_wait_ms=a.max_wait_ms)
     crop = a.crop_mode.lower() in ("1", "true", "yes", "on")
     app = create_app(batcher, tok, image_id, vision=(a.base_size, a.image_size, crop), max_new_tokens=a.max_new_tokens)

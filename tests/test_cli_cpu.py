@@ -61,7 +61,8 @@ def test_run_writes_reference_schema_files(tmp_path, monkeypatch):
     calls = {}
 
     class StubEngine:
-        def decode_pages(self, pages, vs, seg0, seg1, image_id, params):
+        def decode_requests(self, requests, vs, image_id, params):
+            (pages, (seg0, seg1)), = requests
             calls.update(shape=pages[0].shape, seg0=list(seg0), seg1=list(seg1), image_id=image_id, max_new=params.max_new_tokens,
                          ngram=params.no_repeat_ngram_size, vs=(vs.base_size, vs.image_size, vs.crop_mode))
             return [E.DecodeOutcome(913, 3, [11, 12, 13])]

@@ -29,15 +29,16 @@ def test_delta_tracker_holds_back_incomplete_utf8():
 
 
 def _req(i, key="a", on_tokens=None):
+    # requests batch together when vision settings / decode parameters agree (prompts may differ per request)
     return PageRequest(page=np.zeros((2, 2, 3), np.uint8), seg0=(1,), seg1=(2, 3) if key == "a" else (9,), image_token_id=7,
-                       vision=(1024, 640, True), params=(64, 20, 1), on_tokens=on_tokens)
+                       vision=(1024, 640, True), params=(64, 20, 1) if key == "a" else (32, 20, 1), on_tokens=on_tokens)
 
 
 def test_batcher_groups_concurrent_compatible_requests():
     seen = []
 
     def run(batch):
-        seen.append([r.seg1 for r in batch])
+        seen.append([r.params for r in batch])
         time.sleep(0.01)
         for r in batch:
             if r.on_tokens:
@@ -147,7 +148,7 @@ def test_chat_completion_roundtrip_and_message_flattening():
     assert d["object"] == "chat.completion" and d["choices"][0]["message"] == {"role": "assistant", "content": "".join(chr(0x4E00 + i) for i in (1, 2, 3))}
     assert d["usage"] == {"prompt_tokens": 281, "completion_tokens": 3, "total_tokens": 284}
     # parts are flattened in reverse (generation.rs:251): "<image>\nFree OCR." after the system section
-    assert seen["shape"] == (8, 6, 3) and seen["params"] == (32, 20, 1) and seen["image_id"] == 777
+    assert seen["shape"] == (8, 6, 3) and seen["params"][:3] == (32, 20, 1) and seen["params"][3] is False and seen["image_id"] == 777
     assert seen["seg1"] == (104, 104) and len(seen["seg0"]) == 8  # 8 words of the system section, then <image>
     assert client.get("/v1/models").json()["data"][0]["id"] == "deepseek-ocr" and client.get("/v1/health").json() == {"status": "ok"}
     b.close()
