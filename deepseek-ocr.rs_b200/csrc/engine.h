@@ -150,6 +150,9 @@ class Engine {
   int fused_max_rows_ = getenv("DSOCR_FUSED_MAX_ROWS") ? atoi(getenv("DSOCR_FUSED_MAX_ROWS")) : 1024;
   DevBuf sk_ws_, sk_flags_;  // stream-K partial slots + hand-off flags of the decode-time expert GEMMs
   bool quantized_ = false;
+  // DSQ engines: prefill and decode steps of > 4 pages run the dequant-fused tensor-core GEMM (linear_dq.cuh) through
+  // decoder_forward; DSOCR_DSQ_GEMV=1 switches back to the per-row GEMVs of decoder_forward_dsq (A/B)
+  bool dsq_gemm_ = getenv("DSOCR_DSQ_GEMV") == nullptr;
   // A/B switch: decode steps of <= 4 pages through the batched kernels (float engine) / per-linear GEMVs (DSQ)
   bool small_fused_ = getenv("DSOCR_DSQ_UNFUSED") == nullptr && getenv("DSOCR_NO_SMALL_FUSED") == nullptr;
   QuantWeight q_lm_head_;

@@ -41,7 +41,7 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
   LinearTile* tiles1 = ws("moe_tiles1", (size_t)max_chunks * (mi / 128) * sizeof(LinearTile)).as<LinearTile>();
   LinearTile* tiles2 = ws("moe_tiles2", (size_t)max_chunks * (H / 128) * sizeof(LinearTile)).as<LinearTile>();
   // decode mode: every expert owns a fixed-capacity segment of `cap` rows (a token picks an expert at most once)
-  const bool fused = decode_mode && rows <= fused_max_rows_;
+  const bool fused = decode_mode && rows <= fused_max_rows_ && !quantized_;  // DSQ weights: table-grouped dequant-fused GEMMs
   const long long cap = rows;
   const int Eg = E + c.n_shared;  // decode: routed experts + the shared experts as extra groups of the grouped GEMMs
   const long long perm_rows = fused ? std::max<long long>(n_assign, (long long)Eg * cap) : n_assign;
@@ -65,7 +65,12 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
 
   // Small-M (decode) projections are split along K so that they fill the GPU; the f32 partials are reduced
   // in a fixed order by the consumer kernel (RoPE, RMSNorm, SwiGLU-reduce, MoE combine) -> deterministic.
-  const int sp_qkv = linear_plan_splits(rows, 3 * H, H, num_sms_);
+  // weights of a call: the engine's 16-bit matrices, or the snapshot's quantised planes (dequant-fused kernel, linear_dq.cuh)
+  auto setw = [&](LinearCall& lc, const DevBuf& w0, const QuantWeight& q0, const DevBuf* w1 = nullptr, const QuantWeight* q1 = nullptr) {
+    if (quantized_) { lc.q0 = &q0; lc.q1 = q1; }
+    else { lc.w0 = w0.p; lc.w1 = w1 ? w1->p : nullptr; lc.w_tiled = w_tiled_; }
+  };
+  const int sp_qkv = linear_plan_splits(rows, quantized_ ? H : 3 * H, H, num_sms_);
   const int sp_o = linear_plan_splits(rows, H, H, num_sms_);
   const int sp_dgu = linear_plan_splits(rows, c.inter, H, num_sms_);
   const int sp_dd = linear_plan_splits(rows, H, c.inter, num_sms_);
@@ -90,12 +95,21 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
       pend = nullptr; pend_n = 0;
     }
     have_xn = false;
-    {
+    if (!quantized_) {
       LinearCall lc;  // fused q/k/v projection
       lc.tag = "dec_qkv"; lc.w0 = L.qkv_w.p; lc.x = xn16; lc.x_rows = 2 * rows; lc.x_parts = 2; lc.x_lo_row_off = (int)rows;
       lc.M = (int)rows; lc.N = 3 * H; lc.K = H; lc.ldo = 3 * H; lc.out_mode = lin::OUT_F32;
       lc.out = sp_qkv > 1 ? partA : qkv; lc.k_splits = sp_qkv; lc.split_stride = rows * 3 * H;
       lc.w_tiled = w_tiled_; linear(lc, dt_, num_sms_, stream_);
+    } else {
+      const QuantWeight* wq[3] = {&L.q_q, &L.q_k, &L.q_v};  // the snapshot keeps q / k / v as separate records
+      for (int i = 0; i < 3; ++i) {
+        LinearCall lc;
+        lc.tag = "dec_qkv"; lc.q0 = wq[i]; lc.x = xn16; lc.x_rows = 2 * rows; lc.x_parts = 2; lc.x_lo_row_off = (int)rows;
+        lc.M = (int)rows; lc.N = H; lc.K = H; lc.ldo = 3 * H; lc.out_mode = lin::OUT_F32;
+        lc.out = (sp_qkv > 1 ? partA : qkv) + (long long)i * H; lc.k_splits = sp_qkv; lc.split_stride = rows * 3 * H;
+        linear(lc, dt_, num_sms_, stream_);
+      }
     }
     if (fused) {
       rope_attn_decode(sp_qkv > 1 ? partA : qkv, sp_qkv, rows * 3 * H, rope_cos_.as<float>(), rope_sin_.as<float>(),
@@ -108,11 +122,11 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
     }
     {
       LinearCall lc;  // o_proj (+ residual add, fused here or in the following RMSNorm when split)
-      lc.tag = "dec_o_proj"; lc.w0 = L.o_w.p; lc.x = ctx16; lc.x_rows = 2 * rows; lc.x_parts = 2; lc.x_lo_row_off = (int)rows;
+      lc.tag = "dec_o_proj"; setw(lc, L.o_w, L.q_o); lc.x = ctx16; lc.x_rows = 2 * rows; lc.x_parts = 2; lc.x_lo_row_off = (int)rows;
       lc.M = (int)rows; lc.N = H; lc.K = H; lc.ldo = H;
       if (sp_o > 1) { lc.out = partA; lc.out_mode = lin::OUT_F32; lc.k_splits = sp_o; lc.split_stride = rows * H; }
       else { lc.out = x; lc.out_mode = lin::OUT_F32_ADD; }
-      lc.w_tiled = w_tiled_; linear(lc, dt_, num_sms_, stream_);
+      linear(lc, dt_, num_sms_, stream_);
     }
     const bool fused_moe = fused && L.moe;
     if (!fused_moe)
@@ -121,7 +135,7 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
     if (!L.moe) {
       {
         LinearCall lc;  // gate/up + SwiGLU (run_dense_mlp, block.rs:1166-1177)
-        lc.tag = "dec_dense_gate_up"; lc.w0 = L.gate_w.p; lc.w1 = L.up_w.p; lc.x = xn16; lc.x_rows = 2 * rows; lc.x_parts = 2; lc.x_lo_row_off = (int)rows;
+        lc.tag = "dec_dense_gate_up"; setw(lc, L.gate_w, L.q_gate, &L.up_w, &L.q_up); lc.x = xn16; lc.x_rows = 2 * rows; lc.x_parts = 2; lc.x_lo_row_off = (int)rows;
         lc.M = (int)rows; lc.N = c.inter; lc.K = H; lc.ldo = c.inter;
         if (sp_dgu > 1) {
           lc.out = partA; lc.out_mode = lin::OUT_F32_DUAL; lc.k_splits = sp_dgu; lc.dual_stride = rows * c.inter;
@@ -129,18 +143,18 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
         } else {
           lc.out = h16; lc.out_lo = (uint16_t*)h16 + rows * c.inter; lc.out_mode = lin::OUT_T_SPLIT;
         }
-        lc.w_tiled = w_tiled_; linear(lc, dt_, num_sms_, stream_);
+        linear(lc, dt_, num_sms_, stream_);
         if (sp_dgu > 1) swiglu_reduce(partA, sp_dgu, 2 * rows * c.inter, rows * c.inter, h16, rows * c.inter, rows * c.inter, dt_, stream_);
       }
       {
         LinearCall lc;
-        lc.tag = "dec_dense_down"; lc.w0 = L.down_w.p; lc.x = h16; lc.x_rows = 2 * rows; lc.x_parts = 2; lc.x_lo_row_off = (int)rows;
+        lc.tag = "dec_dense_down"; setw(lc, L.down_w, L.q_down); lc.x = h16; lc.x_rows = 2 * rows; lc.x_parts = 2; lc.x_lo_row_off = (int)rows;
         lc.M = (int)rows; lc.N = H; lc.K = c.inter; lc.ldo = H;
         if (sp_dd > 1) {
           lc.out = partB; lc.out_mode = lin::OUT_F32; lc.k_splits = sp_dd; lc.split_stride = rows * H;
           pend = partB; pend_n = sp_dd; pend_stride = rows * H;
         } else { lc.out = x; lc.out_mode = lin::OUT_F32_ADD; }
-        lc.w_tiled = w_tiled_; linear(lc, dt_, num_sms_, stream_);
+        linear(lc, dt_, num_sms_, stream_);
       }
     } else {
       // run_moe (block.rs:1215-1395).  In decode the shared-experts branch (3 small kernels) runs on a forked
@@ -164,44 +178,44 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
       }
       {
         LinearCall lc;  // routed experts: gate/up + SwiGLU, grouped
-        lc.tag = "moe_expert_gate_up"; lc.w0 = L.exp_gate.p; lc.w1 = L.exp_up.p; lc.w_rows = (long long)(fused ? Eg : E) * mi;
+        lc.tag = "moe_expert_gate_up"; setw(lc, L.exp_gate, L.q_exp_gate, &L.exp_up, &L.q_exp_up); lc.w_rows = (long long)(fused ? Eg : E) * mi;
         const long long pr = fused ? (long long)Eg * cap : n_assign;
         lc.x = xperm16; lc.x_rows = 2 * pr; lc.x_parts = 2; lc.x_lo_row_off = (int)pr;
         lc.M = (int)pr; lc.N = mi; lc.K = H;
         lc.out = hperm16; lc.out_lo = (uint16_t*)hperm16 + pr * mi; lc.ldo = mi; lc.out_mode = lin::OUT_T_SPLIT;
         if (fused) { lc.dyn_groups = Eg; lc.dyn_cap = (int)cap; lc.group_counts = lcounts; lc.bn = fbn; if (streamk_) { lc.sk_ws = sk_ws_.as<float>(); lc.sk_flags = sk_flags_.as<int>(); } }
         else { lc.tiles = tiles1; lc.num_tiles_dev = ntiles; lc.max_tiles = max_chunks * (mi / 128); lc.bn = bn; }
-        lc.w_tiled = w_tiled_; linear(lc, dt_, num_sms_, stream_);
+        linear(lc, dt_, num_sms_, stream_);
       }
       {
         LinearCall lc;  // routed experts: down, grouped
-        lc.tag = "moe_expert_down"; lc.w0 = L.exp_down.p; lc.w_rows = (long long)(fused ? Eg : E) * H;
+        lc.tag = "moe_expert_down"; setw(lc, L.exp_down, L.q_exp_down); lc.w_rows = (long long)(fused ? Eg : E) * H;
         const long long pr = fused ? (long long)Eg * cap : n_assign;
         lc.x = hperm16; lc.x_rows = 2 * pr; lc.x_parts = 2; lc.x_lo_row_off = (int)pr;
         lc.M = (int)pr; lc.N = H; lc.K = mi; lc.out = yperm; lc.ldo = H; lc.out_mode = lin::OUT_F32;
         if (fused) { lc.dyn_groups = Eg; lc.dyn_cap = (int)cap; lc.group_counts = lcounts; lc.bn = fbn; if (streamk_) { lc.sk_ws = sk_ws_.as<float>(); lc.sk_flags = sk_flags_.as<int>(); } }
         else { lc.tiles = tiles2; lc.num_tiles_dev = ntiles + 1; lc.max_tiles = max_chunks * (H / 128); lc.bn = bn; }
-        lc.w_tiled = w_tiled_; linear(lc, dt_, num_sms_, stream_);
+        linear(lc, dt_, num_sms_, stream_);
       }
       if (!fused) {
         LinearCall lc;  // shared experts (one fused SwiGLU MLP, weights.rs:390-400)
-        lc.tag = "moe_shared_gate_up"; lc.w0 = L.sh_gate.p; lc.w1 = L.sh_up.p; lc.x = xn16; lc.x_rows = 2 * rows; lc.x_parts = 2; lc.x_lo_row_off = (int)rows;
+        lc.tag = "moe_shared_gate_up"; setw(lc, L.sh_gate, L.q_sh_gate, &L.sh_up, &L.q_sh_up); lc.x = xn16; lc.x_rows = 2 * rows; lc.x_parts = 2; lc.x_lo_row_off = (int)rows;
         lc.M = (int)rows; lc.N = (int)S; lc.K = H; lc.ldo = S;
         if (sp_sgu > 1) {
           lc.out = partA; lc.out_mode = lin::OUT_F32_DUAL; lc.k_splits = sp_sgu; lc.dual_stride = rows * S; lc.split_stride = 2 * rows * S;
         } else {
           lc.out = h16; lc.out_lo = (uint16_t*)h16 + rows * S; lc.out_mode = lin::OUT_T_SPLIT;
         }
-        lc.w_tiled = w_tiled_; linear(lc, dt_, num_sms_, sb);
+        linear(lc, dt_, num_sms_, sb);
         if (sp_sgu > 1) swiglu_reduce(partA, sp_sgu, 2 * rows * S, rows * S, h16, rows * S, rows * S, dt_, sb);
       }
       if (!fused) {
         LinearCall lc;
-        lc.tag = "moe_shared_down"; lc.w0 = L.sh_down.p; lc.x = h16; lc.x_rows = 2 * rows; lc.x_parts = 2; lc.x_lo_row_off = (int)rows;
+        lc.tag = "moe_shared_down"; setw(lc, L.sh_down, L.q_sh_down); lc.x = h16; lc.x_rows = 2 * rows; lc.x_parts = 2; lc.x_lo_row_off = (int)rows;
         lc.M = (int)rows; lc.N = H; lc.K = (int)S; lc.ldo = H;
         if (sp_sd > 1) { lc.out = partB; lc.out_mode = lin::OUT_F32; lc.k_splits = sp_sd; lc.split_stride = rows * H; }
         else { lc.out = x; lc.out_mode = lin::OUT_F32_ADD; }
-        lc.w_tiled = w_tiled_; linear(lc, dt_, num_sms_, sb);
+        linear(lc, dt_, num_sms_, sb);
       }
       if (fork) {
         cuda_check(cudaEventRecord(ev_join_, sb), "join record");
@@ -227,9 +241,9 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
     rmsnorm_split(x, final_norm_.as<float>(), xf16, (long long)n_final * H, nullptr, final_rows, n_final, H, c.rms_eps,
                   pend, pend_n, pend_stride, dt_, stream_);
   LinearCall lc;
-  lc.tag = "lm_head"; lc.w0 = lm_head_.p; lc.x = xf16; lc.x_rows = 2 * n_final; lc.x_parts = 2; lc.x_lo_row_off = n_final;
+  lc.tag = "lm_head"; setw(lc, lm_head_, q_lm_head_); lc.x = xf16; lc.x_rows = 2 * n_final; lc.x_parts = 2; lc.x_lo_row_off = n_final;
   lc.M = n_final; lc.N = c.vocab; lc.K = H; lc.out = logits; lc.ldo = c.vocab; lc.out_mode = lin::OUT_F32;
-  lc.w_tiled = w_tiled_; linear(lc, dt_, num_sms_, stream_);
+  linear(lc, dt_, num_sms_, stream_);
 }
 
 void Engine::set_moe_stats(bool on) {
@@ -547,7 +561,7 @@ void Engine::generate(const GenRequest& rq, int64_t* const* out_tokens, int* n_o
   for (const Chunk& ch : chunks) {
     kv_page_base_ = ch.page0;
     embed_gather(d_src + ch.row0, embed_.p, img_rows, x, ch.rows, H, dt_, stream_);
-    if (quantized_) decoder_forward_dsq(x, ch.rows, d_row_page + ch.row0, d_row_pos + ch.row0, smax, d_last + ch.page0, ch.n_pages, logits + (size_t)ch.page0 * V);
+    if (quantized_ && !dsq_gemm_) decoder_forward_dsq(x, ch.rows, d_row_page + ch.row0, d_row_pos + ch.row0, smax, d_last + ch.page0, ch.n_pages, logits + (size_t)ch.page0 * V);
     else decoder_forward(x, ch.rows, d_row_page + ch.row0, d_row_pos + ch.row0, smax, d_last + ch.page0, ch.n_pages, logits + (size_t)ch.page0 * V, false);
   }
   kv_page_base_ = 0;
@@ -622,7 +636,7 @@ void Engine::generate(const GenRequest& rq, int64_t* const* out_tokens, int* n_o
     decode_rows(d_hist, smax, d_hist_len, d_src, d_row_pos, P, stream_);
     embed_gather(d_src, embed_.p, nullptr, x, P, H, dt_, stream_);
     if (P <= 4 && small_fused_ && (quantized_ || w_tiled_) && !record_taps_) decoder_step_fused_small(x, P, d_row_page, d_row_pos, smax, logits);
-    else if (quantized_) decoder_forward_dsq(x, P, d_row_page, d_row_pos, smax, d_row_page, P, logits);
+    else if (quantized_ && !dsq_gemm_) decoder_forward_dsq(x, P, d_row_page, d_row_pos, smax, d_row_page, P, logits);
     else decoder_forward(x, P, d_row_page, d_row_pos, smax, d_row_page /* identity: every row */, P, logits, true);
     copy_logits(step);
     select();

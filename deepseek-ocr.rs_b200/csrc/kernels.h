@@ -25,6 +25,7 @@ std::string kernel_timing_end_json();
 // ------------------------------------------------------------------------- tensor-core linear
 struct LinearTile { int w_row0, x_row0, rows, n0, group, r0; };  // == lin::Tile
 
+struct QuantWeight;
 struct LinearCall {
   // weights: [w_rows, K] 16-bit, row pitch ldw (0 = K).  w1 != nullptr selects the dual (SwiGLU) kernel.
   const void* w0 = nullptr;
@@ -32,6 +33,10 @@ struct LinearCall {
   long long w_rows = 0;  // 0 = N
   long long ldw = 0;
   bool w_tiled = false;  // w0/w1 are in the pre-tiled streaming layout (retile_weights); rows padded to 128
+  // DSQ snapshot weights (Q8_0 / Q4_K / Q6_K / f32 fallback planes, dsq.h) instead of w0 / w1: the dequant-fused kernel
+  // of linear_dq.cuh; needs x_parts == 2, no batched X and no device-scheduled groups
+  const QuantWeight* q0 = nullptr;
+  const QuantWeight* q1 = nullptr;
   // activations: [x_rows, K] 16-bit, row pitch ldx (0 = K); x_parts = 2 adds the lo part at row x_lo_row_off
   const void* x = nullptr;
   long long x_rows = 0;

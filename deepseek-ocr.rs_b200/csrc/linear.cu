@@ -2,6 +2,8 @@
 #include "linear_tc.cuh"
 #include "linear_sk.cuh"
 #include "linear_pair.cuh"
+#include "linear_dq.cuh"
+#include "dsq.h"
 #include "kernels.h"
 #include "tmap.h"
 
@@ -139,6 +141,47 @@ bool linear_pair(const LinearCall& c, DType dt, int num_sms, cudaStream_t stream
   return true;
 }
 
+// Dequant-fused GEMM over DSQ snapshot weights (linear_dq.cuh)
+template <typename T, int BN, int NA>
+void launch_dq_inst(const LinearCall& c, const lin::Params& p, const lin::DqWeights& q, const CUtensorMap& x,
+                    const CUtensorMap& x16, int grid, cudaStream_t stream) {
+  using C = lin::DqCfg<BN, NA>;
+  auto kern = lin::linear_dq_kernel<T, BN, NA>;
+  // per call: the attribute is per device and engines on several GPUs may share this process
+  cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes), "linear_dq: set max dynamic smem");
+  kern<<<grid, lin::kDqThreads, C::kSmemBytes, stream>>>(x, x16, p, q);
+  launch_check(c.tag ? c.tag : "linear_dq");
+}
+
+template <typename T>
+void launch_dq(int bn, const LinearCall& c, const lin::Params& p, const lin::DqWeights& q, const CUtensorMap& x,
+               const CUtensorMap& x16, int grid, cudaStream_t stream) {
+  if (c.q1) {
+    switch (bn) {
+      case 32: launch_dq_inst<T, 32, 2>(c, p, q, x, x16, grid, stream); return;
+      case 64: launch_dq_inst<T, 64, 2>(c, p, q, x, x16, grid, stream); return;
+      case 128: launch_dq_inst<T, 128, 2>(c, p, q, x, x16, grid, stream); return;
+    }
+  } else {
+    switch (bn) {
+      case 32: launch_dq_inst<T, 32, 1>(c, p, q, x, x16, grid, stream); return;
+      case 64: launch_dq_inst<T, 64, 1>(c, p, q, x, x16, grid, stream); return;
+      case 128: launch_dq_inst<T, 128, 1>(c, p, q, x, x16, grid, stream); return;
+      case 256: launch_dq_inst<T, 256, 1>(c, p, q, x, x16, grid, stream); return;
+    }
+  }
+  throw std::runtime_error("linear_dq: unsupported token tile " + std::to_string(bn));
+}
+
+int dq_fmt(const QuantWeight& w) {
+  switch (w.fmt) {
+    case DsqDType::Q8_0: return 8;
+    case DsqDType::Q4K: return 12;
+    case DsqDType::Q6K: return 14;
+    default: return 0;  // float records are stored as f32 rows
+  }
+}
+
 // Decode-time expert GEMM over fixed-capacity groups (linear_sk.cuh).
 void linear_streamk(const LinearCall& c, DType dt, int num_sms, cudaStream_t stream) {
   const bool dual = c.w1 != nullptr;
@@ -182,9 +225,18 @@ int linear_plan_splits(long long M, int N, int K, int num_sms) {
 void linear(const LinearCall& c, DType dt, int num_sms, cudaStream_t stream) {
   if (c.K % lin::BK != 0) throw std::runtime_error("linear: K must be a multiple of 64, got " + std::to_string(c.K));
   if (c.M <= 0 && !c.tiles && !c.dyn_groups) return;
-  if (c.dyn_groups && c.sk_ws) { linear_streamk(c, dt, num_sms, stream); return; }
-  if (linear_pair(c, dt, num_sms, stream)) return;
-  const bool dual = c.w1 != nullptr;
+  if (c.q0) {
+    if (c.x_parts != 2 || c.nbatch > 1 || c.dyn_groups || c.w_tiled || c.w0 || c.w1)
+      throw std::runtime_error("linear: the dequant-fused kernel needs hi/lo activations, plain or table-grouped tiles");
+    if (c.q0->K != c.K || (c.q1 && (c.q1->K != c.K || c.q1->N != c.q0->N || c.q1->count != c.q0->count)))
+      throw std::runtime_error("linear: DSQ weight shape does not match the call");
+    const int be = dsq_block_elems(c.q0->fmt), be1 = c.q1 ? dsq_block_elems(c.q1->fmt) : 0;
+    if ((be && c.K % be) || (be1 && c.K % be1)) throw std::runtime_error("linear: K is not a multiple of the quantisation block");
+  } else {
+    if (c.dyn_groups && c.sk_ws) { linear_streamk(c, dt, num_sms, stream); return; }
+    if (linear_pair(c, dt, num_sms, stream)) return;
+  }
+  const bool dual = c.w1 != nullptr || c.q1 != nullptr;
   const int bn = c.bn ? c.bn : linear_pick_bn(c.tiles ? c.tile_rows_hint : c.M, dual);
 
   lin::Params p{};
@@ -223,8 +275,11 @@ void linear(const LinearCall& c, DType dt, int num_sms, cudaStream_t stream) {
   }
 
   const long long w_rows = c.w_rows ? c.w_rows : c.N;
-  CUtensorMap w0 = tmap::make_2d_16bit(c.w0, w_rows, c.K, c.ldw ? c.ldw : c.K, lin::BM, lin::BK);
-  CUtensorMap w1 = dual ? tmap::make_2d_16bit(c.w1, w_rows, c.K, c.ldw ? c.ldw : c.K, lin::BM, lin::BK) : w0;
+  CUtensorMap w0{}, w1{};
+  if (!c.q0) {
+    w0 = tmap::make_2d_16bit(c.w0, w_rows, c.K, c.ldw ? c.ldw : c.K, lin::BM, lin::BK);
+    w1 = dual ? tmap::make_2d_16bit(c.w1, w_rows, c.K, c.ldw ? c.ldw : c.K, lin::BM, lin::BK) : w0;
+  }
   CUtensorMap x;
   if (p.nbatch > 1) {
     // X[row, batch, k]: row stride ldx elements, batch stride x_batch_stride elements.
@@ -240,6 +295,18 @@ void linear(const LinearCall& c, DType dt, int num_sms, cudaStream_t stream) {
     p.x_box16 = 1;
   }
   const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+  if (c.q0) {
+    lin::DqWeights q{};
+    auto planes = [](const QuantWeight& w) {
+      return DsqPlanes{(const uint8_t*)w.a.p, (const uint8_t*)w.b.p, (const uint8_t*)w.c.p, (const uint8_t*)w.d.p};
+    };
+    q.w0 = planes(*c.q0); q.fmt0 = dq_fmt(*c.q0);
+    q.w1 = planes(c.q1 ? *c.q1 : *c.q0); q.fmt1 = dq_fmt(c.q1 ? *c.q1 : *c.q0);
+    q.w_rows = c.q0->N * c.q0->count;
+    if (dt == DType::BF16) launch_dq<__nv_bfloat16>(bn, c, p, q, x, x16, grid, stream);
+    else launch_dq<__half>(bn, c, p, q, x, x16, grid, stream);
+    return;
+  }
   if (dt == DType::BF16) launch_t<__nv_bfloat16>(bn, c, p, w0, w1, x, x16, grid, stream);
   else launch_t<__half>(bn, c, p, w0, w1, x, x16, grid, stream);
 }

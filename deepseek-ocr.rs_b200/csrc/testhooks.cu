@@ -2,6 +2,7 @@
 // engine launches.
 #include "dsocr_test.h"
 #include "kernels.h"
+#include "dsq.h"
 #include "util.h"
 
 #include <algorithm>
@@ -162,6 +163,70 @@ extern "C" int dsocr_test_vision_attention(int dtype, int B, int S, int H, const
     std::vector<uint16_t> ho(oe);
     d2h(ho.data(), dout.p, oe * 2);
     for (size_t i = 0; i < oe; ++i) out[i] = f16_to_32(ho[i], dt);
+    return 0;
+  });
+}
+
+extern "C" int dsocr_test_linear_dq(int dtype, uint32_t q_dtype, int groups, const int* counts, int M, int N, int K,
+                                    const uint8_t* blocks, const uint8_t* blocks1, const float* x, int bn, int k_splits,
+                                    float* out) {
+  return guarded([&]() -> int {
+    const DType dt = to_dtype(dtype);
+    const DsqDType qt = static_cast<DsqDType>(q_dtype);
+    if (!dsq_block_elems(qt) || K % dsq_block_elems(qt) || K % 64) throw std::runtime_error("K must be a multiple of the block size and of 64");
+    if (groups < 1 || (groups > 1 && !counts)) throw std::runtime_error("grouped call needs counts");
+    QuantWeight q0, q1;
+    const long long rows_total = (long long)N * groups;
+    dsq_alloc(q0, qt, N, K, groups);
+    dsq_upload_rows(q0, 0, blocks, qt, rows_total);
+    if (blocks1) { dsq_alloc(q1, qt, N, K, groups); dsq_upload_rows(q1, 0, blocks1, qt, rows_total); }
+    const size_t xe = (size_t)M * K, oe = (size_t)M * N;
+    std::vector<uint16_t> hx = to16_split(x, xe, dt);
+    DevBuf dx(hx.size() * 2);
+    h2d(dx.p, hx.data(), hx.size() * 2);
+    const bool dual = blocks1 != nullptr;
+    const int ns = k_splits > 1 ? k_splits : 1;
+    DevBuf dout(oe * 4 * ns * ((dual && ns > 1) ? 2 : 1));
+    cuda_check(cudaMemset(dout.p, 0, dout.bytes), "memset");
+    LinearCall c;
+    c.q0 = &q0; c.q1 = dual ? &q1 : nullptr;
+    c.x = dx.p; c.x_rows = 2LL * M; c.x_parts = 2; c.x_lo_row_off = M;
+    c.M = M; c.N = N; c.K = K; c.out = dout.p; c.ldo = N; c.out_mode = 2 /* OUT_F32 */; c.bn = bn;
+    std::vector<LinearTile> tiles;
+    DevBuf dtiles, dnt;
+    if (groups > 1) {
+      const int tb = bn ? bn : 128;
+      int row = 0;
+      for (int g = 0; g < groups; ++g) {
+        for (int r0 = 0; r0 < counts[g]; r0 += tb)
+          for (int wb = 0; wb < (N + 127) / 128; ++wb) {
+            LinearTile t{};
+            t.w_row0 = g * N + wb * 128; t.x_row0 = row + r0; t.rows = std::min(tb, counts[g] - r0); t.n0 = wb * 128; t.group = g; t.r0 = r0;
+            tiles.push_back(t);
+          }
+        row += counts[g];
+      }
+      if (row != M) throw std::runtime_error("counts must sum to M");
+      dtiles.alloc(tiles.size() * sizeof(LinearTile));
+      h2d(dtiles.p, tiles.data(), tiles.size() * sizeof(LinearTile));
+      c.tiles = dtiles.as<LinearTile>(); c.max_tiles = (int)tiles.size(); c.bn = tb; c.w_rows = rows_total;
+    }
+    if (ns > 1) {
+      if (groups > 1) throw std::runtime_error("split-K is not available for grouped calls");
+      c.k_splits = ns; c.split_stride = (long long)oe * (dual ? 2 : 1);
+      if (dual) { c.out_mode = 4 /* OUT_F32_DUAL */; c.dual_stride = (long long)oe; }
+    }
+    linear(c, dt, sm_count(), 0);
+    cuda_check(cudaDeviceSynchronize(), "linear_dq kernel");
+    if (ns == 1) { d2h(out, dout.p, oe * 4); return 0; }
+    std::vector<float> part(dout.bytes / 4);
+    d2h(part.data(), dout.p, dout.bytes);
+    const size_t stride = oe * (dual ? 2 : 1);
+    for (size_t i = 0; i < oe; ++i) {
+      float g = 0.f, u = 0.f;
+      for (int sidx = 0; sidx < ns; ++sidx) { g += part[sidx * stride + i]; if (dual) u += part[sidx * stride + oe + i]; }
+      out[i] = dual ? g / (1.f + expf(-g)) * u : g;
+    }
     return 0;
   });
 }

@@ -39,6 +39,14 @@ DSOCR_API int dsocr_test_vision_attention(int dtype, int B, int S, int H, const 
  * producer threads run.  out[rows, K] f32. */
 DSOCR_API int dsocr_test_dsq_dequant64(uint32_t q_dtype, const uint8_t* blocks, int rows, int K, float* out);
 
+/* Dequant-fused tensor-core GEMM (csrc/linear_dq.cuh): out[M,N] = x[M,K] * dequant(W)[N,K]^T, or with blocks1 != NULL
+ * silu(x.W0^T) * (x.W1^T).  blocks / blocks1: on-disk ggml blocks (q_dtype 8 / 12 / 14) of `groups` stacked [N,K] matrices;
+ * groups > 1: x rows are grouped, counts[g] rows use matrix g (the table-grouped MoE form).  x is split into hi + lo
+ * 16-bit parts like the decoder's activations.  k_splits > 1: deterministic split-K, the f32 partials are summed here. */
+DSOCR_API int dsocr_test_linear_dq(int dtype, uint32_t q_dtype, int groups, const int* counts, int M, int N, int K,
+                                   const uint8_t* blocks, const uint8_t* blocks1, const float* x, int bn, int k_splits,
+                                   float* out);
+
 /* Host-only hooks of the sampling path (csrc/sampler.cpp; sampling.rs:34-96 + rand 0.8 StdRng).
  * dsocr_test_chacha_words: first n keystream words of the block RNG for a 32-byte key and a round count (12 = StdRng);
  * dsocr_test_stdrng_u64: first n next_u64() draws of StdRng::seed_from_u64(seed);
