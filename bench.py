@@ -56,7 +56,10 @@ def parse_args():
     ap.add_argument("--cpu-tokens", type=int, default=64, help="decode tokens in the CPU-baseline sample")
     ap.add_argument("--agree-pages", type=int, default=4, help="pages of the GPU batch compared token by token with the CPU oracle")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the f32-KV / batch-1 / CUPTI side measurements")
+    ap.add_argument("--no-extras", action="store_true", help="skip the f32-KV / batch-1 / CUPTI / DSQ side measurements")
+    ap.add_argument("--dsq-formats", default="q4k", help="comma list of DSQ snapshot formats for the configs[3] side line (q4k, q8_0, q6k; empty = none)")
+    ap.add_argument("--dsq-pages", type=int, default=128, help="Gundam pages of the DSQ pages/s measurement")
+    ap.add_argument("--dsq-tokens", type=int, default=4096, help="output length of the DSQ batch-1 decode measurement (configs[3]: 4096)")
     ap.add_argument("--profile-json", default="", help="write the per-kernel timing breakdown here")
     ap.add_argument("--kv-cache", default="f16", choices=["f32", "f16"],
                     help="KV cache storage of the headline run: f16 (half the decode-attention bytes; token agreement with the f32 "
@@ -198,6 +201,51 @@ def cpu_reference_sample(args, cfg, ckdir: Path, page: np.ndarray, max_new: int,
             "cpu_decode_tok_s": 1.0 / per_tok, "sample_tokens": n_tok,
             "sample_wall_s": total + t["vision.compute_embeddings"] + t["vision.prepare_inputs"],
             "tokens": toks, "oracles": oracles}
+
+
+# ------------------------------------------------------------------------------------------- DSQ side line
+def dsq_side_line(args, cfg, ckdir: Path, fmt: str, pages, vs, device: int) -> dict:
+    from dsocr.engine import DecodeParameters, load_model
+    from dsocr.export import export_snapshot
+
+    snap = ckdir / f"model.{fmt}.lib.dsq"
+    t_export = None
+    if not snap.exists():
+        t0 = time.time()
+        export_snapshot(str(ckdir / "config.json"), str(ckdir / "model.safetensors"), str(snap), fmt)
+        t_export = time.time() - t0
+    eng = load_model(str(ckdir / "config.json"), str(ckdir / "model.safetensors"), str(snap), device, args.dtype)
+    eng.set_option("kv_cache_f16", 1 if args.kv_cache == "f16" else 0)
+    eng.set_option("decode_batch", args.batch)
+    params = DecodeParameters(max_new_tokens=args.max_new_tokens, no_repeat_ngram_size=20, eos_token_id=None)
+    out = {"snapshot_GB": snap.stat().st_size / 1e9, "export_s": t_export}
+    # pages/s through the public call on a bounded page set (host pages in, tokens out)
+    eng.decode_pages(pages[:8], vs, [], prompt_tail(cfg), cfg.image_token_id, DecodeParameters(max_new_tokens=8, eos_token_id=None))
+    t0 = time.time()
+    res = eng.decode_pages(pages, vs, [], prompt_tail(cfg), cfg.image_token_id, params)
+    wall = time.time() - t0
+    tm = eng.timings()
+    out.update({"pages": len(pages), "e2e_pages_per_s": len(pages) / wall, "stage_ms": tm,
+                "prefill_rows": sum(r.prompt_tokens for r in res),
+                "prefill_tok_s": sum(r.prompt_tokens for r in res) / max(1e-9, tm["decode.prefill"] * 1e-3),
+                "decode_tok_s": sum(r.response_tokens for r in res) / max(1e-9, tm["decode.iterative"] * 1e-3)})
+    # batch-1 decode, long output (the reference's own `generate` shape)
+    n_img = 903 if args.mode == "gundam" else 273
+    ids1 = [0] + [cfg.image_token_id] * n_img + prompt_tail(cfg)
+    mask1 = [0] + [1] * n_img + [0] * len(prompt_tail(cfg))
+    rows1 = (np.random.default_rng(0).standard_normal((n_img, cfg.hidden_size)) * 0.7).astype(np.float32)
+    eng.generate_batch([ids1], [mask1], [rows1], DecodeParameters(max_new_tokens=8, no_repeat_ngram_size=20, eos_token_id=None))
+    o1 = eng.generate_batch([ids1], [mask1], [rows1], DecodeParameters(max_new_tokens=args.dsq_tokens, no_repeat_ngram_size=20, eos_token_id=None))
+    it_ms = eng.timings()["decode.iterative"]
+    n1 = len(o1[0])
+    per_tok = {"q4k": 449e6, "q8_0": 610e6}.get(fmt)  # algorithmic weight bytes per token
+    kvb = 2 if args.kv_cache == "f16" else 4
+    kv_per_tok = 2 * cfg.hidden_size * cfg.num_layers * kvb * (len(ids1) + n1 / 2.0)
+    tok_s = (n1 - 1) / max(1e-9, it_ms * 1e-3)
+    out["decode_batch1"] = {"tokens": n1, "prompt_tokens": len(ids1), "tok_s": tok_s, "ms_per_token": it_ms / max(1, n1 - 1),
+                            "hbm_GBps_weights_plus_kv": (per_tok + kv_per_tok) * tok_s / 1e9 if per_tok else None}
+    eng.close()
+    return out
 
 
 # ------------------------------------------------------------------------------------------- roofline
@@ -498,6 +546,17 @@ def main():
                                      "path": "fused small-batch decode step (6 launches per layer), CUDA graph + PDL"}
         except Exception as ex:  # diagnostics only: never take the headline number down
             line["decode_batch1"] = {"error": str(ex)}
+    if world == 1 and not args.no_extras and args.dsq_formats and args.config == "full":
+        # BASELINE configs[3]: the same engine over a DSQ snapshot (exported here with the library's own writer from the
+        # random-init checkpoint, dtype assignment of the reference exporter).  Prefill and multi-page decode run the
+        # dequant-fused tensor-core GEMM (linear_dq.cuh), batch-1 decode the fused GEMV step (dsq_decode.cu).
+        eng.close()
+        line["dsq"] = {}
+        for fmt in [f for f in args.dsq_formats.split(",") if f]:
+            try:
+                line["dsq"][fmt] = dsq_side_line(args, cfg, ckdir, fmt, pages[: min(len(pages), args.dsq_pages)], vs, local_rank)
+            except Exception as ex:  # diagnostics only
+                line["dsq"][fmt] = {"error": str(ex)}
     if world == 1 and not args.no_cpu_baseline:
         try:
             r = cpu_reference_sample(args, cfg, ckdir, pages[0], args.max_new_tokens, args.cpu_tokens)

@@ -12,12 +12,11 @@ template <typename T, int GW, int RB, int KV, int MINB>
 void launch(const VAttnCall& c, cudaStream_t stream) {
   using C = vattn::Cfg<KV>;
   auto kern = vattn::vattn_kernel<T, GW, RB, KV, MINB>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;  // per instantiation
+  once.run([&] {
     cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes),
                "vattn: set max dynamic smem");
-    configured = true;
-  }
+  });
   const long long ld = 3LL * c.H * vattn::D;
   CUtensorMap tq = tmap::make_2d_16bit(c.qkv, c.rows, ld, ld, vattn::BQ, vattn::D);
   CUtensorMap tkv = tmap::make_2d_16bit(c.qkv, c.rows, ld, ld, KV, vattn::D);

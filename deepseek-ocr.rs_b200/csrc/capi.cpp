@@ -735,4 +735,4 @@ extern "C" int dsocr_moe_stats(dsocr_engine* e, double* out2) {
   });
 }
 
-extern "C" long long dsocr_launch_count(const dsocr_engine*) { return launch_counter(); }
+extern "C" long long dsocr_launch_count(const dsocr_engine*) { return launch_counter().load(); }

@@ -2,20 +2,23 @@
 #include "dsocr.h"
 #include "util.h"
 
+#include <atomic>
 #include <map>
+#include <thread>
 #include <stdio.h>
 
 namespace dsocr {
 static thread_local std::string g_last_error;
 void set_last_error(const std::string& msg) { g_last_error = msg; }
-long long& launch_counter() {
-  static long long n = 0;
+std::atomic<long long>& launch_counter() {
+  static std::atomic<long long> n{0};
   return n;
 }
 
 namespace {
-struct TimingState {
-  bool on = false;
+struct TimingState {  // a diagnostic of ONE engine at a time: only launches of the thread that enabled it are recorded
+  std::atomic<bool> on{false};
+  std::thread::id owner;
   cudaStream_t stream = nullptr;
   std::vector<cudaEvent_t> pool;
   std::vector<std::pair<const char*, const char*>> names;  // (phase, kernel) that ended at event i+1
@@ -35,14 +38,15 @@ struct TimingState {
 void launch_check(const char* what) {
   ++launch_counter();
   cuda_check(cudaGetLastError(), what);
-  if (g_timing.on) {
+  if (g_timing.on.load(std::memory_order_relaxed) && g_timing.owner == std::this_thread::get_id()) {
     cuda_check(cudaEventRecord(g_timing.next(), g_timing.stream), "timing event");
     g_timing.names.push_back({g_timing.phase, what});
   }
 }
 void kernel_timing_phase(const char* phase) { g_timing.phase = phase; }
-bool kernel_timing_enabled() { return g_timing.on; }
+bool kernel_timing_enabled() { return g_timing.on.load() && g_timing.owner == std::this_thread::get_id(); }
 void kernel_timing_begin(cudaStream_t stream) {
+  g_timing.owner = std::this_thread::get_id();
   g_timing.on = true;
   g_timing.stream = stream;
   g_timing.used = 0;

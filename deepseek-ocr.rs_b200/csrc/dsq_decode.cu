@@ -501,12 +501,11 @@ dsq_fused_gemv_kernel(const __grid_constant__ Launch L) {
 
 template <int FA, int FB>
 void launch_pair(const Launch& L, int blocks, int threads, size_t smem, int max_rpg, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce once;  // per instantiation
+  once.run([&] {
     cuda_check(cudaFuncSetAttribute(dsq_fused_gemv_kernel<FA, FB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem), "smem attr");
     cuda_check(cudaFuncSetAttribute(dsq_fused_gemv_kernel<FA, FB, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem), "smem attr");
-    attr_set = true;
-  }
+  });
   if (max_rpg == 1) launch_pdl(dsq_fused_gemv_kernel<FA, FB, 1>, dim3(blocks), dim3(threads), smem, stream, L);
   else launch_pdl(dsq_fused_gemv_kernel<FA, FB, 4>, dim3(blocks), dim3(threads), smem, stream, L);
 }

@@ -54,6 +54,10 @@ static ModelConfig parse_config(const std::string& path) {
   if (const Json* v = lang("use_mla")) if (v->as_bool(false)) throw std::runtime_error("use_mla=true is not supported");
   if (const Json* v = lang("norm_topk_prob")) if (v->as_bool(false)) throw std::runtime_error("norm_topk_prob=true is not supported");
   if (const Json* v = lang("scoring_func")) if (v->kind == Json::Str && v->str != "softmax") throw std::runtime_error("MoE scoring `" + v->str + "` not yet supported");
+  // run_moe options this engine's router / combine kernels do not implement: fail at load instead of computing wrong numbers
+  if (const Json* v = lang("routed_scaling_factor")) if (fabs(v->as_num(1.0) - 1.0) > 1e-6) throw std::runtime_error("routed_scaling_factor != 1 is not supported");
+  if (const Json* v = lang("topk_method")) if (v->kind == Json::Str && v->str != "greedy") throw std::runtime_error("MoE topk_method `" + v->str + "` is not supported");
+  if (geti("moe_layer_freq", 1) != 1) throw std::runtime_error("moe_layer_freq != 1 is not supported");
   if (const Json* vc = root.get("vision_config")) {
     if (const Json* w = vc->get("width")) {
       if (const Json* s = w->get("sam_vit_b")) {
@@ -315,6 +319,7 @@ void Engine::load_weights(const std::string& path, const DsqReader* dsq) {
         std::vector<float> w = to_f32(t), wt((size_t)E * H);
         for (long long e = 0; e < E; ++e) for (long long k = 0; k < H; ++k) wt[k * E + e] = w[e * H + k];
         upload_f32(L.router_wt, wt);
+        if (st.has(p + "mlp.gate.e_score_correction_bias")) throw std::runtime_error("router score-correction bias is not supported");
         for (long long e = 0; e < E; ++e) {
           const std::string q = p + "mlp.experts." + std::to_string(e) + ".";
           load_quant(L.q_exp_gate, *dsq, q + "gate_proj.weight", mi, (int)H, (int)E, (int)e);

@@ -56,6 +56,8 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
     cuda_check(cudaMemsetAsync(counts_layers, 0, (size_t)c.layers * Eg * 4, stream_), "moe counts memset");
     // token tile of the expert GEMMs; the kernel enumerates the non-empty (expert, chunk, block) units itself
     fbn = cap <= 32 ? 32 : (cap <= 64 ? 64 : 128);
+    static const int fbn_env = getenv("DSOCR_FBN") ? atoi(getenv("DSOCR_FBN")) : 0;  // A/B switch
+    if (fbn_env == 32 || fbn_env == 64 || fbn_env == 128) fbn = fbn_env;
     if (!sk_flags_.p) {  // stream-K hand-off flags: zero once, the kernel returns them zeroed
       sk_flags_.alloc((size_t)num_sms_ * 8);
       cuda_check(cudaMemsetAsync(sk_flags_.p, 0, (size_t)num_sms_ * 8, stream_), "stream-K flags");
@@ -659,7 +661,7 @@ void Engine::generate(const GenRequest& rq, int64_t* const* out_tokens, int* n_o
     if (!use_graph || step == 1) {
       run_step(step);
     } else if (!graph_exec) {
-      const long long before = launch_counter();
+      const long long before = launch_counter().load();
       cuda_check(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal), "graph capture begin");
       try {
         run_step(step);
@@ -669,7 +671,7 @@ void Engine::generate(const GenRequest& rq, int64_t* const* out_tokens, int* n_o
         throw;
       }
       cuda_check(cudaStreamEndCapture(stream_, &graph), "graph capture end");
-      graph_launches = launch_counter() - before;
+      graph_launches = launch_counter().load() - before;
       cuda_check(cudaGraphInstantiate(&graph_exec, graph, 0), "graph instantiate");
       cuda_check(cudaGraphLaunch(graph_exec, stream_), "graph launch");
     } else {

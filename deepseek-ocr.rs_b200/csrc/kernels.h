@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 
@@ -14,8 +16,21 @@ inline void cuda_check(cudaError_t e, const char* what) {
 }
 // Every kernel launch of this library goes through launch_check: it surfaces launch errors and counts the
 // launches (dsocr_launch_count).
-long long& launch_counter();
+std::atomic<long long>& launch_counter();
 void launch_check(const char* what);
+// One-time set-up that CUDA keeps PER DEVICE (cudaFuncSetAttribute): engines on several GPUs may live in one process
+// and be driven from several threads, so "configured" is tracked per device ordinal under a lock.
+struct PerDeviceOnce {
+  std::mutex m;
+  unsigned long long mask = 0;
+  template <typename F>
+  void run(F&& f) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(m);
+    if (!((mask >> (dev & 63)) & 1ull)) { f(); mask |= 1ull << (dev & 63); }
+  }
+};
 // Optional per-kernel timing: while enabled, launch_check records a CUDA event after every launch on the
 // engine stream; consecutive event deltas are aggregated by kernel name (kernels on one stream serialise).
 void kernel_timing_begin(cudaStream_t stream);

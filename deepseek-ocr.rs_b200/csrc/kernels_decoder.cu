@@ -1447,13 +1447,15 @@ void kv_attention(const float* q, const void* kc, const void* vc, bool kv_f16, c
       if (kv_f16) {
         DISPATCH_T(dt, {
           auto kern = pattn::pattn_kernel<T, __half>;
-          cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pattn::Cfg<1>::kSmemBytes), "prefill attention smem");
+          static PerDeviceOnce once;  // per instantiation
+          once.run([&] { cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pattn::Cfg<1>::kSmemBytes), "prefill attention smem"); });
           kern<<<pgrid, pattn::kThreads, pattn::Cfg<1>::kSmemBytes, s>>>(q, (const __half*)kc, (const __half*)vc, row0, plen, (T*)ctx, lo_off_elems, heads, smax, scale_log2);
         });
       } else {
         DISPATCH_T(dt, {
           auto kern = pattn::pattn_kernel<T, float>;
-          cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pattn::Cfg<2>::kSmemBytes), "prefill attention smem");
+          static PerDeviceOnce once;  // per instantiation
+          once.run([&] { cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pattn::Cfg<2>::kSmemBytes), "prefill attention smem"); });
           kern<<<pgrid, pattn::kThreads, pattn::Cfg<2>::kSmemBytes, s>>>(q, (const float*)kc, (const float*)vc, row0, plen, (T*)ctx, lo_off_elems, heads, smax, scale_log2);
         });
       }
@@ -1461,14 +1463,13 @@ void kv_attention(const float* q, const void* kc, const void* vc, bool kv_f16, c
       return;
     }
     // 64-query x 32-key shared-memory tiles, f32 FMA
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;
+    once.run([&] {
       cuda_check(cudaFuncSetAttribute(kv_attention_prefill_tiled_kernel<__half, __half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPfSmemBytes), "prefill attention smem");
       cuda_check(cudaFuncSetAttribute(kv_attention_prefill_tiled_kernel<__half, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPfSmemBytes), "prefill attention smem");
       cuda_check(cudaFuncSetAttribute(kv_attention_prefill_tiled_kernel<__nv_bfloat16, __half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPfSmemBytes), "prefill attention smem");
       cuda_check(cudaFuncSetAttribute(kv_attention_prefill_tiled_kernel<__nv_bfloat16, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPfSmemBytes), "prefill attention smem");
-      configured = true;
-    }
+    });
     const long long max_len = std::min<long long>(smax, rows);  // blocks past a page's end exit at once
     dim3 tgrid((unsigned)((max_len + kPfQ - 1) / kPfQ), (unsigned)n_pages, (unsigned)heads);
     if (kv_f16) {
@@ -1505,11 +1506,8 @@ static void launch_router(const float* x, const float* wgt, int* topk_idx, float
     router_kernel<E, 1, 1024><<<(unsigned)rows, 1024, smem, s>>>(x, wgt, topk_idx, topk_w, counts, rows, H, topk);
   } else {            // prefill: 8 tokens per block reuse every gate-weight load 8x
     const size_t smem = (size_t)(8 * H + 256 * 8) * 4;
-    static bool configured = false;
-    if (!configured) {
-      cuda_check(cudaFuncSetAttribute(router_kernel<E, 8, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024), "router smem");
-      configured = true;
-    }
+    static PerDeviceOnce once;  // per instantiation
+    once.run([&] { cuda_check(cudaFuncSetAttribute(router_kernel<E, 8, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024), "router smem"); });
     router_kernel<E, 8, 256><<<(unsigned)((rows + 7) / 8), 256, smem, s>>>(x, wgt, topk_idx, topk_w, counts, rows, H, topk);
   }
 }

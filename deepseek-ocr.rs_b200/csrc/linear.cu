@@ -21,12 +21,11 @@ void launch_inst(const LinearCall& c, const lin::Params& p, const CUtensorMap& w
                  const CUtensorMap& x, const CUtensorMap& x16, int grid, cudaStream_t stream) {
   using C = lin::Cfg<BN, NA, NB>;
   auto kern = lin::linear_kernel<T, BN, NA, NB>;
-  static bool configured = false;  // per instantiation
-  if (!configured) {
+  static PerDeviceOnce once;  // per instantiation
+  once.run([&] {
     cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes),
                "linear: set max dynamic smem");
-    configured = true;
-  }
+  });
   kern<<<grid, lin::kThreads, C::kSmemBytes, stream>>>(w0, w1, x, x16, p);
   launch_check(c.tag ? c.tag : "linear");
 }
@@ -60,12 +59,11 @@ void launch_sk_inst(const LinearCall& c, const lin::SkParams& p, const CUtensorM
                     const CUtensorMap& x16, int grid, cudaStream_t stream) {
   using C = lin::Cfg<BN, NA, 2>;
   auto kern = lin::linear_sk_kernel<T, BN, NA>;
-  static bool configured = false;  // per instantiation
-  if (!configured) {
+  static PerDeviceOnce once;  // per instantiation
+  once.run([&] {
     cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes),
                "linear_sk: set max dynamic smem");
-    configured = true;
-  }
+  });
   kern<<<grid, lin::kThreads, C::kSmemBytes, stream>>>(w0, w1, x16, p);
   launch_check(c.tag ? c.tag : "linear_sk");
 }
@@ -89,8 +87,9 @@ template <typename T, int ACT, int MODE>
 void launch_pair_inst(const LinearCall& c, const lin::PairParams& p, const CUtensorMap& w, const CUtensorMap& x,
                       const CUtensorMap& o, int num_sms, cudaStream_t stream) {
   auto kern = lin::linear_pair_kernel<T, ACT, MODE>;
-  static int max_pairs = 0;  // per instantiation
-  if (!max_pairs) {
+  static std::atomic<int> max_pairs_s{0};  // per instantiation (the same for every device of one box)
+  static PerDeviceOnce once;
+  once.run([&] {
     cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lin::kPairSmemBytes),
                "linear_pair: set max dynamic smem");
     cudaLaunchConfig_t cfg{};
@@ -98,8 +97,9 @@ void launch_pair_inst(const LinearCall& c, const lin::PairParams& p, const CUten
     int n = 0;
     cuda_check(cudaOccupancyMaxActiveClusters(&n, kern, &cfg), "linear_pair: cluster occupancy");
     if (n < 1) throw std::runtime_error("linear_pair: no CTA pair fits on this device");
-    max_pairs = std::min(n, num_sms / 2);
-  }
+    max_pairs_s = std::min(n, num_sms / 2);
+  });
+  const int max_pairs = max_pairs_s.load();
   const int pairs = std::min(max_pairs, p.num_tiles);
   kern<<<2 * pairs, lin::kPairThreads, lin::kPairSmemBytes, stream>>>(w, x, o, p);
   launch_check(c.tag ? c.tag : "linear_pair");
@@ -147,8 +147,8 @@ void launch_dq_inst(const LinearCall& c, const lin::Params& p, const lin::DqWeig
                     const CUtensorMap& x16, int grid, cudaStream_t stream) {
   using C = lin::DqCfg<BN, NA>;
   auto kern = lin::linear_dq_kernel<T, BN, NA>;
-  // per call: the attribute is per device and engines on several GPUs may share this process
-  cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes), "linear_dq: set max dynamic smem");
+  static PerDeviceOnce once;  // per instantiation
+  once.run([&] { cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes), "linear_dq: set max dynamic smem"); });
   kern<<<grid, lin::kDqThreads, C::kSmemBytes, stream>>>(x, x16, p, q);
   launch_check(c.tag ? c.tag : "linear_dq");
 }

@@ -1,0 +1,31 @@
+"""Single-process dispatcher on real engines: two engine replicas driven from two threads of one process - on
+two GPUs when the box has them, else both on GPU 0 - must return, page for page, what one engine returns (kernels keep
+their per-device set-up, counters and error slots apart: ADVICE r1)."""
+import pytest
+import torch
+
+from oracle import preprocess as P
+from tests.helpers import tiny_model
+
+pytestmark = pytest.mark.gpu
+
+
+def test_two_engines_one_process_match_single_engine():
+    from dsocr.dispatch import EnginePool
+    from dsocr.engine import DecodeParameters, VisionSettings, load_model
+
+    cfg, ck, d = tiny_model("bf16")
+    devices = [0, 1] if torch.cuda.device_count() >= 2 else [0, 0]
+    pool = EnginePool.load(d + "/config.json", d + "/model.safetensors", None, devices, "bf16", max_group=6)
+    pages = [P.synthetic_page(640 + 16 * (i % 3), 640, seed=40 + i) for i in range(23)]
+    vs, params = VisionSettings(640, 640, False), DecodeParameters(12, eos_token_id=None)
+    tail = [5, 6, 7]
+    for _ in range(2):  # second pass: graphs / workspaces already warm on both engines
+        got = pool.decode_pages(pages, vs, [], tail, cfg.image_token_id, params)
+    assert sum(map(sum, pool.last_assignment)) == len(pages) and all(pool.last_assignment), pool.last_assignment
+    pool.close()
+    one = load_model(d + "/config.json", d + "/model.safetensors", None, 0, "bf16")
+    ref = one.decode_pages(pages, vs, [], tail, cfg.image_token_id, params)
+    one.close()
+    assert [g.generated_tokens for g in got] == [r.generated_tokens for r in ref]
+    assert [g.prompt_tokens for g in got] == [r.prompt_tokens for r in ref]
