@@ -699,6 +699,50 @@ extern "C" int dsocr_decode_requests(dsocr_engine* e, int n_requests, const dsoc
   });
 }
 
+// ---- expert-parallel groups (BASELINE configs[4])
+struct dsocr_ep_group { std::vector<dsocr_engine*> engines; };
+
+extern "C" int dsocr_ep_group_create(dsocr_engine* const* engines, int n, int max_pages_per_engine, dsocr_ep_group** out) {
+  return api("expert-parallel group", [&] {
+    if (!engines || !out || n < 2 || n > 8 || max_pages_per_engine < 1) throw std::runtime_error("invalid argument");
+    for (int i = 0; i < n; ++i) if (!engines[i] || !engines[i]->impl) throw std::runtime_error("null engine handle");
+    // peer mappings: every engine's device must be able to address the others' buffers (NVLink / NVSwitch P2P; the
+    // same device is allowed, which is how the single-GPU tests run a 2-rank group)
+    for (int i = 0; i < n; ++i) {
+      const int di = engines[i]->impl->device();
+      cuda_check(cudaSetDevice(di), "cudaSetDevice");
+      for (int j = 0; j < n; ++j) {
+        const int dj = engines[j]->impl->device();
+        if (di == dj) continue;
+        int ok = 0;
+        cuda_check(cudaDeviceCanAccessPeer(&ok, di, dj), "cudaDeviceCanAccessPeer");
+        if (!ok) throw std::runtime_error("device " + std::to_string(di) + " cannot address device " + std::to_string(dj) + " (no P2P)");
+        const cudaError_t st = cudaDeviceEnablePeerAccess(dj, 0);
+        if (st != cudaSuccess && st != cudaErrorPeerAccessAlreadyEnabled) cuda_check(st, "cudaDeviceEnablePeerAccess");
+        cudaGetLastError();
+      }
+    }
+    const int cap = max_pages_per_engine * n;
+    std::vector<Engine::EpBuffers> bufs(n);
+    for (int i = 0; i < n; ++i) bufs[i] = engines[i]->impl->ep_attach(i, n, cap);
+    for (int i = 0; i < n; ++i) {
+      EpPeers p;
+      p.world = n; p.rank = i; p.eloc = engines[i]->impl->cfg().n_experts / n; p.cap = cap;
+      for (int j = 0; j < n; ++j) { p.counts[j] = bufs[j].counts; p.xperm[j] = bufs[j].xperm; p.y[j] = bufs[j].y; p.flags[j] = bufs[j].flags; }
+      engines[i]->impl->ep_set_peers(p);
+    }
+    auto g = std::make_unique<dsocr_ep_group>();
+    g->engines.assign(engines, engines + n);
+    *out = g.release();
+  });
+}
+
+extern "C" void dsocr_ep_group_destroy(dsocr_ep_group* g) {
+  if (!g) return;
+  for (dsocr_engine* e : g->engines) if (e && e->impl) e->impl->ep_detach();
+  delete g;
+}
+
 extern "C" int dsocr_engine_set_stream(dsocr_engine* e, void* cuda_stream) {
   return api("", [&] { bind(e); e->impl->set_stream(reinterpret_cast<cudaStream_t>(cuda_stream)); });
 }

@@ -117,6 +117,14 @@ class Engine {
   void decoder_step_fused_small(float* x, long long rows, const int* row_page, const int* row_pos, int smax, float* logits);
  public:
   bool quantized() const { return quantized_; }
+  // ---- expert-parallel decode (BASELINE configs[4]; csrc/capi.cpp dsocr_ep_group_create wires a group of engines up)
+  // ep_attach allocates this rank's shared buffers (segment counters, dispatched rows, expert outputs, barrier flags) and
+  // the contiguous weight stacks of its local experts; ep_set_peers installs the peer address tables.
+  struct EpBuffers { int* counts; void* xperm; float* y; int* flags; };
+  EpBuffers ep_attach(int rank, int world, int cap);
+  void ep_set_peers(const EpPeers& peers);
+  void ep_detach();
+  int ep_world() const { return ep_peers_.world; }
  private:
   void sam_forward(int Bv, int G, const void* patches16, float* sam_out);
   void clip_forward(int Bv, int g3, const float* sam_out, float* clip_out);
@@ -176,6 +184,10 @@ class Engine {
   int rope_len_ = 0;
 
   std::map<std::string, DevBuf> ws_;
+  EpPeers ep_peers_;                       // world == 1: not expert parallel
+  int ep_cap_ = 0;                         // rows per expert segment (pages per rank x world)
+  DevBuf ep_counts_, ep_xperm_, ep_hperm_, ep_y_, ep_flags_, ep_gen_;
+  std::vector<DevBuf> ep_gate_, ep_up_, ep_down_;  // per layer: [eloc + n_shared] weight groups of this rank
   std::vector<DevBuf> kcache_, vcache_;
   // KV cache of page p of the current pass lives at page (kv_page_base_ + p) of the call's cache (chunked prefill)
   size_t kv_page_bytes_ = 0;

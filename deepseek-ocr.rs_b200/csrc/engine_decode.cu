@@ -42,18 +42,25 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
   LinearTile* tiles2 = ws("moe_tiles2", (size_t)max_chunks * (H / 128) * sizeof(LinearTile)).as<LinearTile>();
   // decode mode: every expert owns a fixed-capacity segment of `cap` rows (a token picks an expert at most once)
   const bool fused = decode_mode && rows <= fused_max_rows_ && !quantized_;  // DSQ weights: table-grouped dequant-fused GEMMs
-  const long long cap = rows;
-  const int Eg = E + c.n_shared;  // decode: routed experts + the shared experts as extra groups of the grouped GEMMs
+  // expert parallel: this rank computes its eloc local experts (+ the shared experts of its own tokens) for the tokens of
+  // every rank; segments live in buffers the peers can address
+  const bool ep = decode_mode && ep_peers_.world > 1;
+  if (ep && (!fused || rows * ep_peers_.world > ep_cap_))
+    throw std::runtime_error("expert-parallel decode needs the fused float schedule and at most " + std::to_string(ep_cap_ / ep_peers_.world) + " pages per rank");
+  const long long cap = ep ? ep_cap_ : rows;
+  const int Eg = (ep ? ep_peers_.eloc : E) + c.n_shared;  // decode: routed experts + the shared experts as extra groups of the grouped GEMMs
   const long long perm_rows = fused ? std::max<long long>(n_assign, (long long)Eg * cap) : n_assign;
   int* perm_pos = ws("moe_perm", n_assign * 4).as<int>();
-  void* xperm16 = ws("moe_xperm16", 2 * perm_rows * H * 2).p;
-  void* hperm16 = ws("moe_hperm16", 2 * perm_rows * mi * 2).p;
-  float* yperm = ws("moe_yperm32", perm_rows * H * 4).as<float>();
+  void* xperm16 = ep ? ep_xperm_.p : ws("moe_xperm16", 2 * perm_rows * H * 2).p;
+  void* hperm16 = ep ? ep_hperm_.p : ws("moe_hperm16", 2 * perm_rows * mi * 2).p;
+  float* yperm = ep ? ep_y_.as<float>() : ws("moe_yperm32", perm_rows * H * 4).as<float>();
   int* counts_layers = nullptr;
   int fbn = 32;
   if (fused) {
-    counts_layers = ws("moe_counts_layers", (size_t)c.layers * Eg * 4).as<int>();
+    counts_layers = ep ? ep_counts_.as<int>() : ws("moe_counts_layers", (size_t)c.layers * Eg * 4).as<int>();
     cuda_check(cudaMemsetAsync(counts_layers, 0, (size_t)c.layers * Eg * 4, stream_), "moe counts memset");
+    // every rank has consumed the previous step's segments and zeroed its counters before anyone dispatches again
+    if (ep) ep_barrier(ep_peers_, ep_gen_.as<int>(), stream_);
     // token tile of the expert GEMMs; the kernel enumerates the non-empty (expert, chunk, block) units itself
     fbn = cap <= 32 ? 32 : (cap <= 64 ? 64 : 128);
     static const int fbn_env = getenv("DSOCR_FBN") ? atoi(getenv("DSOCR_FBN")) : 0;  // A/B switch
@@ -166,7 +173,8 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
         // o_proj partial reduce + residual + RMSNorm(ln2) + router + top-k + dispatch in one kernel
         post_attn(x, sp_o > 1 ? partA : nullptr, sp_o > 1 ? sp_o : 0, rows * H, L.ln2.as<float>(), L.router_wt.as<float>(),
                   xn16, rows * H, topk_idx, topk_w, lcounts, perm_pos, xperm16, (long long)Eg * cap * H, (int)cap, rows, H, E, K,
-                  c.n_shared, c.rms_eps, dt_, stream_);
+                  c.n_shared, c.rms_eps, dt_, stream_, ep ? &ep_peers_ : nullptr, l * Eg);
+        if (ep) ep_barrier(ep_peers_, ep_gen_.as<int>(), stream_);  // all ranks' rows have arrived in the owners' segments
       } else {
         moe_router(xn32, L.router_wt.as<float>(), topk_idx, topk_w, counts, rows, H, E, K, stream_);
         moe_plan(counts, offsets, cursor, tiles1, ntiles, tiles2, ntiles + 1, E, bn, mi, H, stream_);
@@ -180,7 +188,7 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
       }
       {
         LinearCall lc;  // routed experts: gate/up + SwiGLU, grouped
-        lc.tag = "moe_expert_gate_up"; setw(lc, L.exp_gate, L.q_exp_gate, &L.exp_up, &L.q_exp_up); lc.w_rows = (long long)(fused ? Eg : E) * mi;
+        lc.tag = "moe_expert_gate_up"; setw(lc, ep ? ep_gate_[l] : L.exp_gate, L.q_exp_gate, ep ? &ep_up_[l] : &L.exp_up, &L.q_exp_up); lc.w_rows = (long long)(fused ? Eg : E) * mi;
         const long long pr = fused ? (long long)Eg * cap : n_assign;
         lc.x = xperm16; lc.x_rows = 2 * pr; lc.x_parts = 2; lc.x_lo_row_off = (int)pr;
         lc.M = (int)pr; lc.N = mi; lc.K = H;
@@ -191,7 +199,7 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
       }
       {
         LinearCall lc;  // routed experts: down, grouped
-        lc.tag = "moe_expert_down"; setw(lc, L.exp_down, L.q_exp_down); lc.w_rows = (long long)(fused ? Eg : E) * H;
+        lc.tag = "moe_expert_down"; setw(lc, ep ? ep_down_[l] : L.exp_down, L.q_exp_down); lc.w_rows = (long long)(fused ? Eg : E) * H;
         const long long pr = fused ? (long long)Eg * cap : n_assign;
         lc.x = hperm16; lc.x_rows = 2 * pr; lc.x_parts = 2; lc.x_lo_row_off = (int)pr;
         lc.M = (int)pr; lc.N = H; lc.K = mi; lc.out = yperm; lc.ldo = H; lc.out_mode = lin::OUT_F32;
@@ -225,9 +233,10 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
       }
       if (fused) {
         const bool last = l + 1 == c.layers;
+        if (ep) ep_barrier(ep_peers_, ep_gen_.as<int>(), stream_);  // every owner's expert outputs are complete
         combine_norm(x, yperm, perm_pos, topk_w, K, nullptr, 0, rows * H,
                      last ? final_norm_.as<float>() : dec_[l + 1].ln1.as<float>(), last ? xf16 : xn16, rows * H, rows, H,
-                     c.rms_eps, c.n_shared, (int)(E * cap), (int)cap, dt_, stream_);
+                     c.rms_eps, c.n_shared, (int)((Eg - c.n_shared) * cap), (int)cap, dt_, stream_, ep ? &ep_peers_ : nullptr);
         if (last) final_done = true; else have_xn = true;
       } else {
         moe_combine(yperm, perm_pos, topk_w, x, rows, K, H, sp_sd > 1 ? partB : nullptr, sp_sd, rows * H, stream_);
@@ -246,6 +255,54 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
   lc.tag = "lm_head"; setw(lc, lm_head_, q_lm_head_); lc.x = xf16; lc.x_rows = 2 * n_final; lc.x_parts = 2; lc.x_lo_row_off = n_final;
   lc.M = n_final; lc.N = c.vocab; lc.K = H; lc.out = logits; lc.ldo = c.vocab; lc.out_mode = lin::OUT_F32;
   linear(lc, dt_, num_sms_, stream_);
+}
+
+Engine::EpBuffers Engine::ep_attach(int rank, int world, int cap) {
+  const ModelConfig& c = cfg_;
+  if (quantized_) throw std::runtime_error("expert-parallel decode is not available for DSQ engines");
+  if (world < 2 || world > 8 || c.n_experts % world) throw std::runtime_error("expert-parallel world size must divide the expert count (2..8)");
+  cuda_check(cudaSetDevice(device_), "cudaSetDevice");
+  cuda_check(cudaStreamSynchronize(stream_), "ep attach sync");
+  const int eloc = c.n_experts / world, Eg = eloc + c.n_shared;
+  const long long H = c.hidden, mi = c.moe_inter;
+  ep_cap_ = cap;
+  ep_counts_.alloc((size_t)c.layers * Eg * 4);
+  ep_xperm_.alloc((size_t)2 * Eg * cap * H * 2);
+  ep_hperm_.alloc((size_t)2 * Eg * cap * mi * 2);
+  ep_y_.alloc((size_t)Eg * cap * H * 4);
+  ep_flags_.alloc(64); ep_gen_.alloc(16);
+  cuda_check(cudaMemset(ep_counts_.p, 0, ep_counts_.bytes), "ep memset");
+  cuda_check(cudaMemset(ep_flags_.p, 0, 64), "ep memset");
+  cuda_check(cudaMemset(ep_gen_.p, 0, 16), "ep memset");
+  // contiguous weight stacks of this rank: its eloc routed experts, then the shared experts (groups E.. of the full
+  // stacks); a group's bytes are contiguous in the row-major and in the pre-tiled layout alike
+  ep_gate_.clear(); ep_up_.clear(); ep_down_.clear();
+  ep_gate_.resize(c.layers); ep_up_.resize(c.layers); ep_down_.resize(c.layers);
+  const size_t gb = (size_t)mi * H * 2;  // bytes of one expert's gate / up / down matrix
+  for (int l = 0; l < c.layers; ++l) {
+    DecLayerW& L = dec_[l];
+    if (!L.moe) continue;
+    auto stack = [&](DevBuf& dst, const DevBuf& src) {
+      dst.alloc((size_t)Eg * gb);
+      cuda_check(cudaMemcpy(dst.p, (const char*)src.p + (size_t)rank * eloc * gb, (size_t)eloc * gb, cudaMemcpyDeviceToDevice), "ep weights");
+      cuda_check(cudaMemcpy((char*)dst.p + (size_t)eloc * gb, (const char*)src.p + (size_t)c.n_experts * gb, (size_t)c.n_shared * gb, cudaMemcpyDeviceToDevice), "ep weights");
+    };
+    stack(ep_gate_[l], L.exp_gate); stack(ep_up_[l], L.exp_up); stack(ep_down_[l], L.exp_down);
+  }
+  ep_peers_ = EpPeers();
+  ep_peers_.rank = rank; ep_peers_.eloc = eloc; ep_peers_.cap = cap;  // world stays 1 until the peer tables are installed
+  return EpBuffers{ep_counts_.as<int>(), ep_xperm_.p, ep_y_.as<float>(), ep_flags_.as<int>()};
+}
+
+void Engine::ep_set_peers(const EpPeers& peers) { ep_peers_ = peers; }
+
+void Engine::ep_detach() {
+  cudaSetDevice(device_);
+  cudaStreamSynchronize(stream_);
+  ep_peers_ = EpPeers();
+  ep_cap_ = 0;
+  ep_counts_.release(); ep_xperm_.release(); ep_hperm_.release(); ep_y_.release(); ep_flags_.release(); ep_gen_.release();
+  ep_gate_.clear(); ep_up_.clear(); ep_down_.clear();
 }
 
 void Engine::set_moe_stats(bool on) {
@@ -637,7 +694,7 @@ void Engine::generate(const GenRequest& rq, int64_t* const* out_tokens, int* n_o
   auto run_step = [&](int step) {
     decode_rows(d_hist, smax, d_hist_len, d_src, d_row_pos, P, stream_);
     embed_gather(d_src, embed_.p, nullptr, x, P, H, dt_, stream_);
-    if (P <= 4 && small_fused_ && (quantized_ || w_tiled_) && !record_taps_) decoder_step_fused_small(x, P, d_row_page, d_row_pos, smax, logits);
+    if (P <= 4 && small_fused_ && (quantized_ || w_tiled_) && !record_taps_ && ep_peers_.world == 1) decoder_step_fused_small(x, P, d_row_page, d_row_pos, smax, logits);
     else if (quantized_ && !dsq_gemm_) decoder_forward_dsq(x, P, d_row_page, d_row_pos, smax, d_row_page, P, logits);
     else decoder_forward(x, P, d_row_page, d_row_pos, smax, d_row_page /* identity: every row */, P, logits, true);
     copy_logits(step);
@@ -656,7 +713,8 @@ void Engine::generate(const GenRequest& rq, int64_t* const* out_tokens, int* n_o
       deliver();
       bool all = true;
       for (int p = 0; p < P; ++p) all &= fin[p] != 0;
-      if (all) break;
+      // expert parallel: the ranks of a group step in lock-step (their barriers pair up), so nobody leaves early
+      if (all && ep_peers_.world == 1) break;
     }
     if (!use_graph || step == 1) {
       run_step(step);

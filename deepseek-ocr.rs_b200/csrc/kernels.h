@@ -184,12 +184,30 @@ void moe_active_stat(const int* counts, int n, unsigned long long* stats, cudaSt
 void rope_attn_decode(const float* qkv, int n_splits, long long split_stride, const float* cos_t, const float* sin_t,
                       void* kc, void* vc, bool kv_f16, const int* row_page, const int* row_pos, void* ctx,
                       long long lo_off_elems, long long rows, int heads, int smax, float scale, DType dt, cudaStream_t s);
+// Expert-parallel decode (BASELINE configs[4]): `world` engine replicas, rank r owns the routed experts
+// [r*eloc, (r+1)*eloc).  Every table entry is the address, valid on THIS device, of the named buffer of rank i
+// (peer mappings over NVLink / NVSwitch; the rank's own buffers for i == rank).
+//   counts[i] : int  [layers][eloc + n_shared]      rows that arrived in each local expert segment of rank i
+//   xperm[i]  : T    [2 (hi, lo)][(eloc + n_shared) * cap][H]   token rows dispatched to rank i's experts
+//   y[i]      : f32  [(eloc + n_shared) * cap][H]   expert outputs of rank i
+//   flags[i]  : int  [world]                        arrival generation of every rank at rank i's barrier
+struct EpPeers {
+  int world = 1, rank = 0, eloc = 0, cap = 0;
+  int* counts[8] = {};
+  void* xperm[8] = {};
+  float* y[8] = {};
+  int* flags[8] = {};
+};
+// cross-GPU barrier of the EP group on the engines' streams: every rank's prior device work (peer stores included) is
+// visible to every rank's subsequent kernels.  gen: device counter of this rank (one increment per barrier).
+void ep_barrier(const EpPeers& ep, int* gen, cudaStream_t s);
 void post_attn(float* x, const float* partials, int n_splits, long long split_stride, const float* w, const float* wgt,
                void* xn16, long long xn_lo_off, int* topk_idx, float* topk_w, int* counts, int* perm_pos, void* xperm,
                long long xperm_lo_off, int cap, long long rows, int H, int E, int topk, int n_shared, float eps, DType dt,
-               cudaStream_t s);
+               cudaStream_t s, const EpPeers* ep = nullptr, int ep_counts_off = 0);
 void combine_norm(float* x, const float* y, const int* perm_pos, const float* topk_w, int topk, const float* partials,
                   int n_splits, long long split_stride, const float* w_next, void* out16, long long lo_off_elems,
-                  long long rows, int H, float eps, int n_shared, int shared_row0, int cap, DType dt, cudaStream_t s);
+                  long long rows, int H, float eps, int n_shared, int shared_row0, int cap, DType dt, cudaStream_t s,
+                  const EpPeers* ep = nullptr);
 
 }  // namespace dsocr

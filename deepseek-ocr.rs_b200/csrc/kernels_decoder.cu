@@ -818,7 +818,7 @@ post_attn_kernel(float* __restrict__ x, const float* __restrict__ partials, int 
                  const float* __restrict__ w, const float* __restrict__ wgt, T* __restrict__ xn16, long long xn_lo_off,
                  int* __restrict__ topk_idx, float* __restrict__ topk_w, int* __restrict__ counts,
                  int* __restrict__ perm_pos, T* __restrict__ xperm, long long xperm_lo_off, int cap, int H, int topk,
-                 int n_shared, float eps) {
+                 int n_shared, float eps, const EpPeers ep, int ep_counts_off) {
   constexpr int KS = 1024 / E;
   constexpr int PER = (E + 31) / 32;
   extern __shared__ float sm[];
@@ -913,7 +913,16 @@ post_attn_kernel(float* __restrict__ x, const float* __restrict__ partials, int 
     }
     // one slot reservation per selected expert, all in flight at once (lane k owns choice k)
     if (lane < topk) {
-      const int pos = my_e * cap + atomicAdd(&counts[my_e], 1);
+      int pos;
+      if (ep.world > 1) {
+        // expert parallel: the slot is reserved in the OWNER rank's segment counter (system-scope atomic through the
+        // peer mapping); perm_pos = owner << 24 | row inside the owner's segment buffer
+        const int owner = my_e / ep.eloc, le = my_e - owner * ep.eloc;
+        const int slot = atomicAdd_system(ep.counts[owner] + ep_counts_off + le, 1);
+        pos = (owner << 24) | (le * cap + slot);
+      } else {
+        pos = my_e * cap + atomicAdd(&counts[my_e], 1);
+      }
       topk_idx[row * topk + lane] = my_e;
       topk_w[row * topk + lane] = my_w;
       perm_pos[row * topk + lane] = pos;
@@ -921,18 +930,51 @@ post_attn_kernel(float* __restrict__ x, const float* __restrict__ partials, int 
     }
   }
   __syncthreads();
-  // the shared experts ride in the same grouped GEMMs as groups E, E+1, ...: every token, slot = its row
-  if (row == 0 && t < n_shared) counts[E + t] = (int)gridDim.x;
+  // the shared experts ride in the same grouped GEMMs as groups E, E+1, ... (EP: eloc, eloc+1, ... of the token's own
+  // rank): every token, slot = its row
+  const int g_shared = ep.world > 1 ? ep.eloc : E;
+  if (row == 0 && t < n_shared) counts[g_shared + t] = (int)gridDim.x;
   for (int idx = t; idx < (topk + n_shared) * n4; idx += 1024) {  // copy the normed row into its expert slots
     const int k = idx / n4, c4 = idx % n4;
     const float4 o4 = reinterpret_cast<const float4*>(xn_s)[c4];
     const float o[4] = {o4.x, o4.y, o4.z, o4.w};
     uint2 hi, lo;
     split4<T>(o, hi, lo);
-    const long long dst = (k < topk ? (long long)sel_pos[k] : (long long)(E + k - topk) * cap + row) * H;
-    reinterpret_cast<uint2*>(xperm + dst)[c4] = hi;
-    reinterpret_cast<uint2*>(xperm + xperm_lo_off + dst)[c4] = lo;
+    T* base = xperm;
+    long long dst;
+    if (k >= topk) dst = ((long long)(g_shared + k - topk) * cap + row) * H;
+    else if (ep.world > 1) { base = reinterpret_cast<T*>(ep.xperm[sel_pos[k] >> 24]); dst = (long long)(sel_pos[k] & 0xFFFFFF) * H; }
+    else dst = (long long)sel_pos[k] * H;
+    reinterpret_cast<uint2*>(base + dst)[c4] = hi;
+    reinterpret_cast<uint2*>(base + xperm_lo_off + dst)[c4] = lo;
   }
+  if (ep.world > 1) __threadfence_system();  // peer stores are performed before the kernel (and the barrier after it) completes
+}
+
+// Cross-GPU barrier of an expert-parallel group (one warp): publish this rank's arrival generation in every peer's
+// flag row, then wait until every rank has arrived at this rank.  Bounded spin: a protocol error traps instead of
+// hanging the box.
+__global__ void ep_barrier_kernel(const EpPeers ep, int* __restrict__ gen_ptr) {
+  __shared__ int s_gen;
+  if (threadIdx.x == 0) { s_gen = *gen_ptr + 1; *gen_ptr = s_gen; }
+  __syncthreads();
+  const int gen = s_gen;
+  __threadfence_system();
+  if ((int)threadIdx.x < ep.world) {
+    const int peer = threadIdx.x;
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(ep.flags[peer] + ep.rank), "r"(gen) : "memory");
+    const int* mine = ep.flags[ep.rank] + peer;
+    unsigned long long spins = 0;
+    for (;;) {
+      int v;
+      asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+      if (v >= gen) break;
+      if (++spins > (1ull << 25)) {  // tens of seconds; a legitimate wait is microseconds to milliseconds
+        printf("ep_barrier timeout: rank %d waiting for rank %d at generation %d (has %d)\n", ep.rank, peer, gen, v); __trap(); }
+    }
+  }
+  __syncthreads();
+  __threadfence_system();
 }
 
 // (3) MoE combine + shared-experts split-K reduce + residual add + the NEXT RMSNorm (next layer's ln1 or the
@@ -942,14 +984,19 @@ __global__ void __launch_bounds__(THREADS)
 combine_norm_kernel(float* __restrict__ x, const float* __restrict__ y, const int* __restrict__ perm_pos,
                     const float* __restrict__ topk_w, int topk, const float* __restrict__ partials, int n_splits,
                     long long split_stride, const float* __restrict__ w_next, T* __restrict__ out16,
-                    long long lo_off_elems, int H, float eps, int n_shared, int shared_row0, int cap) {
+                    long long lo_off_elems, int H, float eps, int n_shared, int shared_row0, int cap, const EpPeers ep) {
   const long long row = blockIdx.x;
   const int n4 = H / 4;
   float4 v[ITERS];
   float ss = 0.f;
   float wk[8]; int pk[8];
+  const float* yk[8];  // expert-output buffer holding row pk[k]: this rank's, or (expert parallel) the owner rank's over the peer mapping
 #pragma unroll
-  for (int k = 0; k < 8; ++k) { wk[k] = k < topk ? topk_w[row * topk + k] : 0.f; pk[k] = k < topk ? perm_pos[row * topk + k] : 0; }
+  for (int k = 0; k < 8; ++k) { wk[k] = k < topk ? topk_w[row * topk + k] : 0.f; pk[k] = k < topk ? perm_pos[row * topk + k] : 0; yk[k] = y; }
+  if (ep.world > 1) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) if (k < topk) { yk[k] = ep.y[pk[k] >> 24]; pk[k] &= 0xFFFFFF; }
+  }
   // shared experts computed as extra groups of the grouped GEMM: rows shared_row0 + s*cap + row, weight 1
 #pragma unroll
   for (int k = 0; k < 8; ++k)
@@ -967,7 +1014,7 @@ combine_norm_kernel(float* __restrict__ x, const float* __restrict__ y, const in
         pv[sidx] = sidx < n_splits ? reinterpret_cast<const float4*>(partials + sidx * split_stride + row * H)[i] : make_float4(0, 0, 0, 0);
       float4 yv[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) yv[k] = k < topk ? reinterpret_cast<const float4*>(y + (long long)pk[k] * H)[i] : make_float4(0, 0, 0, 0);
+      for (int k = 0; k < 8; ++k) yv[k] = k < topk ? __ldcv(reinterpret_cast<const float4*>(yk[k] + (long long)pk[k] * H) + i) : make_float4(0, 0, 0, 0);
 #pragma unroll
       for (int sidx = 0; sidx < MAXS; ++sidx) { a.x += pv[sidx].x; a.y += pv[sidx].y; a.z += pv[sidx].z; a.w += pv[sidx].w; }
       float4 acc = make_float4(0, 0, 0, 0);
@@ -1606,28 +1653,39 @@ void rope_attn_decode(const float* qkv, int n_splits, long long split_stride, co
   }
   launch_check("rope_attn_decode");
 }
+void ep_barrier(const EpPeers& ep, int* gen, cudaStream_t s) {
+  ep_barrier_kernel<<<1, 32, 0, s>>>(ep, gen);
+  launch_check("ep_barrier");
+}
 void post_attn(float* x, const float* partials, int n_splits, long long split_stride, const float* w, const float* wgt,
                void* xn16, long long xn_lo_off, int* topk_idx, float* topk_w, int* counts, int* perm_pos, void* xperm,
                long long xperm_lo_off, int cap, long long rows, int H, int E, int topk, int n_shared, float eps, DType dt,
-               cudaStream_t s) {
+               cudaStream_t s, const EpPeers* epp, int ep_counts_off) {
   if (H % 256 || H / 4 > 1024 || topk > 16 || rows > cap) throw std::runtime_error("post_attn: unsupported shape");
+  EpPeers ep;
+  if (epp) ep = *epp;
+  if (ep.world > 1 && (E % ep.world || ep.eloc != E / ep.world || (ep.eloc + n_shared) * (long long)cap >= (1 << 24)))
+    throw std::runtime_error("post_attn: unsupported expert-parallel layout");
   const size_t smem = (size_t)(H + 1024) * 4;
   DISPATCH_T(dt, {
-    if (E == 64) post_attn_kernel<T, 64><<<(unsigned)rows, 1024, smem, s>>>(x, partials, n_splits, split_stride, w, wgt, (T*)xn16, xn_lo_off, topk_idx, topk_w, counts, perm_pos, (T*)xperm, xperm_lo_off, cap, H, topk, n_shared, eps);
-    else if (E == 32) post_attn_kernel<T, 32><<<(unsigned)rows, 1024, smem, s>>>(x, partials, n_splits, split_stride, w, wgt, (T*)xn16, xn_lo_off, topk_idx, topk_w, counts, perm_pos, (T*)xperm, xperm_lo_off, cap, H, topk, n_shared, eps);
-    else if (E == 16) post_attn_kernel<T, 16><<<(unsigned)rows, 1024, smem, s>>>(x, partials, n_splits, split_stride, w, wgt, (T*)xn16, xn_lo_off, topk_idx, topk_w, counts, perm_pos, (T*)xperm, xperm_lo_off, cap, H, topk, n_shared, eps);
+    if (E == 64) post_attn_kernel<T, 64><<<(unsigned)rows, 1024, smem, s>>>(x, partials, n_splits, split_stride, w, wgt, (T*)xn16, xn_lo_off, topk_idx, topk_w, counts, perm_pos, (T*)xperm, xperm_lo_off, cap, H, topk, n_shared, eps, ep, ep_counts_off);
+    else if (E == 32) post_attn_kernel<T, 32><<<(unsigned)rows, 1024, smem, s>>>(x, partials, n_splits, split_stride, w, wgt, (T*)xn16, xn_lo_off, topk_idx, topk_w, counts, perm_pos, (T*)xperm, xperm_lo_off, cap, H, topk, n_shared, eps, ep, ep_counts_off);
+    else if (E == 16) post_attn_kernel<T, 16><<<(unsigned)rows, 1024, smem, s>>>(x, partials, n_splits, split_stride, w, wgt, (T*)xn16, xn_lo_off, topk_idx, topk_w, counts, perm_pos, (T*)xperm, xperm_lo_off, cap, H, topk, n_shared, eps, ep, ep_counts_off);
     else throw std::runtime_error("post_attn: unsupported expert count " + std::to_string(E));
   });
   launch_check("post_attn_norm_router_dispatch");
 }
 void combine_norm(float* x, const float* y, const int* perm_pos, const float* topk_w, int topk, const float* partials,
                   int n_splits, long long split_stride, const float* w_next, void* out16, long long lo_off_elems,
-                  long long rows, int H, float eps, int n_shared, int shared_row0, int cap, DType dt, cudaStream_t s) {
+                  long long rows, int H, float eps, int n_shared, int shared_row0, int cap, DType dt, cudaStream_t s,
+                  const EpPeers* epp) {
   if (H > 1536 || n_splits > 16 || topk + n_shared > 8) throw std::runtime_error("combine_norm: unsupported shape");
+  EpPeers ep;
+  if (epp) ep = *epp;
   if (!partials && H <= 1280) {  // decode: one float4 per thread, a single round of loads
-    DISPATCH_T(dt, (combine_norm_kernel<T, 1, 320, 1><<<(unsigned)rows, 320, 0, s>>>(x, y, perm_pos, topk_w, topk, nullptr, 0, split_stride, w_next, (T*)out16, lo_off_elems, H, eps, n_shared, shared_row0, cap)));
+    DISPATCH_T(dt, (combine_norm_kernel<T, 1, 320, 1><<<(unsigned)rows, 320, 0, s>>>(x, y, perm_pos, topk_w, topk, nullptr, 0, split_stride, w_next, (T*)out16, lo_off_elems, H, eps, n_shared, shared_row0, cap, ep)));
   } else {
-    DISPATCH_T(dt, (combine_norm_kernel<T, 16, 128, 3><<<(unsigned)rows, 128, 0, s>>>(x, y, perm_pos, topk_w, topk, partials, partials ? n_splits : 0, split_stride, w_next, (T*)out16, lo_off_elems, H, eps, n_shared, shared_row0, cap)));
+    DISPATCH_T(dt, (combine_norm_kernel<T, 16, 128, 3><<<(unsigned)rows, 128, 0, s>>>(x, y, perm_pos, topk_w, topk, partials, partials ? n_splits : 0, split_stride, w_next, (T*)out16, lo_off_elems, H, eps, n_shared, shared_row0, cap, ep)));
   }
   launch_check("moe_combine_norm");
 }

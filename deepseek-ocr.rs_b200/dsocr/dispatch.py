@@ -7,6 +7,7 @@ collective: the page list is cut into groups that the workers pull from a shared
 outputs, EOS) takes the next group instead of idling behind a static split."""
 from __future__ import annotations
 
+import ctypes as C
 import queue
 import threading
 from typing import Any, Callable, List, Optional, Sequence
@@ -66,10 +67,72 @@ class EnginePool:
         return cls(engines, max_group)
 
     def close(self):
+        self.disable_expert_parallel()
         for e in self.engines:
             e.close()
 
+    # ---- expert-parallel decode (BASELINE configs[4]; include/dsocr.h dsocr_ep_group_create) -------------------------
+    _ep_group = None
+    _ep_max_pages = 0
+
+    def enable_expert_parallel(self, max_pages_per_engine: int = 128):
+        """Links the pool's engines into one expert-parallel group: from now on decode_pages / decode_requests give every
+        engine one equally sized shard per round and run the rounds in lock-step (the group's cross-GPU barriers pair up)."""
+        from .binding import check, lib
+
+        if self._ep_group is not None:
+            return
+        n = len(self.engines)
+        handles = (C.c_void_p * n)(*[e._h for e in self.engines])
+        group = C.c_void_p()
+        check(lib().dsocr_ep_group_create(handles, n, int(max_pages_per_engine), C.byref(group)), "ep_group_create")
+        self._ep_group, self._ep_max_pages = group, int(max_pages_per_engine)
+
+    def disable_expert_parallel(self):
+        if self._ep_group is not None:
+            from .binding import lib
+
+            lib().dsocr_ep_group_destroy(self._ep_group)
+            self._ep_group = None
+
+    def _run_lockstep(self, n_items: int, call: Callable[[Any, range], Sequence[Any]]) -> List[Any]:
+        n = len(self.engines)
+        results: List[Any] = [None] * n_items
+        self.last_assignment = [[] for _ in self.engines]
+        per_round = n * self._ep_max_pages
+        start = 0
+        while start < n_items:
+            count = min(per_round, n_items - start)
+            base, extra = divmod(count, n)
+            if base + (1 if extra else 0) > self._ep_max_pages or base <= 4:
+                raise ValueError(f"expert-parallel rounds need 5..{self._ep_max_pages} pages per engine, got {base} (+{extra})")
+            shards, s0 = [], start
+            for w in range(n):
+                size = base + (1 if w < extra else 0)
+                shards.append(range(s0, s0 + size))
+                s0 += size
+            errors: List[BaseException] = []
+
+            def worker(w: int):
+                try:
+                    out = call(self.engines[w], shards[w])
+                    for i, o in zip(shards[w], out):
+                        results[i] = o
+                    self.last_assignment[w].append(len(shards[w]))
+                except BaseException as ex:  # noqa: BLE001
+                    errors.append(ex)
+
+            th = [threading.Thread(target=worker, args=(w,), name=f"dsocr-ep{w}") for w in range(n)]
+            [t.start() for t in th]
+            [t.join() for t in th]
+            if errors:
+                raise errors[0]
+            start += count
+        return results
+
     def _run(self, n_items: int, call: Callable[[Any, range], Sequence[Any]]) -> List[Any]:
+        if self._ep_group is not None:
+            return self._run_lockstep(n_items, call)
         groups = plan_groups(n_items, len(self.engines), self.max_group)
         q: "queue.Queue[range]" = queue.Queue()
         for g in groups:

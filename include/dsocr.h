@@ -237,6 +237,19 @@ DSOCR_API int dsocr_decode_staged(dsocr_engine* e, const int64_t* seg0, int n_se
                                   int64_t image_token_id, const dsocr_decode_params* params, dsocr_token_cb cb,
                                   void* user, int64_t* const* out_tokens, int* n_out, int* prompt_tokens);
 
+/* Expert-parallel decode (BASELINE.json configs[4]; the reference rejects ep_size > 1, block.rs:1248-1252, so this has no
+ * counterpart to mirror): n engines of ONE process, one per GPU, form a group in which rank r computes the routed experts
+ * [r*E/n, (r+1)*E/n) for the tokens of every rank during the batched decode steps.  Pages stay data-parallel (each engine
+ * decodes its own pages, attention / dense layers / shared experts / lm_head local); per MoE layer the token rows go to the
+ * owners' expert segments by peer stores over NVLink (slot reservation = system-scope atomic on the owner's counter) and the
+ * expert outputs come back by peer loads, with flag barriers between the phases - no NCCL on the data path.  While a group
+ * exists its engines must be driven in lock-step: dsocr_generate_batch / dsocr_decode_* are called on all n engines
+ * concurrently (one host thread each) with the same max_new_tokens, at most max_pages_per_engine pages each and more than
+ * 4 pages per call; steps are not cut short when an engine's pages all hit EOS.  Prefill stays local. */
+typedef struct dsocr_ep_group dsocr_ep_group;
+DSOCR_API int dsocr_ep_group_create(dsocr_engine* const* engines, int n, int max_pages_per_engine, dsocr_ep_group** out);
+DSOCR_API void dsocr_ep_group_destroy(dsocr_ep_group* g);
+
 /* Run all engine work on a caller-owned CUDA stream (cudaStream_t passed as void*), e.g. torch's current
  * stream, so that the caller's CUDA events bracket the engine's kernels. */
 DSOCR_API int dsocr_engine_set_stream(dsocr_engine* e, void* cuda_stream);
