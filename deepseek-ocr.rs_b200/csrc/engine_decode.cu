@@ -81,9 +81,9 @@ void Engine::decoder_forward(float* x, long long rows, const int* row_page, cons
   };
   const int sp_qkv = linear_plan_splits(rows, quantized_ ? H : 3 * H, H, num_sms_);
   const int sp_o = linear_plan_splits(rows, H, H, num_sms_);
-  const int sp_dgu = linear_plan_splits(rows, c.inter, H, num_sms_);
+  const int sp_dgu = linear_plan_splits(rows, c.inter, H, num_sms_, true);
   const int sp_dd = linear_plan_splits(rows, H, c.inter, num_sms_);
-  const int sp_sgu = linear_plan_splits(rows, (int)S, H, num_sms_);
+  const int sp_sgu = linear_plan_splits(rows, (int)S, H, num_sms_, true);
   const int sp_sd = linear_plan_splits(rows, H, (int)S, num_sms_);
   const long long part_elems = std::max<long long>({(long long)sp_qkv * rows * 3 * H, (long long)sp_o * rows * H,
                                                     (long long)sp_dgu * 2 * rows * c.inter, (long long)sp_dd * rows * H,

@@ -92,7 +92,7 @@ struct LinearCall {
   long long dual_stride = 0;
 };
 // number of k-splits that fills the GPU for a small-M problem (1 = do not split)
-int linear_plan_splits(long long M, int N, int K, int num_sms);
+int linear_plan_splits(long long M, int N, int K, int num_sms, bool dual = false);
 
 int linear_pick_bn(long long m, bool dual);
 // Re-lays a row-major 16-bit weight [n, k] (k % 64 == 0) out as 128x64 tiles, each 16 KB contiguous and already in

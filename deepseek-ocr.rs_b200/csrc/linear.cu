@@ -212,9 +212,12 @@ int linear_pick_bn(long long m, bool dual) {
   return 256;
 }
 
-int linear_plan_splits(long long M, int N, int K, int num_sms) {
-  if (M > 256) return 1;
-  const int base = (N + lin::BM - 1) / lin::BM;
+int linear_plan_splits(long long M, int N, int K, int num_sms, bool dual) {
+  // Decode-sized problems (a few hundred token rows) have fewer output tiles than the GPU has SMs and each tile is a
+  // chain of K/64 dependent stages: cut K so that the tiles x splits fill the SMs.  Large M (prefill) never splits.
+  if (M > 1024) return 1;
+  const int bn = linear_pick_bn(M, dual);
+  const int base = ((N + lin::BM - 1) / lin::BM) * (int)((M + bn - 1) / bn);
   const int num_kb = K / lin::BK;
   const int s = std::min(num_kb / 2, num_sms / base);
   if (s < 2) return 1;

@@ -39,19 +39,116 @@ struct DqCfg {
   static_assert(2 * kAccCols <= 512, "TMEM overflow");
 };
 
+// 8 consecutive weights (one 16-byte chunk of the 128-byte stage row) -> hi / lo 16-bit parts at the swizzled position
 template <typename T>
-__device__ __forceinline__ void dq_store_row(const float* w, uint8_t* hi_row, uint8_t* lo_row, int rsw) {
+__device__ __forceinline__ void dq_store_chunk(const float (&w)[8], uint8_t* hi_row, uint8_t* lo_row, int c, int rsw) {
+  __align__(16) T hi[8];
+  __align__(16) T lo[8];
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    __align__(16) T hi[8];
-    __align__(16) T lo[8];
+  for (int i = 0; i < 8; ++i) {
+    hi[i] = Elem<T>::from(w[i]);
+    lo[i] = Elem<T>::from(w[i] - Elem<T>::to(hi[i]));
+  }
+  *reinterpret_cast<uint4*>(hi_row + ((c ^ rsw) << 4)) = *reinterpret_cast<uint4*>(hi);
+  *reinterpret_cast<uint4*>(lo_row + ((c ^ rsw) << 4)) = *reinterpret_cast<uint4*>(lo);
+}
+
+// One 64-wide k-block of one weight row, straight from the quantised planes into the stage: the same arithmetic as
+// dsq_dequant64 (csrc/dsq_dequant.h, the CPU-pinned routine; both are held to the oracle by tests/test_linear_dq_gpu.py)
+// with 128-bit loads and no intermediate array in local memory.
+template <typename T>
+__device__ __forceinline__ void dq_stage_row(int fmt, const dsocr::DsqPlanes& p, long long row, int K, int kb, uint8_t* hi_row,
+                                             uint8_t* lo_row, int rsw) {
+  const int k0 = kb * 64;
+  if (fmt == 8) {  // Q8_0: int8 qs [rows][K], f16 d [rows][K/32]
+    const int4* q = reinterpret_cast<const int4*>(p.a + row * K + k0);
+    const __half* dp = reinterpret_cast<const __half*>(p.b) + row * (K / 32) + (k0 >> 5);
+    const float d0 = __half2float(dp[0]), d1 = __half2float(dp[1]);
+    int4 v[4] = {q[0], q[1], q[2], q[3]};
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      hi[i] = Elem<T>::from(w[c * 8 + i]);
-      lo[i] = Elem<T>::from(w[c * 8 + i] - Elem<T>::to(hi[i]));
+    for (int c = 0; c < 8; ++c) {
+      const int4 t = v[c >> 1];
+      const int w0 = (c & 1) ? t.z : t.x, w1 = (c & 1) ? t.w : t.y;
+      const float d = c < 4 ? d0 : d1;
+      float w[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        w[i] = d * (float)(int)(signed char)(w0 >> (8 * i));
+        w[4 + i] = d * (float)(int)(signed char)(w1 >> (8 * i));
+      }
+      dq_store_chunk<T>(w, hi_row, lo_row, c, rsw);
     }
-    *reinterpret_cast<uint4*>(hi_row + ((c ^ rsw) << 4)) = *reinterpret_cast<uint4*>(hi);
-    *reinterpret_cast<uint4*>(lo_row + ((c ^ rsw) << 4)) = *reinterpret_cast<uint4*>(lo);
+  } else if (fmt == 12) {  // Q4_K: 144-byte super-blocks as on disk
+    const int sb = k0 >> 8, g = (k0 >> 6) & 3;
+    const uint8_t* blk = p.a + (row * (K / 256) + sb) * 144;
+    const uint4 head = *reinterpret_cast<const uint4*>(blk);  // d, dmin, scales[12]
+    const float d = __half2float(__ushort_as_half((unsigned short)(head.x & 0xFFFF)));
+    const float dmin = __half2float(__ushort_as_half((unsigned short)(head.x >> 16)));
+    const uint32_t sw[3] = {head.y, head.z, head.w};
+    auto sbyte = [&](int i) { return (int)((sw[i >> 2] >> (8 * (i & 3))) & 0xFF); };
+    int sc[2], mn[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {  // ggml get_scale_min_k4
+      const int j = 2 * g + h;
+      if (j < 4) { sc[h] = sbyte(j) & 63; mn[h] = sbyte(j + 4) & 63; }
+      else { sc[h] = (sbyte(j + 4) & 0xF) | ((sbyte(j - 4) >> 6) << 4); mn[h] = (sbyte(j + 4) >> 4) | ((sbyte(j) >> 6) << 4); }
+    }
+    const float d1 = d * (float)sc[0], m1 = dmin * (float)mn[0], d2 = d * (float)sc[1], m2 = dmin * (float)mn[1];
+    const uint4* qp = reinterpret_cast<const uint4*>(blk + 16 + g * 32);
+    const uint4 qa = qp[0], qb = qp[1];
+    const uint32_t qw[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int cc = c & 3;  // bytes [8cc, 8cc + 8): low nibbles -> weights 8cc.., high nibbles -> weights 32 + 8cc..
+      const uint32_t w0 = qw[2 * cc], w1 = qw[2 * cc + 1];
+      const int sh = c < 4 ? 0 : 4;
+      const float dd = c < 4 ? d1 : d2, mm = c < 4 ? m1 : m2;
+      float w[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        w[i] = dd * (float)((w0 >> (8 * i + sh)) & 0xF) - mm;
+        w[4 + i] = dd * (float)((w1 >> (8 * i + sh)) & 0xF) - mm;
+      }
+      dq_store_chunk<T>(w, hi_row, lo_row, c, rsw);
+    }
+  } else if (fmt == 14) {  // Q6_K: ql [rows][K/2], qh [rows][K/4], int8 scales [rows][K/16], f16 d [rows][K/256]
+    const int sb = k0 >> 8, within = k0 & 255, half = within >> 7, upper = (within >> 6) & 1;
+    const uint4* qlp = reinterpret_cast<const uint4*>(p.a + row * (K / 2) + sb * 128 + half * 64);
+    const uint4* qhp = reinterpret_cast<const uint4*>(p.b + row * (K / 4) + sb * 64 + half * 32);
+    const uint2 scw = *reinterpret_cast<const uint2*>(p.c + row * (K / 16) + sb * 16 + half * 8);
+    const float d = __half2float(reinterpret_cast<const __half*>(p.d)[row * (K / 256) + sb]);
+    const uint4 l0 = qlp[0], l1 = qlp[1], l2 = qlp[2], l3 = qlp[3], h0 = qhp[0], h1 = qhp[1];
+    const uint32_t ql[16] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w, l2.x, l2.y, l2.z, l2.w, l3.x, l3.y, l3.z, l3.w};
+    const uint32_t qh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+    auto scale = [&](int i) { const uint32_t wv = i < 4 ? scw.x : scw.y; return (float)(int)(signed char)(wv >> (8 * (i & 3))); };
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      // chunk c < 4: weights l = 8c.. (from ql[l], qh[l] bits 0-1 / 4-5); c >= 4: weights 32 + l, l = 8(c-4).. (ql[l+32], bits 2-3 / 6-7)
+      const int l0i = (c & 3) * 8;
+      const int is = l0i >> 4;
+      const int sidx = is + (c < 4 ? 0 : 2) + (upper ? 4 : 0);
+      const float ds = d * scale(sidx);
+      const int lsh = upper ? 4 : 0;
+      const int hsh = (c < 4 ? 0 : 2) + (upper ? 4 : 0);
+      float w[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int l = l0i + i;
+        const int lb = l + (c < 4 ? 0 : 32);
+        const int lo4 = (int)((ql[lb >> 2] >> (8 * (lb & 3) + lsh)) & 0xF);
+        const int hi2 = (int)((qh[l >> 2] >> (8 * (l & 3) + hsh)) & 3);
+        w[i] = ds * (float)((lo4 | (hi2 << 4)) - 32);
+      }
+      dq_store_chunk<T>(w, hi_row, lo_row, c, rsw);
+    }
+  } else {  // f32 rows (float fallback of the exporter's chain)
+    const float4* wp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.a) + row * K + k0);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float4 a = wp[2 * c], b = wp[2 * c + 1];
+      const float w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      dq_store_chunk<T>(w, hi_row, lo_row, c, rsw);
+    }
   }
 }
 
@@ -268,13 +365,17 @@ linear_dq_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         uint8_t* st = smem + stage * C::kStageBytes + r * 128;
 #pragma unroll
         for (int a = 0; a < NA; ++a) {
-          float w[64];
-          if (w_ok) dsocr::dsq_dequant64(a ? q.fmt1 : q.fmt0, a ? q.w1 : q.w0, wrow, p.K, kb, w);
-          else {
+          uint8_t* hi_row = st + (2 * a) * C::kABytes;
+          uint8_t* lo_row = st + (2 * a + 1) * C::kABytes;
+          if (w_ok) {
+            dq_stage_row<T>(a ? q.fmt1 : q.fmt0, a ? q.w1 : q.w0, wrow, p.K, kb, hi_row, lo_row, rsw);
+          } else {
 #pragma unroll
-            for (int i = 0; i < 64; ++i) w[i] = 0.f;
+            for (int c = 0; c < 8; ++c) {
+              *reinterpret_cast<uint4*>(hi_row + (c << 4)) = make_uint4(0, 0, 0, 0);
+              *reinterpret_cast<uint4*>(lo_row + (c << 4)) = make_uint4(0, 0, 0, 0);
+            }
           }
-          dq_store_row<T>(w, st + (2 * a) * C::kABytes, st + (2 * a + 1) * C::kABytes, rsw);
         }
         ptx::fence_proxy_async();
         ptx::mbar_arrive(&full[stage]);
