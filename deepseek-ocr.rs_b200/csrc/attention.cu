@@ -1,4 +1,6 @@
 // Host launchers for the vision attention kernel (attention_tc.cuh).
+#include <cstdlib>
+
 #include "attention_tc.cuh"
 #include "kernels.h"
 #include "linear_tc.cuh"
@@ -8,10 +10,10 @@ namespace dsocr {
 
 namespace {
 
-template <typename T, int GW, int RB, int KV, int MINB>
-void launch(const VAttnCall& c, cudaStream_t stream) {
+template <typename T, int GW, int RB, int KV, int MINB, int POLY>
+void launch_poly(const VAttnCall& c, cudaStream_t stream) {
   using C = vattn::Cfg<KV>;
-  auto kern = vattn::vattn_kernel<T, GW, RB, KV, MINB>;
+  auto kern = vattn::vattn_kernel<T, GW, RB, KV, MINB, POLY>;
   static PerDeviceOnce once;  // per instantiation
   once.run([&] {
     cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes),
@@ -27,6 +29,22 @@ void launch(const VAttnCall& c, cudaStream_t stream) {
   dim3 grid((c.S + vattn::BQ - 1) / vattn::BQ, c.B * c.H);
   kern<<<grid, vattn::kThreads, C::kSmemBytes, stream>>>(tq, tkv, p);
   launch_check(c.tag ? c.tag : "vision_attention");
+}
+
+// Exponentials per 16 that run as an FMA-pipe polynomial instead of MUFU.EX2 (DSOCR_VATTN_POLY = 0 or 3 is an A/B
+// switch for the profiles; the default is what measured fastest on the 64-grid global attention).
+int vattn_poly() {
+  static const int v = [] {
+    const char* e = getenv("DSOCR_VATTN_POLY");
+    return e ? atoi(e) : 3;
+  }();
+  return v;
+}
+
+template <typename T, int GW, int RB, int KV, int MINB>
+void launch(const VAttnCall& c, cudaStream_t stream) {
+  if (vattn_poly() == 3) launch_poly<T, GW, RB, KV, MINB, 3>(c, stream);
+  else launch_poly<T, GW, RB, KV, MINB, 0>(c, stream);
 }
 
 template <typename T>

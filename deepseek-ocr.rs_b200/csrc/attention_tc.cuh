@@ -64,8 +64,100 @@ __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// 2^x on the FMA / ALU pipes (x <= 2^8 region of interest; very negative x flush to 2^-126): round to the nearest
+// integer with the 1.5 * 2^23 trick, a cubic in the remainder f in [-0.5, 0.5] (relative error 7.5e-5, well under the
+// 16-bit rounding of P), the integer added into the exponent field.  Takes a share of the exponentials off the MUFU
+// pipe (16 per clock per SM), which bounds the softmax of the large-grid attention.
+__device__ __forceinline__ float ex2_poly3(float x) {
+  x = fmaxf(x, -126.f);
+  const float xr = x + 12582912.f;
+  const float f = x - (xr - 12582912.f);
+  float pl = fmaf(0.0551716685295105f, f, 0.2426111251115799f);
+  pl = fmaf(pl, f, 0.6932609677314758f);
+  pl = fmaf(pl, f, 0.9999280571937561f);
+  return __int_as_float(__float_as_int(pl) + (__float_as_int(xr) << 23));
+}
+
+// t = S * scale * log2(e) + relw[kw] for one 16-column chunk; columns past kvalid are -inf in the TAIL variants
+template <int GW, int NG, bool TAIL>
+__device__ __forceinline__ void chunk_t(const uint32_t (&v)[16], int c0, float scale, const float* relw, int kvalid,
+                                        float (&t)[16], float (&gmax)[NG]) {
+  constexpr int GWD = GW > 0 ? GW : 1;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int c = c0 + i;
+    float x = GW > 0 ? fmaf(__uint_as_float(v[i]), scale, relw[c % GWD]) : __uint_as_float(v[i]) * scale;
+    if (TAIL && c >= kvalid) x = -INFINITY;
+    t[i] = x;
+    const int g = GW > 0 ? c / GWD : 0;
+    gmax[g] = fmaxf(gmax[g], x);
+  }
+}
+
+// Maximum of t per key group over the S tile (TMEM loads one chunk ahead of the arithmetic).
+template <int GW, int KV, int NG, bool TAIL>
+__device__ __forceinline__ void max_pass(uint32_t ts, float scale, const float* relw, int kvalid, float (&gmax)[NG]) {
+  constexpr int NCH = KV / 16;
+#pragma unroll
+  for (int g = 0; g < NG; ++g) gmax[g] = -INFINITY;
+  uint32_t v[2][16];
+  ptx::tmem_ld_32x16(ts, v[0]);
+#pragma unroll
+  for (int ci = 0; ci < NCH; ++ci) {
+    ptx::tmem_ld_wait_dep(v[ci & 1]);
+    if (ci + 1 < NCH) ptx::tmem_ld_32x16(ts + (ci + 1) * 16, v[(ci + 1) & 1]);
+    float t[16];
+    chunk_t<GW, NG, TAIL>(v[ci & 1], ci * 16, scale, relw, kvalid, t, gmax);
+  }
+}
+
+// p = 2^(t - mrow[group]) -> 16-bit, 128B-swizzled smem row; group maxima of t and the f32 row sum on the side.
+// POLY of every 16 exponentials run on the FMA pipe (ex2_poly3), the rest on MUFU.
+template <typename T, int GW, int KV, int NG, int POLY, bool TAIL>
+__device__ __forceinline__ void exp_pass(uint32_t ts, float scale, const float* relw, const float (&mrow)[NG], int kvalid,
+                                         uint8_t* prow, int rsw, float (&gmax)[NG], float& rowsum) {
+  constexpr int NCH = KV / 16;
+  constexpr int GWD = GW > 0 ? GW : 1;
+#pragma unroll
+  for (int g = 0; g < NG; ++g) gmax[g] = -INFINITY;
+  float sum0 = 0.f, sum1 = 0.f;
+  uint32_t v[2][16];
+  ptx::tmem_ld_32x16(ts, v[0]);
+#pragma unroll
+  for (int ci = 0; ci < NCH; ++ci) {
+    ptx::tmem_ld_wait_dep(v[ci & 1]);
+    if (ci + 1 < NCH) ptx::tmem_ld_32x16(ts + (ci + 1) * 16, v[(ci + 1) & 1]);
+    const int c0 = ci * 16;
+    float t[16], e[16];
+    chunk_t<GW, NG, TAIL>(v[ci & 1], c0, scale, relw, kvalid, t, gmax);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float x = t[i] - mrow[GW > 0 ? (c0 + i) / GWD : 0];
+      // spread the polynomial ones over the chunk so that MUFU and FMA work interleave
+      const bool poly = POLY > 0 && (i % (16 / (POLY > 0 ? POLY : 1))) == 0 && i / (16 / (POLY > 0 ? POLY : 1)) < POLY;
+      e[i] = poly ? ex2_poly3(x) : ptx::ex2_approx(x);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) { sum0 += e[i]; sum1 += e[i + 1]; }
+#pragma unroll
+    for (int g8 = 0; g8 < 2; ++g8) {
+      const int c = c0 + g8 * 8;
+      const int atom = c >> 6;
+      const int chunk = ((c & 63) >> 3) ^ rsw;
+      uint4 pk;
+      pk.x = pack2<T>(e[g8 * 8 + 0], e[g8 * 8 + 1]);
+      pk.y = pack2<T>(e[g8 * 8 + 2], e[g8 * 8 + 3]);
+      pk.z = pack2<T>(e[g8 * 8 + 4], e[g8 * 8 + 5]);
+      pk.w = pack2<T>(e[g8 * 8 + 6], e[g8 * 8 + 7]);
+      *reinterpret_cast<uint4*>(prow + atom * (BQ * 128) + chunk * 16) = pk;
+    }
+  }
+  rowsum = sum0 + sum1;
+}
+
 // GW = token-grid width (0 = no bias), RB = grid rows per key block, KV = keys per block.
-template <typename T, int GW, int RB, int KV, int MINB>
+// POLY = exponentials per 16 taken by the FMA-pipe polynomial.
+template <typename T, int GW, int RB, int KV, int MINB, int POLY>
 __global__ void __launch_bounds__(kThreads, MINB)
 vattn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, const Params p) {
   using C = Cfg<KV>;
@@ -187,96 +279,66 @@ vattn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
     uint8_t* prow = smem + C::kOffP + r * 128;
     const int rsw = r & 7;
     constexpr float kRescaleThreshold = 8.0f;  // p <= 2^8 stays well inside the f16 / bf16 / f32-accumulate range
+    constexpr int NG = HAS_BIAS ? RB : 1;      // key groups of a block that share one relh term (whole grid rows)
+    const uint32_t ts = tmem_s + lane_off;
 
     for (int j = 0; j < p.nblk; ++j) {
-      float relh[HAS_BIAS ? RB : 1];
-      if (HAS_BIAS) {
+      float relh[NG];
 #pragma unroll
-        for (int rr = 0; rr < RB; ++rr) {
-          const int kh = j * RB + rr;
-          relh[rr] = kh < GW ? zrow[qh - kh + GW - 1] * kLog2e : 0.f;
-        }
+      for (int rr = 0; rr < NG; ++rr) {
+        const int kh = j * RB + rr;
+        relh[rr] = (HAS_BIAS && kh < GW) ? zrow[qh - kh + GW - 1] * kLog2e : 0.f;
       }
       const int kvalid = p.S - j * KV;  // keys with column index >= kvalid are padding (last block only)
-      const bool tail = kvalid < KV;
+      const bool tail = kvalid < KV;    // uniform over the CTA: the masked variants of the passes are separate code
       ptx::mbar_wait(s_full, j & 1);
       ptx::tc_fence_after();
 
-      // pass 1: block maximum of t = S*scale*log2e + relw[kw] (+ relh[kh] added per grid row afterwards)
-      float gmax[HAS_BIAS ? RB : 1];
+      float gmax[NG];
+      if (j == 0) {
+        // first block: the reference maximum is the block maximum (a pass without exponentials)
+        if (tail) max_pass<GW, KV, NG, true>(ts, p.scale_log2, relw, kvalid, gmax);
+        else max_pass<GW, KV, NG, false>(ts, p.scale_log2, relw, kvalid, gmax);
 #pragma unroll
-      for (int rr = 0; rr < (HAS_BIAS ? RB : 1); ++rr) gmax[rr] = -INFINITY;
-#pragma unroll
-      for (int c0 = 0; c0 < KV; c0 += 16) {
-        uint32_t v[16];
-        ptx::tmem_ld_32x16(tmem_s + lane_off + c0, v);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int c = c0 + i;
-          float t = HAS_BIAS ? fmaf(__uint_as_float(v[i]), p.scale_log2, relw[c % GWD]) : __uint_as_float(v[i]) * p.scale_log2;
-          if (tail && c >= kvalid) t = -INFINITY;
-          gmax[HAS_BIAS ? c / GWD : 0] = fmaxf(gmax[HAS_BIAS ? c / GWD : 0], t);
-        }
+        for (int rr = 0; rr < NG; ++rr) m = fmaxf(m, gmax[rr] + relh[rr]);
       }
-      float bmax = -INFINITY;
+      // One pass per block in the steady state: p = 2^(t + relh - m) against the CURRENT reference maximum, written
+      // (16-bit) to swizzled smem while the block maximum is tracked on the side.  Only when a row's block maximum
+      // exceeds its reference by more than 2^8 (lazy rescale) is the reference moved, O (TMEM) and l rescaled, and the
+      // pass repeated - warp-uniformly, because tcgen05.ld/st are warp-collective (lanes that keep their maximum
+      // rescale by 1).  The second attempt cannot ask again.
+      float rowsum;
+#pragma unroll 1
+      for (;;) {
+        float mrow[NG];
 #pragma unroll
-      for (int rr = 0; rr < (HAS_BIAS ? RB : 1); ++rr) bmax = fmaxf(bmax, gmax[rr] + (HAS_BIAS ? relh[rr] : 0.f));
-      // lazy rescale: move the reference maximum only when the block maximum exceeds it by > 2^8; O (TMEM)
-      // and l follow.  tcgen05.ld/st are warp-collective, so the TMEM part is taken warp-uniformly
-      // (lanes that keep their maximum rescale by 1).
-      const bool need = bmax > m + kRescaleThreshold;
-      float alpha = 1.f;
-      if (need) {
-        alpha = ptx::ex2_approx(m - bmax);  // first block: ex2(-inf) = 0
-        l *= alpha;
-        m = bmax;
-      }
-      if (j > 0 && __any_sync(0xffffffffu, need)) {
-        ptx::mbar_wait(o_full, (j - 1) & 1);  // P.V of the previous block has landed in O
-        ptx::tc_fence_after();
+        for (int rr = 0; rr < NG; ++rr) mrow[rr] = m - relh[rr];
+        if (tail) exp_pass<T, GW, KV, NG, POLY, true>(ts, p.scale_log2, relw, mrow, kvalid, prow, rsw, gmax, rowsum);
+        else exp_pass<T, GW, KV, NG, POLY, false>(ts, p.scale_log2, relw, mrow, kvalid, prow, rsw, gmax, rowsum);
+        float bmax = -INFINITY;
 #pragma unroll
-        for (int c0 = 0; c0 < D; c0 += 16) {
-          uint32_t v[16];
-          ptx::tmem_ld_32x16(tmem_o + lane_off + c0, v);
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-          ptx::tmem_st_32x16(tmem_o + lane_off + c0, v);
+        for (int rr = 0; rr < NG; ++rr) bmax = fmaxf(bmax, gmax[rr] + relh[rr]);
+        const bool need = bmax > m + kRescaleThreshold;
+        if (!__any_sync(0xffffffffu, need)) break;
+        float alpha = 1.f;
+        if (need) {
+          alpha = ptx::ex2_approx(m - bmax);
+          l *= alpha;
+          m = bmax;
         }
-        ptx::tmem_st_wait();
-      }
-      // pass 2: p = 2^(t + relh - m), written (16-bit) to swizzled smem
-      float mrow[HAS_BIAS ? RB : 1];
+        if (j > 0) {
+          ptx::mbar_wait(o_full, (j - 1) & 1);  // P.V of the previous block has landed in O
+          ptx::tc_fence_after();
 #pragma unroll
-      for (int rr = 0; rr < (HAS_BIAS ? RB : 1); ++rr) mrow[rr] = m - (HAS_BIAS ? relh[rr] : 0.f);
-      float rowsum = 0.f;
+          for (int c0 = 0; c0 < D; c0 += 16) {
+            uint32_t v[16];
+            ptx::tmem_ld_32x16(tmem_o + lane_off + c0, v);
+            ptx::tmem_ld_wait();
 #pragma unroll
-      for (int c0 = 0; c0 < KV; c0 += 16) {
-        uint32_t v[16];
-        ptx::tmem_ld_32x16(tmem_s + lane_off + c0, v);
-        ptx::tmem_ld_wait();
-        float e[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int c = c0 + i;
-          const float t = HAS_BIAS ? fmaf(__uint_as_float(v[i]), p.scale_log2, relw[c % GWD]) : __uint_as_float(v[i]) * p.scale_log2;
-          float pe = ptx::ex2_approx(t - mrow[HAS_BIAS ? c / GWD : 0]);
-          if (tail && c >= kvalid) pe = 0.f;
-          e[i] = pe;
-          rowsum += pe;
-        }
-#pragma unroll
-        for (int g8 = 0; g8 < 2; ++g8) {
-          const int c = c0 + g8 * 8;
-          const int atom = c >> 6;
-          const int chunk = ((c & 63) >> 3) ^ rsw;
-          uint4 pk;
-          pk.x = pack2<T>(e[g8 * 8 + 0], e[g8 * 8 + 1]);
-          pk.y = pack2<T>(e[g8 * 8 + 2], e[g8 * 8 + 3]);
-          pk.z = pack2<T>(e[g8 * 8 + 4], e[g8 * 8 + 5]);
-          pk.w = pack2<T>(e[g8 * 8 + 6], e[g8 * 8 + 7]);
-          *reinterpret_cast<uint4*>(prow + atom * (BQ * 128) + chunk * 16) = pk;
+            for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            ptx::tmem_st_32x16(tmem_o + lane_off + c0, v);
+          }
+          ptx::tmem_st_wait();
         }
       }
       l += rowsum;

@@ -142,6 +142,15 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
                : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// The same wait, tied to the 16 destination registers of an earlier tcgen05.ld: the compiler cannot move a use of
+// them above the wait (needed when loads are issued one chunk ahead of the arithmetic).
+__device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&v)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+               :
+               : "memory");
+}
 
 // 32 lanes x 32 consecutive 32-bit columns -> 32 registers per thread (thread t = lane base+t).
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
