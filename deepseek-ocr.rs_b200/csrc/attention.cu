@@ -36,7 +36,7 @@ void launch_poly(const VAttnCall& c, cudaStream_t stream) {
 int vattn_poly() {
   static const int v = [] {
     const char* e = getenv("DSOCR_VATTN_POLY");
-    return e ? atoi(e) : 3;
+    return e ? atoi(e) : 0;
   }();
   return v;
 }
@@ -49,12 +49,23 @@ void launch(const VAttnCall& c, cudaStream_t stream) {
 
 template <typename T>
 void dispatch(const VAttnCall& c, cudaStream_t stream) {
+  // DSOCR_VATTN_KV128=1: the single-score-stage configurations (128-key blocks, no QK / softmax overlap) - A/B switch
+  static const bool kv128 = getenv("DSOCR_VATTN_KV128") != nullptr;
+  if (kv128) {
+    switch (c.grid) {
+      case 0: launch<T, 0, 0, 128, 2>(c, stream); return;
+      case 64: launch<T, 64, 2, 128, 2>(c, stream); return;
+      case 32: launch<T, 32, 4, 128, 2>(c, stream); return;
+      case 16: launch<T, 16, 8, 128, 2>(c, stream); return;
+      default: break;
+    }
+  }
   switch (c.grid) {
-    case 0: launch<T, 0, 0, 128, 2>(c, stream); break;
-    case 64: launch<T, 64, 2, 128, 2>(c, stream); break;
+    case 0: launch<T, 0, 0, 64, 2>(c, stream); break;
+    case 64: launch<T, 64, 1, 64, 2>(c, stream); break;
     case 40: launch<T, 40, 2, 80, 2>(c, stream); break;
-    case 32: launch<T, 32, 4, 128, 2>(c, stream); break;
-    case 16: launch<T, 16, 8, 128, 2>(c, stream); break;
+    case 32: launch<T, 32, 2, 64, 2>(c, stream); break;
+    case 16: launch<T, 16, 4, 64, 2>(c, stream); break;
     case 14: launch<T, 14, 8, 112, 2>(c, stream); break;
     default: throw std::runtime_error("vision attention: unsupported token grid " + std::to_string(c.grid));
   }

@@ -38,17 +38,26 @@ struct Params {
 
 template <int KV>
 struct Cfg {
-  static constexpr int kQBytes = BQ * D * 2;
-  static constexpr int kKVBytes = KV * D * 2;
+  // Stages: NS score tiles in TMEM (S_i+1 = Q K_i+1^T is computed while the softmax warps work on S_i), NP probability
+  // tiles in shared memory, NST K / V tiles.  Budget per CTA for two CTAs per SM: 256 TMEM columns (O uses [192, 256)),
+  // ~113 KB of shared memory.
+  static constexpr int NS = 2 * KV <= 192 ? 2 : 1;
   static constexpr int kPAtoms = (KV + 63) / 64;
   static constexpr int kPBytes = kPAtoms * BQ * 128;
+  static constexpr int NP = (NS == 2 && kPAtoms == 1) ? 2 : 1;
+  static constexpr int NST = NS == 1 ? 2 : (KV <= 64 ? 4 : 3);
+  static constexpr int kQBytes = BQ * D * 2;
+  static constexpr int kKVBytes = KV * D * 2;
   static constexpr int kOffK = kQBytes;
-  static constexpr int kOffV = kOffK + 2 * kKVBytes;
-  static constexpr int kOffP = kOffV + 2 * kKVBytes;
-  static constexpr int kOffBar = kOffP + kPBytes;
-  static constexpr int kSmemBytes = kOffBar + 128;
+  static constexpr int kOffV = kOffK + NST * kKVBytes;
+  static constexpr int kOffP = (kOffV + NST * kKVBytes + 1023) / 1024 * 1024;
+  static constexpr int kOffBar = kOffP + NP * kPBytes;
+  static constexpr int kSmemBytes = kOffBar + 256;
+  static constexpr int kTmemO = 192;
   static_assert(KV % 16 == 0 && KV <= 128, "KV");
   static_assert(kKVBytes % 1024 == 0, "stage alignment");
+  static_assert(NS * KV <= kTmemO, "TMEM budget");
+  static_assert(2 * (kSmemBytes + 1024) <= 233472, "two CTAs per SM");
 };
 
 template <typename T>
@@ -165,15 +174,18 @@ vattn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
   constexpr int GWD = GW > 0 ? GW : 1;  // divisor that is never zero
   static_assert(!HAS_BIAS || KV == RB * GW, "key block must be whole grid rows");
   extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int NS = C::NS, NP = C::NP, NST = C::NST;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBar);
   uint64_t* q_full = bars;
-  uint64_t* k_full = bars + 1;    // [2]
-  uint64_t* v_full = bars + 3;    // [2]
-  uint64_t* kv_empty = bars + 5;  // [2]
-  uint64_t* s_full = bars + 7;
-  uint64_t* p_full = bars + 8;
-  uint64_t* o_full = bars + 9;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* k_full = bars + 1;             // [NST]
+  uint64_t* v_full = k_full + NST;         // [NST]
+  uint64_t* kv_empty = v_full + NST;       // [NST]
+  uint64_t* s_full = kv_empty + NST;       // [NS]  S_i complete in TMEM
+  uint64_t* p_full = s_full + NS;          // [NP]  P_i in shared memory and S_i fully read
+  uint64_t* p_free = p_full + NP;          // [NP]  P_i . V_i complete: the P stage may be overwritten
+  uint64_t* o_full = p_free + NP;          // every P_i . V_i (phase = i & 1); only waited on by the rescale path
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  static_assert((2 + 3 * NST + NS + 2 * NP) * 8 + 4 <= 256, "barrier block");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -189,9 +201,9 @@ vattn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
     ptx::prefetch_tmap(&tm_q);
     ptx::prefetch_tmap(&tm_kv);
     ptx::mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&k_full[i], 1); ptx::mbar_init(&v_full[i], 1); ptx::mbar_init(&kv_empty[i], 1); }
-    ptx::mbar_init(s_full, 1);
-    ptx::mbar_init(p_full, 128);
+    for (int i = 0; i < NST; ++i) { ptx::mbar_init(&k_full[i], 1); ptx::mbar_init(&v_full[i], 1); ptx::mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < NS; ++i) ptx::mbar_init(&s_full[i], 1);
+    for (int i = 0; i < NP; ++i) { ptx::mbar_init(&p_full[i], 128); ptx::mbar_init(&p_free[i], 1); }
     ptx::mbar_init(o_full, 1);
     ptx::fence_barrier_init();
   }
@@ -200,17 +212,17 @@ vattn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tmem_s = tmem;        // S: columns [0, KV)
-  const uint32_t tmem_o = tmem + 128;  // O_blk: columns [128, 192)
+  const uint32_t tmem_s = tmem;               // S stages: columns [s * KV, (s + 1) * KV)
+  const uint32_t tmem_o = tmem + C::kTmemO;   // O: columns [192, 256)
 
   if (warp == 0) {
     if (ptx::elect_one()) {
       ptx::mbar_expect_tx(q_full, C::kQBytes);
       ptx::tma_load_2d(smem, &tm_q, q_full, col_q, row_base + q0);
       for (int j = 0; j < p.nblk; ++j) {
-        const int s = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        ptx::mbar_wait(&kv_empty[s], ph ^ 1);
+        const int s = j % NST;
+        const uint32_t ph = (j / NST) & 1;
+        ptx::mbar_wait_long(&kv_empty[s], ph ^ 1);
         ptx::mbar_expect_tx(&k_full[s], C::kKVBytes);
         ptx::tma_load_2d(smem + C::kOffK + s * C::kKVBytes, &tm_kv, &k_full[s], col_k, row_base + j * KV);
         ptx::mbar_expect_tx(&v_full[s], C::kKVBytes);
@@ -223,34 +235,36 @@ vattn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
       constexpr uint32_t idesc_pv = ptx::idesc_f16(Elem<T>::kFmt, BQ, D, 0, 1);  // B (= V) is MN-major
       const uint32_t sq = ptx::smem_u32(smem);
       const uint32_t sp = ptx::smem_u32(smem + C::kOffP);
-      auto issue_qk = [&](int j) {
-        const int s = j & 1;
-        ptx::mbar_wait(&k_full[s], (j >> 1) & 1);
+      auto issue_qk = [&](int j) {  // S_j = Q K_j^T into score stage j % NS
+        const int s = j % NST;
+        ptx::mbar_wait_long(&k_full[s], (j / NST) & 1);
         ptx::tc_fence_after();
         const uint32_t sk = ptx::smem_u32(smem + C::kOffK + s * C::kKVBytes);
 #pragma unroll
         for (int k = 0; k < D / 16; ++k)
-          ptx::mma_f16_ss(tmem_s, ptx::smem_desc_sw128(sq + k * 32, 16, 1024), ptx::smem_desc_sw128(sk + k * 32, 16, 1024),
-                          idesc_qk, k ? 1u : 0u);
-        ptx::mma_commit(s_full);
+          ptx::mma_f16_ss(tmem_s + (j % NS) * KV, ptx::smem_desc_sw128(sq + k * 32, 16, 1024),
+                          ptx::smem_desc_sw128(sk + k * 32, 16, 1024), idesc_qk, k ? 1u : 0u);
+        ptx::mma_commit(&s_full[j % NS]);
       };
-      ptx::mbar_wait(q_full, 0);
-      issue_qk(0);
+      ptx::mbar_wait_long(q_full, 0);
+      for (int j = 0; j < NS && j < p.nblk; ++j) issue_qk(j);
       for (int j = 0; j < p.nblk; ++j) {
-        const int s = j & 1;
-        ptx::mbar_wait(p_full, j & 1);  // P_j in smem, S_j fully read
-        ptx::mbar_wait(&v_full[s], (j >> 1) & 1);
+        const int s = j % NST;
+        ptx::mbar_wait_long(&p_full[j % NP], (j / NP) & 1);  // P_j in smem, S_j fully read
+        ptx::mbar_wait_long(&v_full[s], (j / NST) & 1);
         ptx::tc_fence_after();
         const uint32_t sv = ptx::smem_u32(smem + C::kOffV + s * C::kKVBytes);
+        const uint32_t spj = sp + (j % NP) * C::kPBytes;
 #pragma unroll
         for (int kk = 0; kk < KV / 16; ++kk) {
-          const uint64_t ad = ptx::smem_desc_sw128(sp + (kk >> 2) * (BQ * 128) + (kk & 3) * 32, 16, 1024);
+          const uint64_t ad = ptx::smem_desc_sw128(spj + (kk >> 2) * (BQ * 128) + (kk & 3) * 32, 16, 1024);
           const uint64_t bd = ptx::smem_desc_sw128(sv + kk * 2048, KV * 128, 1024);
           ptx::mma_f16_ss(tmem_o, ad, bd, idesc_pv, (j | kk) ? 1u : 0u);
         }
         ptx::mma_commit(o_full);
+        ptx::mma_commit(&p_free[j % NP]);
         ptx::mma_commit(&kv_empty[s]);
-        if (j + 1 < p.nblk) issue_qk(j + 1);
+        if (j + NS < p.nblk) issue_qk(j + NS);  // its score stage was released by p_full above
       }
     }
   } else {
@@ -262,6 +276,7 @@ vattn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
     const int qc = q_ok ? q : p.S - 1;
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     constexpr float kLog2e = 1.4426950408889634f;
+    constexpr int NG = HAS_BIAS ? RB : 1;      // key groups of a block that share one relh term (whole grid rows)
 
     float relw[HAS_BIAS ? GW : 1];
     const float* zrow = nullptr;
@@ -274,24 +289,35 @@ vattn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
 #pragma unroll
       for (int kw = 0; kw < GW; ++kw) relw[kw] = zw[-kw] * kLog2e;
     }
+    // the Zh terms of block j + 1 are requested while block j is processed (an L2 round trip per block otherwise:
+    // 25 % of the softmax warps' stall samples in the capture before this change)
+    float relh_next[NG];
+    auto load_relh = [&](int j) {
+#pragma unroll
+      for (int rr = 0; rr < NG; ++rr) {
+        const int kh = j * RB + rr;
+        relh_next[rr] = (HAS_BIAS && kh < GW) ? zrow[qh - kh + GW - 1] : 0.f;
+      }
+    };
+    load_relh(0);
 
     float m = -INFINITY, l = 0.f;  // m: reference maximum (log2 domain) all stored probabilities are relative to
     uint8_t* prow = smem + C::kOffP + r * 128;
     const int rsw = r & 7;
     constexpr float kRescaleThreshold = 8.0f;  // p <= 2^8 stays well inside the f16 / bf16 / f32-accumulate range
-    constexpr int NG = HAS_BIAS ? RB : 1;      // key groups of a block that share one relh term (whole grid rows)
-    const uint32_t ts = tmem_s + lane_off;
 
     for (int j = 0; j < p.nblk; ++j) {
       float relh[NG];
 #pragma unroll
-      for (int rr = 0; rr < NG; ++rr) {
-        const int kh = j * RB + rr;
-        relh[rr] = (HAS_BIAS && kh < GW) ? zrow[qh - kh + GW - 1] * kLog2e : 0.f;
-      }
+      for (int rr = 0; rr < NG; ++rr) relh[rr] = relh_next[rr] * kLog2e;
+      if (j + 1 < p.nblk) load_relh(j + 1);
       const int kvalid = p.S - j * KV;  // keys with column index >= kvalid are padding (last block only)
       const bool tail = kvalid < KV;    // uniform over the CTA: the masked variants of the passes are separate code
-      ptx::mbar_wait(s_full, j & 1);
+      const uint32_t ts = tmem_s + (j % NS) * KV + lane_off;
+      uint8_t* pj = prow + (j % NP) * C::kPBytes;
+      ptx::mbar_wait_long(&s_full[j % NS], (j / NS) & 1);
+      // the P stage is free once P_(j-NP) . V has completed (with one score stage s_full already implies it)
+      if (NS > 1 && j >= NP) ptx::mbar_wait(&p_free[j % NP], ((j / NP) - 1) & 1);
       ptx::tc_fence_after();
 
       float gmax[NG];
@@ -313,8 +339,8 @@ vattn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
         float mrow[NG];
 #pragma unroll
         for (int rr = 0; rr < NG; ++rr) mrow[rr] = m - relh[rr];
-        if (tail) exp_pass<T, GW, KV, NG, POLY, true>(ts, p.scale_log2, relw, mrow, kvalid, prow, rsw, gmax, rowsum);
-        else exp_pass<T, GW, KV, NG, POLY, false>(ts, p.scale_log2, relw, mrow, kvalid, prow, rsw, gmax, rowsum);
+        if (tail) exp_pass<T, GW, KV, NG, POLY, true>(ts, p.scale_log2, relw, mrow, kvalid, pj, rsw, gmax, rowsum);
+        else exp_pass<T, GW, KV, NG, POLY, false>(ts, p.scale_log2, relw, mrow, kvalid, pj, rsw, gmax, rowsum);
         float bmax = -INFINITY;
 #pragma unroll
         for (int rr = 0; rr < NG; ++rr) bmax = fmaxf(bmax, gmax[rr] + relh[rr]);
@@ -344,10 +370,14 @@ vattn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
       l += rowsum;
       ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       ptx::tc_fence_before();
-      ptx::mbar_arrive(p_full);
+      ptx::mbar_arrive(&p_full[j % NP]);
     }
     // epilogue: O / l
-    ptx::mbar_wait(o_full, (p.nblk - 1) & 1);
+    // The last P.V is awaited on ITS P-stage barrier, not on o_full: with two score stages a warp reaches this point
+    // while up to two products are outstanding, and a parity wait can only tell "one phase behind" from "complete"
+    // (o_full two phases behind reads as complete - the last two key blocks were missing from fast warps' rows).
+    // p_free[s] was already awaited for the stage's previous product, so it is at most one phase behind here.
+    ptx::mbar_wait(&p_free[(p.nblk - 1) % NP], ((p.nblk - 1) / NP) & 1);
     ptx::tc_fence_after();
     const float inv = 1.f / l;
     T* orow = reinterpret_cast<T*>(p.out) + (long long)(row_base + qc) * (p.H * D) + h * D;

@@ -72,6 +72,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Wait of a single producer / issuer thread that may last a whole pipeline stage: the try_wait carries a suspend-time
+// hint, so the thread sleeps in hardware until the phase completes instead of polling (in the attention kernel the
+// polling loops of the TMA and MMA warps were 46 % of all issued instructions and shared issue slots with the softmax
+// warps).  Same bounded-spin guard as mbar_wait.
+__device__ __forceinline__ void mbar_wait_long(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+        : "memory");
+    if (ok) return;
+    if (++spins > (1u << 24)) {
+      printf("mbar_wait_long timeout block %d thread %d\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
