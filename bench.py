@@ -474,7 +474,7 @@ def main():
         # kernel durations inside the production CUDA-graph replay, by (shortened) kernel name, next to the event-timed list
         try:
             pj = json.loads(Path(args.profile_json).read_text())
-            ck = sorted(((k.split("(")[0][-110:], v[0] * 1e-3, v[1]) for k, v in cupti.items()), key=lambda t: -t[1])
+            ck = sorted(((k.replace("(anonymous namespace)::", "").replace("<unnamed>::", "").split("(")[0][-110:], v[0] * 1e-3, v[1]) for k, v in cupti.items()), key=lambda t: -t[1])
             pj["cupti_graph_kernels"] = [{"name": n, "ms": round(ms, 3), "launches": c, "avg_us": round(ms * 1e3 / max(1, c), 2)} for n, ms, c in ck[:60]]
             Path(args.profile_json).write_text(json.dumps(pj, indent=1))
         except Exception as ex:  # diagnostics only

@@ -811,64 +811,86 @@ rope_attn_decode_bulk_kernel(const float* __restrict__ qkv, int n_splits, long l
 }
 
 // (2) o_proj split-K reduce + residual add + RMSNorm(ln2) + router + top-k + dispatch into fixed-capacity
-// expert segments (slot = atomic counter per expert; the grouped GEMM reads the counters), one block per row.
-template <typename T, int E>
+// expert segments (slot = atomic counter per expert; the grouped GEMM reads the counters).  One block handles R
+// consecutive rows: with hundreds of rows per step the router gate (H x E f32, 327 KB) is then read from L2 once per R
+// rows instead of once per row and the launch fits one wave of blocks (R = 4: 1024 rows -> 256 blocks on 296 slots;
+// one row per block was 3.5 waves of ~10 us latency chains).  Per-row arithmetic and summation order do not depend on R.
+template <typename T, int E, int R>
 __global__ void __launch_bounds__(1024)
 post_attn_kernel(float* __restrict__ x, const float* __restrict__ partials, int n_splits, long long split_stride,
                  const float* __restrict__ w, const float* __restrict__ wgt, T* __restrict__ xn16, long long xn_lo_off,
                  int* __restrict__ topk_idx, float* __restrict__ topk_w, int* __restrict__ counts,
-                 int* __restrict__ perm_pos, T* __restrict__ xperm, long long xperm_lo_off, int cap, int H, int topk,
+                 int* __restrict__ perm_pos, T* __restrict__ xperm, long long xperm_lo_off, int cap, int rows, int H, int topk,
                  int n_shared, float eps, const EpPeers ep, int ep_counts_off) {
   constexpr int KS = 1024 / E;
   constexpr int PER = (E + 31) / 32;
   extern __shared__ float sm[];
-  float* xn_s = sm;            // [H]
-  float* part = sm + H;        // [1024]
-  __shared__ float red[32];
-  __shared__ int sel_pos[16];
-  const long long row = blockIdx.x;
+  float* xn_s = sm;                 // [R][H]   the rows: first x + partials, then the normalised values
+  float* part = sm + R * H;         // [R][1024] router partial sums
+  __shared__ float red[R][32];      // sums of squares per (row, warp-sized slice of the row)
+  __shared__ int sel_pos[R][16];
+  const long long row0 = (long long)blockIdx.x * R;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const int n4 = H / 4;
-  float4 v = make_float4(0, 0, 0, 0);
-  float ss = 0.f;
-  if (t < n4) {
-    v = reinterpret_cast<float4*>(x + row * H)[t];
-    for (int sidx = 0; sidx < n_splits; ++sidx) {
-      const float4 pv = reinterpret_cast<const float4*>(partials + sidx * split_stride + row * H)[t];
-      v.x += pv.x; v.y += pv.y; v.z += pv.z; v.w += pv.w;
+  const int n4 = H / 4;             // a multiple of 32: a warp never straddles two rows
+  const int nslice = n4 / 32;
+
+  for (int idx = t; idx < R * n4; idx += 1024) {
+    const int rr = idx / n4, c4 = idx - rr * n4;
+    const long long row = row0 + rr;
+    float4 v = make_float4(0, 0, 0, 0);
+    if (row < rows) {
+      v = reinterpret_cast<float4*>(x + row * H)[c4];
+      for (int sidx = 0; sidx < n_splits; ++sidx) {
+        const float4 pv = reinterpret_cast<const float4*>(partials + sidx * split_stride + row * H)[c4];
+        v.x += pv.x; v.y += pv.y; v.z += pv.z; v.w += pv.w;
+      }
+      reinterpret_cast<float4*>(x + row * H)[c4] = v;
     }
-    reinterpret_cast<float4*>(x + row * H)[t] = v;
-    ss = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    reinterpret_cast<float4*>(xn_s + rr * H)[c4] = v;
+    const float ss = warp_sum(v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w);
+    if (lane == 0) red[rr][c4 >> 5] = ss;
   }
-  ss = warp_sum(ss);
-  if (lane == 0) red[warp] = ss;
   __syncthreads();
-  float tot = 0.f;
-#pragma unroll
-  for (int i = 0; i < 32; ++i) tot += red[i];
-  const float inv = rsqrtf(tot / (float)H + eps);
-  if (t < n4) {
-    const float4 ww = reinterpret_cast<const float4*>(w)[t];
+  for (int idx = t; idx < R * n4; idx += 1024) {
+    const int rr = idx / n4, c4 = idx - rr * n4;
+    const long long row = row0 + rr;
+    float tot = 0.f;
+    for (int i = 0; i < nslice; ++i) tot += red[rr][i];
+    const float inv = rsqrtf(tot / (float)H + eps);
+    const float4 v = reinterpret_cast<const float4*>(xn_s + rr * H)[c4];
+    const float4 ww = reinterpret_cast<const float4*>(w)[c4];
     float o[4] = {v.x * inv * ww.x, v.y * inv * ww.y, v.z * inv * ww.z, v.w * inv * ww.w};
-    reinterpret_cast<float4*>(xn_s)[t] = make_float4(o[0], o[1], o[2], o[3]);
-    uint2 hi, lo;
-    split4<T>(o, hi, lo);
-    reinterpret_cast<uint2*>(xn16 + row * H)[t] = hi;
-    reinterpret_cast<uint2*>(xn16 + xn_lo_off + row * H)[t] = lo;
+    reinterpret_cast<float4*>(xn_s + rr * H)[c4] = make_float4(o[0], o[1], o[2], o[3]);
+    if (row < rows) {
+      uint2 hi, lo;
+      split4<T>(o, hi, lo);
+      reinterpret_cast<uint2*>(xn16 + row * H)[c4] = hi;
+      reinterpret_cast<uint2*>(xn16 + xn_lo_off + row * H)[c4] = lo;
+    }
   }
   __syncthreads();
-  {  // router logits: thread = (k-slice, expert)
+  {  // router logits: thread = (k-slice, expert); a gate weight is loaded once and used for the block's R rows
     const int e = t % E, ks = t / E;
     const int kper = H / KS;
     const float* wp = wgt + (long long)(ks * kper) * E + e;
     const float* xp = xn_s + ks * kper;
-    float acc = 0.f;
+    float acc[R];
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr) acc[rr] = 0.f;
 #pragma unroll 16  // 16 independent L2 loads in flight per thread: the gate GEMV is latency bound
-    for (int k = 0; k < kper; ++k) acc = fmaf(xp[k], wp[(long long)k * E], acc);
-    part[ks * E + e] = acc;
+    for (int k = 0; k < kper; ++k) {
+      const float wv = wp[(long long)k * E];
+#pragma unroll
+      for (int rr = 0; rr < R; ++rr) acc[rr] = fmaf(xp[rr * H + k], wv, acc[rr]);
+    }
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr) part[rr * 1024 + ks * E + e] = acc[rr];
   }
   __syncthreads();
-  if (warp == 0) {
+  if (warp < R && row0 + warp < rows) {  // one warp per row: softmax + top-k + slot reservation
+    const int rr = warp;
+    const long long row = row0 + rr;
+    const float* prt = part + rr * 1024;
     float p[PER];
     float mx = -INFINITY;
 #pragma unroll
@@ -878,7 +900,7 @@ post_attn_kernel(float* __restrict__ x, const float* __restrict__ partials, int 
       if (ee < E) {
         s = 0.f;
 #pragma unroll
-        for (int q = 0; q < KS; ++q) s += part[q * E + ee];
+        for (int q = 0; q < KS; ++q) s += prt[q * E + ee];
       }
       p[j] = s;
       mx = fmaxf(mx, s);
@@ -926,25 +948,29 @@ post_attn_kernel(float* __restrict__ x, const float* __restrict__ partials, int 
       topk_idx[row * topk + lane] = my_e;
       topk_w[row * topk + lane] = my_w;
       perm_pos[row * topk + lane] = pos;
-      sel_pos[lane] = pos;
+      sel_pos[rr][lane] = pos;
     }
   }
   __syncthreads();
   // the shared experts ride in the same grouped GEMMs as groups E, E+1, ... (EP: eloc, eloc+1, ... of the token's own
   // rank): every token, slot = its row
   const int g_shared = ep.world > 1 ? ep.eloc : E;
-  if (row == 0 && t < n_shared) counts[g_shared + t] = (int)gridDim.x;
-  for (int idx = t; idx < (topk + n_shared) * n4; idx += 1024) {  // copy the normed row into its expert slots
-    const int k = idx / n4, c4 = idx % n4;
-    const float4 o4 = reinterpret_cast<const float4*>(xn_s)[c4];
+  if (blockIdx.x == 0 && t < n_shared) counts[g_shared + t] = rows;
+  const int per_row = (topk + n_shared) * n4;
+  for (int idx = t; idx < R * per_row; idx += 1024) {  // copy the normed rows into their expert slots
+    const int rr = idx / per_row, rem = idx - rr * per_row;
+    const long long row = row0 + rr;
+    if (row >= rows) break;
+    const int k = rem / n4, c4 = rem % n4;
+    const float4 o4 = reinterpret_cast<const float4*>(xn_s + rr * H)[c4];
     const float o[4] = {o4.x, o4.y, o4.z, o4.w};
     uint2 hi, lo;
     split4<T>(o, hi, lo);
     T* base = xperm;
     long long dst;
     if (k >= topk) dst = ((long long)(g_shared + k - topk) * cap + row) * H;
-    else if (ep.world > 1) { base = reinterpret_cast<T*>(ep.xperm[sel_pos[k] >> 24]); dst = (long long)(sel_pos[k] & 0xFFFFFF) * H; }
-    else dst = (long long)sel_pos[k] * H;
+    else if (ep.world > 1) { base = reinterpret_cast<T*>(ep.xperm[sel_pos[rr][k] >> 24]); dst = (long long)(sel_pos[rr][k] & 0xFFFFFF) * H; }
+    else dst = (long long)sel_pos[rr][k] * H;
     reinterpret_cast<uint2*>(base + dst)[c4] = hi;
     reinterpret_cast<uint2*>(base + xperm_lo_off + dst)[c4] = lo;
   }
@@ -1666,13 +1692,30 @@ void post_attn(float* x, const float* partials, int n_splits, long long split_st
   if (epp) ep = *epp;
   if (ep.world > 1 && (E % ep.world || ep.eloc != E / ep.world || (ep.eloc + n_shared) * (long long)cap >= (1 << 24)))
     throw std::runtime_error("post_attn: unsupported expert-parallel layout");
-  const size_t smem = (size_t)(H + 1024) * 4;
+  // rows per block: 4 once the step has enough rows to fill the GPU that way (the gate is then read once per 4 rows)
+  const char* r_str = getenv("DSOCR_POST_ATTN_ROWS");  // A/B switch, also how the tests reach R = 4 with few pages
+  const int r_env = r_str ? atoi(r_str) : 0;
+  const int R = r_env == 1 || r_env == 4 ? r_env : (rows >= 256 ? 4 : 1);
+  const size_t smem = (size_t)R * (H + 1024) * 4;
+  const unsigned blocks = (unsigned)((rows + R - 1) / R);
+#define POST_ATTN_LAUNCH(EE, RR)                                                                                          \
+  do {                                                                                                                    \
+    auto kern = post_attn_kernel<T, EE, RR>;                                                                              \
+    if (smem > 48 * 1024) {                                                                                               \
+      static PerDeviceOnce once;                                                                                          \
+      once.run([&] { cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), "post_attn smem"); }); \
+    }                                                                                                                     \
+    kern<<<blocks, 1024, smem, s>>>(x, partials, n_splits, split_stride, w, wgt, (T*)xn16, xn_lo_off, topk_idx, topk_w,    \
+                                    counts, perm_pos, (T*)xperm, xperm_lo_off, cap, (int)rows, H, topk, n_shared, eps, ep, \
+                                    ep_counts_off);                                                                       \
+  } while (0)
   DISPATCH_T(dt, {
-    if (E == 64) post_attn_kernel<T, 64><<<(unsigned)rows, 1024, smem, s>>>(x, partials, n_splits, split_stride, w, wgt, (T*)xn16, xn_lo_off, topk_idx, topk_w, counts, perm_pos, (T*)xperm, xperm_lo_off, cap, H, topk, n_shared, eps, ep, ep_counts_off);
-    else if (E == 32) post_attn_kernel<T, 32><<<(unsigned)rows, 1024, smem, s>>>(x, partials, n_splits, split_stride, w, wgt, (T*)xn16, xn_lo_off, topk_idx, topk_w, counts, perm_pos, (T*)xperm, xperm_lo_off, cap, H, topk, n_shared, eps, ep, ep_counts_off);
-    else if (E == 16) post_attn_kernel<T, 16><<<(unsigned)rows, 1024, smem, s>>>(x, partials, n_splits, split_stride, w, wgt, (T*)xn16, xn_lo_off, topk_idx, topk_w, counts, perm_pos, (T*)xperm, xperm_lo_off, cap, H, topk, n_shared, eps, ep, ep_counts_off);
+    if (E == 64) { if (R == 4) POST_ATTN_LAUNCH(64, 4); else POST_ATTN_LAUNCH(64, 1); }
+    else if (E == 32) { if (R == 4) POST_ATTN_LAUNCH(32, 4); else POST_ATTN_LAUNCH(32, 1); }
+    else if (E == 16) { if (R == 4) POST_ATTN_LAUNCH(16, 4); else POST_ATTN_LAUNCH(16, 1); }
     else throw std::runtime_error("post_attn: unsupported expert count " + std::to_string(E));
   });
+#undef POST_ATTN_LAUNCH
   launch_check("post_attn_norm_router_dispatch");
 }
 void combine_norm(float* x, const float* y, const int* perm_pos, const float* topk_w, int topk, const float* partials,

@@ -29,9 +29,13 @@ struct PairParams {
 constexpr int kPairN = 256;                        // tokens per tile (MMA N); each CTA loads 128 of them
 constexpr int kPairStageBytes = 2 * BM * BK * 2;   // 128 weight rows + 128 token rows, 64 k each
 constexpr int kPairStages = 5;
-// 16-bit outputs leave through shared memory + TMA stores: per token-column part two buffers of [16 tokens][128 features]
+// Outputs leave through shared memory: per token-column part two buffers of [16 tokens][128 features], 16-bit ones as
+// TMA tile stores, f32 residual updates (x += y, optionally through a row map) as one 512-byte bulk REDUCTION per token
+// row - the add happens in the memory system, the SM never loads the old value (the per-thread read-modify-write this
+// replaces kept the K = 768 projections at 0.4 of their HBM bound)
 constexpr int kPairOutBufBytes = 16 * BM * 2;
-constexpr int kPairOutBytes = 4 * 2 * kPairOutBufBytes;
+constexpr int kPairOutBufBytesF32 = 16 * BM * 4;
+constexpr int kPairOutBytes = 4 * 2 * kPairOutBufBytesF32;
 constexpr int kPairSmemBytes = kPairStages * kPairStageBytes + kPairOutBytes + 1024 + 256;
 constexpr int kPairEpiWarps = 16;                  // 4 per TMEM lane quarter: the epilogue, not the MMA, is the
 constexpr int kPairThreads = 64 + 32 * kPairEpiWarps;  // long pole for K = 768 -> more warps to hide its latencies
@@ -194,7 +198,9 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
       ++it;
       ptx::mbar_wait(&tfull[buf], bphase);
       ptx::tc_fence_after();
-      const int n = wb * 256 + (int)rank * BM + quarter * 32 + lane;  // output feature owned by this thread
+      const int n0 = wb * 256 + (int)rank * BM;                       // first output feature of this CTA's slab
+      const bool slab_full = n0 + BM <= p.N && (p.ldo & 3) == 0;      // bulk reductions need whole 16-byte-aligned rows
+      const int n = n0 + quarter * 32 + lane;                         // output feature owned by this thread
       const float bias = (p.bias && n < p.N) ? p.bias[n] : 0.f;
       const uint32_t trow = tmem_base + buf * kPairN + ((uint32_t)(quarter * 32) << 16);
       const int c0 = part * kChunksPerPart;
@@ -235,6 +241,27 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
           continue;
         }
         const int nvalid = min(kPairChunk, rows - c * kPairChunk);
+        if ((MODE == kPairMapped || MODE == OUT_F32_ADD) && slab_full) {
+          float* stage = reinterpret_cast<float*>(out_stage + (part * 2 + (ci & 1)) * kPairOutBufBytesF32);
+#pragma unroll
+          for (int j = 0; j < kPairChunk; ++j) {
+            float tv = __uint_as_float(v[ci & 1][j]) + bias;
+            if (ACT == ACT_GELU_ERF) tv = gelu_erf(tv);
+            else if (ACT == ACT_QUICK_GELU) tv = quick_gelu(tv);
+            stage[j * BM + quarter * 32 + lane] = tv;
+          }
+          ptx::fence_proxy_async();
+          const bool issuer = (ew & 3) == 0;       // lanes 0..15 of this warp own one token row each
+          if (issuer) ptx::bulk_wait_read_all();   // their earlier reductions have left shared memory
+          ptx::named_bar_sync(1 + part, 128);
+          if (issuer && lane < nvalid) {
+            const long long orow = MODE == kPairMapped ? (long long)my_orow : (long long)x_row0 + c * kPairChunk + lane;
+            if (orow >= 0)
+              ptx::bulk_reduce_add_f32(reinterpret_cast<float*>(p.out) + orow * p.ldo + n0, stage + lane * BM, BM * 4);
+            ptx::bulk_commit_group();
+          }
+          continue;
+        }
         if (nvalid == kPairChunk) pair_store_chunk<T, ACT, MODE, true>(v[ci & 1], bias, kPairChunk, p, x_row0 + c * kPairChunk, n, my_orow);
         else pair_store_chunk<T, ACT, MODE, false>(v[ci & 1], bias, nvalid, p, x_row0 + c * kPairChunk, n, my_orow);
       }
@@ -248,6 +275,7 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
   }
 
   if (MODE == OUT_T && warp >= 2 && ((warp - 2) & 3) == 0 && lane == 0) ptx::bulk_wait_read_all();
+  if ((MODE == kPairMapped || MODE == OUT_F32_ADD) && warp >= 2 && ((warp - 2) & 3) == 0) ptx::bulk_wait_read_all();
   // nobody leaves while the partner may still read this CTA's shared memory or signal its barriers
   __syncwarp();
   ptx::tc_fence_before();

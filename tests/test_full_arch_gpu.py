@@ -2,6 +2,8 @@
 129 280) with random-init weights of the exact shapes: the instantiations the tiny fixtures never reach
 (`post_attn_kernel<T,64>`, `router_kernel<64>`, `dsq_router_kernel<64,16>`, the 129 280-wide lm_head + select_token) and
 the error accumulated over the real depth.  Same tolerances as the tiny-model tests."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -64,6 +66,14 @@ def test_full_decoder_batched_and_batch1(setup):
     params = DecodeParameters(max_new_tokens=steps, no_repeat_ngram_size=20, eos_token_id=None)
     sel, logits = eng.generate_forced(ids, masks, rows, params, forced, want_logits=True)
     free = eng.generate_batch(ids, masks, rows, params)
+    # post_attn_kernel<T, 64, 4> (4 rows per block, picked from 256 rows per step on) forced onto these 5 pages: the
+    # per-row arithmetic does not depend on the rows-per-block choice, so the tokens must be the same ones
+    os.environ["DSOCR_POST_ATTN_ROWS"] = "4"
+    try:
+        free_r4 = eng.generate_batch(ids, masks, rows, params)
+    finally:
+        del os.environ["DSOCR_POST_ATTN_ROWS"]
+    assert free_r4 == free
     eng.set_option("kv_cache_f16", 1)
     try:
         free16 = eng.generate_batch(ids, masks, rows, params)

@@ -223,6 +223,20 @@ def test_linear_pair_16bit_out_activations(act):
     assert torch.allclose(y, r, rtol=2 ** -7, atol=1e-2)
 
 
+@pytest.mark.parametrize("M,N,K", [(2500, 768, 3072), (4096, 1024, 1024), (2049, 768, 768)])
+def test_linear_pair_residual_add_plain(M, N, K):
+    """x += y through the bulk-reduction epilogue (no row map): row tails of the last 16-token chunk and of the last
+    256-token tile, every element updated exactly once."""
+    g = torch.Generator().manual_seed(M + K)
+    x = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) * 0.03
+    b = torch.randn(N, generator=g)
+    base = torch.randn(M, N, generator=g)
+    y = run_linear(BF16, x, w, bias=b, out_mode=3, out_init=base.numpy())
+    r = base + ref_linear(BF16, x, w, bias=b)
+    assert torch.allclose(y, r, rtol=1e-3, atol=5e-3), (y - r).abs().max()
+
+
 def test_linear_pair_residual_add_with_row_map():
     g = torch.Generator().manual_seed(12)
     M, N, K = 2940, 768, 768   # 15 windows of 14x14 tokens, some of them padding
