@@ -813,8 +813,8 @@ rope_attn_decode_bulk_kernel(const float* __restrict__ qkv, int n_splits, long l
 // (2) o_proj split-K reduce + residual add + RMSNorm(ln2) + router + top-k + dispatch into fixed-capacity
 // expert segments (slot = atomic counter per expert; the grouped GEMM reads the counters).  One block handles R
 // consecutive rows: with hundreds of rows per step the router gate (H x E f32, 327 KB) is then read from L2 once per R
-// rows instead of once per row and the launch fits one wave of blocks (R = 4: 1024 rows -> 256 blocks on 296 slots;
-// one row per block was 3.5 waves of ~10 us latency chains).  Per-row arithmetic and summation order do not depend on R.
+// rows instead of once per row and the launch fits one wave of blocks (R = 8: 1024 rows -> 128 blocks; one row per block
+// was 7 waves of ~10 us latency chains, a 1024-thread block being alone on its SM).  Per-row arithmetic and summation order do not depend on R.
 template <typename T, int E, int R>
 __global__ void __launch_bounds__(1024)
 post_attn_kernel(float* __restrict__ x, const float* __restrict__ partials, int n_splits, long long split_stride,
@@ -1687,15 +1687,20 @@ void post_attn(float* x, const float* partials, int n_splits, long long split_st
                void* xn16, long long xn_lo_off, int* topk_idx, float* topk_w, int* counts, int* perm_pos, void* xperm,
                long long xperm_lo_off, int cap, long long rows, int H, int E, int topk, int n_shared, float eps, DType dt,
                cudaStream_t s, const EpPeers* epp, int ep_counts_off) {
-  if (H % 256 || H / 4 > 1024 || topk > 16 || rows > cap) throw std::runtime_error("post_attn: unsupported shape");
+  if (H % 256 || H > 1536 || topk > 16 || rows > cap) throw std::runtime_error("post_attn: unsupported shape");
   EpPeers ep;
   if (epp) ep = *epp;
   if (ep.world > 1 && (E % ep.world || ep.eloc != E / ep.world || (ep.eloc + n_shared) * (long long)cap >= (1 << 24)))
     throw std::runtime_error("post_attn: unsupported expert-parallel layout");
-  // rows per block: 4 once the step has enough rows to fill the GPU that way (the gate is then read once per 4 rows)
-  const char* r_str = getenv("DSOCR_POST_ATTN_ROWS");  // A/B switch, also how the tests reach R = 4 with few pages
+  // rows per block: the smallest of 1 / 2 / 4 / 8 that puts the step into ONE wave of blocks (a 1024-thread block at
+  // ~55 registers per thread is alone on its SM); the gate is then read from L2 once per R rows
+  const char* r_str = getenv("DSOCR_POST_ATTN_ROWS");  // A/B switch, also how the tests reach R > 1 with few pages
   const int r_env = r_str ? atoi(r_str) : 0;
-  const int R = r_env == 1 || r_env == 4 ? r_env : (rows >= 256 ? 4 : 1);
+  int R = 1;
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  while (R < 8 && (rows + R - 1) / R > sms) R *= 2;
+  if (r_env == 1 || r_env == 2 || r_env == 4 || r_env == 8) R = r_env;
   const size_t smem = (size_t)R * (H + 1024) * 4;
   const unsigned blocks = (unsigned)((rows + R - 1) / R);
 #define POST_ATTN_LAUNCH(EE, RR)                                                                                          \
@@ -1703,18 +1708,24 @@ void post_attn(float* x, const float* partials, int n_splits, long long split_st
     auto kern = post_attn_kernel<T, EE, RR>;                                                                              \
     if (smem > 48 * 1024) {                                                                                               \
       static PerDeviceOnce once;                                                                                          \
-      once.run([&] { cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), "post_attn smem"); }); \
+      once.run([&] { cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (1536 + 1024) * 4), "post_attn smem"); }); \
     }                                                                                                                     \
     kern<<<blocks, 1024, smem, s>>>(x, partials, n_splits, split_stride, w, wgt, (T*)xn16, xn_lo_off, topk_idx, topk_w,    \
                                     counts, perm_pos, (T*)xperm, xperm_lo_off, cap, (int)rows, H, topk, n_shared, eps, ep, \
                                     ep_counts_off);                                                                       \
   } while (0)
+#define POST_ATTN_R(EE)                                                                                                   \
+  do {                                                                                                                    \
+    if (R == 8) POST_ATTN_LAUNCH(EE, 8); else if (R == 4) POST_ATTN_LAUNCH(EE, 4);                                        \
+    else if (R == 2) POST_ATTN_LAUNCH(EE, 2); else POST_ATTN_LAUNCH(EE, 1);                                               \
+  } while (0)
   DISPATCH_T(dt, {
-    if (E == 64) { if (R == 4) POST_ATTN_LAUNCH(64, 4); else POST_ATTN_LAUNCH(64, 1); }
-    else if (E == 32) { if (R == 4) POST_ATTN_LAUNCH(32, 4); else POST_ATTN_LAUNCH(32, 1); }
-    else if (E == 16) { if (R == 4) POST_ATTN_LAUNCH(16, 4); else POST_ATTN_LAUNCH(16, 1); }
+    if (E == 64) POST_ATTN_R(64);
+    else if (E == 32) POST_ATTN_R(32);
+    else if (E == 16) POST_ATTN_R(16);
     else throw std::runtime_error("post_attn: unsupported expert count " + std::to_string(E));
   });
+#undef POST_ATTN_R
 #undef POST_ATTN_LAUNCH
   launch_check("post_attn_norm_router_dispatch");
 }

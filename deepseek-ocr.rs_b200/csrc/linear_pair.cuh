@@ -241,7 +241,7 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
           continue;
         }
         const int nvalid = min(kPairChunk, rows - c * kPairChunk);
-        if ((MODE == kPairMapped || MODE == OUT_F32_ADD) && slab_full) {
+        if ((MODE == kPairMapped || MODE == OUT_F32_ADD || MODE == OUT_F32) && slab_full) {
           float* stage = reinterpret_cast<float*>(out_stage + (part * 2 + (ci & 1)) * kPairOutBufBytesF32);
 #pragma unroll
           for (int j = 0; j < kPairChunk; ++j) {
@@ -256,8 +256,9 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
           ptx::named_bar_sync(1 + part, 128);
           if (issuer && lane < nvalid) {
             const long long orow = MODE == kPairMapped ? (long long)my_orow : (long long)x_row0 + c * kPairChunk + lane;
-            if (orow >= 0)
-              ptx::bulk_reduce_add_f32(reinterpret_cast<float*>(p.out) + orow * p.ldo + n0, stage + lane * BM, BM * 4);
+            float* dst = reinterpret_cast<float*>(p.out) + orow * p.ldo + n0;
+            if (MODE == OUT_F32) ptx::bulk_store(dst, stage + lane * BM, BM * 4);  // plain f32 rows (the rel-pos products)
+            else if (orow >= 0) ptx::bulk_reduce_add_f32(dst, stage + lane * BM, BM * 4);
             ptx::bulk_commit_group();
           }
           continue;
@@ -275,7 +276,7 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
   }
 
   if (MODE == OUT_T && warp >= 2 && ((warp - 2) & 3) == 0 && lane == 0) ptx::bulk_wait_read_all();
-  if ((MODE == kPairMapped || MODE == OUT_F32_ADD) && warp >= 2 && ((warp - 2) & 3) == 0) ptx::bulk_wait_read_all();
+  if ((MODE == kPairMapped || MODE == OUT_F32_ADD || MODE == OUT_F32) && warp >= 2 && ((warp - 2) & 3) == 0) ptx::bulk_wait_read_all();
   // nobody leaves while the partner may still read this CTA's shared memory or signal its barriers
   __syncwarp();
   ptx::tc_fence_before();

@@ -133,6 +133,12 @@ __device__ __forceinline__ void bulk_reduce_add_f32(float* gdst, const void* sme
                "r"(smem_u32(smem_src)), "r"(bytes)
                : "memory");
 }
+// 1-D bulk store shared -> global (16-byte aligned addresses and size), completion through the bulk async-group.
+__device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
+               "r"(bytes)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // wait until the issuing thread's bulk groups have finished READING their shared-memory sources
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }

@@ -66,14 +66,15 @@ def test_full_decoder_batched_and_batch1(setup):
     params = DecodeParameters(max_new_tokens=steps, no_repeat_ngram_size=20, eos_token_id=None)
     sel, logits = eng.generate_forced(ids, masks, rows, params, forced, want_logits=True)
     free = eng.generate_batch(ids, masks, rows, params)
-    # post_attn_kernel<T, 64, 4> (4 rows per block, picked from 256 rows per step on) forced onto these 5 pages: the
+    # post_attn_kernel<T, 64, R> with R = 2 / 4 / 8 rows per block (picked for large steps) forced onto these 5 pages: the
     # per-row arithmetic does not depend on the rows-per-block choice, so the tokens must be the same ones
-    os.environ["DSOCR_POST_ATTN_ROWS"] = "4"
-    try:
-        free_r4 = eng.generate_batch(ids, masks, rows, params)
-    finally:
-        del os.environ["DSOCR_POST_ATTN_ROWS"]
-    assert free_r4 == free
+    for r in ("2", "4", "8"):
+        os.environ["DSOCR_POST_ATTN_ROWS"] = r
+        try:
+            free_r = eng.generate_batch(ids, masks, rows, params)
+        finally:
+            del os.environ["DSOCR_POST_ATTN_ROWS"]
+        assert free_r == free, f"{r} rows per block"
     eng.set_option("kv_cache_f16", 1)
     try:
         free16 = eng.generate_batch(ids, masks, rows, params)
