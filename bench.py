@@ -529,7 +529,7 @@ def main():
         "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
         "config": {"workload": workload, "l2": "per-step working set (weights 6.7 GB + KV + activations) exceeds the 126 MB L2",
                    "parallelism": f"one fixed set of {args.pages} pages sharded round-robin over {world} GPU(s), "
-                                  f"{args.batch} pages per lock-step decode group, no collective"},
+                                  f"{min(args.batch, len(pages))} pages per lock-step decode group, no collective"},
         "e2e": {"value": e2e_val, "unit": "pages/s", "h2d_bytes_per_step": h2d_bytes * world, "d2h_bytes_per_step": d2h_bytes * world,
                 "host_memory": "pinned", "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches_e2e,

@@ -27,13 +27,24 @@ struct dsocr_engine {
   struct DevCoef { DevBuf start, len, coef; int ksize = 0; };
   std::map<std::pair<int, int>, DevCoef> coefs;
   DevBuf pages_raw, horiz;
+  // decode_pages / decode_requests stage their pages on a side stream (H2D copy + resample per page, an event every
+  // kPagesPerEvent pages) so that the copies of later pages run under the vision tower of the earlier ones
+  static constexpr int kPagesPerEvent = 8;
+  cudaStream_t copy_stream = nullptr;
+  std::vector<cudaEvent_t> page_events;
+  std::vector<int> tile_page;  // staged tile index -> page index
+  bool staged_async = false;
+  ~dsocr_engine() {
+    for (cudaEvent_t ev : page_events) cudaEventDestroy(ev);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
+  }
   bool host_preprocess = false;
   int decode_batch = 512;  // requests decoded in lock-step per group
 };
 
 namespace {
 void gpu_prepare_page(dsocr_engine* e, const uint8_t* src, int w, int h, dsocr_vision_settings vs, uint8_t* global_dst,
-                      uint8_t* tiles_dst, int gw, int gh, int n_tiles);
+                      uint8_t* tiles_dst, int gw, int gh, int n_tiles, cudaStream_t st = nullptr);
 int status_of(const std::exception& e) {
   const std::string m = e.what();
   if (m.find("prompt/image embedding mismatch") != std::string::npos) return DSOCR_ERR_MISMATCH;
@@ -404,40 +415,48 @@ const dsocr_engine::DevCoef& coef_for(dsocr_engine* e, int in_size, int out_size
 
 // resize_bicubic on the device: src [h,w,3] u8 -> either the global canvas or the tile stack (see resample_v)
 void gpu_resize(dsocr_engine* e, const uint8_t* src, int w, int h, int dw, int dh, uint8_t* dst, int canvas, int x_off,
-                int y_off, int tile, int tiles_w) {
+                int y_off, int tile, int tiles_w, cudaStream_t st) {
   Engine& en = *e->impl;
   const auto& cx = coef_for(e, w, dw);
   const auto& cy = coef_for(e, h, dh);
   if (e->horiz.bytes < (size_t)h * dw * 3) {
     cuda_check(cudaStreamSynchronize(en.stream()), "horiz grow sync");
+    if (st != en.stream()) cuda_check(cudaStreamSynchronize(st), "horiz grow sync");
     e->horiz.alloc((size_t)h * dw * 3);
   }
-  resample_h(src, w, h, e->horiz.as<uint8_t>(), dw, cx.start.as<int>(), cx.len.as<int>(), cx.coef.as<int>(), cx.ksize, en.stream());
+  resample_h(src, w, h, e->horiz.as<uint8_t>(), dw, cx.start.as<int>(), cx.len.as<int>(), cx.coef.as<int>(), cx.ksize, st);
   resample_v(e->horiz.as<uint8_t>(), dw, dh, dst, cy.start.as<int>(), cy.len.as<int>(), cy.coef.as<int>(), cy.ksize, canvas,
-             x_off, y_off, tile, tiles_w, en.stream());
+             x_off, y_off, tile, tiles_w, st);
 }
 
 // prepare_vision_input_from_image for one page already resident on the device (raw RGB8)
 void gpu_prepare_page(dsocr_engine* e, const uint8_t* src, int w, int h, dsocr_vision_settings vs, uint8_t* global_dst,
-                      uint8_t* tiles_dst, int gw, int gh, int n_tiles) {
+                      uint8_t* tiles_dst, int gw, int gh, int n_tiles, cudaStream_t st) {
   Engine& en = *e->impl;
+  if (!st) st = en.stream();
   const int G = vs.crop_mode ? (int)vs.base_size : (int)vs.image_size, P = (int)vs.image_size;
   if (w == G && h == G) {
-    cuda_check(cudaMemcpyAsync(global_dst, src, (size_t)G * G * 3, cudaMemcpyDeviceToDevice, en.stream()), "global copy");
+    cuda_check(cudaMemcpyAsync(global_dst, src, (size_t)G * G * 3, cudaMemcpyDeviceToDevice, st), "global copy");
   } else {
     int nw, nh, xo, yo;
     global_view_geometry(w, h, G, &nw, &nh, &xo, &yo);
-    cuda_check(cudaMemsetAsync(global_dst, 127, (size_t)G * G * 3, en.stream()), "canvas fill");
-    gpu_resize(e, src, w, h, nw, nh, global_dst, G, xo, yo, 0, 0);
+    cuda_check(cudaMemsetAsync(global_dst, 127, (size_t)G * G * 3, st), "canvas fill");
+    gpu_resize(e, src, w, h, nw, nh, global_dst, G, xo, yo, 0, 0, st);
   }
-  if (n_tiles > 0) gpu_resize(e, src, w, h, P * gw, P * gh, tiles_dst, 0, 0, 0, P, gw);
+  if (n_tiles > 0) gpu_resize(e, src, w, h, P * gw, P * gh, tiles_dst, 0, 0, 0, P, gw, st);
 }
 
+// async_ok: the caller keeps the host pages alive until the decode that follows has finished (decode_pages / decode_requests),
+// so the copies may still be in flight on return; the vision tower waits for the event covering the views of each chunk.
 void stage_pages_gpu(dsocr_engine* e, int n_pages, const uint8_t* const* rgb, const int* widths, const int* heights,
-                     dsocr_vision_settings vs) {
+                     dsocr_vision_settings vs, bool async_ok) {
   Engine& en = *e->impl;
   auto& sg = e->staged;
   const double t0 = now_ms();
+  const bool async = async_ok && !kernel_timing_enabled() && !getenv("DSOCR_SYNC_STAGING");
+  if (async && !e->copy_stream) cuda_check(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking), "copy stream");
+  cudaStream_t st = async ? e->copy_stream : en.stream();
+  e->staged_async = false;
   const int G = vs.crop_mode ? (int)vs.base_size : (int)vs.image_size, P = (int)vs.image_size;
   sg.ntiles.assign(n_pages, 0); sg.cw.assign(n_pages, 1); sg.ch.assign(n_pages, 1);
   sg.n_pages = n_pages; sg.vs = vs;
@@ -451,26 +470,42 @@ void stage_pages_gpu(dsocr_engine* e, int n_pages, const uint8_t* const* rgb, co
     total_tiles += sg.ntiles[p];
   }
   const size_t gbytes = (size_t)G * G * 3, tbytes = (size_t)P * P * 3;
-  if (e->pages_raw.bytes < raw_bytes || sg.globals.bytes < gbytes * n_pages || sg.tiles.bytes < std::max<size_t>(16, tbytes * total_tiles))
+  if (e->pages_raw.bytes < raw_bytes || sg.globals.bytes < gbytes * n_pages || sg.tiles.bytes < std::max<size_t>(16, tbytes * total_tiles)) {
     cuda_check(cudaStreamSynchronize(en.stream()), "stage grow sync");
+    if (e->copy_stream) cuda_check(cudaStreamSynchronize(e->copy_stream), "stage grow sync");
+  }
   e->pages_raw.ensure(raw_bytes);
   sg.globals.ensure(gbytes * n_pages);
   sg.tiles.ensure(std::max<size_t>(16, tbytes * total_tiles));
+  constexpr int ppe = dsocr_engine::kPagesPerEvent;
+  if (async) {
+    const size_t n_ev = (size_t)(n_pages + ppe - 1) / ppe;
+    while (e->page_events.size() < n_ev) {
+      cudaEvent_t ev;
+      cuda_check(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "page event");
+      e->page_events.push_back(ev);
+    }
+    e->tile_page.clear();
+    for (int p = 0; p < n_pages; ++p) e->tile_page.insert(e->tile_page.end(), sg.ntiles[p], p);
+  }
   size_t toff = 0;
   for (int p = 0; p < n_pages; ++p) {
     uint8_t* src = e->pages_raw.as<uint8_t>() + raw_off[p];
-    cuda_check(cudaMemcpyAsync(src, rgb[p], (size_t)widths[p] * heights[p] * 3, cudaMemcpyHostToDevice, en.stream()), "page H2D");
+    cuda_check(cudaMemcpyAsync(src, rgb[p], (size_t)widths[p] * heights[p] * 3, cudaMemcpyHostToDevice, st), "page H2D");
     gpu_prepare_page(e, src, widths[p], heights[p], vs, sg.globals.as<uint8_t>() + gbytes * p, sg.tiles.as<uint8_t>() + toff,
-                     sg.cw[p], sg.ch[p], sg.ntiles[p]);
+                     sg.cw[p], sg.ch[p], sg.ntiles[p], st);
     toff += tbytes * sg.ntiles[p];
+    if (async && ((p + 1) % ppe == 0 || p + 1 == n_pages)) cuda_check(cudaEventRecord(e->page_events[p / ppe], st), "page event record");
   }
-  cuda_check(cudaStreamSynchronize(en.stream()), "stage sync");
+  if (async) e->staged_async = true;
+  else cuda_check(cudaStreamSynchronize(st), "stage sync");
   en.timings.prepare = now_ms() - t0;
 }
 
 void stage_pages(dsocr_engine* e, int n_pages, const uint8_t* const* rgb, const int* widths, const int* heights,
-                 dsocr_vision_settings vs) {
-  if (!e->host_preprocess) { stage_pages_gpu(e, n_pages, rgb, widths, heights, vs); return; }
+                 dsocr_vision_settings vs, bool async_ok = false) {
+  e->staged_async = false;
+  if (!e->host_preprocess) { stage_pages_gpu(e, n_pages, rgb, widths, heights, vs, async_ok); return; }
   Engine& en = *e->impl;
   auto& sg = e->staged;
   // prepare_vision_inputs (model/mod.rs:2457-2492): integer resample / tiling on the host cores
@@ -555,8 +590,22 @@ void decode_request_group(dsocr_engine* e, const std::vector<RequestSpec>& reqs,
   if (n_images > 0) {
     std::vector<Engine::PageViews> pages(n_images);
     for (int p = 0; p < n_images; ++p) { pages[p].n_tiles = sg.ntiles[img0 + p]; pages[p].crop_w = sg.cw[img0 + p]; pages[p].crop_h = sg.ch[img0 + p]; }
-    rows = en.vision_encode(n_images, sg.globals.as<uint8_t>() + gbytes * img0, false, G, sg.tiles.as<uint8_t>() + tbytes * tile0,
-                            false, P, pages, &counts);
+    if (e->staged_async) {
+      // pages are still arriving on the copy stream: before a chunk of views is read, wait for the event that covers
+      // the last page the chunk touches (copies and resamples complete in page order)
+      en.view_ready = [e, &en, img0, tile0](bool local, int last_view) {
+        const int page = local ? e->tile_page[tile0 + last_view] : img0 + last_view;
+        cuda_check(cudaStreamWaitEvent(en.stream(), e->page_events[page / dsocr_engine::kPagesPerEvent], 0), "page event wait");
+      };
+    }
+    try {
+      rows = en.vision_encode(n_images, sg.globals.as<uint8_t>() + gbytes * img0, false, G, sg.tiles.as<uint8_t>() + tbytes * tile0,
+                              false, P, pages, &counts);
+    } catch (...) {
+      en.view_ready = nullptr;
+      throw;
+    }
+    en.view_ready = nullptr;
     cuda_check(cudaStreamSynchronize(en.stream()), "vision sync");
   }
   total.vision += now_ms() - t1;
@@ -664,9 +713,12 @@ extern "C" int dsocr_decode_pages(dsocr_engine* e, int n_pages, const uint8_t* c
     try {
       bind(e);
       if (!params) throw std::runtime_error("null decode params");
-      stage_pages(e, n_pages, rgb, widths, heights, vs);
+      stage_pages(e, n_pages, rgb, widths, heights, vs, /*async_ok=*/true);
       decode_staged(e, seg0, n_seg0, seg1, n_seg1, image_token_id, params, cb, user, out_tokens, n_out, prompt_tokens, stage);
+      e->staged_async = false;
     } catch (const std::exception& ex) {
+      if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);  // the caller may free its pages once we return
+      e->staged_async = false;
       throw std::runtime_error(stage.empty() ? std::string(ex.what()) : stage + ": " + ex.what());
     }
   });
@@ -690,10 +742,13 @@ extern "C" int dsocr_decode_requests(dsocr_engine* e, int n_requests, const dsoc
         for (int i = 0; i < q.n_images; ++i) { rgb.push_back(q.rgb[i]); ws.push_back(q.widths[i]); hs.push_back(q.heights[i]); }
         for (int i = 0; i < q.n_segments; ++i) { reqs[r].seg.push_back(q.segments[i]); reqs[r].seg_len.push_back(q.segment_lens[i]); }
       }
-      if (!rgb.empty()) stage_pages(e, (int)rgb.size(), rgb.data(), ws.data(), hs.data(), vs);
-      else { e->staged.n_pages = 0; e->staged.vs = vs; e->impl->timings.prepare = 0; }
+      if (!rgb.empty()) stage_pages(e, (int)rgb.size(), rgb.data(), ws.data(), hs.data(), vs, /*async_ok=*/true);
+      else { e->staged.n_pages = 0; e->staged.vs = vs; e->impl->timings.prepare = 0; e->staged_async = false; }
       decode_staged_requests(e, reqs, image_token_id, params, cb, user, out_tokens, n_out, prompt_tokens, stage);
+      e->staged_async = false;
     } catch (const std::exception& ex) {
+      if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);  // the caller may free its pages once we return
+      e->staged_async = false;
       throw std::runtime_error(stage.empty() ? std::string(ex.what()) : stage + ": " + ex.what());
     }
   });

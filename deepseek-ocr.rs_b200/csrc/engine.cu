@@ -769,6 +769,7 @@ void Engine::vision_views(int Bv, int G, const void* img_dev, bool is_f32, float
   for (int b0 = 0; b0 < Bv; b0 += max_views) {
     const int nb = std::min(max_views, Bv - b0);
     const long long rows = (long long)nb * g * g;
+    if (view_ready) view_ready(tag[0] == 'l', b0 + nb - 1);
     void* patches = ws("patches16", rows * 768 * 2).p;
     if (is_f32) patchify_f32((const float*)img_dev + (size_t)b0 * 3 * G * G, patches, nb, G, dt_, stream_);
     else patchify_u8((const uint8_t*)img_dev + (size_t)b0 * 3 * G * G, patches, nb, G, dt_, stream_);

@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <map>
 #include <memory>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -106,6 +107,9 @@ class Engine {
   int device() const { return device_; }
   int sm_count() const { return num_sms_; }
   cudaStream_t stream() const { return stream_; }
+  // optional: called by the vision tower before it reads the views [.., last_view] of a chunk (local = crop tiles);
+  // the C ABI uses it to wait for pages that are still being copied in on a side stream
+  std::function<void(bool local, int last_view)> view_ready;
   Timings timings;
   std::string device_name;
 
