@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <thread>
 
@@ -30,6 +31,9 @@ struct dsocr_engine {
   // decode_pages / decode_requests stage their pages on a side stream (H2D copy + resample per page, an event every
   // kPagesPerEvent pages) so that the copies of later pages run under the vision tower of the earlier ones
   static constexpr int kPagesPerEvent = 8;
+  static constexpr int kStageAhead = 96;  // pages issued beyond the ones a vision chunk is about to read
+  std::function<void(int)> stage_fn;      // valid only while the call that owns the host pages is running
+  int stage_next = 0;
   cudaStream_t copy_stream = nullptr;
   std::vector<cudaEvent_t> page_events;
   std::vector<int> tile_page;  // staged tile index -> page index
@@ -488,17 +492,35 @@ void stage_pages_gpu(dsocr_engine* e, int n_pages, const uint8_t* const* rgb, co
     e->tile_page.clear();
     for (int p = 0; p < n_pages; ++p) e->tile_page.insert(e->tile_page.end(), sg.ntiles[p], p);
   }
-  size_t toff = 0;
-  for (int p = 0; p < n_pages; ++p) {
-    uint8_t* src = e->pages_raw.as<uint8_t>() + raw_off[p];
-    cuda_check(cudaMemcpyAsync(src, rgb[p], (size_t)widths[p] * heights[p] * 3, cudaMemcpyHostToDevice, st), "page H2D");
-    gpu_prepare_page(e, src, widths[p], heights[p], vs, sg.globals.as<uint8_t>() + gbytes * p, sg.tiles.as<uint8_t>() + toff,
-                     sg.cw[p], sg.ch[p], sg.ntiles[p], st);
-    toff += tbytes * sg.ntiles[p];
-    if (async && ((p + 1) % ppe == 0 || p + 1 == n_pages)) cuda_check(cudaEventRecord(e->page_events[p / ppe], st), "page event record");
+  std::vector<size_t> tile_off(n_pages);
+  {
+    size_t toff = 0;
+    for (int p = 0; p < n_pages; ++p) { tile_off[p] = toff; toff += tbytes * sg.ntiles[p]; }
   }
-  if (async) e->staged_async = true;
-  else cuda_check(cudaStreamSynchronize(st), "stage sync");
+  // pages [stage_next, upto) -> copy + resample on `st`.  In the asynchronous form this is called again and again by the
+  // vision tower (a chunk ahead of what it reads): a stream accepts only ~1000 pending operations, so issuing all pages at
+  // once would block the host here for the whole transfer and nothing would overlap.
+  e->stage_next = 0;
+  e->stage_fn = [=](int upto) {
+    auto& sgr = e->staged;
+    upto = std::min(upto, n_pages);
+    for (int p = e->stage_next; p < upto; ++p) {
+      uint8_t* src = e->pages_raw.as<uint8_t>() + raw_off[p];
+      cuda_check(cudaMemcpyAsync(src, rgb[p], (size_t)widths[p] * heights[p] * 3, cudaMemcpyHostToDevice, st), "page H2D");
+      gpu_prepare_page(e, src, widths[p], heights[p], vs, sgr.globals.as<uint8_t>() + gbytes * p, sgr.tiles.as<uint8_t>() + tile_off[p],
+                       sgr.cw[p], sgr.ch[p], sgr.ntiles[p], st);
+      if (async && ((p + 1) % ppe == 0 || p + 1 == n_pages)) cuda_check(cudaEventRecord(e->page_events[p / ppe], st), "page event record");
+    }
+    e->stage_next = std::max(e->stage_next, upto);
+  };
+  if (async) {
+    e->stage_fn(dsocr_engine::kStageAhead / 2);  // enough for the first chunk of global views; the hook keeps it topped up
+    e->staged_async = true;
+  } else {
+    e->stage_fn(n_pages);
+    e->stage_fn = nullptr;
+    cuda_check(cudaStreamSynchronize(st), "stage sync");
+  }
   en.timings.prepare = now_ms() - t0;
 }
 
@@ -595,6 +617,7 @@ void decode_request_group(dsocr_engine* e, const std::vector<RequestSpec>& reqs,
       // the last page the chunk touches (copies and resamples complete in page order)
       en.view_ready = [e, &en, img0, tile0](bool local, int last_view) {
         const int page = local ? e->tile_page[tile0 + last_view] : img0 + last_view;
+        if (e->stage_fn) e->stage_fn((page / dsocr_engine::kPagesPerEvent + 1) * dsocr_engine::kPagesPerEvent + dsocr_engine::kStageAhead);
         cuda_check(cudaStreamWaitEvent(en.stream(), e->page_events[page / dsocr_engine::kPagesPerEvent], 0), "page event wait");
       };
     }
@@ -715,10 +738,10 @@ extern "C" int dsocr_decode_pages(dsocr_engine* e, int n_pages, const uint8_t* c
       if (!params) throw std::runtime_error("null decode params");
       stage_pages(e, n_pages, rgb, widths, heights, vs, /*async_ok=*/true);
       decode_staged(e, seg0, n_seg0, seg1, n_seg1, image_token_id, params, cb, user, out_tokens, n_out, prompt_tokens, stage);
-      e->staged_async = false;
+      e->staged_async = false; e->stage_fn = nullptr;
     } catch (const std::exception& ex) {
       if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);  // the caller may free its pages once we return
-      e->staged_async = false;
+      e->staged_async = false; e->stage_fn = nullptr;
       throw std::runtime_error(stage.empty() ? std::string(ex.what()) : stage + ": " + ex.what());
     }
   });
@@ -745,10 +768,10 @@ extern "C" int dsocr_decode_requests(dsocr_engine* e, int n_requests, const dsoc
       if (!rgb.empty()) stage_pages(e, (int)rgb.size(), rgb.data(), ws.data(), hs.data(), vs, /*async_ok=*/true);
       else { e->staged.n_pages = 0; e->staged.vs = vs; e->impl->timings.prepare = 0; e->staged_async = false; }
       decode_staged_requests(e, reqs, image_token_id, params, cb, user, out_tokens, n_out, prompt_tokens, stage);
-      e->staged_async = false;
+      e->staged_async = false; e->stage_fn = nullptr;
     } catch (const std::exception& ex) {
       if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);  // the caller may free its pages once we return
-      e->staged_async = false;
+      e->staged_async = false; e->stage_fn = nullptr;
       throw std::runtime_error(stage.empty() ? std::string(ex.what()) : stage + ": " + ex.what());
     }
   });
