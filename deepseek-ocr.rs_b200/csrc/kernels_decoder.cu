@@ -1106,21 +1106,44 @@ router_kernel(const float* __restrict__ x, const float* __restrict__ wgt, int* _
   const float* wp = wgt + (long long)(ks * kper) * E + e;
   const float* xp = xs + ks * kper;
   if constexpr (TOK >= 16) {
-    // many tokens per block (prefill): four k at a time, the token rows read as float4 (one 128-bit broadcast load per
-    // token and 4 k instead of four 32-bit ones); per token the products are added in the same k order as below
+    // Many tokens per block (prefill).  One expert x all tokens per thread needs one shared-memory load per FMA, and a
+    // warp-wide load returns 128 B per clock whether or not it is a broadcast: that, not the FMAs, bounded the kernel
+    // (369 us per 31 k rows).  Here a thread owns 4 experts x 4 tokens of its k-slice: per 4 k it loads four float4 of gate
+    // weights (coalesced over the expert groups) and four float4 of activations for 64 FMAs.  Per (token, expert) the
+    // products are still added in ascending k inside the slice, so the logits are bit-identical to the scalar loop.
+    static_assert(TOK == 16 && E % 4 == 0, "router: 4 x 4 register tile");
+    constexpr int EG = E / 4;
+    const int slot = threadIdx.x % E;
+    const int eg = slot % EG, tg = slot / EG;   // expert group (4 experts), token group (4 tokens)
+    float a4[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int jx = 0; jx < 4; ++jx) a4[i][jx] = 0.f;
+    const float* wq = wgt + (long long)(ks * kper) * E + 4 * eg;
+    const float* xq = xs + (4 * tg) * H + ks * kper;
 #pragma unroll 2
     for (int k = 0; k < kper; k += 4) {
-      const float w0 = wp[(long long)k * E], w1 = wp[(long long)(k + 1) * E], w2 = wp[(long long)(k + 2) * E],
-                  w3 = wp[(long long)(k + 3) * E];
+      float4 wv[4], xv[4];
 #pragma unroll
-      for (int t = 0; t < TOK; ++t) {
-        const float4 xv = *reinterpret_cast<const float4*>(xp + t * H + k);
-        acc[t] = fmaf(xv.x, w0, acc[t]);
-        acc[t] = fmaf(xv.y, w1, acc[t]);
-        acc[t] = fmaf(xv.z, w2, acc[t]);
-        acc[t] = fmaf(xv.w, w3, acc[t]);
+      for (int kk = 0; kk < 4; ++kk) wv[kk] = *reinterpret_cast<const float4*>(wq + (long long)(k + kk) * E);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) xv[t] = *reinterpret_cast<const float4*>(xq + t * H + k);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float xk[4] = {xv[t].x, xv[t].y, xv[t].z, xv[t].w};
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          a4[t][0] = fmaf(xk[kk], wv[kk].x, a4[t][0]);
+          a4[t][1] = fmaf(xk[kk], wv[kk].y, a4[t][1]);
+          a4[t][2] = fmaf(xk[kk], wv[kk].z, a4[t][2]);
+          a4[t][3] = fmaf(xk[kk], wv[kk].w, a4[t][3]);
+        }
       }
     }
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      *reinterpret_cast<float4*>(part + (ks * TOK + 4 * tg + t) * E + 4 * eg) = make_float4(a4[t][0], a4[t][1], a4[t][2], a4[t][3]);
   } else {
 #pragma unroll 8
     for (int k = 0; k < kper; ++k) {
@@ -1128,9 +1151,9 @@ router_kernel(const float* __restrict__ x, const float* __restrict__ wgt, int* _
 #pragma unroll
       for (int t = 0; t < TOK; ++t) acc[t] = fmaf(xp[t * H + k], w, acc[t]);
     }
-  }
 #pragma unroll
-  for (int t = 0; t < TOK; ++t) part[(ks * TOK + t) * E + e] = acc[t];
+    for (int t = 0; t < TOK; ++t) part[(ks * TOK + t) * E + e] = acc[t];
+  }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int t = warp; t < ntok; t += THREADS / 32) {

@@ -88,7 +88,7 @@ __device__ __forceinline__ void mbar_wait_long(uint64_t* bar, uint32_t parity) {
         : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
         : "memory");
     if (ok) return;
-    if (++spins > (1u << 24)) {
+    if (++spins > (1u << 20)) {
       printf("mbar_wait_long timeout block %d thread %d\n", blockIdx.x, threadIdx.x);
       __trap();
     }

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Counts, per kernel of libdsocr.so, the SASS mnemonics that prove which hardware path a kernel uses (the PTX names never
-appear in SASS): UTC*MMA = tcgen05.mma, UTMALDG / UTMASTG = TMA tensor copies, UBLKCP = 1-D bulk copies, UTCBAR /
+appear in SASS): UTC*MMA = tcgen05.mma, UTMALDG / UTMASTG = TMA tensor copies, UBLKCP = 1-D bulk copies, UBLKRED = bulk reductions (cp.reduce.async.bulk), UTCBAR /
 SYNCS = tcgen05.commit / mbarrier traffic, LDTM / STTM = tcgen05.ld / st (TMEM), MUFU = special-function unit, PRMT =
 byte permutes (the byte->float path of the GEMVs), I2F = the conversion unit they avoid.  Needs no GPU (cuobjdump).
 Usage: python scripts/sass_evidence.py [lib] > profiles/r01_sass_evidence.csv"""
@@ -11,7 +11,7 @@ import sys
 from pathlib import Path
 
 LIB = Path(sys.argv[1]) if len(sys.argv) > 1 else Path(__file__).resolve().parent.parent / "deepseek-ocr.rs_b200" / "lib" / "libdsocr.so"
-KEYS = ["UTC.*MMA", "UTMALDG", "UTMASTG", "UBLKCP", "UTCBAR", "SYNCS", "LDTM", "STTM", "MUFU", "PRMT", "I2F", "HMMA", "FFMA", "LDG", "LDS", "total"]
+KEYS = ["UTC.*MMA", "UTMALDG", "UTMASTG", "UBLKCP", "UBLKRED", "UTCBAR", "SYNCS", "LDTM", "STTM", "MUFU", "PRMT", "I2F", "HMMA", "FFMA", "LDG", "LDS", "total"]
 
 
 def demangle(names):
