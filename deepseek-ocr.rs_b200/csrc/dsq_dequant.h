@@ -1,6 +1,6 @@
 // Dequantisation of one 64-wide k-block of one weight row from the device plane layouts of QuantWeight (dsq.h) - the
 // unit of work of the dequant-fused tensor-core GEMM (one thread per weight row of a 128 x 64 MMA stage, see
-// experimental/linear_dq.cuh).  __host__ __device__ so that the index arithmetic is checked on the CPU against the
+// linear_dq.cuh).  __host__ __device__ so that the index arithmetic is checked on the CPU against the
 // oracle's dequantisers (tests/test_dsq_dequant_cpu.py) before it ever runs on a GPU.
 //   Q8_0 : a = int8 [rows][K], b = f16 d [rows][K/32]
 //   Q4_K : a = 144-byte blocks as on disk [rows][K/256]

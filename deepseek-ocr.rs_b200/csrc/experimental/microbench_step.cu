@@ -1,4 +1,5 @@
-// Stand-alone micro-benchmark for the decision in DESIGN.md section 8, item 1 (not part of libdsocr.so; not yet run):
+// Stand-alone micro-benchmark behind the "persistent batch-1 decode step" decision (not part of libdsocr.so; results:
+// profiles/r02_microbench_step.log):
 // what does one *dependent phase* of a batch-1 decode step cost as
 //   (a) a kernel node of a CUDA graph (76 dependent launches per token today, ~7 us each),
 //   (b) the same with programmatic dependent launch,
