@@ -498,6 +498,9 @@ def main():
         entry = {"kernel": r["name"], "bound": m["bound"], "achieved": ach, "peak": m["peak"], "unit": m["unit"],
                  "frac": ach / m["peak"], "traffic": tr.get("dram_bytes_per_launch") if tr else None,
                  "traffic_source": tr.get("source") if tr else None,
+                 # the captured launch is not an average launch of this run: its own algorithmic bytes and the ratio
+                 "traffic_over_algorithmic_of_captured_launch": (tr["dram_bytes_per_launch"] / tr["algorithmic_bytes_of_that_launch"])
+                 if tr and tr.get("algorithmic_bytes_of_that_launch") else None,
                  "algorithmic_per_launch": m.get("bytes", m.get("flops")), "launches_per_pass": r["launches"],
                  "avg_launch_us": avg_s * 1e6, "share_of_pass": r["ms"] / total_kernel_ms}
         if r["name"] in cupti_match and cupti:
