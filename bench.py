@@ -310,6 +310,12 @@ def main():
                 f"{args.pages} synthetic pages sharded over the GPUs, {args.max_new_tokens}-token budget, greedy, "
                 f"no_repeat_ngram_size=20, {args.kv_cache} KV cache, random-init weights ({args.config} architecture)")
 
+    # the workload description both arms print (the reference arm runs "on this arm's config")
+    pages_per_rank = (args.pages + world - 1) // world
+    run_config = {"workload": workload, "l2": "per-step working set (weights 6.7 GB + KV + activations) exceeds the 126 MB L2",
+                  "parallelism": f"one fixed set of {args.pages} pages sharded round-robin over {world} GPU(s), "
+                                 f"{min(args.batch, pages_per_rank)} pages per lock-step decode group, no collective"}
+
     if args.impl == "reference":
         # CPU restatement of the reference's algorithm on the host cores; rank 0 only.
         if rank != 0:
@@ -328,7 +334,7 @@ def main():
             "impl": "reference", "metric": "pages/sec/box", "value": best["pages_per_s"], "unit": "pages/s",
             "n_gpus": args.gpus, "steps": len(vals), "warmup": 0, "ms_per_step": best["seconds_per_page"] * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload},
+            "config": run_config,
             "cpu_baseline": {"value": best["pages_per_s"], "unit": "pages/s", "cores": best["cores"], "kind": "port",
                              "sample": sample, "stages_s": best["stages_s"], "decode_tok_s": best["cpu_decode_tok_s"]},
             "e2e": {"value": best["pages_per_s"], "unit": "pages/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -530,9 +536,7 @@ def main():
         "metric": "pages/sec/box", "value": value, "unit": "pages/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": workload, "l2": "per-step working set (weights 6.7 GB + KV + activations) exceeds the 126 MB L2",
-                   "parallelism": f"one fixed set of {args.pages} pages sharded round-robin over {world} GPU(s), "
-                                  f"{min(args.batch, len(pages))} pages per lock-step decode group, no collective"},
+        "config": run_config,
         "e2e": {"value": e2e_val, "unit": "pages/s", "h2d_bytes_per_step": h2d_bytes * world, "d2h_bytes_per_step": d2h_bytes * world,
                 "host_memory": "pinned", "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches_e2e,
