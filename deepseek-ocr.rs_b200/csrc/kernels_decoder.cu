@@ -1091,11 +1091,25 @@ router_kernel(const float* __restrict__ x, const float* __restrict__ wgt, int* _
   float* part = sm + TOK * H;
   const long long row0 = (long long)blockIdx.x * TOK;
   const int ntok = (int)min((long long)TOK, rows - row0);
-  for (int i = threadIdx.x; i < TOK * H / 4; i += THREADS) {
-    const int t = i / (H / 4);
-    float4 v = make_float4(0, 0, 0, 0);
-    if (t < ntok) v = reinterpret_cast<const float4*>(x + (row0 + t) * H)[i % (H / 4)];
-    reinterpret_cast<float4*>(xs)[i] = v;
+  if constexpr (TOK >= 16) {
+    // token rows global -> shared with cp.async (zero-filled past the last row): all 16-byte pieces of a thread are in
+    // flight at once instead of one register round trip per piece (22 % of the kernel's stall samples were the stores
+    // of this loop waiting for their loads)
+    for (int i = threadIdx.x; i < TOK * H / 4; i += THREADS) {
+      const int t = i / (H / 4);
+      const float* src = x + (row0 + (t < ntok ? t : 0)) * H + (size_t)(i % (H / 4)) * 4;
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(xs + (size_t)i * 4);
+      const int bytes = t < ntok ? 16 : 0;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+    }
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+  } else {
+    for (int i = threadIdx.x; i < TOK * H / 4; i += THREADS) {
+      const int t = i / (H / 4);
+      float4 v = make_float4(0, 0, 0, 0);
+      if (t < ntok) v = reinterpret_cast<const float4*>(x + (row0 + t) * H)[i % (H / 4)];
+      reinterpret_cast<float4*>(xs)[i] = v;
+    }
   }
   __syncthreads();
   const int e = threadIdx.x % E, ks = threadIdx.x / E;
@@ -1122,22 +1136,39 @@ router_kernel(const float* __restrict__ x, const float* __restrict__ wgt, int* _
       for (int jx = 0; jx < 4; ++jx) a4[i][jx] = 0.f;
     const float* wq = wgt + (long long)(ks * kper) * E + 4 * eg;
     const float* xq = xs + (4 * tg) * H + ks * kper;
-#pragma unroll 2
-    for (int k = 0; k < kper; k += 4) {
-      float4 wv[4], xv[4];
+    // The gate weights come from L2 (~700 cycles) and a thread's FMAs of one 4-k step take ~300: the weights of the next
+    // three steps are kept in flight in a register ring of four (the capture of the form without it: 38 % of all stall
+    // samples on the first FMA that consumes a freshly loaded weight).  kper / 4 is a multiple of 4 for every supported shape.
+    constexpr int PD = 4;
+    float4 wr[PD][4];
+    const int nstep = kper / 4;
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) wv[kk] = *reinterpret_cast<const float4*>(wq + (long long)(k + kk) * E);
+    for (int d = 0; d < PD - 1; ++d)
 #pragma unroll
-      for (int t = 0; t < 4; ++t) xv[t] = *reinterpret_cast<const float4*>(xq + t * H + k);
+      for (int kk = 0; kk < 4; ++kk)
+        wr[d][kk] = d < nstep ? *reinterpret_cast<const float4*>(wq + (long long)(4 * d + kk) * E) : make_float4(0, 0, 0, 0);
+    for (int s0 = 0; s0 < nstep; s0 += PD) {
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const float xk[4] = {xv[t].x, xv[t].y, xv[t].z, xv[t].w};
+      for (int d = 0; d < PD; ++d) {
+        const int st = s0 + d, k = 4 * st;
+        const int pre = st + PD - 1;  // step whose weights are requested now, into the slot used last iteration
+        if (pre < nstep) {
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          a4[t][0] = fmaf(xk[kk], wv[kk].x, a4[t][0]);
-          a4[t][1] = fmaf(xk[kk], wv[kk].y, a4[t][1]);
-          a4[t][2] = fmaf(xk[kk], wv[kk].z, a4[t][2]);
-          a4[t][3] = fmaf(xk[kk], wv[kk].w, a4[t][3]);
+          for (int kk = 0; kk < 4; ++kk) wr[(d + PD - 1) % PD][kk] = *reinterpret_cast<const float4*>(wq + (long long)(4 * pre + kk) * E);
+        }
+        float4 xv[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) xv[t] = *reinterpret_cast<const float4*>(xq + t * H + k);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float xk[4] = {xv[t].x, xv[t].y, xv[t].z, xv[t].w};
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            a4[t][0] = fmaf(xk[kk], wr[d][kk].x, a4[t][0]);
+            a4[t][1] = fmaf(xk[kk], wr[d][kk].y, a4[t][1]);
+            a4[t][2] = fmaf(xk[kk], wr[d][kk].z, a4[t][2]);
+            a4[t][3] = fmaf(xk[kk], wr[d][kk].w, a4[t][3]);
+          }
         }
       }
     }
@@ -1621,7 +1652,7 @@ static void launch_router(const float* x, const float* wgt, int* topk_idx, float
   } else {            // prefill: 16 tokens per block reuse every gate-weight load 16x (the gate is re-read from L2 by every block:
                       // 8 tokens per block moved 1.2 GB per launch of 30 k rows); same k-slices, same summation order
     const size_t smem = (size_t)(16 * H + 256 * 16) * 4;
-    if (smem > 110 * 1024 || (H / (256 / E)) % 4) throw std::runtime_error("router: unsupported hidden size");
+    if (smem > 110 * 1024 || (H / (256 / E)) % 16) throw std::runtime_error("router: unsupported hidden size");
     static PerDeviceOnce once;  // per instantiation
     once.run([&] { cuda_check(cudaFuncSetAttribute(router_kernel<E, 16, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024), "router smem"); });
     router_kernel<E, 16, 256><<<(unsigned)((rows + 15) / 16), 256, smem, s>>>(x, wgt, topk_idx, topk_w, counts, rows, H, topk);
