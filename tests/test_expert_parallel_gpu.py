@@ -25,11 +25,15 @@ def _prompts(cfg, n, seed):
     return ids, masks, rows
 
 
-@pytest.mark.parametrize("world", [2, 4])
-def test_expert_parallel_matches_data_parallel(world, monkeypatch):
+@pytest.mark.parametrize("world,rows_per_block", [(2, None), (4, None), (2, "4")])
+def test_expert_parallel_matches_data_parallel(world, rows_per_block, monkeypatch):
     from dsocr.dispatch import EnginePool
     from dsocr.engine import DecodeParameters
 
+    if rows_per_block:
+        # the router / dispatch kernel with several rows per block (what steps of >= 149 rows use), here with the peer
+        # slot reservation of the expert-parallel branch; 7 pages per engine also exercise its row tail
+        monkeypatch.setenv("DSOCR_POST_ATTN_ROWS", rows_per_block)
     cfg, ck, d = tiny_model("bf16")
     ndev = torch.cuda.device_count()
     devices = [i % max(1, min(ndev, world)) for i in range(world)]
